@@ -1,0 +1,171 @@
+/*
+ * rg_engine.h -- C ABI of the B200-native ReplayGain 1.0 analysis engine.
+ *
+ * This is the drop-in boundary for the analysis path of M-Igashi/mp3rgain v1.5.0.  The
+ * reference has no FFI of its own: its boundary is the Rust module `mp3rgain::replaygain`
+ * (src/replaygain.rs), so each entry point below names the Rust item it stands in for.  A Rust
+ * shim maps those pub fns 1:1 onto these symbols.
+ *
+ * Conventions: plain pointers and sizes, no torch / CUDA types; every call returns 0 (RG_OK) or
+ * a negative rg_status and never unwinds; all outputs are caller-allocated; no callbacks.
+ * Host pointers unless a parameter is explicitly documented as a DEVICE pointer.
+ * The library has no CPU compute path: without a usable CUDA device rg_engine_create fails with
+ * RG_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef MP3RGAIN_B200_RG_ENGINE_H
+#define MP3RGAIN_B200_RG_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_HIST_SIZE 12000           /* src/replaygain.rs:630 HISTOGRAM_SIZE */
+#define RG_HIST_OFFSET 2000          /* src/replaygain.rs:635 HISTOGRAM_OFFSET */
+#define RG_PINK_REF 64.82            /* src/replaygain.rs:44  PINK_REF */
+#define RG_REPLAYGAIN_REFERENCE_DB 89.0 /* src/replaygain.rs:37 (display only) */
+
+/* Status codes. The strings returned by rg_status_str() are the reference's anyhow messages
+ * (src/replaygain.rs:805,822,834,842-846,857,863,869-872). */
+typedef enum {
+    RG_OK = 0,
+    RG_ERR_INVALID_ARG = -1,
+    RG_ERR_NO_DEVICE = -2,          /* no CUDA device / driver: the engine has no CPU fallback */
+    RG_ERR_CUDA = -3,               /* a CUDA call failed; rg_last_error() has the detail */
+    RG_ERR_OPEN = -4,               /* "Failed to open: {path}"            (host wrappers only) */
+    RG_ERR_PROBE = -5,              /* "Failed to probe format"  -- no MPEG audio frame found */
+    RG_ERR_NO_AUDIO_TRACK = -6,     /* "No audio track found" */
+    RG_ERR_TRACK_INDEX = -7,        /* "Track index {i} out of range (file has 1 audio track(s))" */
+    RG_ERR_UNKNOWN_SAMPLE_RATE = -8,/* "Unknown sample rate" */
+    RG_ERR_UNSUPPORTED_RATE = -9,   /* "Unsupported sample rate: {sr} Hz. Supported rates: ..." */
+    RG_ERR_UNSUPPORTED_FORMAT = -10,/* MP4/AAC container or a layer/version this engine does not decode */
+    RG_ERR_NO_MEMORY = -11
+} rg_status;
+
+/* rg_config.flags */
+#define RG_FLAG_EXACT_IIR      0x1u /* bit-exact serial IIR for every track (parity mode).  Default is the
+                                       time-blocked IIR which re-runs edge-flagged tracks through the exact kernel. */
+#define RG_FLAG_KEEP_INFO_FRAME 0x2u /* decode a leading Xing/Info/VBRI frame as audio instead of skipping it */
+#define RG_FLAG_CLAMP_PCM      0x4u /* clamp decoded PCM to [-1,1] before analysis (symphonia-behaviour switch) */
+
+typedef struct rg_engine rg_engine;   /* opaque: CUDA context, streams, device scratch, pinned staging */
+typedef struct rg_corpus rg_corpus;   /* opaque: a batch of file images resident in device memory */
+
+typedef struct {
+    int32_t  device;            /* CUDA ordinal (one engine per GPU; one process per GPU when sharded) */
+    uint32_t flags;             /* RG_FLAG_* */
+    uint64_t scratch_bytes;     /* device scratch budget for decoded PCM + intermediates; 0 = default (24 GiB) */
+} rg_config;
+
+/* One file image.  Stands in for the `&Path` argument of analyze_track (src/replaygain.rs:929):
+ * the caller has read (or mmapped / pinned) the file; the engine borrows the bytes until the call returns. */
+typedef struct {
+    const uint8_t* data;
+    uint64_t       len;
+    int32_t        track_index; /* -1 = Option::None; MP3 has exactly one audio track, so only -1 and 0 succeed */
+    int32_t        reserved;
+} rg_input;
+
+/* ReplayGainResult (src/replaygain.rs:56-68) + per-entry status + diagnostics. */
+typedef struct {
+    double   loudness_db;
+    double   gain_db;           /* RG_PINK_REF - loudness_db */
+    double   peak;              /* normalised units, not clamped */
+    uint32_t sample_rate;
+    int32_t  file_type;         /* 0 = Mp3, 1 = Aac (AudioFileType, src/replaygain.rs:47-53) */
+    int32_t  status;            /* rg_status for this entry */
+    uint32_t channels;
+    uint32_t n_frames;          /* MPEG audio frames decoded */
+    uint32_t n_windows;         /* 50 ms windows that reached finish_window */
+    uint32_t n_dropped_windows; /* windows whose bin index fell outside [0,12000) (src/replaygain.rs:757) */
+    uint32_t n_edge_windows;    /* windows whose 1000*log10 value sat within the edge tolerance of an integer */
+    uint32_t exact_rerun;       /* 1 if the time-blocked pass flagged this track and the exact kernel re-ran it */
+    uint32_t reserved;
+} rg_track_result;
+
+/* AlbumGainResult minus the per-track vector (src/replaygain.rs:78-88). */
+typedef struct {
+    double album_loudness_db;
+    double album_gain_db;
+    double album_peak;
+} rg_album_result;
+
+/* PeakAmplitudeResult (src/replaygain.rs:1125-1132). */
+typedef struct {
+    double   peak;
+    double   peak_pcm;          /* peak * 32768 */
+    uint32_t sample_rate;
+    int32_t  status;
+} rg_peak_result;
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+/* replaygain::is_available (src/replaygain.rs:1119): 1 when a CUDA device is usable, else 0. */
+int  rg_is_available(void);
+int  rg_engine_create(const rg_config* cfg, rg_engine** out);
+void rg_engine_destroy(rg_engine* e);
+const char* rg_status_str(int status);
+/* Tuning knobs (not part of the reference surface). Keys: "iir_block_windows" (50 ms windows per time block of
+ * the time-blocked IIR, default 16), "iir_warm_windows" (zero-state warm-up windows before each block, default 2),
+ * "edge_tol" (distance of 1000*log10(ms) from an integer below which the time-blocked pass hands the track to the
+ * exact kernel, default 1e-6).  Returns RG_ERR_INVALID_ARG for an unknown key. */
+int rg_engine_set_option(rg_engine* e, const char* key, double value);
+/* Thread-local detail string for the last failing call (CUDA error text etc.). */
+const char* rg_last_error(void);
+
+/* ---- analysis from host buffers (the end-to-end path: H2D copies happen inside) -------------- */
+/* analyze_track / analyze_track_with_index (src/replaygain.rs:929-941), batched: n independent files.
+ * Per-entry failures are reported in out[i].status (track mode: src/main.rs:1988-1999 keeps going).
+ * hist_out: NULL or n*RG_HIST_SIZE u32 counters (the reference's private TrackAnalysisInternal.histogram). */
+int rg_analyze_tracks(rg_engine* e, const rg_input* in, size_t n, rg_track_result* out, uint32_t* hist_out);
+
+/* analyze_album / analyze_album_with_index (src/replaygain.rs:1033-1074).  Fails the call with the first
+ * bad entry's status (the `?` at :1055).  album_hist_out: NULL or RG_HIST_SIZE u64 counters. */
+int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_track_result* out,
+                     rg_album_result* album, uint64_t* album_hist_out);
+
+/* find_peak_amplitude (src/replaygain.rs:1140-1249), batched. */
+int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_result* out);
+
+/* process_audio_buffer + analyzer on caller-supplied planar f32 PCM (src/replaygain.rs:953-980, 702-771):
+ * the stage-B entry point (decoder bypassed, like the reference's unit tests at :1298-1365).
+ * planes[c] = channel c, frames samples each; nch 1 or 2.  hist_out NULL or RG_HIST_SIZE u32. */
+int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int nch, size_t frames, uint32_t sample_rate,
+                       rg_track_result* out, uint32_t* hist_out);
+
+/* ---- device-resident corpora (inputs already in HBM; what the kernel-only throughput times) -- */
+int  rg_corpus_upload(rg_engine* e, const rg_input* in, size_t n, rg_corpus** out);
+void rg_corpus_free(rg_engine* e, rg_corpus* c);
+uint64_t rg_corpus_bytes(const rg_corpus* c);
+int rg_analyze_corpus(rg_engine* e, rg_corpus* c, rg_track_result* out, uint32_t* hist_out);
+
+/* ---- album mode across GPUs (one engine per rank) --------------------------------------------- */
+/* Analyse this rank's shard and ADD its tracks' histograms into d_album_hist (DEVICE pointer, RG_HIST_SIZE u64,
+ * caller-zeroed) and fold its peak into *d_album_peak (DEVICE pointer, one f64, caller-zeroed).  The caller then
+ * all-reduces both buffers (sum / max) over NCCL and calls rg_album_finish on every rank: the accumulate loop of
+ * src/replaygain.rs:1053-1062 with the cross-device exchange in the middle. */
+int rg_analyze_album_shard(rg_engine* e, rg_corpus* c, rg_track_result* out,
+                           uint64_t* d_album_hist, double* d_album_peak);
+/* get_loudness on the merged histogram + PINK_REF (src/replaygain.rs:1065-1066), computed on the device. */
+int rg_album_finish(rg_engine* e, const uint64_t* d_album_hist, const double* d_album_peak, rg_album_result* album);
+
+/* ---- introspection for measurement and parity tests ------------------------------------------- */
+typedef struct {
+    uint64_t kernel_launches;   /* kernels launched by this engine since creation */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t tracks, frames, exact_reruns;
+    float    last_ms_index, last_ms_huffman, last_ms_hybrid, last_ms_synth, last_ms_iir, last_ms_hist;
+    float    last_ms_total;     /* CUDA-event time of the last analyse call's device work */
+} rg_stats;
+int rg_engine_stats(rg_engine* e, rg_stats* out);
+
+/* Decode only: planar f32 PCM of one file image into caller buffers (parity hook for the decoder stages).
+ * pcm: nch_max*max_frames floats (plane c at pcm + c*max_frames). Returns samples per channel in *frames_out. */
+int rg_decode_pcm(rg_engine* e, const rg_input* in, float* pcm, size_t max_frames,
+                  size_t* frames_out, uint32_t* channels_out, uint32_t* sample_rate_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP3RGAIN_B200_RG_ENGINE_H */

@@ -1,0 +1,327 @@
+// k_analysis.cuh -- stage B on the device: equal-loudness IIR cascade (K4) and
+// window -> bin -> histogram -> 95th percentile (K5).
+//
+// K4 replaces EqualLoudnessFilter::process + the sum-of-squares half of ReplayGainAnalyzer
+// (reference src/replaygain.rs:586-616, 720-740, 966-975).  K5 replaces finish_window,
+// LoudnessHistogram::get_loudness and the album accumulate (src/replaygain.rs:743-765, 665-682, 1056-1059).
+//
+// Arithmetic contract (this file is compiled with -fmad=false; every f64 op below is spelled with an
+// _rn intrinsic so nothing is contracted or reassociated):
+//   EXACT mode: per sample, t_i = b_i*x[n-i] - a_i*y[n-i] (two products, one subtract), S = t_1+...+t_10
+//   left to right, y = (1e-10 + b_0*x[n]) + S -- the reference's order.  The *32768 input scale
+//   (src/replaygain.rs:969) is folded into b_i: multiplying by 2^15 commutes with rounding, so
+//   (2^15*b_i)*x is bit-identical to b_i*(2^15*x).  The leading "0.0 +" of Rust's iterator sum is dropped:
+//   it can only change the sign of an all-zero partial sum, which the final add of a non-negative-zero
+//   term erases.
+//   FAST mode: same recurrence evaluated with FMAs and with the y[n-1] term added last (1-FMA recurrence
+//   latency); chains start from zero state n_warm samples early.  Not bit-identical to the reference;
+//   K5 flags every window whose bin decision is within `edge_tol` of flipping and the host re-runs those
+//   tracks through the EXACT kernel.
+#pragma once
+#include "rg_internal.h"
+
+// [rate][0..9]  = a_1..a_10 (Yule)      [rate][10..20] = 32768*b_0..b_10 (Yule)
+// [rate][21..22]= a_1,a_2 (Butter)      [rate][23..25] = b_0..b_2 (Butter)
+#define RG_CC_STRIDE 26
+__constant__ double c_rg_coef[12][RG_CC_STRIDE];
+
+struct IirState {
+    double xh[10], yh[10];  // Yule histories: xh[i] = x[n-1-i], yh[i] = y[n-1-i]
+    double bx[2], by[2];    // Butterworth histories
+};
+
+template <bool FAST>
+__device__ __forceinline__ double iir_step(IirState& s, const double* __restrict__ c, float xf) {
+    const double x0 = (double)xf;
+    double y0;
+    if (!FAST) {
+        double S = __dsub_rn(__dmul_rn(c[11], s.xh[0]), __dmul_rn(c[0], s.yh[0]));
+#pragma unroll
+        for (int i = 1; i < 10; i++) {
+            double t = __dsub_rn(__dmul_rn(c[11 + i], s.xh[i]), __dmul_rn(c[i], s.yh[i]));
+            S = __dadd_rn(S, t);
+        }
+        y0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c[10], x0)), S);
+    } else {
+        double acc = __fma_rn(c[10], x0, 1e-10);
+#pragma unroll
+        for (int i = 9; i >= 0; i--) acc = __fma_rn(c[11 + i], s.xh[i], acc);
+#pragma unroll
+        for (int i = 9; i >= 1; i--) acc = __fma_rn(-c[i], s.yh[i], acc);
+        y0 = __fma_rn(-c[0], s.yh[0], acc);
+    }
+#pragma unroll
+    for (int i = 9; i >= 1; i--) { s.xh[i] = s.xh[i - 1]; s.yh[i] = s.yh[i - 1]; }
+    s.xh[0] = x0;
+    s.yh[0] = y0;
+
+    double z0;
+    if (!FAST) {
+        double t1 = __dsub_rn(__dmul_rn(c[24], s.bx[0]), __dmul_rn(c[21], s.by[0]));
+        double t2 = __dsub_rn(__dmul_rn(c[25], s.bx[1]), __dmul_rn(c[22], s.by[1]));
+        z0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c[23], y0)), __dadd_rn(t1, t2));
+    } else {
+        double acc = __fma_rn(c[23], y0, 1e-10);
+        acc = __fma_rn(c[25], s.bx[1], acc);
+        acc = __fma_rn(c[24], s.bx[0], acc);
+        acc = __fma_rn(-c[22], s.by[1], acc);
+        z0 = __fma_rn(-c[21], s.by[0], acc);
+    }
+    s.bx[1] = s.bx[0]; s.bx[0] = y0;
+    s.by[1] = s.by[0]; s.by[0] = z0;
+    return z0;
+}
+
+// Per-chain window accounting.
+struct WinAcc {
+    double sum;
+    double* out;
+    uint32_t tot, win;
+};
+
+template <bool FAST, bool ACCUM>
+__device__ __forceinline__ void iir_sample(IirState& s, const double* __restrict__ c, WinAcc& w, float& peak, float xf) {
+    double z = iir_step<FAST>(s, c, xf);
+    if (ACCUM) {
+        peak = fmaxf(peak, fabsf(xf));
+        if (FAST) w.sum = __fma_rn(z, z, w.sum);
+        else w.sum = __dadd_rn(w.sum, __dmul_rn(z, z));
+        if (++w.tot == w.win) {
+            *w.out++ = w.sum;
+            w.sum = 0.0;
+            w.tot = 0;
+        }
+    }
+}
+
+// Feed n consecutive samples starting at p: scalar head up to 16-byte alignment, float4 body, scalar tail.
+template <bool FAST, bool ACCUM>
+__device__ __forceinline__ void iir_run(IirState& s, const double* __restrict__ c, WinAcc& w, float& peak,
+                                        const float* __restrict__ p, uint32_t n) {
+    while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 15u)) {
+        iir_sample<FAST, ACCUM>(s, c, w, peak, __ldg(p));
+        p++; n--;
+    }
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    uint32_t n20 = n / 20;
+    if (n20) {
+        float4 buf[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) buf[k] = __ldg(p4 + k);
+        for (uint32_t it = 0; it < n20; it++) {
+            float4 cur[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) cur[k] = buf[k];
+            p4 += 5;
+            if (it + 1 < n20) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) buf[k] = __ldg(p4 + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].x);
+                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].y);
+                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].z);
+                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].w);
+            }
+        }
+    }
+    p = reinterpret_cast<const float*>(p4);
+    n -= n20 * 20;
+    while (n > 0) {
+        iir_sample<FAST, ACCUM>(s, c, w, peak, __ldg(p));
+        p++; n--;
+    }
+}
+
+// K4: one thread per chain.  All chains of one launch share a sample rate (rate_idx is a kernel argument so the
+// coefficient reads are uniform constant-bank operands).
+template <bool FAST>
+__global__ void __launch_bounds__(128)
+k_iir(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base, int rate_idx) {
+    uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chains) return;
+    const RgChain ch = chains[ci];
+    const double* c = c_rg_coef[rate_idx];
+    IirState s;
+#pragma unroll
+    for (int i = 0; i < 10; i++) { s.xh[i] = 0.0; s.yh[i] = 0.0; }
+    s.bx[0] = s.bx[1] = s.by[0] = s.by[1] = 0.0;
+    WinAcc w;
+    w.sum = 0.0; w.out = ch.wsum; w.tot = 0; w.win = ch.win;
+    float peak = 0.0f;
+    if (FAST && ch.n_warm) iir_run<FAST, false>(s, c, w, peak, ch.src, ch.n_warm);
+    iir_run<FAST, true>(s, c, w, peak, ch.src + ch.n_warm, ch.n_main);
+    if (w.tot) *w.out = w.sum;  // the track's final partial window (src/replaygain.rs:907)
+    peaks[chain_base + ci] = peak;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: one CTA per track.  Window sums -> bin index -> shared 12000-bin histogram (warp-aggregated atomics)
+// -> suffix scan for the 95th percentile -> optional flush to the global per-track / album histograms.
+
+__device__ __forceinline__ void hist_add_aggregated(uint32_t* hist, int idx, bool valid) {
+    // lanes of a warp that hit the same bin elect one leader which adds the group's population
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    unsigned peers = __match_any_sync(active, idx);
+    int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&hist[idx], (uint32_t)__popc(peers));
+}
+
+#define K5_THREADS 256
+__global__ void __launch_bounds__(K5_THREADS)
+k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict__ chain_peaks,
+                  RgTrackOut* __restrict__ out, uint32_t* __restrict__ hist_out /* n*12000 or null */,
+                  unsigned long long* __restrict__ album_hist /* 12000 or null */,
+                  unsigned long long* __restrict__ album_peak_bits /* or null */, double edge_tol,
+                  int defer_album_on_edge /* skip the album adds when this track has edge windows (it will be re-run) */) {
+    __shared__ uint32_t hist[RG_HIST_BINS];
+    __shared__ uint32_t s_cnt[3];           // counted, dropped, edge
+    __shared__ uint32_t s_chunk[K5_THREADS];   // per-track window counts fit 32 bits
+    __shared__ float s_peak[K5_THREADS / 32];
+    __shared__ int s_found;
+
+    const RgTrackWin t = tracks[blockIdx.x];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < RG_HIST_BINS; i += K5_THREADS) hist[i] = 0;
+    if (tid < 3) s_cnt[tid] = 0;
+    if (tid == 0) s_found = -1;
+    __syncthreads();
+
+    const uint32_t n_win = t.n_full + (t.rem ? 1u : 0u);
+    uint32_t dropped = 0, edge = 0, counted = 0;
+    const uint32_t n_round = (n_win + K5_THREADS - 1) / K5_THREADS * K5_THREADS;
+    for (uint32_t w = tid; w < n_round; w += K5_THREADS) {
+        bool valid = false;
+        int idx = 0;
+        if (w < n_win) {
+            const double tot = (double)(w < t.n_full ? t.win : t.rem);
+            const double l = t.wsum0[w], r = t.wsum1[w];
+            // (lsum + rsum) / totsamp * 0.5 ; 1000*log10(ms + 1e-37) ; `as i32` (saturating, NaN -> 0)
+            const double ms = __dmul_rn(__ddiv_rn(__dadd_rn(l, r), tot), 0.5);
+            const double val = __dmul_rn(1000.0, log10(__dadd_rn(ms, 1e-37)));
+            const int v = __double2int_rz(val);  // cvt.rzi.s32.f64: truncates, saturates, NaN -> 0
+            const long long li = (long long)v + RG_HIST_OFF;
+            if (fabs(val - rint(val)) < edge_tol) edge++;
+            if (li >= 0 && li < RG_HIST_BINS) { valid = true; idx = (int)li; counted++; }
+            else dropped++;
+        }
+        hist_add_aggregated(hist, idx, valid);
+    }
+    // peak over this track's chains
+    float pk = 0.0f;
+    for (uint32_t c = t.chain_begin + tid; c < t.chain_end; c += K5_THREADS) pk = fmaxf(pk, chain_peaks[c]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        pk = fmaxf(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+        edge += __shfl_xor_sync(0xffffffffu, edge, o);
+        counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    }
+    if ((tid & 31) == 0) {
+        s_peak[tid >> 5] = pk;
+        atomicAdd(&s_cnt[0], counted);
+        atomicAdd(&s_cnt[1], dropped);
+        atomicAdd(&s_cnt[2], edge);
+    }
+    __syncthreads();
+
+    // get_loudness: threshold = ceil(total * (1.0 - 0.95)); scan from the top bin down.
+    const unsigned long long total = s_cnt[0];
+    constexpr int CH = (RG_HIST_BINS + K5_THREADS - 1) / K5_THREADS;  // bins per thread, thread 0 owns the TOP chunk
+    const int hi = RG_HIST_BINS - 1 - tid * CH;                       // my highest bin
+    unsigned long long mine = 0;
+    for (int k = 0; k < CH; k++) {
+        int b = hi - k;
+        if (b >= 0) mine += hist[b];
+    }
+    s_chunk[tid] = (uint32_t)mine;
+    __syncthreads();
+    if (total > 0) {
+        const unsigned long long threshold = (unsigned long long)ceil((double)total * (1.0 - 0.95));
+        unsigned long long before = 0;  // counts in chunks above mine
+        for (int k = 0; k < tid; k++) before += s_chunk[k];
+        if (before < threshold && before + mine >= threshold) {
+            unsigned long long cnt = before;
+            for (int k = 0; k < CH; k++) {
+                int b = hi - k;
+                if (b < 0) break;
+                cnt += hist[b];
+                if (cnt >= threshold) { s_found = b; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float p = 0.0f;
+        for (int k = 0; k < K5_THREADS / 32; k++) p = fmaxf(p, s_peak[k]);
+        RgTrackOut o;
+        o.loudness_db = (total == 0 || s_found < 0) ? -20.0 : (double)(s_found - RG_HIST_OFF) / 100.0;
+        o.gain_db = __dsub_rn(64.82, o.loudness_db);
+        o.peak = (double)p;
+        o.n_windows = n_win;
+        o.n_dropped = s_cnt[1];
+        o.n_edge = s_cnt[2];
+        o.pad = 0;
+        out[blockIdx.x] = o;
+        if (album_peak_bits && (t.flags & 1u) && !(defer_album_on_edge && s_cnt[2] > 0)) atomicMax(album_peak_bits, (unsigned long long)__double_as_longlong((double)p));
+    }
+    if (hist_out) {
+        uint32_t* dst = hist_out + (size_t)blockIdx.x * RG_HIST_BINS;
+        for (int i = tid; i < RG_HIST_BINS; i += K5_THREADS) dst[i] = hist[i];
+    }
+    if (album_hist && (t.flags & 1u) && !(defer_album_on_edge && s_cnt[2] > 0)) {
+        for (int i = tid; i < RG_HIST_BINS; i += K5_THREADS) {
+            uint32_t v = hist[i];
+            if (v) atomicAdd(&album_hist[i], (unsigned long long)v);
+        }
+    }
+}
+
+__global__ void k_scatter_f32(const float* __restrict__ in, const uint32_t* __restrict__ pos, float* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[pos[i]] = in[i];
+}
+
+// get_loudness on a merged u64 album histogram (src/replaygain.rs:1065-1066); single CTA.
+__global__ void __launch_bounds__(K5_THREADS)
+k_album_percentile(const unsigned long long* __restrict__ album_hist, const unsigned long long* __restrict__ album_peak_bits,
+                   double* __restrict__ out3 /* loudness, gain, peak */) {
+    __shared__ unsigned long long s_chunk[K5_THREADS];
+    __shared__ int s_found;
+    const int tid = threadIdx.x;
+    constexpr int CH = (RG_HIST_BINS + K5_THREADS - 1) / K5_THREADS;
+    const int hi = RG_HIST_BINS - 1 - tid * CH;
+    unsigned long long mine = 0;
+    for (int k = 0; k < CH; k++) {
+        int b = hi - k;
+        if (b >= 0) mine += album_hist[b];
+    }
+    s_chunk[tid] = mine;
+    if (tid == 0) s_found = -1;
+    __syncthreads();
+    unsigned long long total = 0;
+    for (int k = 0; k < K5_THREADS; k++) total += s_chunk[k];
+    if (total > 0) {
+        const unsigned long long threshold = (unsigned long long)ceil((double)total * (1.0 - 0.95));
+        unsigned long long before = 0;
+        for (int k = 0; k < tid; k++) before += s_chunk[k];
+        if (before < threshold && before + mine >= threshold) {
+            unsigned long long cnt = before;
+            for (int k = 0; k < CH; k++) {
+                int b = hi - k;
+                if (b < 0) break;
+                cnt += album_hist[b];
+                if (cnt >= threshold) { s_found = b; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double l = (total == 0 || s_found < 0) ? -20.0 : (double)(s_found - RG_HIST_OFF) / 100.0;
+        out3[0] = l;
+        out3[1] = __dsub_rn(64.82, l);
+        out3[2] = __longlong_as_double((long long)*album_peak_bits);
+    }
+}

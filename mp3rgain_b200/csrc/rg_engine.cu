@@ -1,0 +1,444 @@
+// rg_engine.cu -- C ABI (include/rg_engine.h) and host orchestration of the sm_100a kernels.
+// There is no CPU compute path in this file: every analysis call launches the kernels in k_*.cuh.
+#include "../../include/rg_engine.h"
+#include "rg_internal.h"
+#include "rg_coeffs.h"
+#include "k_analysis.cuh"
+#include "rg_decode.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int fail_cuda(cudaError_t err, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at rg_engine.cu:%d: %s", what, line, cudaGetErrorString(err));
+    g_last_error = buf;
+    return RG_ERR_CUDA;
+}
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t _e = (call);                                         \
+        if (_e != cudaSuccess) return fail_cuda(_e, #call, __LINE__);    \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// One track's decoded (or caller-supplied) PCM, resident on the device.
+struct PcmTrack {
+    const float* d_ch[2] = {nullptr, nullptr};
+    size_t frames = 0;
+    int nch = 0;
+    int rate_idx = -1;
+    uint32_t sample_rate = 0;
+    int status = RG_OK;
+};
+
+struct rg_engine {
+    int device = 0;
+    uint32_t flags = 0;
+    uint64_t scratch_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // options
+    uint32_t block_windows = 16, warm_windows = 2;
+    double edge_tol = 1e-6;
+    // device scratch
+    DevBuf d_pcm_in, d_chains, d_wsum, d_peaks, d_twin, d_tout, d_hist, d_album, d_misc;
+    HostBuf h_stage, h_tout;
+    rg_stats stats = {};
+    DecodeScratch dec;
+};
+
+struct rg_corpus {
+    DevBuf d_bytes;
+    std::vector<uint64_t> off, len;
+    std::vector<int32_t> track_index;
+    uint64_t total = 0;
+};
+
+static int rate_index(uint32_t sr) {
+    for (int r = 0; r < RG_NUM_RATES; r++)
+        if (RG_RATES[r] == sr) return r;
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int rg_is_available(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n > 0 ? 1 : 0;
+}
+
+extern "C" const char* rg_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char* rg_status_str(int status) {
+    switch (status) {
+        case RG_OK: return "ok";
+        case RG_ERR_INVALID_ARG: return "invalid argument";
+        case RG_ERR_NO_DEVICE: return "no CUDA device available (this engine has no CPU fallback)";
+        case RG_ERR_CUDA: return "CUDA error";
+        case RG_ERR_OPEN: return "Failed to open";
+        case RG_ERR_PROBE: return "Failed to probe format";
+        case RG_ERR_NO_AUDIO_TRACK: return "No audio track found";
+        case RG_ERR_TRACK_INDEX: return "Track index out of range (file has 1 audio track(s))";
+        case RG_ERR_UNKNOWN_SAMPLE_RATE: return "Unknown sample rate";
+        case RG_ERR_UNSUPPORTED_RATE:
+            return "Unsupported sample rate. Supported rates: 96000, 88200, 64000, 48000, 44100, 32000, 24000, "
+                   "22050, 16000, 12000, 11025, 8000";
+        case RG_ERR_UNSUPPORTED_FORMAT: return "Unsupported format (not an MPEG-1 Layer III stream)";
+        case RG_ERR_NO_MEMORY: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
+    if (!out) return RG_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&n);
+    if (e0 != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        g_last_error = "no CUDA device: rg_engine has no CPU fallback";
+        return RG_ERR_NO_DEVICE;
+    }
+    int dev = cfg ? cfg->device : 0;
+    if (dev < 0 || dev >= n) return RG_ERR_INVALID_ARG;
+    CK(cudaSetDevice(dev));
+    rg_engine* e = new rg_engine();
+    e->device = dev;
+    e->flags = cfg ? cfg->flags : 0;
+    e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (24ull << 30);
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+    // coefficient table -> constant memory, b's of the Yule stage pre-scaled by 2^15 (see k_analysis.cuh)
+    static double cc[12][RG_CC_STRIDE];
+    for (int r = 0; r < 12; r++) {
+        const double* row = RG_COEFS[r];
+        for (int i = 1; i <= 10; i++) cc[r][i - 1] = row[i];
+        for (int i = 0; i <= 10; i++) cc[r][10 + i] = row[11 + i] * 32768.0;
+        cc[r][21] = row[23]; cc[r][22] = row[24];
+        cc[r][23] = row[25]; cc[r][24] = row[26]; cc[r][25] = row[27];
+    }
+    CK(cudaMemcpyToSymbol(c_rg_coef, cc, sizeof cc));
+    int rc = decode_init_tables(e->dec);
+    if (rc != RG_OK) { delete e; return rc; }
+    *out = e;
+    return RG_OK;
+}
+
+extern "C" void rg_engine_destroy(rg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (DevBuf* b : {&e->d_pcm_in, &e->d_chains, &e->d_wsum, &e->d_peaks, &e->d_twin, &e->d_tout, &e->d_hist,
+                      &e->d_album, &e->d_misc})
+        b->release();
+    e->h_stage.release();
+    e->h_tout.release();
+    e->dec.release();
+    for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value) {
+    if (!e || !key) return RG_ERR_INVALID_ARG;
+    if (!strcmp(key, "iir_block_windows")) { if (value < 1) return RG_ERR_INVALID_ARG; e->block_windows = (uint32_t)value; return RG_OK; }
+    if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
+    if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
+    if (!strcmp(key, "exact_iir")) { if (value != 0) e->flags |= RG_FLAG_EXACT_IIR; else e->flags &= ~RG_FLAG_EXACT_IIR; return RG_OK; }
+    return RG_ERR_INVALID_ARG;
+}
+
+extern "C" int rg_engine_stats(rg_engine* e, rg_stats* out) {
+    if (!e || !out) return RG_ERR_INVALID_ARG;
+    *out = e->stats;
+    return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage B over device-resident PCM.  `tracks` entries with status != RG_OK or frames == 0 are skipped
+// (frames == 0 yields the reference's empty-histogram answer: -20 dB).
+struct StageBOut {
+    std::vector<RgTrackOut> res;     // per track
+    std::vector<uint8_t> rerun;      // per track: exact kernel re-ran it
+};
+
+static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, const std::vector<uint32_t>& which,
+                         bool exact, double* d_wsum_base, std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin,
+                         size_t& wsum_doubles) {
+    // wsum layout: for each selected track, channel 0 windows then channel 1 windows
+    chains.clear();
+    twin.clear();
+    size_t woff = 0;
+    for (uint32_t ti : which) {
+        const PcmTrack& t = tracks[ti];
+        RgTrackWin tw{};
+        uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
+        uint32_t n_full = 0, rem = 0;
+        if (t.status == RG_OK && t.frames > 0 && win > 0) {
+            n_full = (uint32_t)(t.frames / win);
+            rem = (uint32_t)(t.frames % win);
+        }
+        uint32_t n_win = n_full + (rem ? 1 : 0);
+        tw.n_full = n_full; tw.rem = rem; tw.win = win;
+        tw.chain_begin = (uint32_t)chains.size();
+        tw.wsum0 = d_wsum_base + woff;
+        tw.wsum1 = (t.nch >= 2) ? d_wsum_base + woff + n_win : tw.wsum0;
+        if (n_win) {
+            int nch = t.nch >= 2 ? 2 : 1;
+            for (int c = 0; c < nch; c++) {
+                double* wbase = d_wsum_base + woff + (size_t)c * n_win;
+                if (exact) {
+                    RgChain ch{};
+                    ch.src = t.d_ch[c]; ch.wsum = wbase; ch.n_warm = 0; ch.n_main = (uint32_t)t.frames;
+                    ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
+                    chains.push_back(ch);
+                } else {
+                    const uint32_t bw = e->block_windows, ww = e->warm_windows;
+                    for (uint32_t w0 = 0; w0 < n_win; w0 += bw) {
+                        uint32_t w1 = std::min(n_win, w0 + bw);
+                        uint64_t s0 = (uint64_t)w0 * win;
+                        uint64_t s1 = std::min<uint64_t>((uint64_t)w1 * win, t.frames);
+                        uint64_t warm = std::min<uint64_t>(s0, (uint64_t)ww * win);
+                        RgChain ch{};
+                        ch.src = t.d_ch[c] + (s0 - warm);
+                        ch.wsum = wbase + w0;
+                        ch.n_warm = (uint32_t)warm;
+                        ch.n_main = (uint32_t)(s1 - s0);
+                        ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
+                        chains.push_back(ch);
+                    }
+                }
+            }
+            woff += (size_t)n_win * nch;
+        }
+        tw.chain_end = (uint32_t)chains.size();
+        twin.push_back(tw);
+    }
+    wsum_doubles = woff;
+}
+
+// Runs K4 (+K5) for the selected tracks.  Outputs land in d_tout[slot] / d_hist[slot] where slot = position in `which`.
+static int launch_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, const std::vector<uint32_t>& which, bool exact,
+                          bool want_hist, unsigned long long* d_album_hist, unsigned long long* d_album_peak,
+                          bool defer_album_on_edge, std::vector<RgTrackOut>& h_out, uint32_t* hist_host, size_t hist_stride_tracks) {
+    (void)hist_stride_tracks;
+    const size_t n = which.size();
+    if (!n) return RG_OK;
+    // size the window-sum buffer first
+    size_t total_w = 0;
+    for (uint32_t ti : which) {
+        const PcmTrack& t = tracks[ti];
+        uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
+        if (t.status == RG_OK && t.frames > 0 && win > 0) total_w += (size_t)((t.frames + win - 1) / win) * (t.nch >= 2 ? 2 : 1);
+    }
+    CK(e->d_wsum.ensure(std::max<size_t>(total_w, 1) * sizeof(double)));
+    std::vector<RgChain> chains;
+    std::vector<RgTrackWin> twin;
+    size_t wd = 0;
+    build_chains(e, tracks, which, exact, e->d_wsum.as<double>(), chains, twin, wd);
+    for (auto& tw : twin) tw.flags = (d_album_hist != nullptr) ? 1u : 0u;
+
+    // group chains by sample rate so each launch reads one coefficient row through uniform constant operands
+    std::vector<uint32_t> order(chains.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    bool mixed = false;
+    for (size_t i = 1; i < chains.size(); i++) if (chains[i].rate_idx != chains[0].rate_idx) { mixed = true; break; }
+    std::vector<RgChain> sorted;
+    std::vector<uint32_t> newpos;
+    if (mixed) {
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return chains[a].rate_idx < chains[b].rate_idx; });
+        // peaks are indexed by ORIGINAL chain id (the K5 track ranges), so keep a per-chain slot in the sorted copy
+        sorted.resize(chains.size());
+        newpos.resize(chains.size());
+        for (uint32_t i = 0; i < order.size(); i++) { sorted[i] = chains[order[i]]; newpos[i] = order[i]; }
+    }
+    const std::vector<RgChain>& launch_chains = mixed ? sorted : chains;
+
+    CK(e->d_chains.ensure(std::max<size_t>(chains.size(), 1) * sizeof(RgChain)));
+    CK(e->d_peaks.ensure(std::max<size_t>(chains.size(), 1) * sizeof(float) * 2));
+    CK(e->d_twin.ensure(n * sizeof(RgTrackWin)));
+    CK(e->d_tout.ensure(n * sizeof(RgTrackOut)));
+    if (want_hist) CK(e->d_hist.ensure(n * RG_HIST_BINS * sizeof(uint32_t)));
+    if (!chains.empty())
+        CK(cudaMemcpyAsync(e->d_chains.p, launch_chains.data(), chains.size() * sizeof(RgChain), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_twin.p, twin.data(), n * sizeof(RgTrackWin), cudaMemcpyHostToDevice, e->stream));
+    e->stats.h2d_bytes += chains.size() * sizeof(RgChain) + n * sizeof(RgTrackWin);
+
+    float* d_peaks_sorted = e->d_peaks.as<float>();                      // written by K4 in launch order
+    float* d_peaks_orig = e->d_peaks.as<float>() + chains.size();        // original order (only when mixed)
+    CK(cudaEventRecord(e->ev[4], e->stream));
+    size_t i0 = 0;
+    while (i0 < launch_chains.size()) {
+        size_t i1 = i0;
+        uint32_t r = launch_chains[i0].rate_idx;
+        while (i1 < launch_chains.size() && launch_chains[i1].rate_idx == r) i1++;
+        uint32_t cnt = (uint32_t)(i1 - i0);
+        const int T = exact ? 32 : 128;
+        uint32_t blocks = (cnt + T - 1) / T;
+        if (exact)
+            k_iir<false><<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, (int)r);
+        else
+            k_iir<true><<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, (int)r);
+        // note: chain_base passed as i0 but the kernel indexes peaks[chain_base + ci] with ci relative to the sub-array
+        e->stats.kernel_launches++;
+        i0 = i1;
+    }
+    CK(cudaGetLastError());
+    const float* d_peaks_for_k5 = d_peaks_sorted;
+    if (mixed) {
+        // scatter peaks back to original chain order with a tiny gather on the host-provided permutation
+        CK(e->d_misc.ensure(chains.size() * sizeof(uint32_t)));
+        CK(cudaMemcpyAsync(e->d_misc.p, newpos.data(), chains.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        k_scatter_f32<<<(unsigned)((chains.size() + 255) / 256), 256, 0, e->stream>>>(d_peaks_sorted, e->d_misc.as<uint32_t>(), d_peaks_orig,
+                                                                                      (uint32_t)chains.size());
+        e->stats.kernel_launches++;
+        d_peaks_for_k5 = d_peaks_orig;
+    }
+    CK(cudaEventRecord(e->ev[5], e->stream));
+    const double tol = exact ? 1e-9 : e->edge_tol;
+    k_hist_percentile<<<(unsigned)n, K5_THREADS, 0, e->stream>>>(e->d_twin.as<RgTrackWin>(), d_peaks_for_k5, e->d_tout.as<RgTrackOut>(),
+                                                               want_hist ? e->d_hist.as<uint32_t>() : nullptr, d_album_hist,
+                                                               d_album_peak, tol, defer_album_on_edge ? 1 : 0);
+    e->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->ev[6], e->stream));
+    h_out.resize(n);
+    CK(e->h_tout.ensure(n * sizeof(RgTrackOut)));
+    CK(cudaMemcpyAsync(e->h_tout.p, e->d_tout.p, n * sizeof(RgTrackOut), cudaMemcpyDeviceToHost, e->stream));
+    e->stats.d2h_bytes += n * sizeof(RgTrackOut);
+    if (hist_host && want_hist) {
+        CK(cudaMemcpyAsync(hist_host, e->d_hist.p, n * RG_HIST_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        e->stats.d2h_bytes += n * RG_HIST_BINS * sizeof(uint32_t);
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    memcpy(h_out.data(), e->h_tout.p, n * sizeof(RgTrackOut));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]) == cudaSuccess) e->stats.last_ms_iir += ms;
+    if (cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]) == cudaSuccess) e->stats.last_ms_hist += ms;
+    return RG_OK;
+}
+
+// Full stage B with the time-blocked pass + exact re-run of edge-flagged tracks (or exact for all when RG_FLAG_EXACT_IIR).
+// hist_host: null or tracks.size()*12000 u32.  d_album_*: device accumulators or null.
+static int run_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, std::vector<RgTrackOut>& res, std::vector<uint8_t>& rerun,
+                       uint32_t* hist_host, unsigned long long* d_album_hist, unsigned long long* d_album_peak) {
+    const size_t n = tracks.size();
+    res.assign(n, RgTrackOut{});
+    rerun.assign(n, 0);
+    std::vector<uint32_t> all(n);
+    for (uint32_t i = 0; i < n; i++) all[i] = i;
+    const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0;
+    std::vector<RgTrackOut> out;
+    int rc = launch_stage_b(e, tracks, all, exact, hist_host != nullptr, d_album_hist, d_album_peak, !exact, out, hist_host, n);
+    if (rc != RG_OK) return rc;
+    for (size_t i = 0; i < n; i++) res[i] = out[i];
+    if (exact) return RG_OK;
+    std::vector<uint32_t> flagged;
+    for (uint32_t i = 0; i < n; i++) if (res[i].n_edge > 0) flagged.push_back(i);
+    if (flagged.empty()) return RG_OK;
+    std::vector<uint32_t> hist_tmp;
+    if (hist_host) hist_tmp.resize(flagged.size() * RG_HIST_BINS);
+    rc = launch_stage_b(e, tracks, flagged, true, hist_host != nullptr, d_album_hist, d_album_peak, false, out,
+                        hist_host ? hist_tmp.data() : nullptr, flagged.size());
+    if (rc != RG_OK) return rc;
+    for (size_t k = 0; k < flagged.size(); k++) {
+        uint32_t i = flagged[k];
+        res[i] = out[k];
+        rerun[i] = 1;
+        if (hist_host) memcpy(hist_host + (size_t)i * RG_HIST_BINS, hist_tmp.data() + k * RG_HIST_BINS, RG_HIST_BINS * sizeof(uint32_t));
+    }
+    e->stats.exact_reruns += flagged.size();
+    return RG_OK;
+}
+
+static void fill_result(rg_track_result* o, const PcmTrack& t, const RgTrackOut& r, uint8_t rerun, uint32_t n_frames) {
+    memset(o, 0, sizeof *o);
+    o->status = t.status;
+    o->sample_rate = t.sample_rate;
+    o->channels = (uint32_t)t.nch;
+    o->file_type = 0;
+    o->n_frames = n_frames;
+    if (t.status != RG_OK) return;
+    o->loudness_db = r.loudness_db;
+    o->gain_db = r.gain_db;
+    o->peak = r.peak;
+    o->n_windows = r.n_windows;
+    o->n_dropped_windows = r.n_dropped;
+    o->n_edge_windows = r.n_edge;
+    o->exact_rerun = rerun;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int nch, size_t frames, uint32_t sample_rate,
+                                  rg_track_result* out, uint32_t* hist_out) {
+    if (!e || !out || !planes || nch < 1 || !planes[0] || (nch >= 2 && !planes[1])) return RG_ERR_INVALID_ARG;
+    CK(cudaSetDevice(e->device));
+    e->stats.last_ms_iir = e->stats.last_ms_hist = 0;
+    PcmTrack t;
+    t.nch = nch >= 2 ? 2 : 1;
+    t.frames = frames;
+    t.sample_rate = sample_rate;
+    t.rate_idx = rate_index(sample_rate);
+    if (t.rate_idx < 0) {
+        memset(out, 0, sizeof *out);
+        out->status = RG_ERR_UNSUPPORTED_RATE;
+        out->sample_rate = sample_rate;
+        return RG_ERR_UNSUPPORTED_RATE;
+    }
+    size_t plane = (frames + 3) & ~(size_t)3;
+    CK(e->d_pcm_in.ensure(std::max<size_t>(plane * t.nch, 4) * sizeof(float)));
+    for (int c = 0; c < t.nch; c++) {
+        float* d = e->d_pcm_in.as<float>() + (size_t)c * plane;
+        if (frames) CK(cudaMemcpyAsync(d, planes[c], frames * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        t.d_ch[c] = d;
+        e->stats.h2d_bytes += frames * sizeof(float);
+    }
+    std::vector<PcmTrack> tracks{t};
+    std::vector<RgTrackOut> res;
+    std::vector<uint8_t> rerun;
+    int rc = run_stage_b(e, tracks, res, rerun, hist_out, nullptr, nullptr);
+    if (rc != RG_OK) return rc;
+    fill_result(out, t, res[0], rerun[0], 0);
+    e->stats.tracks += 1;
+    return RG_OK;
+}
+
+#include "rg_engine_decode.inl"
