@@ -1,0 +1,552 @@
+/*
+ * mp3_oracle.c -- CPU ORACLE, stage A: MPEG-1 Layer III bytes -> planar f32 PCM (test infrastructure, NOT product code).
+ *
+ * The reference (mp3rgain v1.5.0) does not contain this stage: src/replaygain.rs:807-822, 861-863, 882, 896 call the
+ * third-party crate symphonia-bundle-mp3 0.5.5 (Cargo.toml:26, Cargo.lock:244-247), whose source is absent from
+ * /root/reference.  This file therefore restates the published algorithm, ISO/IEC 11172-3 Layer III, not any file of
+ * the reference; bit parity with symphonia is UNPINNED.  It is cross-checked (tolerance) against FFmpeg's mp3float
+ * decoder in tests/test_oracle_mp3.py.
+ *
+ * Demuxer behaviour mirrors what the reference's call sites imply (see DESIGN.md "symphonia switches"):
+ *   - a leading ID3v2 tag is skipped; a first frame carrying a Xing/Info/VBRI tag is not emitted (unless flag 0x2);
+ *   - FormatOptions::default() => no gapless trimming: every decoded sample is analysed;
+ *   - a frame whose main_data_begin reaches before the start of the reservoir, or whose side info is invalid,
+ *     is a DecodeError => the reference `continue`s (src/replaygain.rs:896-900): its PCM is dropped;
+ *   - a truncated final frame is EOF (src/replaygain.rs:884-888);
+ *   - output is unclamped f32 (flag 0x4 clamps to [-1,1]).
+ *
+ * Arithmetic contract (mirrored operation-for-operation by the CUDA kernels; compile with -ffp-contract=off):
+ *   all float tables come from l3_tables_oracle.h; products and sums round separately except where fmaf() is
+ *   written, and every dot product is a sequential fmaf chain in ascending index order starting from +0.0f.
+ */
+#include "mp3_oracle.h"
+#include "l3_tables_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ lookup structures built once */
+#define HUFF_L1_BITS 9
+typedef struct { uint16_t* tab; int size; } hufftab_t; /* entry: leaf = (len<<8)|sym ; link = 0x8000 | (bits<<10)... see build */
+static hufftab_t g_huff[16];
+static int g_long_start[3][23], g_short_start[3][14];
+static int g_init_done = 0;
+
+/* two-level table: first level indexed by HUFF_L1_BITS bits.  leaf: bit15=0, bits 8..12 = code length, bits 0..7 = sym.
+ * link: bit15=1, bits 10..14 = extra bits n (sub-table indexed by the next n bits), bits 0..9.. offset/4 is not enough for
+ * big books, so links store an index into a side array instead. */
+typedef struct { uint32_t off; uint8_t nbits; } hlink_t;
+static hlink_t g_links[16][512];
+
+static void build_huff(int slot) {
+    int n = L3_HUFF_SIZE[slot - 1], off = L3_HUFF_OFF[slot - 1];
+    const uint8_t* len = &L3_HUFF_LEN[off];
+    const uint8_t* sym = &L3_HUFF_SYM[off];
+    /* codes, left-aligned to 32 bits, in tree order */
+    uint32_t* code = (uint32_t*)malloc(n * sizeof(uint32_t));
+    uint32_t c = 0;
+    for (int i = 0; i < n; i++) { code[i] = c; c += 1u << (32 - len[i]); }
+    /* sub-table sizes per first-level prefix */
+    int maxsub[512];
+    memset(maxsub, 0, sizeof maxsub);
+    for (int i = 0; i < n; i++)
+        if (len[i] > HUFF_L1_BITS) {
+            int p = code[i] >> (32 - HUFF_L1_BITS);
+            if (len[i] - HUFF_L1_BITS > maxsub[p]) maxsub[p] = len[i] - HUFF_L1_BITS;
+        }
+    int total = 1 << HUFF_L1_BITS;
+    for (int p = 0; p < 512; p++) if (maxsub[p]) { g_links[slot][p].off = total; g_links[slot][p].nbits = (uint8_t)maxsub[p]; total += 1 << maxsub[p]; }
+    uint16_t* tab = (uint16_t*)calloc(total, sizeof(uint16_t));
+    for (int i = 0; i < n; i++) {
+        uint16_t leaf = (uint16_t)((len[i] << 8) | sym[i]);
+        if (len[i] <= HUFF_L1_BITS) {
+            int base = code[i] >> (32 - HUFF_L1_BITS), cnt = 1 << (HUFF_L1_BITS - len[i]);
+            for (int k = 0; k < cnt; k++) tab[base + k] = leaf;
+        } else {
+            int p = code[i] >> (32 - HUFF_L1_BITS);
+            int nb = g_links[slot][p].nbits;
+            int sub = (code[i] << HUFF_L1_BITS) >> (32 - nb);
+            int cnt = 1 << (nb - (len[i] - HUFF_L1_BITS));
+            for (int k = 0; k < cnt; k++) tab[g_links[slot][p].off + sub + k] = leaf;
+            tab[p] = 0x8000;
+        }
+    }
+    g_huff[slot].tab = tab;
+    g_huff[slot].size = total;
+    free(code);
+}
+
+static void init_once(void) {
+    if (g_init_done) return;
+    for (int s = 1; s <= L3_NUM_HUFF; s++) build_huff(s);
+    for (int r = 0; r < 3; r++) {
+        int a = 0;
+        for (int i = 0; i < 22; i++) { g_long_start[r][i] = a; a += L3_SFB_LONG_W[r][i]; }
+        g_long_start[r][22] = a;
+        a = 0;
+        for (int i = 0; i < 13; i++) { g_short_start[r][i] = a; a += L3_SFB_SHORT_W[r][i]; }
+        g_short_start[r][13] = a;
+    }
+    g_init_done = 1;
+}
+
+/* ------------------------------------------------------------------ bit reader (MSB first) */
+typedef struct { const uint8_t* p; size_t nbytes; size_t pos; } bits_t; /* pos in bits */
+static inline uint32_t peek32(const bits_t* b) {
+    size_t by = b->pos >> 3;
+    uint64_t v = 0;
+    for (int i = 0; i < 5; i++) v = (v << 8) | (by + i < b->nbytes ? b->p[by + i] : 0);
+    return (uint32_t)(v >> (8 - (b->pos & 7)));
+}
+static inline uint32_t getbits(bits_t* b, int n) {
+    if (n == 0) return 0;
+    uint32_t v = peek32(b) >> (32 - n);
+    b->pos += n;
+    return v;
+}
+
+/* ------------------------------------------------------------------ headers */
+typedef struct { int crc, br_idx, sr_idx, pad, mode, mode_ext, sr, channels, frame_len, side_len, ver; } hdr_t;
+static const int BR_V1_L3[15] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
+static const int SR_V1[3] = {44100, 48000, 32000};
+
+/* Valid Layer III header (any MPEG version so that LSF streams are recognised and reported as unsupported). */
+static int parse_hdr(const uint8_t* p, hdr_t* h) {
+    if (p[0] != 0xFF || (p[1] & 0xE0) != 0xE0) return 0;
+    int ver = (p[1] >> 3) & 3;      /* 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5, 1 = reserved */
+    int layer = (p[1] >> 1) & 3;    /* 1 = Layer III */
+    if (ver == 1 || layer != 1) return 0;
+    h->ver = ver;
+    h->crc = !(p[1] & 1);
+    h->br_idx = p[2] >> 4;
+    h->sr_idx = (p[2] >> 2) & 3;
+    if (h->br_idx == 0 || h->br_idx == 15 || h->sr_idx == 3) return 0;
+    h->pad = (p[2] >> 1) & 1;
+    h->mode = p[3] >> 6;
+    h->mode_ext = (p[3] >> 4) & 3;
+    h->channels = h->mode == 3 ? 1 : 2;
+    if (ver == 3) {
+        h->sr = SR_V1[h->sr_idx];
+        h->frame_len = 144 * BR_V1_L3[h->br_idx] * 1000 / h->sr + h->pad;
+        h->side_len = h->channels == 1 ? 17 : 32;
+    } else {
+        static const int BR_V2[15] = {0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160};
+        h->sr = SR_V1[h->sr_idx] >> (ver == 2 ? 1 : 2);
+        h->frame_len = 72 * BR_V2[h->br_idx] * 1000 / h->sr + h->pad;
+        h->side_len = h->channels == 1 ? 9 : 17;
+    }
+    return 1;
+}
+static int compatible(const hdr_t* a, const hdr_t* ref) {
+    return a->ver == ref->ver && a->sr == ref->sr && a->channels == ref->channels;
+}
+
+static size_t skip_id3v2(const uint8_t* d, size_t len) {
+    if (len >= 10 && d[0] == 'I' && d[1] == 'D' && d[2] == '3' && d[3] != 0xFF && d[4] != 0xFF &&
+        !(d[6] & 0x80) && !(d[7] & 0x80) && !(d[8] & 0x80) && !(d[9] & 0x80)) {
+        size_t sz = ((size_t)d[6] << 21) | ((size_t)d[7] << 14) | ((size_t)d[8] << 7) | d[9];
+        sz += 10;
+        if (d[5] & 0x10) sz += 10; /* footer */
+        return sz <= len ? sz : len;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ side info */
+typedef struct {
+    int part2_3_length, big_values, global_gain, scalefac_compress, window_switching, block_type, mixed;
+    int table_select[3], subblock_gain[3], region0_count, region1_count, preflag, scalefac_scale, count1table;
+} gr_t;
+typedef struct { int main_data_begin; int scfsi[2][4]; gr_t gr[2][2]; int valid; } side_t;
+
+static void parse_side(const uint8_t* p, int nch, side_t* s) {
+    bits_t b = {p, 32, 0};
+    s->valid = 1;
+    s->main_data_begin = getbits(&b, 9);
+    getbits(&b, nch == 1 ? 5 : 3);
+    for (int ch = 0; ch < nch; ch++) for (int i = 0; i < 4; i++) s->scfsi[ch][i] = getbits(&b, 1);
+    for (int g = 0; g < 2; g++)
+        for (int ch = 0; ch < nch; ch++) {
+            gr_t* q = &s->gr[g][ch];
+            q->part2_3_length = getbits(&b, 12);
+            q->big_values = getbits(&b, 9);
+            q->global_gain = getbits(&b, 8);
+            q->scalefac_compress = getbits(&b, 4);
+            q->window_switching = getbits(&b, 1);
+            if (q->window_switching) {
+                q->block_type = getbits(&b, 2);
+                q->mixed = getbits(&b, 1);
+                q->table_select[0] = getbits(&b, 5);
+                q->table_select[1] = getbits(&b, 5);
+                q->table_select[2] = 0;
+                for (int i = 0; i < 3; i++) q->subblock_gain[i] = getbits(&b, 3);
+                q->region0_count = (q->block_type == 2 && !q->mixed) ? 8 : 7;
+                q->region1_count = 20 - q->region0_count;
+                if (q->block_type == 0) s->valid = 0;
+            } else {
+                for (int i = 0; i < 3; i++) q->table_select[i] = getbits(&b, 5);
+                q->region0_count = getbits(&b, 4);
+                q->region1_count = getbits(&b, 3);
+                q->block_type = 0;
+                q->mixed = 0;
+                q->subblock_gain[0] = q->subblock_gain[1] = q->subblock_gain[2] = 0;
+            }
+            q->preflag = getbits(&b, 1);
+            q->scalefac_scale = getbits(&b, 1);
+            q->count1table = getbits(&b, 1);
+            if (q->big_values > 288) s->valid = 0;
+        }
+}
+
+/* ------------------------------------------------------------------ decoder state */
+typedef struct {
+    float prev[2][32][18];    /* IMDCT overlap */
+    float ring[2][16][32];    /* last 16 DCT-32 vectors per channel, ring[head] newest */
+    int head[2];
+    int sf_l[2][2][22];       /* [gr][ch] long scalefactors */
+    int sf_s[2][2][13][3];    /* [gr][ch] short scalefactors */
+} dec_t;
+
+/* part 2: scalefactors (ISO 11172-3 2.4.2.7) */
+static void read_scalefactors(bits_t* b, const side_t* s, int g, int ch, dec_t* d) {
+    const gr_t* q = &s->gr[g][ch];
+    int slen1 = L3_SLEN[0][q->scalefac_compress], slen2 = L3_SLEN[1][q->scalefac_compress];
+    int* sl = d->sf_l[g][ch];
+    int(*ss)[3] = d->sf_s[g][ch];
+    memset(sl, 0, 22 * sizeof(int));
+    memset(ss, 0, 13 * 3 * sizeof(int));
+    if (q->block_type == 2) {
+        int s0 = 0;
+        if (q->mixed) {
+            for (int sfb = 0; sfb < 8; sfb++) sl[sfb] = getbits(b, slen1);
+            s0 = 3;
+        }
+        for (int sfb = s0; sfb < 6; sfb++) for (int w = 0; w < 3; w++) ss[sfb][w] = getbits(b, slen1);
+        for (int sfb = 6; sfb < 12; sfb++) for (int w = 0; w < 3; w++) ss[sfb][w] = getbits(b, slen2);
+    } else {
+        static const int lo[4] = {0, 6, 11, 16}, hi[4] = {6, 11, 16, 21};
+        for (int grp = 0; grp < 4; grp++) {
+            int sl_bits = grp < 2 ? slen1 : slen2;
+            for (int sfb = lo[grp]; sfb < hi[grp]; sfb++) {
+                if (g == 1 && s->scfsi[ch][grp]) sl[sfb] = d->sf_l[0][ch][sfb];
+                else sl[sfb] = getbits(b, sl_bits);
+            }
+        }
+    }
+}
+
+/* part 3: Huffman.  Returns the number of lines decoded (start of the all-zero tail). */
+static int read_huffman(bits_t* b, size_t end, const gr_t* q, int sr_row, int16_t* is) {
+    memset(is, 0, 576 * sizeof(int16_t));
+    int bv2 = q->big_values * 2;
+    int r0, r1;
+    if (q->window_switching) { r0 = 36; r1 = 576; }
+    else {
+        r0 = g_long_start[sr_row][q->region0_count + 1];
+        int k = q->region0_count + q->region1_count + 2;
+        r1 = g_long_start[sr_row][k > 22 ? 22 : k];
+    }
+    int i = 0;
+    for (; i < bv2; i += 2) {
+        int region = i < r0 ? 0 : (i < r1 ? 1 : 2);
+        int slot = L3_TABSEL[q->table_select[region]][0], linbits = L3_TABSEL[q->table_select[region]][1];
+        int x = 0, y = 0;
+        if (slot) {
+            uint32_t w = peek32(b);
+            uint16_t e = g_huff[slot].tab[w >> (32 - HUFF_L1_BITS)];
+            if (e & 0x8000) {
+                const hlink_t* l = &g_links[slot][w >> (32 - HUFF_L1_BITS)];
+                e = g_huff[slot].tab[l->off + ((w << HUFF_L1_BITS) >> (32 - l->nbits))];
+            }
+            b->pos += e >> 8;
+            x = (e >> 4) & 15;
+            y = e & 15;
+            if (x == 15 && linbits) x += getbits(b, linbits);
+            if (x && getbits(b, 1)) x = -x;
+            if (y == 15 && linbits) y += getbits(b, linbits);
+            if (y && getbits(b, 1)) y = -y;
+        }
+        is[i] = (int16_t)x;
+        is[i + 1] = (int16_t)y;
+    }
+    if (b->pos > end) { /* big_values overran part2_3_length: treat the granule-channel as silence */
+        memset(is, 0, 576 * sizeof(int16_t));
+        b->pos = end;
+        return 0;
+    }
+    const uint8_t* cb = L3_C1_BITS[q->count1table];
+    const uint8_t* cl = L3_C1_LENS[q->count1table];
+    while (b->pos < end && i <= 572) {
+        uint32_t w = peek32(b);
+        int v = -1;
+        for (int k = 0; k < 16; k++)
+            if ((w >> (32 - cl[k])) == cb[k]) { v = k; break; }
+        b->pos += cl[v];
+        int q4[4] = {(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1};
+        for (int k = 0; k < 4; k++) if (q4[k] && getbits(b, 1)) q4[k] = -1;
+        if (b->pos > end) break; /* quad straddles the end of the granule: discard it */
+        for (int k = 0; k < 4; k++) is[i + k] = (int16_t)q4[k];
+        i += 4;
+    }
+    b->pos = end;
+    return i;
+}
+
+/* requantisation (ISO 2.4.3.4) in bitstream order */
+static void requantize(const gr_t* q, int sr_row, const int* sf_l, int (*sf_s)[3], const int16_t* is, float* xr) {
+    int mult = q->scalefac_scale ? 4 : 2;
+    int i = 0;
+    if (q->block_type != 2 || q->mixed) {
+        int nl = q->block_type == 2 ? 8 : 22;
+        for (int sfb = 0; sfb < nl; sfb++) {
+            int e = q->global_gain - 210 - mult * (sf_l[sfb] + (q->preflag ? L3_PRETAB[sfb] : 0));
+            float g = L3_GAIN[e - L3_GAIN_MIN];
+            for (int k = 0; k < L3_SFB_LONG_W[sr_row][sfb]; k++, i++) {
+                int v = is[i];
+                float m = L3_POW43[v < 0 ? -v : v] * g;
+                xr[i] = v < 0 ? -m : m;
+            }
+        }
+    }
+    if (q->block_type == 2) {
+        for (int sfb = q->mixed ? 3 : 0; sfb < 13; sfb++) {
+            int wdt = L3_SFB_SHORT_W[sr_row][sfb];
+            for (int w = 0; w < 3; w++) {
+                int e = q->global_gain - 210 - 8 * q->subblock_gain[w] - mult * sf_s[sfb][w];
+                float g = L3_GAIN[e - L3_GAIN_MIN];
+                for (int k = 0; k < wdt; k++, i++) {
+                    int v = is[i];
+                    float m = L3_POW43[v < 0 ? -v : v] * g;
+                    xr[i] = v < 0 ? -m : m;
+                }
+            }
+        }
+    }
+}
+
+/* short-block reorder [sfb][win][k] -> [sfb][k][win] */
+static void reorder(const gr_t* q, int sr_row, float* xr) {
+    float tmp[576];
+    memcpy(tmp, xr, sizeof tmp);
+    for (int sfb = q->mixed ? 3 : 0; sfb < 13; sfb++) {
+        int st = g_short_start[sr_row][sfb], wdt = L3_SFB_SHORT_W[sr_row][sfb];
+        for (int w = 0; w < 3; w++)
+            for (int k = 0; k < wdt; k++) xr[3 * st + 3 * k + w] = tmp[3 * st + w * wdt + k];
+    }
+}
+
+static void alias_reduce(const gr_t* q, float* xr) {
+    int nb = q->block_type == 2 ? (q->mixed ? 1 : 0) : 31;
+    for (int sb = 1; sb <= nb; sb++)
+        for (int i = 0; i < 8; i++) {
+            float lo = xr[18 * sb - 1 - i], hi = xr[18 * sb + i];
+            xr[18 * sb - 1 - i] = lo * L3_ALIAS_CS[i] - hi * L3_ALIAS_CA[i];
+            xr[18 * sb + i] = hi * L3_ALIAS_CS[i] + lo * L3_ALIAS_CA[i];
+        }
+}
+
+/* IMDCT + window + overlap-add + frequency inversion for one subband; out[t] = subband sample at time slot t */
+static void hybrid_sb(const float* X, int bt, float* prev, int sb, float* out) {
+    float raw[36];
+    if (bt != 2) {
+        float u[18];
+        for (int m = 0; m < 18; m++) {
+            float a = 0.0f;
+            for (int k = 0; k < 18; k++) a = fmaf(X[k], L3_DCT4_18[m][k], a);
+            u[m] = a;
+        }
+        for (int i = 0; i < 36; i++) raw[i] = u[L3_IMDCT36_IDX[i]] * L3_WINSGN[bt][i];
+    } else {
+        for (int i = 0; i < 36; i++) raw[i] = 0.0f;
+        for (int w = 0; w < 3; w++)
+            for (int i = 0; i < 12; i++) {
+                float a = 0.0f;
+                for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], L3_IMDCT12[i][k], a);
+                raw[6 + 6 * w + i] = raw[6 + 6 * w + i] + a * L3_WINSGN[2][i];
+            }
+    }
+    for (int i = 0; i < 18; i++) {
+        float v = raw[i] + prev[i];
+        prev[i] = raw[18 + i];
+        out[i] = ((sb & 1) && (i & 1)) ? -v : v;
+    }
+}
+
+/* Lee's 32-point DCT-II: B[j] = sum_k S[k] cos((2k+1) j pi / 64) */
+static void dct2_rec(float* x, int n, const float* sec) {
+    if (n == 1) return;
+    int h = n / 2;
+    float g[16], hh[16];
+    for (int i = 0; i < h; i++) {
+        g[i] = x[i] + x[n - 1 - i];
+        hh[i] = (x[i] - x[n - 1 - i]) * sec[i];
+    }
+    dct2_rec(g, h, sec + h);
+    dct2_rec(hh, h, sec + h);
+    for (int k = 0; k < h; k++) {
+        x[2 * k] = g[k];
+        x[2 * k + 1] = (k + 1 < h) ? hh[k] + hh[k + 1] : hh[k];
+    }
+}
+
+/* polyphase synthesis of one time slot: 32 subband samples -> 32 PCM samples */
+static void synth_slot(dec_t* d, int ch, const float* S, float* pcm) {
+    d->head[ch] = (d->head[ch] + 15) & 15;
+    float* B = d->ring[ch][d->head[ch]];
+    memcpy(B, S, 32 * sizeof(float));
+    dct2_rec(B, 32, L3_DCT_SEC);
+    for (int j = 0; j < 32; j++) {
+        float a = 0.0f;
+        for (int p = 0; p < 8; p++) {
+            const float* Ba = d->ring[ch][(d->head[ch] + 2 * p) & 15];
+            const float* Bb = d->ring[ch][(d->head[ch] + 2 * p + 1) & 15];
+            a = fmaf(Ba[L3_SYNTH_IA[j]], L3_SYNTH_WA[p][j], a);
+            a = fmaf(Bb[L3_SYNTH_IB[j]], L3_SYNTH_WB[p][j], a);
+        }
+        pcm[j] = a;
+    }
+}
+
+/* ------------------------------------------------------------------ frame walk shared by decode/analyze */
+typedef struct { size_t pos; hdr_t h; } frame_ref;
+
+static int is_info_frame(const uint8_t* p, const hdr_t* h) {
+    size_t o = 4 + (h->crc ? 2 : 0) + h->side_len;
+    if (o + 4 <= (size_t)h->frame_len && (!memcmp(p + o, "Xing", 4) || !memcmp(p + o, "Info", 4))) return 1;
+    if (36 + 4 <= h->frame_len && !memcmp(p + 36, "VBRI", 4)) return 1;
+    return 0;
+}
+
+typedef void (*pcm_sink)(void* ctx, const float* l, const float* r, int n);
+
+static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_sink sink, void* ctx, mp3o_info* info) {
+    init_once();
+    memset(info, 0, sizeof *info);
+    size_t pos = skip_id3v2(data, len);
+    hdr_t ref;
+    int have_ref = 0, in_sync = 0, first = 1;
+    dec_t* d = (dec_t*)calloc(1, sizeof(dec_t));
+    uint8_t* md = (uint8_t*)malloc(len + 64);
+    size_t md_len = 0;
+    static _Thread_local float xr[2][576], sbs[2][32][18], pcm[2][1152];
+    static _Thread_local int16_t is[2][576];
+    int status = MP3O_ERR_PROBE;
+
+    while (pos + 4 <= len) {
+        hdr_t h;
+        int ok = parse_hdr(data + pos, &h) && (!have_ref || compatible(&h, &ref));
+        if (ok && pos + (size_t)h.frame_len > len) break; /* truncated final frame = EOF */
+        if (ok && !in_sync) {                             /* (re)sync needs the next header to confirm */
+            size_t nx = pos + h.frame_len;
+            hdr_t h2;
+            if (nx + 4 <= len && !(parse_hdr(data + nx, &h2) && compatible(&h2, &h))) ok = 0;
+        }
+        if (!ok) { in_sync = 0; pos++; continue; }
+        in_sync = 1;
+        if (!have_ref) {
+            ref = h; have_ref = 1;
+            info->sample_rate = h.sr; info->channels = h.channels;
+            if (h.ver != 3) { status = MP3O_ERR_UNSUPPORTED_FORMAT; break; }
+            status = 0;
+        }
+        const uint8_t* fp = data + pos;
+        pos += h.frame_len;
+        if (first) {
+            first = 0;
+            if (!(flags & MP3O_FLAG_KEEP_INFO_FRAME) && is_info_frame(fp, &h)) { info->skipped_info_frame = 1; continue; }
+        }
+        int nch = h.channels;
+        size_t so = 4 + (h.crc ? 2 : 0);
+        side_t s;
+        parse_side(fp + so, nch, &s);
+        size_t mdo = so + h.side_len;
+        size_t md_start_ok = s.main_data_begin <= (int)md_len;
+        size_t start = md_len - (md_start_ok ? s.main_data_begin : 0);
+        if ((size_t)h.frame_len > mdo) { memcpy(md + md_len, fp + mdo, h.frame_len - mdo); md_len += h.frame_len - mdo; }
+        if (!s.valid || !md_start_ok) { info->n_dropped_frames++; continue; }
+        memset(md + md_len, 0, 32);
+
+        int sr_row = h.sr_idx; /* rows 0..2 of the band tables are 44100, 48000, 32000 = sr_idx order */
+        bits_t b = {md, md_len + 32, start * 8};
+        for (int g = 0; g < 2; g++) {
+            int nz[2] = {0, 0};
+            for (int ch = 0; ch < nch; ch++) {
+                const gr_t* q = &s.gr[g][ch];
+                size_t end = b.pos + q->part2_3_length;
+                read_scalefactors(&b, &s, g, ch, d);
+                if (b.pos > end) { memset(is[ch], 0, sizeof is[ch]); b.pos = end; nz[ch] = 0; }
+                else nz[ch] = read_huffman(&b, end, q, sr_row, is[ch]);
+                requantize(q, sr_row, d->sf_l[g][ch], d->sf_s[g][ch], is[ch], xr[ch]);
+            }
+            if (nch == 2 && h.mode == 1 && (h.mode_ext & 2)) { /* MS stereo */
+                for (int i = 0; i < 576; i++) {
+                    float m = xr[0][i], sd = xr[1][i];
+                    xr[0][i] = (m + sd) * L3_INV_SQRT2;
+                    xr[1][i] = (m - sd) * L3_INV_SQRT2;
+                }
+            }
+            for (int ch = 0; ch < nch; ch++) {
+                const gr_t* q = &s.gr[g][ch];
+                if (q->block_type == 2) reorder(q, sr_row, xr[ch]);
+                alias_reduce(q, xr[ch]);
+                for (int sb = 0; sb < 32; sb++) {
+                    int bt = (q->block_type == 2 && q->mixed && sb < 2) ? 0 : q->block_type;
+                    hybrid_sb(&xr[ch][18 * sb], bt, d->prev[ch][sb], sb, sbs[ch][sb]);
+                }
+                for (int t = 0; t < 18; t++) {
+                    float S[32];
+                    for (int sb = 0; sb < 32; sb++) S[sb] = sbs[ch][sb][t];
+                    synth_slot(d, ch, S, &pcm[ch][576 * g + 32 * t]);
+                }
+            }
+        }
+        if (flags & MP3O_FLAG_CLAMP_PCM)
+            for (int ch = 0; ch < nch; ch++)
+                for (int i = 0; i < 1152; i++) pcm[ch][i] = pcm[ch][i] > 1.0f ? 1.0f : (pcm[ch][i] < -1.0f ? -1.0f : pcm[ch][i]);
+        sink(ctx, pcm[0], nch == 2 ? pcm[1] : NULL, 1152);
+        info->n_frames++;
+        info->n_samples += 1152;
+    }
+    free(md);
+    free(d);
+    info->status = status;
+    return status;
+}
+
+/* ------------------------------------------------------------------ public entry points */
+typedef struct { float* pcm; size_t max_frames, n; } copy_ctx;
+static void sink_copy(void* c, const float* l, const float* r, int n) {
+    copy_ctx* k = (copy_ctx*)c;
+    if (k->n + n <= k->max_frames) {
+        memcpy(k->pcm + k->n, l, n * sizeof(float));
+        if (r) memcpy(k->pcm + k->max_frames + k->n, r, n * sizeof(float));
+    }
+    k->n += n;
+}
+int mp3o_decode(const uint8_t* data, size_t len, uint32_t flags, float* pcm, size_t max_frames, mp3o_info* info) {
+    copy_ctx c = {pcm, max_frames, 0};
+    return decode_stream(data, len, flags, sink_copy, &c, info);
+}
+
+typedef struct { rgo_state* st; int inited; unsigned sr; int nch; int bad_rate; const mp3o_info* info; } an_ctx;
+static void sink_analyze(void* c, const float* l, const float* r, int n) {
+    an_ctx* a = (an_ctx*)c;
+    if (!a->inited) {
+        a->inited = 1;
+        if (rgo_state_init(a->st, a->info->sample_rate, a->info->channels) != 0) a->bad_rate = 1;
+    }
+    if (!a->bad_rate) rgo_state_feed_f32(a->st, l, r, (size_t)n);
+}
+int mp3o_analyze(const uint8_t* data, size_t len, uint32_t flags, rgo_result* out, uint32_t* hist_out, mp3o_info* info) {
+    rgo_state* st = (rgo_state*)calloc(1, sizeof(rgo_state));
+    an_ctx a = {st, 0, 0, 0, 0, info};
+    int rc = decode_stream(data, len, flags, sink_analyze, &a, info);
+    if (rc == 0) {
+        if (!a.inited) rgo_state_init(st, info->sample_rate, info->channels); /* zero decodable frames: empty histogram */
+        rgo_state_finish(st, out);
+        if (hist_out) memcpy(hist_out, st->hist, sizeof st->hist);
+    }
+    free(st);
+    return rc;
+}

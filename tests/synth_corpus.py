@@ -1,0 +1,93 @@
+"""Synthetic MP3 corpora for tests and bench (ctypes wrapper of tests/synth/synth_mp3.cpp).  TEST/BENCH INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "synth", "synth_mp3.cpp")
+LIB = os.path.join(HERE, "synth", "libsynth_mp3.so")
+_lib = None
+
+BITRATES = [0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320]
+RATES = [44100, 48000, 32000]
+
+
+def build():
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC], check=True, capture_output=True)
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+            build()
+        _lib = C.CDLL(LIB)
+        _lib.synth_group.restype = C.c_size_t
+        _lib.synth_group.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+        _lib.synth_track.restype = C.c_size_t
+        _lib.synth_track.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+    return _lib
+
+
+def make_group(seed, n_frames=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0):
+    lib = _load()
+    cap = n_frames * 1500 + 64
+    buf = np.zeros(cap, np.uint8)
+    n = lib.synth_group(seed, n_frames, sr_idx, br_idx, channels, level_db, buf.ctypes.data, cap)
+    assert n > 0
+    return buf[:n].copy()
+
+
+def make_track(seed, n_frames=6891, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0):
+    """One unique track (every group freshly generated). br_idx 0 = VBR. Returns a numpy uint8 array."""
+    lib = _load()
+    cap = n_frames * 1500 + 64
+    buf = np.zeros(cap, np.uint8)
+    n = lib.synth_track(seed, n_frames, group_len, sr_idx, br_idx, channels, level_db, buf.ctypes.data, cap)
+    assert n > 0
+    return buf[:n].copy()
+
+
+class GroupPool:
+    """A pool of self-contained frame groups; tracks are seeded random sequences of pool groups (each group starts with
+    main_data_begin = 0, so any concatenation is a valid stream).  Lets bench.py build 1,000 distinct 3-minute tracks in
+    seconds: every track is still a different bitstream and decodes to different PCM / filter state."""
+
+    def __init__(self, seed=1, n_groups=256, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0):
+        rng = np.random.default_rng(seed)
+        self.group_len = group_len
+        self.groups = [make_group(int(seed) * 7919 + g, group_len, sr_idx, br_idx, channels,
+                                  level_db + float(rng.uniform(-8, 4))) for g in range(n_groups)]
+
+    def track(self, seed, n_frames):
+        rng = np.random.default_rng(seed)
+        n_groups = (n_frames + self.group_len - 1) // self.group_len
+        idx = rng.integers(0, len(self.groups), n_groups)
+        parts = [self.groups[i] for i in idx]
+        return np.concatenate(parts)
+
+
+def id3v2_tag(size=100):
+    body = bytes(size)
+    sz = len(body)
+    return b"ID3\x04\x00\x00" + bytes([(sz >> 21) & 0x7F, (sz >> 14) & 0x7F, (sz >> 7) & 0x7F, sz & 0x7F]) + body
+
+
+def info_frame(first_frame_header, tag=b"Info"):
+    """A Xing/Info frame matching the stream's version/rate/channel mode (128 kbps slot, zero side info)."""
+    h = bytearray(first_frame_header[:4])
+    h[2] = (9 << 4) | (h[2] & 0x0C)  # bitrate index 9, same sample rate, no padding
+    sr = RATES[(h[2] >> 2) & 3]
+    flen = 144 * 128000 // sr
+    mono = (h[3] >> 6) == 3
+    fr = bytearray(flen)
+    fr[:4] = h
+    o = 4 + (17 if mono else 32)
+    fr[o:o + 4] = tag
+    return bytes(fr)
+
+
+def id3v1_trailer():
+    return b"TAG" + bytes(125)
