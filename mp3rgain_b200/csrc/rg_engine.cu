@@ -79,16 +79,24 @@ struct rg_engine {
     uint32_t block_windows = 16, warm_windows = 2;
     double edge_tol = 1e-6;
     // device scratch
-    DevBuf d_pcm_in, d_chains, d_wsum, d_peaks, d_twin, d_tout, d_hist, d_album, d_misc;
+    DevBuf d_pcm_in, d_chains, d_wsum, d_peaks, d_twin, d_tout, d_hist, d_album, d_album_peak, d_misc;
+    // stage A scratch
+    DevBuf d_tin, d_fbase, d_frames, d_md, d_meta, d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_pcm;
     HostBuf h_stage, h_tout;
     rg_stats stats = {};
     DecodeScratch dec;
+    bool pending_decode_timing = false;
+    std::vector<DevBuf*> all_bufs() {
+        return {&d_pcm_in, &d_chains, &d_wsum, &d_peaks, &d_twin, &d_tout, &d_hist, &d_album, &d_album_peak, &d_misc,
+                &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_pcm};
+    }
 };
 
 struct rg_corpus {
     DevBuf d_bytes;
     std::vector<uint64_t> off, len;
     std::vector<int32_t> track_index;
+    std::vector<uint8_t> is_mp4;
     uint64_t total = 0;
 };
 
@@ -166,9 +174,7 @@ extern "C" void rg_engine_destroy(rg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    for (DevBuf* b : {&e->d_pcm_in, &e->d_chains, &e->d_wsum, &e->d_peaks, &e->d_twin, &e->d_tout, &e->d_hist,
-                      &e->d_album, &e->d_misc})
-        b->release();
+    for (DevBuf* b : e->all_bufs()) b->release();
     e->h_stage.release();
     e->h_tout.release();
     e->dec.release();

@@ -56,6 +56,6 @@ def test_product_never_touches_the_oracle():
                 if fn.endswith((".so", ".pyc", ".log")):
                     continue
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
-                if re.search(r"oracle[/_]|librg_oracle|rgo_|mp3o_", txt):
+                if re.search(r"#include[^\n]*oracle|import[^\n]*oracle|oracle_lib|librg_oracle|\brgo_|\bmp3o_|oracle/", txt):
                     bad.append(os.path.join(dp, fn))
     assert not bad, bad

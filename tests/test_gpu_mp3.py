@@ -1,0 +1,175 @@
+"""GPU parity tests, stage A + B: the CUDA decode kernels (K0-K2) and the whole analyze path through the C ABI against
+the CPU oracle on the same inputs.  Bar: decoded PCM equal sample for sample (float ==), identical 12000-bin histogram,
+identical loudness / gain / peak."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+import synth_corpus
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EXPECTED = json.load(open(os.path.join(GOLD, "fixtures_expected.json")))
+
+
+def _img(name):
+    return np.fromfile(os.path.join(GOLD, name + ".mp3"), np.uint8)
+
+
+def _check_pcm(engine, oracle, img):
+    rc, opcm, info = oracle.decode(img)
+    assert rc == 0
+    gpcm, sr = engine.decode_pcm(img)
+    assert sr == info.sample_rate
+    assert gpcm.shape == opcm.shape
+    bad = np.nonzero(gpcm != opcm)
+    assert len(bad[0]) == 0, (len(bad[0]), bad[0][:5], bad[1][:5], np.abs(gpcm - opcm).max())
+    return info
+
+
+def _check_analysis(engine, oracle, img):
+    rc, ores, ohist, info = oracle.analyze_mp3(img)
+    assert rc == 0
+    res, sts = engine.analyze_images([img], want_hist=True)
+    assert sts[0] == 0
+    r = res[0]
+    assert (r.histogram == ohist).all()
+    assert r.loudness_db == ores.loudness_db and r.gain_db == ores.gain_db and r.peak == ores.peak
+    assert r.n_windows == ores.n_windows and r.n_dropped_windows == ores.n_dropped
+    assert r.n_frames == info.n_frames and r.sample_rate == info.sample_rate and r.channels == info.channels
+    return r
+
+
+@pytest.mark.parametrize("name", ["test_joint_stereo", "test_mono", "test_vbr", "test_stereo"])
+def test_reference_fixtures(name, engine_exact, engine_fast, oracle):
+    img = _img(name)
+    _check_pcm(engine_exact, oracle, img)
+    for eng in (engine_exact, engine_fast):
+        r = _check_analysis(eng, oracle, img)
+        exp = EXPECTED[name]          # independent expectation (FFmpeg PCM -> stage B): +-0.01 dB bar of the north star
+        assert abs(r.loudness_db - exp["loudness_db"]) <= 0.01 + 1e-12
+        assert {str(int(i)): int(r.histogram[i]) for i in np.nonzero(r.histogram)[0]} == exp["histogram"]
+
+
+SYNTH = [dict(seed=3), dict(seed=4, channels=1), dict(seed=5, sr_idx=1), dict(seed=6, br_idx=0),
+         dict(seed=7, sr_idx=2, br_idx=5), dict(seed=8, br_idx=14), dict(seed=9, br_idx=1),
+         dict(seed=10, sr_idx=1, br_idx=0, channels=1)]
+
+
+@pytest.mark.parametrize("kw", SYNTH)
+def test_synthetic_streams_pcm_bit_exact(kw, engine_exact, oracle):
+    img = synth_corpus.make_track(n_frames=300, **kw)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 300
+
+
+@pytest.mark.parametrize("kw", SYNTH[:4])
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_synthetic_streams_analysis(kw, mode, engine_exact, engine_fast, oracle):
+    img = synth_corpus.make_track(n_frames=700, **kw)
+    _check_analysis(engine_exact if mode == "exact" else engine_fast, oracle, img)
+
+
+def test_container_edge_cases(engine_exact, oracle):
+    base = synth_corpus.make_track(seed=11, n_frames=50)
+    variants = [
+        np.frombuffer(synth_corpus.id3v2_tag(300) + synth_corpus.info_frame(bytes(base[:4])) + bytes(base) +
+                      synth_corpus.id3v1_trailer(), np.uint8),
+        base[:-7],
+        np.concatenate([base, np.full(333, 0x55, np.uint8), base]),
+        np.concatenate([np.full(77, 0xFF, np.uint8), base]),
+        base[:500],
+    ]
+    grp = synth_corpus.make_group(5, 8)
+    # cut in the middle of the bit reservoir: leading frames are dropped as DecodeError
+    pos, cuts = 0, []
+    b = bytes(grp)
+    while pos + 4 <= len(b):
+        bi, si, pad = b[pos + 2] >> 4, (b[pos + 2] >> 2) & 3, (b[pos + 2] >> 1) & 1
+        cuts.append(pos)
+        pos += 144 * synth_corpus.BITRATES[bi] * 1000 // synth_corpus.RATES[si] + pad
+    variants.append(grp[cuts[3]:])
+    for img in variants:
+        _check_pcm(engine_exact, oracle, img)
+        _check_analysis(engine_exact, oracle, img)
+
+
+def test_keep_info_frame_flag(oracle):
+    import mp3rgain_b200 as m
+    img = _img("test_joint_stereo")
+    rc, opcm, info = oracle.decode(img, flags=0x2)
+    with m.Engine(device=0, exact=True, flags=0x2) as eng:
+        gpcm, sr = eng.decode_pcm(img)
+    assert info.n_frames == 41 and gpcm.shape == opcm.shape and (gpcm == opcm).all()
+
+
+def test_errors_match_reference_messages(engine_exact):
+    import mp3rgain_b200 as m
+    res, sts = engine_exact.analyze_images([np.zeros(5000, np.uint8), np.zeros(0, np.uint8), _img("test_mono")])
+    assert sts == [-5, -5, 0]                      # "Failed to probe format", twice; a bad entry does not poison the batch
+    res, sts = engine_exact.analyze_images([_img("test_mono")], track_index=3)
+    assert sts == [-7]                             # "Track index 3 out of range (file has 1 audio track(s))"
+    with pytest.raises(m.ReplayGainError) as ei:
+        engine_exact.analyze_images([_img("test_mono")], track_index=3, raise_on_error=True)
+    assert "Track index 3 out of range (file has 1 audio track(s))" in str(ei.value)
+    hdr = bytes([0xFF, 0xF3, 0x80, 0x00])
+    lsf = np.frombuffer((hdr + bytes(72 * 64000 // 22050 - 4)) * 4, np.uint8)
+    res, sts = engine_exact.analyze_images([lsf])
+    assert sts == [-10] and res[0].sample_rate == 22050
+
+
+def test_module_level_api_on_files(oracle, tmp_path):
+    """The reference-shaped entry points: analyze_track / analyze_album / find_peak_amplitude on paths."""
+    import mp3rgain_b200 as m
+    paths = [os.path.join(GOLD, n + ".mp3") for n in ("test_joint_stereo", "test_mono", "test_vbr")]
+    r = m.analyze_track(paths[0])
+    assert r.loudness_db == 58.11 and abs(r.gain_db - 6.71) < 1e-9 and r.gain_steps() == 4 and r.sample_rate == 44100
+    assert r.file_type == m.AudioFileType.Mp3
+    alb = m.analyze_album(paths)
+    hists, peaks = [], []
+    for p in paths:
+        rc, ores, ohist, info = oracle.analyze_mp3(np.fromfile(p, np.uint8))
+        hists.append(ohist)
+        peaks.append(ores.peak)
+    merged, loud, gain, peak = oracle.album_merge(np.stack(hists), peaks)
+    assert alb.album_loudness_db == loud and alb.album_gain_db == gain and alb.album_peak == peak
+    assert [t.loudness_db for t in alb.tracks] == [58.11, 61.12, 58.56]
+    pk = m.find_peak_amplitude(paths[1])
+    assert pk.peak == peaks[1] and pk.peak_pcm == peaks[1] * 32768.0 and pk.sample_rate == 44100
+    with pytest.raises(m.ReplayGainError) as ei:
+        m.analyze_track(str(tmp_path / "missing.mp3"))
+    assert str(ei.value).startswith("Failed to open: ")
+    bad = tmp_path / "bad.mp3"
+    bad.write_bytes(bytes(4000))
+    with pytest.raises(m.ReplayGainError) as ei:
+        m.analyze_album([paths[0], str(bad), paths[1]])      # first failing file aborts the album (src/replaygain.rs:1055)
+    assert str(ei.value).startswith("Failed to probe format")
+
+
+def test_album_histogram_is_sum_of_track_histograms(engine_fast, oracle):
+    imgs = [synth_corpus.make_track(seed=20 + i, n_frames=200 + 37 * i, channels=1 + (i % 2)) for i in range(5)]
+    alb = engine_fast.analyze_album_images(imgs, want_hist=True)
+    hists, peaks = [], []
+    for im in imgs:
+        rc, ores, ohist, info = oracle.analyze_mp3(im)
+        hists.append(ohist)
+        peaks.append(ores.peak)
+    merged, loud, gain, peak = oracle.album_merge(np.stack(hists), peaks)
+    assert (alb.album_histogram == merged.astype(np.uint64)).all()
+    assert alb.album_loudness_db == loud and alb.album_peak == peak
+
+
+def test_batch_of_many_tracks_and_small_scratch(oracle):
+    """Many tracks in one call, forced through several scratch batches, results independent of batching."""
+    import mp3rgain_b200 as m
+    pool = synth_corpus.GroupPool(seed=2, n_groups=24, group_len=16)
+    imgs = [pool.track(100 + i, 160 + 16 * (i % 5)) for i in range(40)]
+    with m.Engine(device=0, exact=False, scratch_bytes=8 << 20) as eng:
+        res, sts = eng.analyze_images(imgs, want_hist=True)
+    assert all(s == 0 for s in sts)
+    for i in (0, 7, 19, 39):
+        rc, ores, ohist, info = oracle.analyze_mp3(imgs[i])
+        assert (res[i].histogram == ohist).all() and res[i].loudness_db == ores.loudness_db and res[i].peak == ores.peak

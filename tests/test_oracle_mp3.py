@@ -1,0 +1,114 @@
+"""CPU tests: pin the oracle's stage A (oracle/mp3_oracle.c).  The reference has no golden vector for this stage (its
+decoder is the external symphonia crate and no reference test runs replaygain::* on an MP3), so the anchors are:
+  * the reference's four MP3 fixtures, with expectations from an independent decoder (FFmpeg mp3float -> stage B),
+    committed in tests/golden/fixtures_expected.json (== SURVEY.md Appendix A);
+  * live cross-checks against FFmpeg on the fixtures and on synthetic streams (skipped when libavcodec is absent).
+Parity with symphonia itself stays UNPINNED."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ffmpeg_ref
+import oracle_lib
+import synth_corpus
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EXPECTED = json.load(open(os.path.join(GOLD, "fixtures_expected.json")))
+
+
+def _img(name):
+    return np.fromfile(os.path.join(GOLD, name + ".mp3"), np.uint8)
+
+
+@pytest.mark.parametrize("name", ["test_joint_stereo", "test_mono", "test_vbr", "test_stereo"])
+def test_fixture_results_match_golden(oracle, name):
+    exp = EXPECTED[name]
+    rc, res, hist, info = oracle.analyze_mp3(_img(name))
+    assert rc == 0
+    assert info.skipped_info_frame == 1            # every fixture starts with a Xing/Info frame
+    assert info.channels == exp["channels"] and info.n_samples == exp["samples"]
+    assert res.n_windows == exp["n_windows"] and res.n_dropped == exp["n_dropped"]
+    assert {str(int(i)): int(hist[i]) for i in np.nonzero(hist)[0]} == exp["histogram"]
+    assert res.loudness_db == exp["loudness_db"]             # identical bins => identical dB (bar: +-0.01 dB)
+    assert abs(res.gain_db - exp["gain_db"]) < 1e-9
+    if name != "test_stereo":                                # gain-saturated copy: peak differs by design
+        assert abs(res.peak - exp["peak"]) < 2e-6
+
+
+def test_truncated_last_frame_is_eof(oracle):
+    # test_stereo.mp3's last frame is 6 bytes short: 39 frames decode (src/replaygain.rs:884-888 UnexpectedEof => break)
+    rc, pcm, info = oracle.decode(_img("test_stereo"))
+    assert rc == 0 and info.n_frames == 39 and pcm.shape == (2, 39 * 1152)
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("name", ["test_joint_stereo", "test_mono", "test_vbr"])
+def test_fixture_pcm_close_to_ffmpeg(oracle, name):
+    img = _img(name)
+    rc, pcm, info = oracle.decode(img)
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 1e-6
+
+
+SYNTH = [dict(seed=3), dict(seed=4, channels=1), dict(seed=5, sr_idx=1), dict(seed=6, br_idx=0),
+         dict(seed=7, sr_idx=2, br_idx=5), dict(seed=8, br_idx=14), dict(seed=9, br_idx=1),
+         dict(seed=10, sr_idx=1, br_idx=0, channels=1)]
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", SYNTH)
+def test_synthetic_streams_decode_like_ffmpeg(oracle, kw):
+    """The synthetic generator's streams are valid (FFmpeg decodes every frame) and the oracle agrees with FFmpeg's
+    PCM to float rounding: validates generator tables and oracle tables against a third party at once."""
+    img = synth_corpus.make_track(n_frames=400, **kw)
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 400 and info.n_dropped_frames == 0
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+    assert 0.03 < np.sqrt((pcm.astype(np.float64) ** 2).mean()) < 0.3
+
+
+def test_container_edge_cases(oracle):
+    base = synth_corpus.make_track(seed=11, n_frames=50)
+    rc0, pcm0, info0 = oracle.decode(base)
+    assert rc0 == 0 and info0.n_frames == 50
+    # ID3v2 tag + Info frame in front, ID3v1 trailer behind: same PCM
+    img = np.frombuffer(synth_corpus.id3v2_tag(300) + synth_corpus.info_frame(bytes(base[:4])) + bytes(base) +
+                        synth_corpus.id3v1_trailer(), np.uint8)
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.skipped_info_frame == 1 and info.n_frames == 50
+    assert (pcm == pcm0).all()
+    # keep-info-frame switch decodes it as one more (silent) frame
+    rc, pcm_k, info_k = oracle.decode(img, flags=0x2)
+    assert info_k.n_frames == 51 and info_k.skipped_info_frame == 0
+    # truncated last frame is dropped
+    rc, pcm_t, info_t = oracle.decode(base[:-7])
+    assert info_t.n_frames == 49 and (pcm_t == pcm0[:, :49 * 1152]).all()
+    # junk between frames: resync, nothing lost before the junk
+    flen = len(synth_corpus.make_group(1, 1))
+    rc, pcm_j, info_j = oracle.decode(np.concatenate([base, np.full(333, 0x55, np.uint8), base]))
+    assert rc == 0 and info_j.n_frames == 100
+    # stream cut in the middle of the bit reservoir: the first frames of the tail refer to missing main data
+    grp = synth_corpus.make_group(5, 8)
+    frames = ffmpeg_ref.split_frames(grp)
+    tail = np.frombuffer(b"".join(frames[3:]), np.uint8)
+    rc, pcm_u, info_u = oracle.decode(tail)
+    assert rc == 0 and info_u.n_frames + info_u.n_dropped_frames == 5
+    # not an MP3 at all / empty
+    rc, _, info = oracle.decode(np.zeros(5000, np.uint8))
+    assert rc == -5
+    rc, _, info = oracle.decode(np.zeros(0, np.uint8))
+    assert rc == -5
+
+
+def test_lsf_stream_is_reported_unsupported(oracle):
+    # MPEG-2 Layer III header (22.05 kHz, 64 kbps): recognised, not decoded (row f4 of SURVEY.md 8, "next")
+    hdr = bytes([0xFF, 0xF3, 0x80, 0x00])
+    flen = 72 * 64000 // 22050
+    img = np.frombuffer((hdr + bytes(flen - 4)) * 4, np.uint8)
+    rc, _, info = oracle.decode(img)
+    assert rc == -10 and info.sample_rate == 22050
