@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""bench.py -- audio-hours/sec analysed (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): BASELINE.json configs[1] -- 1,000 synthetic 3-minute 44.1 kHz stereo CBR-128 MP3 tracks per
+GPU, track-mode ReplayGain analysis.  A "step" is one pass of the whole hot path (frame index -> Huffman -> hybrid /
+polyphase -> IIR -> histogram / percentile) over that batch.  Tracks are independent, so N GPUs shard by track with no
+data-path collective (weak scaling: per-GPU work is fixed).
+
+  value  whole-job audio-hours/sec with the file images already resident in HBM (rg_analyze_corpus)
+  e2e    the same metric through rg_analyze_tracks with HOST (pinned) buffers: H2D of every file image and D2H of the
+         results are inside the timed region
+  roofline / cpu_baseline: see DESIGN.md "Measurement".
+
+`--impl reference` times the reference's CPU path instead.  The reference is Rust + the un-vendored symphonia crate and
+cannot be built in this image (no Rust toolchain, no network), so the stand-in is the plain-C oracle (oracle/) run on all
+host threads over a bounded sample of the same workload -- the one other place this file may execute oracle/.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FRAMES_3MIN = 6891          # 3 min of 44.1 kHz MPEG-1 Layer III frames
+METRIC = "audio-hours/sec analysed"
+
+
+def build_corpus(n_tracks, n_frames, seed):
+    """n_tracks distinct tracks: seeded random sequences of self-contained frame groups from a seeded pool."""
+    import synth_corpus
+    pool = synth_corpus.GroupPool(seed=seed, n_groups=256, group_len=32)
+    return [pool.track(seed * 100003 + i, n_frames) for i in range(n_tracks)]
+
+
+def audio_seconds(n_tracks, n_frames):
+    return n_tracks * n_frames * 1152 / 44100.0
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_run(imgs, threads):
+    """Oracle (CPU restatement of the reference path) over `imgs` with `threads` host threads; returns seconds."""
+    import oracle_lib
+    orc = oracle_lib.load()
+    idx = list(range(len(imgs)))
+    lock = threading.Lock()
+    out = [None] * len(imgs)
+
+    def work():
+        while True:
+            with lock:
+                if not idx:
+                    return
+                i = idx.pop()
+            rc, res, hist, info = orc.analyze_mp3(imgs[i])   # ctypes releases the GIL during the call
+            out[i] = (rc, res.loudness_db)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work) for _ in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=1000, help="tracks per GPU (configs[1]: 1000)")
+    ap.add_argument("--frames", type=int, default=FRAMES_3MIN, help="frames per track (6891 = 3 min)")
+    ap.add_argument("--exact", action="store_true", help="bit-exact serial IIR for every track (parity mode)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncores = os.cpu_count() or 1
+    config = {"workload": f"configs[1]: {args.tracks} synthetic 3-min 44.1 kHz stereo CBR-128 MP3 tracks per GPU, track-mode",
+              "tracks_per_gpu": args.tracks, "frames_per_track": args.frames, "sample_rate": 44100, "channels": 2,
+              "bitrate_kbps": 128, "sharding": f"by-track x{world}", "iir_mode": "exact" if args.exact else "time-blocked+edge-rerun",
+              "l2": "inputs (2.9 GB compressed per GPU, 95 GB of intermediates) are far larger than the 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n_sample = max(2 * ncores, 8)
+        imgs = build_corpus(n_sample, args.frames, seed=1)
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_run(imgs[: max(ncores // 2, 1)], ncores)
+        times = []
+        for _ in range(args.steps):
+            dt, out = cpu_reference_run(imgs, ncores)
+            assert all(o[0] == 0 for o in out)
+            times.append(dt)
+        ms = 1000.0 * sum(times) / len(times)
+        val = audio_seconds(n_sample, args.frames) / 3600.0 / (ms / 1000.0)
+        sample = f"{n_sample} of the workload's tracks per step on {ncores} host threads (oracle/: C restatement of the reference path)"
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "audio-h/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "audio-h/s", "cores": ncores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    import mp3rgain_b200 as m
+    from mp3rgain_b200 import _lib
+    lib = _lib.load()   # raises if the CUDA extension has not been built: there is no fallback
+
+    imgs = build_corpus(args.tracks, args.frames, seed=1 + rank)
+    n = len(imgs)
+    total_bytes = int(sum(len(i) for i in imgs))
+    # pinned host copies of every file image (the e2e path DMA's straight out of these)
+    offs = np.zeros(n + 1, np.int64)
+    for i, im in enumerate(imgs):
+        offs[i + 1] = offs[i] + ((len(im) + 63) & ~63)
+    pinned = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
+    pnp = pinned.numpy()
+    arr = (_lib.RgInput * n)()
+    for i, im in enumerate(imgs):
+        pnp[offs[i]: offs[i] + len(im)] = im
+        arr[i].data = pnp.ctypes.data + int(offs[i])
+        arr[i].len = len(im)
+        arr[i].track_index = -1
+    eng = m.Engine(device=local_rank, exact=args.exact)
+    out = (_lib.RgTrackResult * n)()
+    asec = audio_seconds(n, args.frames)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: corpus resident in HBM before the timed region
+    cor = C.c_void_p()
+    rc = lib.rg_corpus_upload(eng._h, arr, n, C.byref(cor))
+    assert rc == 0, lib.rg_last_error()
+    for _ in range(args.warmup):
+        assert lib.rg_analyze_corpus(eng._h, cor, out, None) == 0
+    st0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, hyb_ms, huf_ms, iir_ms, idx_ms = [], [], [], [], []
+    for _ in range(args.steps):
+        assert lib.rg_analyze_corpus(eng._h, cor, out, None) == 0      # blocks until the results are on the host
+        st = eng.stats()
+        dev_ms.append(st.last_ms_total); hyb_ms.append(st.last_ms_hybrid); huf_ms.append(st.last_ms_huffman)
+        iir_ms.append(st.last_ms_iir); idx_ms.append(st.last_ms_index)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st1 = eng.stats()
+    assert all(out[i].status == 0 for i in range(n))
+    # device time (CUDA events on the engine's stream, whole call), max over ranks
+    step_ms = maxr(float(np.mean(dev_ms)))
+    wall_ms = maxr(1000.0 * wall / args.steps)
+    launches = int(st1.kernel_launches - st0.kernel_launches)
+    reruns = int(st1.exact_reruns - st0.exact_reruns)
+    lib.rg_corpus_free(eng._h, cor)
+
+    # ---- e2e: host buffers in, results out, copies inside the timed region
+    for _ in range(max(1, args.warmup // 3)):
+        assert lib.rg_analyze_tracks(eng._h, arr, n, out, None) == 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        assert lib.rg_analyze_tracks(eng._h, arr, n, out, None) == 0
+    barrier()
+    e2e_ms = maxr(1000.0 * (time.perf_counter() - t0) / args.steps)
+
+    value = world * asec / 3600.0 / (wall_ms / 1000.0)
+    e2e = world * asec / 3600.0 / (e2e_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (k_hybrid_synth): algorithmic bytes = compressed file bytes (SURVEY 8d:
+    # 16,000 B per audio-second at CBR-128) over the kernel's CUDA-event time inside the step
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = float(np.mean(hyb_ms))
+    achieved = total_bytes / (k_ms / 1000.0) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_hybrid_synth_bytes_per_launch_1000_tracks")
+        if traffic is not None and n != 1000:
+            traffic = traffic * n / 1000.0
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_hybrid_synth", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_launch": total_bytes,
+                "kernel_ms": {"k_frame_index": float(np.mean(idx_ms)), "k_huffman": float(np.mean(huf_ms)), "k_hybrid_synth": k_ms,
+                              "k_iir+k_hist": float(np.mean(iir_ms))},
+                "note": "the path is FP-issue bound, not HBM bound (DESIGN.md): staged PCM/spectra traffic is reported in traffic"}
+
+    line = {"metric": METRIC, "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall_ms, "device_ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
+            "exact_reruns": reruns,
+            "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": total_bytes * world,
+                    "d2h_bytes_per_step": n * C.sizeof(_lib.RgTrackResult) * world, "ms_per_step": e2e_ms},
+            "roofline": roofline}
+
+    if rank == 0 and world == 1:
+        # CPU baseline beside it: the oracle (C restatement of the reference path) on a bounded sample, all host threads
+        n_sample = max(2 * ncores, 8)
+        dt, o = cpu_reference_run(imgs[:n_sample], ncores)
+        cpu_val = audio_seconds(n_sample, args.frames) / 3600.0 / dt
+        # parity spot check of the timed results against the oracle on the sample
+        mism = sum(1 for i in range(n_sample) if o[i][1] != out[i].loudness_db)
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "audio-h/s", "cores": ncores, "kind": "port",
+                                "sample": f"first {n_sample} tracks of the workload, one pass, {ncores} host threads, {dt:.1f} s",
+                                "loudness_mismatches_vs_gpu": mism}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

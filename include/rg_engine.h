@@ -107,9 +107,9 @@ int  rg_engine_create(const rg_config* cfg, rg_engine** out);
 void rg_engine_destroy(rg_engine* e);
 const char* rg_status_str(int status);
 /* Tuning knobs (not part of the reference surface). Keys: "iir_block_windows" (50 ms windows per time block of
- * the time-blocked IIR, default 16), "iir_warm_windows" (zero-state warm-up windows before each block, default 2),
+ * the time-blocked IIR, default 16), "iir_warm_windows" (zero-state warm-up windows before each block, default 1),
  * "edge_tol" (distance of 1000*log10(ms) from an integer below which the time-blocked pass hands the track to the
- * exact kernel, default 1e-6).  Returns RG_ERR_INVALID_ARG for an unknown key. */
+ * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9).  Returns RG_ERR_INVALID_ARG for an unknown key. */
 int rg_engine_set_option(rg_engine* e, const char* key, double value);
 /* Thread-local detail string for the last failing call (CUDA error text etc.). */
 const char* rg_last_error(void);

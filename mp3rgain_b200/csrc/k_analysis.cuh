@@ -76,6 +76,8 @@ __device__ __forceinline__ double iir_step(IirState& s, const double* __restrict
 struct WinAcc {
     double sum;
     double* out;
+    float* mout;
+    float wmax;
     uint32_t tot, win;
 };
 
@@ -83,12 +85,15 @@ template <bool FAST, bool ACCUM>
 __device__ __forceinline__ void iir_sample(IirState& s, const double* __restrict__ c, WinAcc& w, float& peak, float xf) {
     double z = iir_step<FAST>(s, c, xf);
     if (ACCUM) {
-        peak = fmaxf(peak, fabsf(xf));
+        w.wmax = fmaxf(w.wmax, fabsf(xf));
         if (FAST) w.sum = __fma_rn(z, z, w.sum);
         else w.sum = __dadd_rn(w.sum, __dmul_rn(z, z));
         if (++w.tot == w.win) {
             *w.out++ = w.sum;
+            *w.mout++ = w.wmax;
+            peak = fmaxf(peak, w.wmax);
             w.sum = 0.0;
+            w.wmax = 0.0f;
             w.tot = 0;
         }
     }
@@ -148,11 +153,15 @@ k_iir(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__
     for (int i = 0; i < 10; i++) { s.xh[i] = 0.0; s.yh[i] = 0.0; }
     s.bx[0] = s.bx[1] = s.by[0] = s.by[1] = 0.0;
     WinAcc w;
-    w.sum = 0.0; w.out = ch.wsum; w.tot = 0; w.win = ch.win;
+    w.sum = 0.0; w.out = ch.wsum; w.mout = ch.wmax; w.wmax = 0.0f; w.tot = 0; w.win = ch.win;
     float peak = 0.0f;
     if (FAST && ch.n_warm) iir_run<FAST, false>(s, c, w, peak, ch.src, ch.n_warm);
     iir_run<FAST, true>(s, c, w, peak, ch.src + ch.n_warm, ch.n_main);
-    if (w.tot) *w.out = w.sum;  // the track's final partial window (src/replaygain.rs:907)
+    if (w.tot) {  // the track's final partial window (src/replaygain.rs:907)
+        *w.out = w.sum;
+        *w.mout = w.wmax;
+        peak = fmaxf(peak, w.wmax);
+    }
     peaks[chain_base + ci] = peak;
 }
 
@@ -175,7 +184,8 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
                   RgTrackOut* __restrict__ out, uint32_t* __restrict__ hist_out /* n*12000 or null */,
                   unsigned long long* __restrict__ album_hist /* 12000 or null */,
                   unsigned long long* __restrict__ album_peak_bits /* or null */, double edge_tol,
-                  int defer_album_on_edge /* skip the album adds when this track has edge windows (it will be re-run) */) {
+                  int defer_album_on_edge /* skip the album adds when this track has edge windows (it will be re-run) */,
+                  int scale_tol /* time-blocked pass: scale edge_tol by the window's input-amplitude / filtered-RMS ratio */) {
     __shared__ uint32_t hist[RG_HIST_BINS];
     __shared__ uint32_t s_cnt[3];           // counted, dropped, edge
     __shared__ uint32_t s_chunk[K5_THREADS];   // per-track window counts fit 32 bits
@@ -203,7 +213,19 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
             const double val = __dmul_rn(1000.0, log10(__dadd_rn(ms, 1e-37)));
             const int v = __double2int_rz(val);  // cvt.rzi.s32.f64: truncates, saturates, NaN -> 0
             const long long li = (long long)v + RG_HIST_OFF;
-            if (fabs(val - rint(val)) < edge_tol) edge++;
+            // Edge test: would a perturbation of the window's mean square at the level of the time-blocked kernel's
+            // rounding differences move trunc(val) across a bin boundary that matters?  The tolerance grows with the
+            // ratio of input amplitude to filtered RMS (heavily attenuated windows carry larger relative error), and
+            // windows far outside the histogram can never change bin membership.
+            if (val > -2002.0 && val < 10001.0) {
+                double tol = edge_tol;
+                if (scale_tol) {
+                    const double amp = 32768.0 * (double)fmaxf(t.wmax0[w], t.wmax1[w]);
+                    const double ratio = amp / sqrt(ms + 1e-300);
+                    tol = edge_tol * fmax(1.0, 0.1 * ratio);
+                }
+                if (fabs(val - rint(val)) < tol) edge++;
+            }
             if (li >= 0 && li < RG_HIST_BINS) { valid = true; idx = (int)li; counted++; }
             else dropped++;
         }

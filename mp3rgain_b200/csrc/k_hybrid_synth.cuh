@@ -6,18 +6,44 @@
 // rebuild that state exactly: runs are independent and the whole corpus decodes in parallel.
 //
 // Arithmetic follows DESIGN.md "f32 decode contract" operation for operation.
+//
+// Instruction budget notes (the kernel is issue-bound, see profiles/): side info and scalefactors of the whole run are
+// parsed once in a parallel prologue; requantisation multiplies by a per-band gain computed once per granule; the IMDCT
+// keeps its DCT-IV matrix row in registers; the polyphase window keeps its 16 coefficients and a sliding set of DCT values
+// in registers; the DCT ring uses two static positions (plus a mirrored tail) so no index is reduced modulo the ring size.
 #pragma once
 
 #define K2_THREADS 256
-#define SB_STRIDE 33     // padded row of 32 subband values
-#define U_STRIDE 37      // padded row of 36 IMDCT outputs
+#define SB_STRIDE 33       // padded row of 32 subband values
+#define U_STRIDE 37        // padded row of 36 IMDCT outputs
+#define K2_MAX_G 66        // RUN_GRANULES (64) + 2 warm-up granules
+#define RING_ROWS 51       // rows 0..50 of the DCT-32 ring (see synth step)
 
-struct GranInfo {
-    int global_gain, sfc, bt, mixed, preflag, sf_shift /* 2 or 4 */, sbg[3];
+struct __align__(16) GranInfo {
     uint32_t part2_bit;   // absolute bit position of part 2 in the main-data stream
     uint32_t md_lim;      // bytes readable (later bytes read as zero)
-    uint32_t nz;          // lines decoded by K1 (0 = silent)
-    int scfsi;            // 4 bits, group 0 = bit 3 (only meaningful for gr 1)
+    uint16_t nz;          // lines decoded by K1 (0 = silent)
+    uint8_t global_gain, sfc, bt, mixed, preflag, sf_shift /* 2 or 4 */;
+    uint8_t sbg[3], scfsi, ms, pad[3];
+};
+
+struct K2Smem {
+    float xr[2][600];                 // requantised spectrum (576 used; aliased as the subband-sample buffer after the IMDCT)
+    float u[2][32][U_STRIDE];
+    float ovl[2][18][32];
+    float ring[2][RING_ROWS][SB_STRIDE];
+    float dct4[18][19];
+    float win[4][36];
+    float im12[12][6];
+    float wa[8][32], wb[8][32];
+    float gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
+    float bandg[2][64];               // per-band requantisation factor of the current granule
+    float cs[8], ca[8];
+    GranInfo gi[K2_MAX_G][2];
+    uint16_t scat[2][576];            // bitstream-order line -> reordered line: [0] pure short, [1] mixed
+    uint8_t code[3][576];             // line -> band code: [0] long, [1] pure short, [2] mixed
+    uint8_t sf[K2_MAX_G][2][64];      // [0..21] long scalefactors, [22..60] short (sfb*3+win)
+    uint8_t idx36[36], ia[32], ib[32];
 };
 
 template <int N, int OFF>
@@ -52,25 +78,27 @@ __device__ __forceinline__ uint32_t md_bits(const uint8_t* __restrict__ mdp, uin
     return (w >> (16 - n - (bit & 7))) & ((1u << n) - 1);
 }
 
-__global__ void __launch_bounds__(K2_THREADS)
+// long-block scalefactor `sfb` (0..20) of a granule-channel whose part 2 starts at gi.part2_bit; `scfsi` = bands skipped
+__device__ __forceinline__ int read_long_sf(const uint8_t* __restrict__ mdp, const GranInfo& gi, int scfsi, int sfb, int slen1, int slen2) {
+    const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+    const int lo = grp == 0 ? 0 : (grp == 1 ? 6 : (grp == 2 ? 11 : 16));
+    uint32_t off = 0;
+    if (grp > 0 && !(scfsi & 8)) off += 6 * slen1;
+    if (grp > 1 && !(scfsi & 4)) off += 5 * slen1;
+    if (grp > 2 && !(scfsi & 2)) off += 5 * slen2;
+    const int sl = grp < 2 ? slen1 : slen2;
+    off += (sfb - lo) * sl;
+    return (int)md_bits(mdp, gi.md_lim, gi.part2_bit + off, sl);
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
                const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
-    __shared__ float s_xr[2][576];
-    __shared__ float s_u[2][32][U_STRIDE];
-    __shared__ float s_ovl[2][18][32];
-    __shared__ float s_sb[2][18][SB_STRIDE];
-    __shared__ float s_ring[2][33][SB_STRIDE];
-    __shared__ float s_dct4[18][19];
-    __shared__ float s_win[4][36];
-    __shared__ float s_im12[12][6];
-    __shared__ float s_wa[8][32], s_wb[8][32];
-    __shared__ float s_gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
-    __shared__ float s_cs[8], s_ca[8];
-    __shared__ uint8_t s_idx36[36], s_ia[32], s_ib[32];
-    __shared__ int s_sfl[2][22];
-    __shared__ int s_sfs[2][39];
-    __shared__ GranInfo s_gi[2];
+    extern __shared__ __align__(16) unsigned char k2_raw[];
+    K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
+    float (*s_sb)[18][SB_STRIDE] = reinterpret_cast<float (*)[18][SB_STRIDE]>(&S.xr[0][0]);  // [2][18][33] <= [2][600]
+    static_assert(2 * 18 * SB_STRIDE <= 2 * 600, "subband buffer must fit in the spectrum buffer it aliases");
 
     const int tid = threadIdx.x;
     const RunDesc run = runs[blockIdx.x];
@@ -78,234 +106,273 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
     const int nch = (int)tr.channels;
     const int sr = (int)tr.sr_idx;
     const uint8_t* mdp = md + tr.md_off;
+    const uint32_t warm = run.g0 < 2 ? run.g0 : 2;
+    const uint32_t gfirst = run.g0 - warm, gcount = run.ng + warm;
 
     // ---- one-time table staging and state reset
-    for (int i = tid; i < 18 * 18; i += K2_THREADS) s_dct4[i / 18][i % 18] = T->dct4_18[i / 18][i % 18];
-    for (int i = tid; i < 4 * 36; i += K2_THREADS) s_win[i / 36][i % 36] = T->winsgn[i / 36][i % 36];
-    for (int i = tid; i < 72; i += K2_THREADS) s_im12[i / 6][i % 6] = T->imdct12[i / 6][i % 6];
-    for (int i = tid; i < 256; i += K2_THREADS) { s_wa[i / 32][i % 32] = T->synth_wa[i / 32][i % 32]; s_wb[i / 32][i % 32] = T->synth_wb[i / 32][i % 32]; }
-    for (int i = tid; i < L3_GAIN_MAX - L3_GAIN_MIN + 1; i += K2_THREADS) s_gain[i] = T->gain[i];
-    if (tid < 8) { s_cs[tid] = T->alias_cs[tid]; s_ca[tid] = T->alias_ca[tid]; }
-    if (tid < 36) s_idx36[tid] = T->imdct36_idx[tid];
-    if (tid < 32) { s_ia[tid] = T->synth_ia[tid]; s_ib[tid] = T->synth_ib[tid]; }
-    for (int i = tid; i < 2 * 18 * 32; i += K2_THREADS) (&s_ovl[0][0][0])[i] = 0.0f;
-    for (int i = tid; i < 2 * 33 * SB_STRIDE; i += K2_THREADS) (&s_ring[0][0][0])[i] = 0.0f;
-    for (int i = tid; i < 2 * 22; i += K2_THREADS) (&s_sfl[0][0])[i] = 0;
-    for (int i = tid; i < 2 * 39; i += K2_THREADS) (&s_sfs[0][0])[i] = 0;
-    __syncthreads();
+    for (int i = tid; i < 18 * 18; i += K2_THREADS) S.dct4[i / 18][i % 18] = T->dct4_18[i / 18][i % 18];
+    for (int i = tid; i < 4 * 36; i += K2_THREADS) S.win[i / 36][i % 36] = T->winsgn[i / 36][i % 36];
+    for (int i = tid; i < 72; i += K2_THREADS) S.im12[i / 6][i % 6] = T->imdct12[i / 6][i % 6];
+    for (int i = tid; i < 256; i += K2_THREADS) { S.wa[i / 32][i % 32] = T->synth_wa[i / 32][i % 32]; S.wb[i / 32][i % 32] = T->synth_wb[i / 32][i % 32]; }
+    for (int i = tid; i < L3_GAIN_MAX - L3_GAIN_MIN + 1; i += K2_THREADS) S.gain[i] = T->gain[i];
+    for (int i = tid; i < 576; i += K2_THREADS) {
+        S.code[0][i] = T->line_sfb_long[sr][i];
+        S.code[1][i] = 22 + T->line_sfb_short[sr][i];
+        const uint8_t c = T->line_sfb_mixed[sr][i];
+        S.code[2][i] = c < 32 ? c : 22 + (c - 32);
+        S.scat[0][i] = T->scatter_short[sr][i];
+        S.scat[1][i] = T->scatter_mixed[sr][i];
+    }
+    if (tid < 8) { S.cs[tid] = T->alias_cs[tid]; S.ca[tid] = T->alias_ca[tid]; }
+    if (tid < 36) S.idx36[tid] = T->imdct36_idx[tid];
+    if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
+    for (int i = tid; i < 2 * 18 * 32; i += K2_THREADS) (&S.ovl[0][0][0])[i] = 0.0f;
+    for (int i = tid; i < 2 * RING_ROWS * SB_STRIDE; i += K2_THREADS) (&S.ring[0][0][0])[i] = 0.0f;
 
-    const uint32_t warm = run.g0 < 2 ? run.g0 : 2;
-    int ring_base = 0;  // row of slot 0 of the current granule is (ring_base + 15) % 33; see row_of()
-
-    for (uint32_t g = run.g0 - warm; g < run.g0 + run.ng; g++) {
+    // ---- prologue 1: side info of every granule-channel of the run
+    for (uint32_t it = tid; it < gcount * nch; it += K2_THREADS) {
+        const uint32_t gl = it / nch, ch = it % nch, g = gfirst + gl;
         const uint32_t frame = g >> 1, gr = g & 1;
         const FrameRec rec = frames[tr.frame_base + frame];
-        const bool ms = nch == 2 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 2);
-        const size_t gc_first = (size_t)tr.gc_base + (size_t)frame * 2 * nch + gr * nch;
-
-        // ---- A: side info of this granule (one thread per channel)
-        if (tid < nch) {
-            const int ch = tid;
-            const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-            const int gbase = (nch == 1 ? 18 : 20);
-            const int rem = gr * nch + ch;
-            uint32_t bit = rec.md_start * 8;
-            for (int k = 0; k < rem; k++) bit += side_field(s, gbase + 59 * k, 12);
-            const int b0 = gbase + 59 * rem;
-            GranInfo gi;
-            gi.global_gain = side_field(s, b0 + 21, 8);
-            gi.sfc = side_field(s, b0 + 29, 4);
-            const int ws = side_field(s, b0 + 33, 1);
-            gi.bt = 0; gi.mixed = 0; gi.sbg[0] = gi.sbg[1] = gi.sbg[2] = 0;
-            if (ws) {
-                gi.bt = side_field(s, b0 + 34, 2);
-                gi.mixed = side_field(s, b0 + 36, 1);
-                gi.sbg[0] = side_field(s, b0 + 47, 3);
-                gi.sbg[1] = side_field(s, b0 + 50, 3);
-                gi.sbg[2] = side_field(s, b0 + 53, 3);
-            }
-            if (gi.bt != 2) gi.mixed = 0;
-            gi.preflag = side_field(s, b0 + 56, 1);
-            gi.sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
-            gi.part2_bit = bit;
-            gi.md_lim = rec.md_end;
-            gi.nz = nz_in[gc_first + ch];
-            gi.scfsi = (gr == 1) ? (int)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;
-            s_gi[ch] = gi;
+        const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
+        const int gbase = (nch == 1 ? 18 : 20);
+        const int rem = gr * nch + ch;
+        uint32_t bit = rec.md_start * 8;
+        for (int k = 0; k < rem; k++) bit += side_field(s, gbase + 59 * k, 12);
+        const int b0 = gbase + 59 * rem;
+        GranInfo gi;
+        gi.global_gain = (uint8_t)side_field(s, b0 + 21, 8);
+        gi.sfc = (uint8_t)side_field(s, b0 + 29, 4);
+        const int ws = side_field(s, b0 + 33, 1);
+        gi.bt = 0; gi.mixed = 0; gi.sbg[0] = gi.sbg[1] = gi.sbg[2] = 0;
+        if (ws) {
+            gi.bt = (uint8_t)side_field(s, b0 + 34, 2);
+            gi.mixed = (uint8_t)side_field(s, b0 + 36, 1);
+            gi.sbg[0] = (uint8_t)side_field(s, b0 + 47, 3);
+            gi.sbg[1] = (uint8_t)side_field(s, b0 + 50, 3);
+            gi.sbg[2] = (uint8_t)side_field(s, b0 + 53, 3);
         }
-        __syncthreads();
+        if (gi.bt != 2) gi.mixed = 0;
+        gi.preflag = (uint8_t)side_field(s, b0 + 56, 1);
+        gi.sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
+        gi.part2_bit = bit;
+        gi.md_lim = rec.md_end;
+        gi.nz = nz_in[(size_t)tr.gc_base + (size_t)frame * 2 * nch + rem];
+        gi.scfsi = (gr == 1) ? (uint8_t)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;
+        gi.ms = (nch == 2 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 2)) ? 1 : 0;
+        gi.pad[0] = gi.pad[1] = gi.pad[2] = 0;
+        S.gi[gl][ch] = gi;
+    }
+    __syncthreads();
 
-        // ---- B: scalefactors straight from the bitstream (part 2 has a closed-form layout)
+    // ---- prologue 2: scalefactors straight from the bitstream (part 2 has a closed-form layout)
+    for (uint32_t it = tid; it < gcount * nch * 64; it += K2_THREADS) {
+        const uint32_t j = it & 63, gc = it >> 6, gl = gc / nch, ch = gc % nch;
+        const GranInfo gi = S.gi[gl][ch];
+        const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
+        int v = 0;
+        if (gi.bt == 2) {
+            if (j < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors
+                if (gi.mixed && j < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + j * slen1, slen1);
+            } else if (j < 22 + 36) {
+                const int q = j - 22, sfb = q / 3;
+                if (!(gi.mixed && sfb < 3)) {
+                    uint32_t off;
+                    if (gi.mixed) off = (sfb < 6) ? (8 + (q - 9)) * slen1 : 17 * slen1 + (q - 18) * slen2;
+                    else off = (sfb < 6) ? q * slen1 : 18 * slen1 + (q - 18) * slen2;
+                    v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
+                }
+            }
+        } else if (j < 21) {
+            const int grp = j < 6 ? 0 : (j < 11 ? 1 : (j < 16 ? 2 : 3));
+            if (!(gi.scfsi & (8 >> grp))) v = read_long_sf(mdp, gi, gi.scfsi, j, slen1, slen2);
+            else {
+                // scfsi: reuse granule 0's scalefactor of the same frame (granule gl-1 of this run; runs start on an even
+                // granule).  A short granule 0 has no long scalefactors (they read as 0) except the 8 of a mixed block.
+                const GranInfo g0 = S.gi[gl - 1][ch];
+                const int a1 = T->slen[0][g0.sfc], a2 = T->slen[1][g0.sfc];
+                if (g0.bt != 2) v = read_long_sf(mdp, g0, 0, j, a1, a2);
+                else if (g0.mixed && j < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + j * a1, a1);
+            }
+        }
+        S.sf[gl][ch][j] = (uint8_t)v;
+    }
+    __syncthreads();
+
+    // per-thread constants of the polyphase window step: thread (ch, half, j) keeps its 16 window coefficients
+    const int w_ch = tid >> 6, w_j = tid & 31, w_half = (tid >> 5) & 1;
+    float wa[8], wb[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][w_j]; wb[p] = S.wb[p][w_j]; }
+    const int w_ia = S.ia[w_j], w_ib = S.ib[w_j];
+
+    for (uint32_t gl = 0; gl < gcount; gl++) {
+        const uint32_t g = gfirst + gl;
+        const size_t gc_first = (size_t)tr.gc_base + (size_t)(g >> 1) * 2 * nch + (g & 1) * nch;
+        const int ring_base = 15 + 18 * (int)(gl & 1);   // row of slot 0: granules alternate between rows 15.. and 33..
+
+        // ---- B: per-band requantisation factor 2^((gain - 210 - ...)/4)
         if (tid < 64 * nch) {
             const int ch = tid >> 6, j = tid & 63;
-            const GranInfo gi = s_gi[ch];
-            const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
-            if (gi.bt == 2) {
-                if (j < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors, the rest read as 0
-                    int v = 0;
-                    if (gi.mixed && j < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + j * slen1, slen1);
-                    s_sfl[ch][j] = v;
-                } else if (j < 22 + 39) {
-                    const int q = j - 22, sfb = q / 3;
-                    int v = 0;
-                    if (sfb < 12 && !(gi.mixed && sfb < 3)) {
-                        uint32_t off;
-                        if (gi.mixed) off = (sfb < 6) ? (8 + (q - 9)) * slen1 : 17 * slen1 + (q - 18) * slen2;
-                        else off = (sfb < 6) ? q * slen1 : 18 * slen1 + (q - 18) * slen2;
-                        v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
-                    }
-                    s_sfs[ch][q] = v;
-                }
-            } else if (j < 21) {
-                const int grp = j < 6 ? 0 : (j < 11 ? 1 : (j < 16 ? 2 : 3));
-                const int lo = grp == 0 ? 0 : (grp == 1 ? 6 : (grp == 2 ? 11 : 16));
-                if (!(gi.scfsi & (8 >> grp))) {  // otherwise keep granule 0's value (scfsi)
-                    uint32_t off = 0;
-                    if (grp > 0 && !(gi.scfsi & 8)) off += 6 * slen1;
-                    if (grp > 1 && !(gi.scfsi & 4)) off += 5 * slen1;
-                    if (grp > 2 && !(gi.scfsi & 2)) off += 5 * slen2;
-                    const int sl = grp < 2 ? slen1 : slen2;
-                    off += (j - lo) * sl;
-                    s_sfl[ch][j] = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sl);
-                }
-            } else if (j == 21) s_sfl[ch][21] = 0;
+            const GranInfo gi = S.gi[gl][ch];
+            if (j < 61) {
+                int e;
+                if (j < 22) e = (int)gi.global_gain - 210 - gi.sf_shift * ((int)S.sf[gl][ch][j] + (gi.preflag ? T->pretab[j] : 0));
+                else e = (int)gi.global_gain - 210 - 8 * gi.sbg[(j - 22) % 3] - gi.sf_shift * (int)S.sf[gl][ch][j];
+                S.bandg[ch][j] = S.gain[e - L3_GAIN_MIN];
+            }
         }
         __syncthreads();
 
-        // ---- C: requantise (+ MS stereo, + short-block reorder folded into the store index)
-        for (int line = tid; line < 576; line += K2_THREADS) {
-            float v[2] = {0.0f, 0.0f};
-            int dst[2] = {line, line};
+        // ---- C: requantise (+ MS stereo, + short-block reorder folded into the store index), two lines per thread
+        for (int pr = tid; pr < 288; pr += K2_THREADS) {
+            float v[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+            int dst[2][2] = {{2 * pr, 2 * pr + 1}, {2 * pr, 2 * pr + 1}};
 #pragma unroll
             for (int ch = 0; ch < 2; ch++) {
                 if (ch >= nch) break;
-                const GranInfo& gi = s_gi[ch];
-                int q = 0;
-                if ((uint32_t)line < gi.nz) q = spectra[(gc_first + ch) * 576 + line];
-                int e;
-                if (gi.bt != 2) {
-                    const int sfb = T->line_sfb_long[sr][line];
-                    e = gi.global_gain - 210 - gi.sf_shift * (s_sfl[ch][sfb] + (gi.preflag ? T->pretab[sfb] : 0));
-                } else {
-                    const int code = gi.mixed ? T->line_sfb_mixed[sr][line] : T->line_sfb_short[sr][line];
-                    if (gi.mixed && code < 32) e = gi.global_gain - 210 - gi.sf_shift * s_sfl[ch][code];
-                    else {
-                        const int c2 = gi.mixed ? code - 32 : code;
-                        e = gi.global_gain - 210 - 8 * gi.sbg[c2 % 3] - gi.sf_shift * s_sfs[ch][c2];
-                    }
-                    // where this bitstream-order line lands after the reorder
-                    dst[ch] = gi.mixed ? T->scatter_mixed[sr][line] : T->scatter_short[sr][line];
+                const GranInfo& gi = S.gi[gl][ch];
+                uint32_t packed = 0;
+                if ((uint32_t)(2 * pr) < gi.nz) packed = *reinterpret_cast<const uint32_t*>(spectra + (gc_first + ch) * 576 + 2 * pr);
+                const int tsel = gi.bt != 2 ? 0 : (gi.mixed ? 2 : 1);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int line = 2 * pr + h;
+                    const int q = (int)(int16_t)(h ? (packed >> 16) : (packed & 0xFFFFu));
+                    const int aq = q < 0 ? -q : q;
+                    const float m = __fmul_rn(__ldg(&T->pow43[aq]), S.bandg[ch][S.code[tsel][line]]);
+                    v[ch][h] = q < 0 ? -m : m;
+                    if (tsel) dst[ch][h] = S.scat[tsel - 1][line];
                 }
-                const int aq = q < 0 ? -q : q;
-                const float m = __fmul_rn(__ldg(&T->pow43[aq]), s_gain[e - L3_GAIN_MIN]);
-                v[ch] = q < 0 ? -m : m;
             }
-            if (ms) {
-                const float a = v[0], b = v[1];
-                v[0] = __fmul_rn(__fadd_rn(a, b), L3_INV_SQRT2);
-                v[1] = __fmul_rn(__fsub_rn(a, b), L3_INV_SQRT2);
+            if (S.gi[gl][0].ms) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float a = v[0][h], b = v[1][h];
+                    v[0][h] = __fmul_rn(__fadd_rn(a, b), L3_INV_SQRT2);
+                    v[1][h] = __fmul_rn(__fsub_rn(a, b), L3_INV_SQRT2);
+                }
             }
-            s_xr[0][dst[0]] = v[0];
-            if (nch == 2) s_xr[1][dst[1]] = v[1];
+            S.xr[0][dst[0][0]] = v[0][0];
+            S.xr[0][dst[0][1]] = v[0][1];
+            if (nch == 2) { S.xr[1][dst[1][0]] = v[1][0]; S.xr[1][dst[1][1]] = v[1][1]; }
         }
         __syncthreads();
 
         // ---- D: alias reduction
         for (int it = tid; it < nch * 31 * 8; it += K2_THREADS) {
-            const int ch = it / 248, r = it % 248, sb = r / 8 + 1, i = r % 8;
-            const GranInfo& gi = s_gi[ch];
-            const bool doit = gi.bt != 2 || (gi.mixed && sb == 1);
-            if (doit) {
-                const float lo = s_xr[ch][18 * sb - 1 - i], hi = s_xr[ch][18 * sb + i];
-                s_xr[ch][18 * sb - 1 - i] = __fsub_rn(__fmul_rn(lo, s_cs[i]), __fmul_rn(hi, s_ca[i]));
-                s_xr[ch][18 * sb + i] = __fadd_rn(__fmul_rn(hi, s_cs[i]), __fmul_rn(lo, s_ca[i]));
+            const int ch = it / 248, r = it % 248, sb = (r >> 3) + 1, i = r & 7;
+            const GranInfo& gi = S.gi[gl][ch];
+            if (gi.bt != 2 || (gi.mixed && sb == 1)) {
+                const float lo = S.xr[ch][18 * sb - 1 - i], hi = S.xr[ch][18 * sb + i];
+                S.xr[ch][18 * sb - 1 - i] = __fsub_rn(__fmul_rn(lo, S.cs[i]), __fmul_rn(hi, S.ca[i]));
+                S.xr[ch][18 * sb + i] = __fadd_rn(__fmul_rn(hi, S.cs[i]), __fmul_rn(lo, S.ca[i]));
             }
         }
         __syncthreads();
 
-        // ---- E: IMDCT (18-point DCT-IV for long blocks, 3 x 12-point for short blocks)
-        for (int it = tid; it < nch * 32 * 18; it += K2_THREADS) {
-            const int ch = it / 576, r = it % 576, sb = r / 18, m = r % 18;
-            const GranInfo& gi = s_gi[ch];
-            const float* X = &s_xr[ch][18 * sb];
-            const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
-            if (!is_short) {
-                float a = 0.0f;
+        // ---- E: IMDCT.  Thread (grp, m) holds row m of the 18-point DCT-IV matrix and sweeps subbands grp, grp+14, ...
+        if (tid < 252) {
+            const int m = tid % 18, grp = tid / 18;
+            float c[18];
 #pragma unroll
-                for (int k = 0; k < 18; k++) a = fmaf(X[k], s_dct4[m][k], a);
-                s_u[ch][sb][m] = a;
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int o = 2 * m + h, w = o / 12, i = o % 12;
+            for (int k = 0; k < 18; k++) c[k] = S.dct4[m][k];
+            for (int item = grp; item < nch * 32; item += 14) {
+                const int ch = item >> 5, sb = item & 31;
+                const GranInfo& gi = S.gi[gl][ch];
+                if (!(gi.bt == 2 && !(gi.mixed && sb < 2))) {
+                    const float2* X2 = reinterpret_cast<const float2*>(&S.xr[ch][18 * sb]);
                     float a = 0.0f;
 #pragma unroll
-                    for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], s_im12[i][k], a);
-                    s_u[ch][sb][o] = __fmul_rn(a, s_win[2][i]);
+                    for (int k = 0; k < 9; k++) {
+                        const float2 x = X2[k];
+                        a = fmaf(x.x, c[2 * k], a);
+                        a = fmaf(x.y, c[2 * k + 1], a);
+                    }
+                    S.u[ch][sb][m] = a;
+                } else {
+                    const float* X = &S.xr[ch][18 * sb];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int o = 2 * m + h, w = o / 12, i = o % 12;
+                        float a = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], S.im12[i][k], a);
+                        S.u[ch][sb][o] = __fmul_rn(a, S.win[2][i]);
+                    }
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // all reads of S.xr are done: from here the buffer is the subband-sample array s_sb
 
         // ---- F: window, overlap-add, frequency inversion -> subband samples [slot][subband]
-        for (int it = tid; it < nch * 18 * 32; it += K2_THREADS) {
-            const int ch = it / 576, r = it % 576, i = r / 32, sb = r % 32;
-            const GranInfo& gi = s_gi[ch];
+        for (int it = tid; it < nch * 576; it += K2_THREADS) {
+            const int ch = it / 576, r = it - ch * 576, i = r >> 5, sb = r & 31;
+            const GranInfo& gi = S.gi[gl][ch];
             const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
             float lo, hi;
             if (!is_short) {
                 const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
-                lo = __fmul_rn(s_u[ch][sb][s_idx36[i]], s_win[bt][i]);
-                hi = __fmul_rn(s_u[ch][sb][s_idx36[18 + i]], s_win[bt][18 + i]);
+                lo = __fmul_rn(S.u[ch][sb][S.idx36[i]], S.win[bt][i]);
+                hi = __fmul_rn(S.u[ch][sb][S.idx36[18 + i]], S.win[bt][18 + i]);
             } else {
-                // raw[j] = sum over windows w (ascending) of y_w[j - 6 - 6w]; j = i (lo) and 18 + i (hi)
-                const float* y = s_u[ch][sb];
-                // lo: j = i
-                if (i < 6) lo = 0.0f;
-                else if (i < 12) lo = y[i - 6];
-                else lo = __fadd_rn(y[i - 6], y[12 + (i - 12)]);
-                // hi: j = 18 + i
-                if (i < 6) hi = __fadd_rn(y[12 + i + 6], y[24 + i]);
-                else if (i < 12) hi = y[24 + i];
-                else hi = 0.0f;
+                // raw[j] = sum over windows w (ascending) of y_w[j - 6 - 6w], y_w at S.u[..][12w + .]
+                const float* y = S.u[ch][sb];
+                if (i < 6) { lo = 0.0f; hi = __fadd_rn(y[18 + i], y[24 + i]); }
+                else if (i < 12) { lo = y[i - 6]; hi = y[24 + i]; }
+                else { lo = __fadd_rn(y[i - 6], y[i]); hi = 0.0f; }
             }
-            float vv = __fadd_rn(lo, s_ovl[ch][i][sb]);
-            s_ovl[ch][i][sb] = hi;
+            float vv = __fadd_rn(lo, S.ovl[ch][i][sb]);
+            S.ovl[ch][i][sb] = hi;
             if ((sb & 1) && (i & 1)) vv = -vv;
             s_sb[ch][i][sb] = vv;
         }
         __syncthreads();
 
-        // ---- G: 32-point DCT-II per time slot (Lee), result into the ring of the last 33 slots
+        // ---- G: 32-point DCT-II per time slot (Lee).  Ring rows: this granule's slots at ring_base + t; when the granule
+        // sits in the upper position its slots 3..17 are mirrored into rows 0..14 so the next granule (lower position) finds
+        // its 15 predecessors at negative offsets without any modular arithmetic.
         if (tid < nch * 18) {
             const int ch = tid / 18, t = tid % 18;
             float x[32];
 #pragma unroll
             for (int k = 0; k < 32; k++) x[k] = s_sb[ch][t][k];
             Dct2<32, 0>::run(x);
-            float* dstrow = s_ring[ch][(ring_base + 15 + t) % 33];
+            float* dstrow = S.ring[ch][ring_base + t];
 #pragma unroll
             for (int k = 0; k < 32; k++) dstrow[k] = x[k];
+            if ((gl & 1) && t >= 3) {
+                float* mir = S.ring[ch][t - 3];
+#pragma unroll
+                for (int k = 0; k < 32; k++) mir[k] = x[k];
+            }
         }
         __syncthreads();
 
-        // ---- H: polyphase window: 16 taps per output sample, PCM to HBM (coalesced 128-byte rows)
-        if (g >= run.g0) {
-            for (int it = tid; it < nch * 18 * 32; it += K2_THREADS) {
-                const int ch = it / 576, r = it % 576, t = r / 32, j = r % 32;
-                const int ia = s_ia[j], ib = s_ib[j];
-                const int row0 = ring_base + 15 + t + 33;
+        // ---- H: polyphase window.  Thread (ch, half, j) produces 9 consecutive slots of output column j, sliding a
+        // register window over the ring: out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain)
+        if (g >= run.g0 && w_ch < nch) {
+            const float* colA = &S.ring[w_ch][ring_base + 9 * w_half][w_ia];
+            const float* colB = &S.ring[w_ch][ring_base + 9 * w_half][w_ib];
+            float A[24], B[24];   // rows t0-15 .. t0+8 relative to this thread's first slot t0
+#pragma unroll
+            for (int r = 0; r < 15; r++) { A[r] = colA[(r - 15) * SB_STRIDE]; B[r] = colB[(r - 15) * SB_STRIDE]; }
+            float* dst = pcm + tr.pcm_off + (size_t)w_ch * tr.pcm_plane + (size_t)g * 576 + 32 * (9 * w_half) + w_j;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                A[15 + t] = colA[t * SB_STRIDE];
+                B[15 + t] = colB[t * SB_STRIDE];
                 float a = 0.0f;
 #pragma unroll
                 for (int p = 0; p < 8; p++) {
-                    a = fmaf(s_ring[ch][(row0 - 2 * p) % 33][ia], s_wa[p][j], a);
-                    a = fmaf(s_ring[ch][(row0 - 2 * p - 1) % 33][ib], s_wb[p][j], a);
+                    a = fmaf(A[15 + t - 2 * p], wa[p], a);
+                    a = fmaf(B[15 + t - 2 * p - 1], wb[p], a);
                 }
                 if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
-                pcm[tr.pcm_off + (size_t)ch * tr.pcm_plane + (size_t)g * 576 + 32 * t + j] = a;
+                dst[32 * t] = a;
             }
         }
-        ring_base = (ring_base + 18) % 33;
-        __syncthreads();
+        // no barrier here: the next granule's steps B..F do not touch the ring and its step G (other ring position, plus
+        // the mirror rows) runs only after five more barriers
     }
 }

@@ -76,10 +76,10 @@ struct rg_engine {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
     // options
-    uint32_t block_windows = 16, warm_windows = 2;
-    double edge_tol = 1e-6;
+    uint32_t block_windows = 16, warm_windows = 1;
+    double edge_tol = 1e-9;
     // device scratch
-    DevBuf d_pcm_in, d_chains, d_wsum, d_peaks, d_twin, d_tout, d_hist, d_album, d_album_peak, d_misc;
+    DevBuf d_pcm_in, d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_album, d_album_peak, d_misc;
     // stage A scratch
     DevBuf d_tin, d_fbase, d_frames, d_md, d_meta, d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_pcm;
     HostBuf h_stage, h_tout;
@@ -87,7 +87,7 @@ struct rg_engine {
     DecodeScratch dec;
     bool pending_decode_timing = false;
     std::vector<DevBuf*> all_bufs() {
-        return {&d_pcm_in, &d_chains, &d_wsum, &d_peaks, &d_twin, &d_tout, &d_hist, &d_album, &d_album_peak, &d_misc,
+        return {&d_pcm_in, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_album, &d_album_peak, &d_misc,
                 &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_pcm};
     }
 };
@@ -164,6 +164,7 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         cc[r][23] = row[25]; cc[r][24] = row[26]; cc[r][25] = row[27];
     }
     CK(cudaMemcpyToSymbol(c_rg_coef, cc, sizeof cc));
+    CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
     int rc = decode_init_tables(e->dec);
     if (rc != RG_OK) { delete e; return rc; }
     *out = e;
@@ -207,7 +208,7 @@ struct StageBOut {
 };
 
 static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, const std::vector<uint32_t>& which,
-                         bool exact, double* d_wsum_base, std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin,
+                         bool exact, double* d_wsum_base, float* d_wmax_base, std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin,
                          size_t& wsum_doubles) {
     // wsum layout: for each selected track, channel 0 windows then channel 1 windows
     chains.clear();
@@ -227,13 +228,16 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
         tw.chain_begin = (uint32_t)chains.size();
         tw.wsum0 = d_wsum_base + woff;
         tw.wsum1 = (t.nch >= 2) ? d_wsum_base + woff + n_win : tw.wsum0;
+        tw.wmax0 = d_wmax_base + woff;
+        tw.wmax1 = (t.nch >= 2) ? d_wmax_base + woff + n_win : tw.wmax0;
         if (n_win) {
             int nch = t.nch >= 2 ? 2 : 1;
             for (int c = 0; c < nch; c++) {
                 double* wbase = d_wsum_base + woff + (size_t)c * n_win;
+                float* mbase = d_wmax_base + woff + (size_t)c * n_win;
                 if (exact) {
                     RgChain ch{};
-                    ch.src = t.d_ch[c]; ch.wsum = wbase; ch.n_warm = 0; ch.n_main = (uint32_t)t.frames;
+                    ch.src = t.d_ch[c]; ch.wsum = wbase; ch.wmax = mbase; ch.n_warm = 0; ch.n_main = (uint32_t)t.frames;
                     ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
                     chains.push_back(ch);
                 } else {
@@ -246,6 +250,7 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
                         RgChain ch{};
                         ch.src = t.d_ch[c] + (s0 - warm);
                         ch.wsum = wbase + w0;
+                        ch.wmax = mbase + w0;
                         ch.n_warm = (uint32_t)warm;
                         ch.n_main = (uint32_t)(s1 - s0);
                         ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
@@ -276,10 +281,11 @@ static int launch_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, con
         if (t.status == RG_OK && t.frames > 0 && win > 0) total_w += (size_t)((t.frames + win - 1) / win) * (t.nch >= 2 ? 2 : 1);
     }
     CK(e->d_wsum.ensure(std::max<size_t>(total_w, 1) * sizeof(double)));
+    CK(e->d_wmax.ensure(std::max<size_t>(total_w, 1) * sizeof(float)));
     std::vector<RgChain> chains;
     std::vector<RgTrackWin> twin;
     size_t wd = 0;
-    build_chains(e, tracks, which, exact, e->d_wsum.as<double>(), chains, twin, wd);
+    build_chains(e, tracks, which, exact, e->d_wsum.as<double>(), e->d_wmax.as<float>(), chains, twin, wd);
     for (auto& tw : twin) tw.flags = (d_album_hist != nullptr) ? 1u : 0u;
 
     // group chains by sample rate so each launch reads one coefficient row through uniform constant operands
@@ -342,7 +348,7 @@ static int launch_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, con
     const double tol = exact ? 1e-9 : e->edge_tol;
     k_hist_percentile<<<(unsigned)n, K5_THREADS, 0, e->stream>>>(e->d_twin.as<RgTrackWin>(), d_peaks_for_k5, e->d_tout.as<RgTrackOut>(),
                                                                want_hist ? e->d_hist.as<uint32_t>() : nullptr, d_album_hist,
-                                                               d_album_peak, tol, defer_album_on_edge ? 1 : 0);
+                                                               d_album_peak, tol, defer_album_on_edge ? 1 : 0, exact ? 0 : 1);
     e->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(e->ev[6], e->stream));

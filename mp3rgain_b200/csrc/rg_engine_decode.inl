@@ -182,7 +182,7 @@ static int run_decode_batch(rg_engine* e, rg_corpus* c, const DecodeOut& d, cons
     }
     CK(cudaEventRecord(e->ev[2], e->stream));
     if (!runs.empty()) {
-        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, 0, e->stream>>>(c->d_bytes.as<uint8_t>(), e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
+        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), e->stream>>>(c->d_bytes.as<uint8_t>(), e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                                          e->d_dtracks.as<DecTrack>(), e->d_runs.as<RunDesc>(), e->dec.d_tab,
                                                                          e->d_spectra.as<int16_t>(), e->d_nz.as<uint16_t>(), e->d_pcm.as<float>(), e->flags);
         e->stats.kernel_launches++;

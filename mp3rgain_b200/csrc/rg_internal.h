@@ -10,6 +10,7 @@
 struct RgChain {
     const float* src;   // first sample fed to the filter (start of warm-up, or of the track)
     double* wsum;       // out: sum of squares of each 50 ms window this chain owns, in order
+    float* wmax;        // out: max |input sample| of each of those windows (normalised units)
     uint32_t n_warm;    // samples run through the filter from zero state before accumulation starts
     uint32_t n_main;    // samples accumulated (whole windows, plus the track's final partial one)
     uint32_t win;       // window length in samples (sample_rate*50/1000, src/replaygain.rs:704)
@@ -20,6 +21,8 @@ struct RgChain {
 struct RgTrackWin {
     const double* wsum0;   // per-window sums, channel 0
     const double* wsum1;   // channel 1 (== wsum0 for mono: add_mono_sample adds sq to both sums)
+    const float* wmax0;    // per-window max |input|, channel 0 / 1
+    const float* wmax1;
     uint32_t n_full;       // complete windows
     uint32_t rem;          // samples in the final partial window (0 = none)
     uint32_t win;

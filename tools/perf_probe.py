@@ -1,0 +1,41 @@
+#!/usr/bin/env python3
+"""Quick stage-timing probe (development aid): N synthetic 3-min tracks, device-resident, per-stage CUDA-event times."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mp3rgain_b200 as m  # noqa: E402
+from mp3rgain_b200 import _lib  # noqa: E402
+import synth_corpus  # noqa: E402
+
+n_tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 6891
+exact = len(sys.argv) > 3 and sys.argv[3] == "exact"
+t = time.time()
+pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32)
+imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
+print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
+lib = _lib.load()
+eng = m.Engine(device=0, exact=exact)
+arr, keep = m.Engine._inputs(imgs, None)
+cor = C.c_void_p()
+t = time.time()
+assert lib.rg_corpus_upload(eng._h, arr, n_tracks, C.byref(cor)) == 0
+print("upload %.3fs" % (time.time() - t), flush=True)
+out = (_lib.RgTrackResult * n_tracks)()
+audio_s = n_tracks * n_frames * 1152 / 44100.0
+for it in range(3):
+    t = time.time()
+    rc = lib.rg_analyze_corpus(eng._h, cor, out, None)
+    dt = time.time() - t
+    st = eng.stats()
+    print("rc", rc, "wall %.3fs  dev total %.1f ms | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f | reruns %d launches %d" % (
+        dt, st.last_ms_total, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist,
+        audio_s / 3600.0 / dt, st.exact_reruns, st.kernel_launches), flush=True)
+print("sample result", out[0].loudness_db, out[0].peak, out[0].n_windows, out[0].n_edge_windows, out[0].exact_rerun)
