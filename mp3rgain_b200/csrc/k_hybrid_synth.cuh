@@ -7,15 +7,20 @@
 //
 // Arithmetic follows DESIGN.md "f32 decode contract" operation for operation.
 //
-// Instruction budget notes (the kernel is issue-bound, see profiles/): side info and scalefactors of the whole run are
-// parsed once in a parallel prologue; requantisation multiplies by a per-band gain computed once per granule; the IMDCT
-// keeps its DCT-IV matrix row in registers; the polyphase window keeps its 16 coefficients and a sliding set of DCT values
-// in registers; the DCT ring uses two static positions (plus a mirrored tail) so no index is reduced modulo the ring size.
+// Instruction budget notes (the kernel is issue-bound, see profiles/):
+//  * side info, scalefactors and the per-band gain-table index of the whole run are computed once in a parallel prologue;
+//  * the IMDCT is mapped one (channel, subband, half) per thread: half 1 evaluates DCT-IV rows 9..17, which are exactly the
+//    18 outputs added to the saved overlap, half 0 rows 0..8, which are exactly the 18 outputs saved for the next granule,
+//    so windowing, overlap-add and frequency inversion fuse into the same thread with the spectrum in registers and the
+//    matrix rows arriving as warp-wide 128-bit shared-memory broadcasts;
+//  * subbands above the last coded line (+1 for the alias butterflies) are skipped (their IMDCT input is exactly zero);
+//  * the polyphase window keeps its 16 coefficients and a sliding set of DCT values in registers; the DCT ring uses two
+//    static positions plus a mirrored tail so no index is reduced modulo the ring size.
 #pragma once
 
 #define K2_THREADS 256
 #define SB_STRIDE 33       // padded row of 32 subband values
-#define U_STRIDE 37        // padded row of 36 IMDCT outputs
+#define OVL_STRIDE 19      // padded row of 18 overlap values
 #define K2_MAX_G 66        // RUN_GRANULES (64) + 2 warm-up granules
 #define RING_ROWS 51       // rows 0..50 of the DCT-32 ring (see synth step)
 
@@ -24,26 +29,25 @@ struct __align__(16) GranInfo {
     uint32_t md_lim;      // bytes readable (later bytes read as zero)
     uint16_t nz;          // lines decoded by K1 (0 = silent)
     uint8_t global_gain, sfc, bt, mixed, preflag, sf_shift /* 2 or 4 */;
-    uint8_t sbg[3], scfsi, ms, pad[3];
+    uint8_t sbg[3], scfsi, ms, sb_limit /* subbands with possibly non-zero IMDCT input */, pad[2];
 };
 
 struct K2Smem {
-    float xr[2][600];                 // requantised spectrum (576 used; aliased as the subband-sample buffer after the IMDCT)
-    float u[2][32][U_STRIDE];
-    float ovl[2][18][32];
+    alignas(16) float xr[2][576];       // requantised, reordered spectrum
+    float sb[2][18][SB_STRIDE];         // subband samples [slot][subband]
+    float ovl[2][2][32][OVL_STRIDE];    // IMDCT overlap, ping-pong by granule parity
     float ring[2][RING_ROWS][SB_STRIDE];
-    float dct4[18][19];
+    alignas(16) float dct4[18][20];     // 18-point DCT-IV matrix, rows padded to 5 float4
     float win[4][36];
-    float im12[12][6];
+    alignas(16) float im12[12][8];      // 12-point IMDCT matrix, rows padded to 2 float4
     float wa[8][32], wb[8][32];
     float gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
-    float bandg[2][64];               // per-band requantisation factor of the current granule
     float cs[8], ca[8];
     GranInfo gi[K2_MAX_G][2];
-    uint16_t scat[2][576];            // bitstream-order line -> reordered line: [0] pure short, [1] mixed
-    uint8_t code[3][576];             // line -> band code: [0] long, [1] pure short, [2] mixed
-    uint8_t sf[K2_MAX_G][2][64];      // [0..21] long scalefactors, [22..60] short (sfb*3+win)
-    uint8_t idx36[36], ia[32], ib[32];
+    uint16_t eidx[K2_MAX_G][2][64];     // per band: index into gain[] ([0..21] long bands, [22..60] short sfb*3+win)
+    uint16_t scat[2][576];              // bitstream-order line -> reordered line: [0] pure short, [1] mixed
+    uint8_t code[3][576];               // line -> band code: [0] long, [1] pure short, [2] mixed
+    uint8_t ia[32], ib[32];
 };
 
 template <int N, int OFF>
@@ -91,14 +95,15 @@ __device__ __forceinline__ int read_long_sf(const uint8_t* __restrict__ mdp, con
     return (int)md_bits(mdp, gi.md_lim, gi.part2_bit + off, sl);
 }
 
+// position of IMDCT-36 output i in the 18-point DCT-IV vector u: i<9: u[i+9]; 9..26: u[26-i]; 27..35: u[i-27]
+__device__ __forceinline__ constexpr int idx36(int i) { return i < 9 ? i + 9 : (i < 27 ? 26 - i : i - 27); }
+
 __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
                const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
-    float (*s_sb)[18][SB_STRIDE] = reinterpret_cast<float (*)[18][SB_STRIDE]>(&S.xr[0][0]);  // [2][18][33] <= [2][600]
-    static_assert(2 * 18 * SB_STRIDE <= 2 * 600, "subband buffer must fit in the spectrum buffer it aliases");
 
     const int tid = threadIdx.x;
     const RunDesc run = runs[blockIdx.x];
@@ -110,10 +115,10 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
     const uint32_t gfirst = run.g0 - warm, gcount = run.ng + warm;
 
     // ---- one-time table staging and state reset
-    for (int i = tid; i < 18 * 18; i += K2_THREADS) S.dct4[i / 18][i % 18] = T->dct4_18[i / 18][i % 18];
-    for (int i = tid; i < 4 * 36; i += K2_THREADS) S.win[i / 36][i % 36] = T->winsgn[i / 36][i % 36];
-    for (int i = tid; i < 72; i += K2_THREADS) S.im12[i / 6][i % 6] = T->imdct12[i / 6][i % 6];
-    for (int i = tid; i < 256; i += K2_THREADS) { S.wa[i / 32][i % 32] = T->synth_wa[i / 32][i % 32]; S.wb[i / 32][i % 32] = T->synth_wb[i / 32][i % 32]; }
+    for (int i = tid; i < 18 * 20; i += K2_THREADS) { const int m = i / 20, k = i - 20 * m; S.dct4[m][k] = k < 18 ? T->dct4_18[m][k] : 0.0f; }
+    for (int i = tid; i < 4 * 36; i += K2_THREADS) (&S.win[0][0])[i] = (&T->winsgn[0][0])[i];
+    for (int i = tid; i < 12 * 8; i += K2_THREADS) { const int r = i >> 3, k = i & 7; S.im12[r][k] = k < 6 ? T->imdct12[r][k] : 0.0f; }
+    for (int i = tid; i < 256; i += K2_THREADS) { (&S.wa[0][0])[i] = (&T->synth_wa[0][0])[i]; (&S.wb[0][0])[i] = (&T->synth_wb[0][0])[i]; }
     for (int i = tid; i < L3_GAIN_MAX - L3_GAIN_MIN + 1; i += K2_THREADS) S.gain[i] = T->gain[i];
     for (int i = tid; i < 576; i += K2_THREADS) {
         S.code[0][i] = T->line_sfb_long[sr][i];
@@ -124,9 +129,8 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         S.scat[1][i] = T->scatter_mixed[sr][i];
     }
     if (tid < 8) { S.cs[tid] = T->alias_cs[tid]; S.ca[tid] = T->alias_ca[tid]; }
-    if (tid < 36) S.idx36[tid] = T->imdct36_idx[tid];
     if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
-    for (int i = tid; i < 2 * 18 * 32; i += K2_THREADS) (&S.ovl[0][0][0])[i] = 0.0f;
+    for (int i = tid; i < 2 * 2 * 32 * OVL_STRIDE; i += K2_THREADS) (&S.ovl[0][0][0][0])[i] = 0.0f;
     for (int i = tid; i < 2 * RING_ROWS * SB_STRIDE; i += K2_THREADS) (&S.ring[0][0][0])[i] = 0.0f;
 
     // ---- prologue 1: side info of every granule-channel of the run
@@ -157,17 +161,24 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         gi.sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
         gi.part2_bit = bit;
         gi.md_lim = rec.md_end;
-        gi.nz = nz_in[(size_t)tr.gc_base + (size_t)frame * 2 * nch + rem];
+        const size_t gcb = (size_t)tr.gc_base + (size_t)frame * 2 * nch + gr * nch;
+        gi.nz = nz_in[gcb + ch];
         gi.scfsi = (gr == 1) ? (uint8_t)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;
         gi.ms = (nch == 2 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 2)) ? 1 : 0;
-        gi.pad[0] = gi.pad[1] = gi.pad[2] = 0;
+        // subbands whose IMDCT input can be non-zero: the coded lines (of either channel under MS), one more subband for
+        // the alias butterflies; short blocks scatter lines across the whole band, so they keep all 32
+        uint32_t nzm = gi.nz;
+        if (gi.ms) nzm = max(nzm, (uint32_t)nz_in[gcb + (ch ^ 1)]);
+        gi.sb_limit = nzm == 0 ? 0 : (gi.bt == 2 ? 32 : (uint8_t)min(32u, (nzm + 17) / 18 + 1));
+        gi.pad[0] = gi.pad[1] = 0;
         S.gi[gl][ch] = gi;
     }
     __syncthreads();
 
-    // ---- prologue 2: scalefactors straight from the bitstream (part 2 has a closed-form layout)
+    // ---- prologue 2: scalefactors straight from the bitstream (part 2 has a closed-form layout) -> gain-table index per band
     for (uint32_t it = tid; it < gcount * nch * 64; it += K2_THREADS) {
         const uint32_t j = it & 63, gc = it >> 6, gl = gc / nch, ch = gc % nch;
+        if (j >= 61) continue;
         const GranInfo gi = S.gi[gl][ch];
         const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
         int v = 0;
@@ -195,7 +206,10 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
                 else if (g0.mixed && j < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + j * a1, a1);
             }
         }
-        S.sf[gl][ch][j] = (uint8_t)v;
+        int e;
+        if (j < 22) e = (int)gi.global_gain - 210 - gi.sf_shift * (v + (gi.preflag ? T->pretab[j] : 0));
+        else e = (int)gi.global_gain - 210 - 8 * gi.sbg[(j - 22) % 3] - gi.sf_shift * v;
+        S.eidx[gl][ch][j] = (uint16_t)(e - L3_GAIN_MIN);
     }
     __syncthreads();
 
@@ -210,22 +224,12 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         const uint32_t g = gfirst + gl;
         const size_t gc_first = (size_t)tr.gc_base + (size_t)(g >> 1) * 2 * nch + (g & 1) * nch;
         const int ring_base = 15 + 18 * (int)(gl & 1);   // row of slot 0: granules alternate between rows 15.. and 33..
-
-        // ---- B: per-band requantisation factor 2^((gain - 210 - ...)/4)
-        if (tid < 64 * nch) {
-            const int ch = tid >> 6, j = tid & 63;
-            const GranInfo gi = S.gi[gl][ch];
-            if (j < 61) {
-                int e;
-                if (j < 22) e = (int)gi.global_gain - 210 - gi.sf_shift * ((int)S.sf[gl][ch][j] + (gi.preflag ? T->pretab[j] : 0));
-                else e = (int)gi.global_gain - 210 - 8 * gi.sbg[(j - 22) % 3] - gi.sf_shift * (int)S.sf[gl][ch][j];
-                S.bandg[ch][j] = S.gain[e - L3_GAIN_MIN];
-            }
-        }
-        __syncthreads();
+        const int par = (int)(gl & 1);
+        const int lim0 = S.gi[gl][0].sb_limit, lim1 = nch == 2 ? S.gi[gl][1].sb_limit : 0;
+        const int pair_lim = 9 * max(lim0, lim1);        // line pairs that any active subband reads
 
         // ---- C: requantise (+ MS stereo, + short-block reorder folded into the store index), two lines per thread
-        for (int pr = tid; pr < 288; pr += K2_THREADS) {
+        for (int pr = tid; pr < pair_lim; pr += K2_THREADS) {
             float v[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
             int dst[2][2] = {{2 * pr, 2 * pr + 1}, {2 * pr, 2 * pr + 1}};
 #pragma unroll
@@ -240,7 +244,7 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
                     const int line = 2 * pr + h;
                     const int q = (int)(int16_t)(h ? (packed >> 16) : (packed & 0xFFFFu));
                     const int aq = q < 0 ? -q : q;
-                    const float m = __fmul_rn(__ldg(&T->pow43[aq]), S.bandg[ch][S.code[tsel][line]]);
+                    const float m = __fmul_rn(__ldg(&T->pow43[aq]), S.gain[S.eidx[gl][ch][S.code[tsel][line]]]);
                     v[ch][h] = q < 0 ? -m : m;
                     if (tsel) dst[ch][h] = S.scat[tsel - 1][line];
                 }
@@ -259,11 +263,11 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         }
         __syncthreads();
 
-        // ---- D: alias reduction
-        for (int it = tid; it < nch * 31 * 8; it += K2_THREADS) {
-            const int ch = it / 248, r = it % 248, sb = (r >> 3) + 1, i = r & 7;
+        // ---- D: alias reduction (8 butterflies per boundary between active subbands); it = ch*256 + (sb-1)*8 + i
+        for (int it = tid; it < nch * 256; it += K2_THREADS) {
+            const int ch = it >> 8, r = it & 255, sb = (r >> 3) + 1, i = r & 7;
             const GranInfo& gi = S.gi[gl][ch];
-            if (gi.bt != 2 || (gi.mixed && sb == 1)) {
+            if (sb < (int)gi.sb_limit && (gi.bt != 2 || (gi.mixed && sb == 1))) {
                 const float lo = S.xr[ch][18 * sb - 1 - i], hi = S.xr[ch][18 * sb + i];
                 S.xr[ch][18 * sb - 1 - i] = __fsub_rn(__fmul_rn(lo, S.cs[i]), __fmul_rn(hi, S.ca[i]));
                 S.xr[ch][18 * sb + i] = __fadd_rn(__fmul_rn(hi, S.cs[i]), __fmul_rn(lo, S.ca[i]));
@@ -271,61 +275,83 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         }
         __syncthreads();
 
-        // ---- E: IMDCT.  Thread (grp, m) holds row m of the 18-point DCT-IV matrix and sweeps subbands grp, grp+14, ...
-        if (tid < 252) {
-            const int m = tid % 18, grp = tid / 18;
-            float c[18];
+        // ---- E+F: IMDCT + window + overlap-add + frequency inversion, one (channel, half, subband) per thread.
+        // half 1 -> the 18 outputs of this granule (DCT-IV rows 9..17), half 0 -> the 18 outputs saved as overlap (rows 0..8).
+        if (tid < 64 * nch) {
+            const int ch = tid >> 6, half = (tid >> 5) & 1, sb = tid & 31;
+            const GranInfo& gi = S.gi[gl][ch];
+            const bool active = sb < (int)gi.sb_limit;
+            const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
+            float o[18];   // half 1: raw[0..17]; half 0: raw[18..35]
+            if (!active) {
 #pragma unroll
-            for (int k = 0; k < 18; k++) c[k] = S.dct4[m][k];
-            for (int item = grp; item < nch * 32; item += 14) {
-                const int ch = item >> 5, sb = item & 31;
-                const GranInfo& gi = S.gi[gl][ch];
-                if (!(gi.bt == 2 && !(gi.mixed && sb < 2))) {
-                    const float2* X2 = reinterpret_cast<const float2*>(&S.xr[ch][18 * sb]);
-                    float a = 0.0f;
+                for (int i = 0; i < 18; i++) o[i] = 0.0f;
+            } else {
+                float X[18];
+                const float2* X2 = reinterpret_cast<const float2*>(&S.xr[ch][18 * sb]);
 #pragma unroll
-                    for (int k = 0; k < 9; k++) {
-                        const float2 x = X2[k];
-                        a = fmaf(x.x, c[2 * k], a);
-                        a = fmaf(x.y, c[2 * k + 1], a);
-                    }
-                    S.u[ch][sb][m] = a;
-                } else {
-                    const float* X = &S.xr[ch][18 * sb];
+                for (int k = 0; k < 9; k++) { const float2 x = X2[k]; X[2 * k] = x.x; X[2 * k + 1] = x.y; }
+                if (!is_short) {
+                    const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
+                    float u[9];
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int o = 2 * m + h, w = o / 12, i = o % 12;
+                    for (int mm = 0; mm < 9; mm++) {
+                        const float4* C4 = reinterpret_cast<const float4*>(S.dct4[9 * half + mm]);
                         float a = 0.0f;
 #pragma unroll
-                        for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], S.im12[i][k], a);
-                        S.u[ch][sb][o] = __fmul_rn(a, S.win[2][i]);
+                        for (int q = 0; q < 4; q++) {
+                            const float4 c = C4[q];
+                            a = fmaf(X[4 * q], c.x, a); a = fmaf(X[4 * q + 1], c.y, a);
+                            a = fmaf(X[4 * q + 2], c.z, a); a = fmaf(X[4 * q + 3], c.w, a);
+                        }
+                        const float4 c = C4[4];
+                        a = fmaf(X[16], c.x, a); a = fmaf(X[17], c.y, a);
+                        u[mm] = a;
+                    }
+                    const float* wrow = &S.win[bt][18 * (1 - half)];
+#pragma unroll
+                    for (int i = 0; i < 18; i++) {
+                        // half 1: output i uses u[idx36(i)] with idx36(i) in 9..17; half 0: output 18+i uses idx36(18+i) in 0..8
+                        const float uv = half ? u[idx36(i) - 9] : u[idx36(18 + i)];
+                        o[i] = __fmul_rn(uv, wrow[i]);
+                    }
+                } else {
+                    // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window order.
+                    // half 1 needs y0[0..11], y1[0..5]; half 0 needs y1[6..11], y2[0..11]: 18 six-term dot products each.
+                    float y[18];
+#pragma unroll
+                    for (int d = 0; d < 18; d++) {
+                        const int w = half ? (d < 12 ? 0 : 1) : (d < 6 ? 1 : 2);
+                        const int i = half ? (d < 12 ? d : d - 12) : (d < 6 ? d + 6 : d - 6);
+                        const float4 c0 = *reinterpret_cast<const float4*>(&S.im12[i][0]);
+                        const float2 c1 = *reinterpret_cast<const float2*>(&S.im12[i][4]);
+                        float a = 0.0f;
+                        a = fmaf(X[w], c0.x, a); a = fmaf(X[3 + w], c0.y, a); a = fmaf(X[6 + w], c0.z, a);
+                        a = fmaf(X[9 + w], c0.w, a); a = fmaf(X[12 + w], c1.x, a); a = fmaf(X[15 + w], c1.y, a);
+                        y[d] = __fmul_rn(a, S.win[2][i]);
+                    }
+                    if (half) {
+#pragma unroll
+                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? 0.0f : (i < 12 ? y[i - 6] : __fadd_rn(y[i - 6], y[12 + (i - 12)]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? __fadd_rn(y[i], y[6 + i]) : (i < 12 ? y[6 + i] : 0.0f);
                     }
                 }
             }
-        }
-        __syncthreads();   // all reads of S.xr are done: from here the buffer is the subband-sample array s_sb
-
-        // ---- F: window, overlap-add, frequency inversion -> subband samples [slot][subband]
-        for (int it = tid; it < nch * 576; it += K2_THREADS) {
-            const int ch = it / 576, r = it - ch * 576, i = r >> 5, sb = r & 31;
-            const GranInfo& gi = S.gi[gl][ch];
-            const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
-            float lo, hi;
-            if (!is_short) {
-                const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
-                lo = __fmul_rn(S.u[ch][sb][S.idx36[i]], S.win[bt][i]);
-                hi = __fmul_rn(S.u[ch][sb][S.idx36[18 + i]], S.win[bt][18 + i]);
+            if (half) {
+                const float* prev = S.ovl[par][ch][sb];
+#pragma unroll
+                for (int i = 0; i < 18; i++) {
+                    float vv = __fadd_rn(o[i], prev[i]);
+                    if ((sb & 1) && (i & 1)) vv = -vv;
+                    S.sb[ch][i][sb] = vv;
+                }
             } else {
-                // raw[j] = sum over windows w (ascending) of y_w[j - 6 - 6w], y_w at S.u[..][12w + .]
-                const float* y = S.u[ch][sb];
-                if (i < 6) { lo = 0.0f; hi = __fadd_rn(y[18 + i], y[24 + i]); }
-                else if (i < 12) { lo = y[i - 6]; hi = y[24 + i]; }
-                else { lo = __fadd_rn(y[i - 6], y[i]); hi = 0.0f; }
+                float* nxt = S.ovl[par ^ 1][ch][sb];
+#pragma unroll
+                for (int i = 0; i < 18; i++) nxt[i] = o[i];
             }
-            float vv = __fadd_rn(lo, S.ovl[ch][i][sb]);
-            S.ovl[ch][i][sb] = hi;
-            if ((sb & 1) && (i & 1)) vv = -vv;
-            s_sb[ch][i][sb] = vv;
         }
         __syncthreads();
 
@@ -336,7 +362,7 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
             const int ch = tid / 18, t = tid % 18;
             float x[32];
 #pragma unroll
-            for (int k = 0; k < 32; k++) x[k] = s_sb[ch][t][k];
+            for (int k = 0; k < 32; k++) x[k] = S.sb[ch][t][k];
             Dct2<32, 0>::run(x);
             float* dstrow = S.ring[ch][ring_base + t];
 #pragma unroll
@@ -372,7 +398,7 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
                 dst[32 * t] = a;
             }
         }
-        // no barrier here: the next granule's steps B..F do not touch the ring and its step G (other ring position, plus
-        // the mirror rows) runs only after five more barriers
+        // no barrier here: the next granule's steps C..E do not touch the ring and its step G (other ring position, plus
+        // the mirror rows) runs only after three more barriers
     }
 }
