@@ -15,7 +15,13 @@
 //    matrix rows arriving as warp-wide 128-bit shared-memory broadcasts;
 //  * subbands above the last coded line (+1 for the alias butterflies) are skipped (their IMDCT input is exactly zero);
 //  * the polyphase window keeps its 16 coefficients and a sliding set of DCT values in registers; the DCT ring uses two
-//    static positions plus a mirrored tail so no index is reduced modulo the ring size.
+//    static positions plus a mirrored tail so no index is reduced modulo the ring size;
+//  * the CTA is warp-specialised: warps 0-3 (front) run the spectral half of granule g+1 (requantise, alias, IMDCT) while
+//    warps 4-7 (back) run the filterbank half of granule g (DCT-32, polyphase window, PCM store); the two halves hand the
+//    subband samples over through a double buffer guarded by named barriers (bar.arrive / bar.sync), so neither half
+//    idles at a CTA-wide barrier while the other works;
+//  * each 32-point DCT is split over two threads along Lee's first butterfly (even outputs from the sum branch, odd outputs
+//    from the difference branch): same operations per element, half the dependent chain.
 #pragma once
 
 #define K2_THREADS 256
@@ -34,7 +40,7 @@ struct __align__(16) GranInfo {
 
 struct K2Smem {
     alignas(16) float xr[2][576];       // requantised, reordered spectrum
-    float sb[2][18][SB_STRIDE];         // subband samples [slot][subband]
+    float sb[2][2][18][SB_STRIDE];      // subband samples [buffer][channel][slot][subband] (front -> back hand-off)
     float ovl[2][2][32][OVL_STRIDE];    // IMDCT overlap, ping-pong by granule parity
     float ring[2][RING_ROWS][SB_STRIDE];
     alignas(16) float dct4[18][20];     // 18-point DCT-IV matrix, rows padded to 5 float4
@@ -175,230 +181,299 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
     }
     __syncthreads();
 
-    // ---- prologue 2: scalefactors straight from the bitstream (part 2 has a closed-form layout) -> gain-table index per band
-    for (uint32_t it = tid; it < gcount * nch * 64; it += K2_THREADS) {
-        const uint32_t j = it & 63, gc = it >> 6, gl = gc / nch, ch = gc % nch;
-        if (j >= 61) continue;
-        const GranInfo gi = S.gi[gl][ch];
-        const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
-        int v = 0;
-        if (gi.bt == 2) {
-            if (j < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors
-                if (gi.mixed && j < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + j * slen1, slen1);
-            } else if (j < 22 + 36) {
-                const int q = j - 22, sfb = q / 3;
-                if (!(gi.mixed && sfb < 3)) {
-                    uint32_t off;
-                    if (gi.mixed) off = (sfb < 6) ? (8 + (q - 9)) * slen1 : 17 * slen1 + (q - 18) * slen2;
-                    else off = (sfb < 6) ? q * slen1 : 18 * slen1 + (q - 18) * slen2;
-                    v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
+    // ---- prologue 2: scalefactors straight from the bitstream (part 2 has a closed-form layout) -> gain-table index per
+    // band.  One warp per granule-channel, one lane per band: every branch on the block type is warp-uniform.
+    {
+        const int lane = tid & 31;
+        for (uint32_t gc = tid >> 5; gc < gcount * nch; gc += K2_THREADS / 32) {
+            const uint32_t gl = gc / nch, ch = gc - gl * nch;
+            const GranInfo gi = S.gi[gl][ch];
+            const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
+            const int base_e = (int)gi.global_gain - 210 - L3_GAIN_MIN;
+            if (gi.bt != 2) {
+                if (lane < 22) {
+                    int v = 0;
+                    if (lane < 21) {
+                        const int grp = lane < 6 ? 0 : (lane < 11 ? 1 : (lane < 16 ? 2 : 3));
+                        if (!(gi.scfsi & (8 >> grp))) v = read_long_sf(mdp, gi, gi.scfsi, lane, slen1, slen2);
+                        else {
+                            // scfsi: reuse granule 0's scalefactor of the same frame (granule gl-1 of this run; runs start
+                            // on an even granule).  A short granule 0 has no long scalefactors (they read as 0) except
+                            // the 8 of a mixed block.
+                            const GranInfo g0 = S.gi[gl - 1][ch];
+                            const int a1 = T->slen[0][g0.sfc], a2 = T->slen[1][g0.sfc];
+                            if (g0.bt != 2) v = read_long_sf(mdp, g0, 0, lane, a1, a2);
+                            else if (g0.mixed && lane < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + lane * a1, a1);
+                        }
+                    }
+                    S.eidx[gl][ch][lane] = (uint16_t)(base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0)));
+                }
+            } else {
+                if (lane < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors
+                    int v = 0;
+                    if (gi.mixed && lane < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + lane * slen1, slen1);
+                    S.eidx[gl][ch][lane] = (uint16_t)(base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0)));
+                }
+                for (int q = lane; q < 39; q += 32) {
+                    const int sfb = q / 3, win = q - 3 * sfb;
+                    int v = 0;
+                    if (sfb < 12 && !(gi.mixed && sfb < 3)) {
+                        uint32_t off;
+                        if (gi.mixed) off = (sfb < 6) ? (8 + (q - 9)) * slen1 : 17 * slen1 + (q - 18) * slen2;
+                        else off = (sfb < 6) ? q * slen1 : 18 * slen1 + (q - 18) * slen2;
+                        v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
+                    }
+                    S.eidx[gl][ch][22 + q] = (uint16_t)(base_e - 8 * gi.sbg[win] - gi.sf_shift * v);
                 }
             }
-        } else if (j < 21) {
-            const int grp = j < 6 ? 0 : (j < 11 ? 1 : (j < 16 ? 2 : 3));
-            if (!(gi.scfsi & (8 >> grp))) v = read_long_sf(mdp, gi, gi.scfsi, j, slen1, slen2);
-            else {
-                // scfsi: reuse granule 0's scalefactor of the same frame (granule gl-1 of this run; runs start on an even
-                // granule).  A short granule 0 has no long scalefactors (they read as 0) except the 8 of a mixed block.
-                const GranInfo g0 = S.gi[gl - 1][ch];
-                const int a1 = T->slen[0][g0.sfc], a2 = T->slen[1][g0.sfc];
-                if (g0.bt != 2) v = read_long_sf(mdp, g0, 0, j, a1, a2);
-                else if (g0.mixed && j < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + j * a1, a1);
-            }
         }
-        int e;
-        if (j < 22) e = (int)gi.global_gain - 210 - gi.sf_shift * (v + (gi.preflag ? T->pretab[j] : 0));
-        else e = (int)gi.global_gain - 210 - 8 * gi.sbg[(j - 22) % 3] - gi.sf_shift * v;
-        S.eidx[gl][ch][j] = (uint16_t)(e - L3_GAIN_MIN);
     }
     __syncthreads();
 
-    // per-thread constants of the polyphase window step: thread (ch, half, j) keeps its 16 window coefficients
-    const int w_ch = tid >> 6, w_j = tid & 31, w_half = (tid >> 5) & 1;
-    float wa[8], wb[8];
-#pragma unroll
-    for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][w_j]; wb[p] = S.wb[p][w_j]; }
-    const int w_ia = S.ia[w_j], w_ib = S.ib[w_j];
+    // ---------------------------------------------------------------------------------------------------------------
+    // Warp specialisation.  Named barriers: 1 = front-internal, 2 = back-internal, 3+b = "sb[b] full", 5+b = "sb[b] empty".
+    auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+    auto bar_arrive = [](int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); };
 
-    for (uint32_t gl = 0; gl < gcount; gl++) {
-        const uint32_t g = gfirst + gl;
-        const size_t gc_first = (size_t)tr.gc_base + (size_t)(g >> 1) * 2 * nch + (g & 1) * nch;
-        const int ring_base = 15 + 18 * (int)(gl & 1);   // row of slot 0: granules alternate between rows 15.. and 33..
-        const int par = (int)(gl & 1);
-        const int lim0 = S.gi[gl][0].sb_limit, lim1 = nch == 2 ? S.gi[gl][1].sb_limit : 0;
-        const int pair_lim = 9 * max(lim0, lim1);        // line pairs that any active subband reads
-
-        // ---- C: requantise (+ MS stereo, + short-block reorder folded into the store index), two lines per thread
-        for (int pr = tid; pr < pair_lim; pr += K2_THREADS) {
-            float v[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
-            int dst[2][2] = {{2 * pr, 2 * pr + 1}, {2 * pr, 2 * pr + 1}};
+    if (tid < 128) {
+        // ===================================== FRONT: requantise -> alias -> IMDCT/overlap =============================
+        // The requantiser's input (packed int16 line pairs tid, tid+128, tid+256 per channel) is fetched one granule ahead,
+        // so the HBM latency of the spectra overlaps a whole granule of compute.
+        uint32_t pre[3][2];
+        auto fetch = [&](uint32_t gl_, uint32_t (&dstv)[3][2]) {
+            const uint32_t g_ = gfirst + gl_;
+            const size_t gcf = (size_t)tr.gc_base + (size_t)(g_ >> 1) * 2 * nch + (g_ & 1) * nch;
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch >= nch) break;
-                const GranInfo& gi = S.gi[gl][ch];
-                uint32_t packed = 0;
-                if ((uint32_t)(2 * pr) < gi.nz) packed = *reinterpret_cast<const uint32_t*>(spectra + (gc_first + ch) * 576 + 2 * pr);
-                const int tsel = gi.bt != 2 ? 0 : (gi.mixed ? 2 : 1);
+            for (int sl = 0; sl < 3; sl++) {
+                const int pr = tid + 128 * sl;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int line = 2 * pr + h;
-                    const int q = (int)(int16_t)(h ? (packed >> 16) : (packed & 0xFFFFu));
-                    const int aq = q < 0 ? -q : q;
-                    const float m = __fmul_rn(__ldg(&T->pow43[aq]), S.gain[S.eidx[gl][ch][S.code[tsel][line]]]);
-                    v[ch][h] = q < 0 ? -m : m;
-                    if (tsel) dst[ch][h] = S.scat[tsel - 1][line];
+                for (int ch = 0; ch < 2; ch++) {
+                    uint32_t v = 0;
+                    if (pr < 288 && ch < nch && (uint32_t)(2 * pr) < S.gi[gl_][ch].nz)
+                        v = __ldg(reinterpret_cast<const uint32_t*>(spectra + (gcf + ch) * 576 + 2 * pr));
+                    dstv[sl][ch] = v;
                 }
             }
-            if (S.gi[gl][0].ms) {
+        };
+        fetch(0, pre);
+        for (uint32_t gl = 0; gl < gcount; gl++) {
+            uint32_t cur[3][2];
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float a = v[0][h], b = v[1][h];
-                    v[0][h] = __fmul_rn(__fadd_rn(a, b), L3_INV_SQRT2);
-                    v[1][h] = __fmul_rn(__fsub_rn(a, b), L3_INV_SQRT2);
-                }
-            }
-            S.xr[0][dst[0][0]] = v[0][0];
-            S.xr[0][dst[0][1]] = v[0][1];
-            if (nch == 2) { S.xr[1][dst[1][0]] = v[1][0]; S.xr[1][dst[1][1]] = v[1][1]; }
-        }
-        __syncthreads();
+            for (int sl = 0; sl < 3; sl++) { cur[sl][0] = pre[sl][0]; cur[sl][1] = pre[sl][1]; }
+            if (gl + 1 < gcount) fetch(gl + 1, pre);
+            const int par = (int)(gl & 1);
+            const int lim0 = S.gi[gl][0].sb_limit, lim1 = nch == 2 ? S.gi[gl][1].sb_limit : 0;
+            const int pair_lim = 9 * max(lim0, lim1);        // line pairs that any active subband reads
 
-        // ---- D: alias reduction (8 butterflies per boundary between active subbands); it = ch*256 + (sb-1)*8 + i
-        for (int it = tid; it < nch * 256; it += K2_THREADS) {
-            const int ch = it >> 8, r = it & 255, sb = (r >> 3) + 1, i = r & 7;
-            const GranInfo& gi = S.gi[gl][ch];
-            if (sb < (int)gi.sb_limit && (gi.bt != 2 || (gi.mixed && sb == 1))) {
-                const float lo = S.xr[ch][18 * sb - 1 - i], hi = S.xr[ch][18 * sb + i];
-                S.xr[ch][18 * sb - 1 - i] = __fsub_rn(__fmul_rn(lo, S.cs[i]), __fmul_rn(hi, S.ca[i]));
-                S.xr[ch][18 * sb + i] = __fadd_rn(__fmul_rn(hi, S.cs[i]), __fmul_rn(lo, S.ca[i]));
-            }
-        }
-        __syncthreads();
-
-        // ---- E+F: IMDCT + window + overlap-add + frequency inversion, one (channel, half, subband) per thread.
-        // half 1 -> the 18 outputs of this granule (DCT-IV rows 9..17), half 0 -> the 18 outputs saved as overlap (rows 0..8).
-        if (tid < 64 * nch) {
-            const int ch = tid >> 6, half = (tid >> 5) & 1, sb = tid & 31;
-            const GranInfo& gi = S.gi[gl][ch];
-            const bool active = sb < (int)gi.sb_limit;
-            const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
-            float o[18];   // half 1: raw[0..17]; half 0: raw[18..35]
-            if (!active) {
+            // ---- C: requantise (+ MS stereo, + short-block reorder folded into the store index), two lines per item
 #pragma unroll
-                for (int i = 0; i < 18; i++) o[i] = 0.0f;
-            } else {
-                float X[18];
-                const float2* X2 = reinterpret_cast<const float2*>(&S.xr[ch][18 * sb]);
+            for (int sl = 0; sl < 3; sl++) {
+                const int pr = tid + 128 * sl;
+                if (pr >= pair_lim) break;
+                float v[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
+                int dst[2][2] = {{2 * pr, 2 * pr + 1}, {2 * pr, 2 * pr + 1}};
 #pragma unroll
-                for (int k = 0; k < 9; k++) { const float2 x = X2[k]; X[2 * k] = x.x; X[2 * k + 1] = x.y; }
-                if (!is_short) {
-                    const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
-                    float u[9];
+                for (int ch = 0; ch < 2; ch++) {
+                    if (ch >= nch) break;
+                    const GranInfo& gi = S.gi[gl][ch];
+                    const uint32_t packed = cur[sl][ch];
+                    const int tsel = gi.bt != 2 ? 0 : (gi.mixed ? 2 : 1);
 #pragma unroll
-                    for (int mm = 0; mm < 9; mm++) {
-                        const float4* C4 = reinterpret_cast<const float4*>(S.dct4[9 * half + mm]);
-                        float a = 0.0f;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const float4 c = C4[q];
-                            a = fmaf(X[4 * q], c.x, a); a = fmaf(X[4 * q + 1], c.y, a);
-                            a = fmaf(X[4 * q + 2], c.z, a); a = fmaf(X[4 * q + 3], c.w, a);
-                        }
-                        const float4 c = C4[4];
-                        a = fmaf(X[16], c.x, a); a = fmaf(X[17], c.y, a);
-                        u[mm] = a;
+                    for (int h = 0; h < 2; h++) {
+                        const int line = 2 * pr + h;
+                        const int q = (int)(int16_t)(h ? (packed >> 16) : (packed & 0xFFFFu));
+                        const int aq = q < 0 ? -q : q;
+                        const float m = __fmul_rn(__ldg(&T->pow43[aq]), S.gain[S.eidx[gl][ch][S.code[tsel][line]]]);
+                        v[ch][h] = q < 0 ? -m : m;
+                        if (tsel) dst[ch][h] = S.scat[tsel - 1][line];
                     }
-                    const float* wrow = &S.win[bt][18 * (1 - half)];
+                }
+                if (S.gi[gl][0].ms) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float a = v[0][h], b = v[1][h];
+                        v[0][h] = __fmul_rn(__fadd_rn(a, b), L3_INV_SQRT2);
+                        v[1][h] = __fmul_rn(__fsub_rn(a, b), L3_INV_SQRT2);
+                    }
+                }
+                S.xr[0][dst[0][0]] = v[0][0];
+                S.xr[0][dst[0][1]] = v[0][1];
+                if (nch == 2) { S.xr[1][dst[1][0]] = v[1][0]; S.xr[1][dst[1][1]] = v[1][1]; }
+            }
+            bar_sync(1, 128);
+
+            // ---- D: alias reduction (8 butterflies per boundary between active subbands); it = ch*256 + (sb-1)*8 + i
+            for (int it = tid; it < nch * 256; it += 128) {
+                const int ch = it >> 8, r = it & 255, sb = (r >> 3) + 1, i = r & 7;
+                const GranInfo& gi = S.gi[gl][ch];
+                if (sb < (int)gi.sb_limit && (gi.bt != 2 || (gi.mixed && sb == 1))) {
+                    const float lo = S.xr[ch][18 * sb - 1 - i], hi = S.xr[ch][18 * sb + i];
+                    S.xr[ch][18 * sb - 1 - i] = __fsub_rn(__fmul_rn(lo, S.cs[i]), __fmul_rn(hi, S.ca[i]));
+                    S.xr[ch][18 * sb + i] = __fadd_rn(__fmul_rn(hi, S.cs[i]), __fmul_rn(lo, S.ca[i]));
+                }
+            }
+            bar_sync(1, 128);
+            if (gl >= 2) bar_sync(5 + par, 256);   // the back half has finished reading sb[par] (granule gl-2)
+
+            // ---- E+F: IMDCT + window + overlap-add + frequency inversion, one (channel, half, subband) per thread.
+            // half 1 -> the 18 outputs of this granule (DCT-IV rows 9..17), half 0 -> the 18 outputs saved as overlap (rows 0..8).
+            if (tid < 64 * nch) {
+                const int ch = tid >> 6, half = (tid >> 5) & 1, sb = tid & 31;
+                const GranInfo& gi = S.gi[gl][ch];
+                const bool active = sb < (int)gi.sb_limit;
+                const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
+                float o[18];   // half 1: raw[0..17]; half 0: raw[18..35]
+                if (!active) {
+#pragma unroll
+                    for (int i = 0; i < 18; i++) o[i] = 0.0f;
+                } else {
+                    float X[18];
+                    const float2* X2 = reinterpret_cast<const float2*>(&S.xr[ch][18 * sb]);
+#pragma unroll
+                    for (int k = 0; k < 9; k++) { const float2 x = X2[k]; X[2 * k] = x.x; X[2 * k + 1] = x.y; }
+                    if (!is_short) {
+                        const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
+                        float u[9];
+#pragma unroll
+                        for (int mm = 0; mm < 9; mm++) {
+                            const float4* C4 = reinterpret_cast<const float4*>(S.dct4[9 * half + mm]);
+                            float a = 0.0f;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const float4 c = C4[q];
+                                a = fmaf(X[4 * q], c.x, a); a = fmaf(X[4 * q + 1], c.y, a);
+                                a = fmaf(X[4 * q + 2], c.z, a); a = fmaf(X[4 * q + 3], c.w, a);
+                            }
+                            const float4 c = C4[4];
+                            a = fmaf(X[16], c.x, a); a = fmaf(X[17], c.y, a);
+                            u[mm] = a;
+                        }
+                        const float* wrow = &S.win[bt][18 * (1 - half)];
+#pragma unroll
+                        for (int i = 0; i < 18; i++) {
+                            // half 1: output i uses u[idx36(i)] (9..17); half 0: output 18+i uses u[idx36(18+i)] (0..8)
+                            const float uv = half ? u[idx36(i) - 9] : u[idx36(18 + i)];
+                            o[i] = __fmul_rn(uv, wrow[i]);
+                        }
+                    } else {
+                        // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window
+                        // order.  half 1 needs y0[0..11], y1[0..5]; half 0 needs y1[6..11], y2[0..11]: 18 dot products each.
+                        float y[18];
+#pragma unroll
+                        for (int d = 0; d < 18; d++) {
+                            const int w = half ? (d < 12 ? 0 : 1) : (d < 6 ? 1 : 2);
+                            const int i = half ? (d < 12 ? d : d - 12) : (d < 6 ? d + 6 : d - 6);
+                            const float4 c0 = *reinterpret_cast<const float4*>(&S.im12[i][0]);
+                            const float2 c1 = *reinterpret_cast<const float2*>(&S.im12[i][4]);
+                            float a = 0.0f;
+                            a = fmaf(X[w], c0.x, a); a = fmaf(X[3 + w], c0.y, a); a = fmaf(X[6 + w], c0.z, a);
+                            a = fmaf(X[9 + w], c0.w, a); a = fmaf(X[12 + w], c1.x, a); a = fmaf(X[15 + w], c1.y, a);
+                            y[d] = __fmul_rn(a, S.win[2][i]);
+                        }
+                        if (half) {
+#pragma unroll
+                            for (int i = 0; i < 18; i++) o[i] = i < 6 ? 0.0f : (i < 12 ? y[i - 6] : __fadd_rn(y[i - 6], y[12 + (i - 12)]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 18; i++) o[i] = i < 6 ? __fadd_rn(y[i], y[6 + i]) : (i < 12 ? y[6 + i] : 0.0f);
+                        }
+                    }
+                }
+                if (half) {
+                    const float* prev = S.ovl[par][ch][sb];
 #pragma unroll
                     for (int i = 0; i < 18; i++) {
-                        // half 1: output i uses u[idx36(i)] with idx36(i) in 9..17; half 0: output 18+i uses idx36(18+i) in 0..8
-                        const float uv = half ? u[idx36(i) - 9] : u[idx36(18 + i)];
-                        o[i] = __fmul_rn(uv, wrow[i]);
+                        float vv = __fadd_rn(o[i], prev[i]);
+                        if ((sb & 1) && (i & 1)) vv = -vv;
+                        S.sb[par][ch][i][sb] = vv;
                     }
                 } else {
-                    // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window order.
-                    // half 1 needs y0[0..11], y1[0..5]; half 0 needs y1[6..11], y2[0..11]: 18 six-term dot products each.
-                    float y[18];
+                    float* nxt = S.ovl[par ^ 1][ch][sb];
 #pragma unroll
-                    for (int d = 0; d < 18; d++) {
-                        const int w = half ? (d < 12 ? 0 : 1) : (d < 6 ? 1 : 2);
-                        const int i = half ? (d < 12 ? d : d - 12) : (d < 6 ? d + 6 : d - 6);
-                        const float4 c0 = *reinterpret_cast<const float4*>(&S.im12[i][0]);
-                        const float2 c1 = *reinterpret_cast<const float2*>(&S.im12[i][4]);
-                        float a = 0.0f;
-                        a = fmaf(X[w], c0.x, a); a = fmaf(X[3 + w], c0.y, a); a = fmaf(X[6 + w], c0.z, a);
-                        a = fmaf(X[9 + w], c0.w, a); a = fmaf(X[12 + w], c1.x, a); a = fmaf(X[15 + w], c1.y, a);
-                        y[d] = __fmul_rn(a, S.win[2][i]);
-                    }
-                    if (half) {
-#pragma unroll
-                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? 0.0f : (i < 12 ? y[i - 6] : __fadd_rn(y[i - 6], y[12 + (i - 12)]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? __fadd_rn(y[i], y[6 + i]) : (i < 12 ? y[6 + i] : 0.0f);
-                    }
+                    for (int i = 0; i < 18; i++) nxt[i] = o[i];
                 }
             }
-            if (half) {
-                const float* prev = S.ovl[par][ch][sb];
-#pragma unroll
-                for (int i = 0; i < 18; i++) {
-                    float vv = __fadd_rn(o[i], prev[i]);
-                    if ((sb & 1) && (i & 1)) vv = -vv;
-                    S.sb[ch][i][sb] = vv;
-                }
-            } else {
-                float* nxt = S.ovl[par ^ 1][ch][sb];
-#pragma unroll
-                for (int i = 0; i < 18; i++) nxt[i] = o[i];
-            }
+            __threadfence_block();
+            bar_arrive(3 + par, 256);   // sb[par] is full
+            bar_sync(1, 128);           // all reads of xr / writes of ovl done before the next granule overwrites them
         }
-        __syncthreads();
+    } else {
+        // ===================================== BACK: DCT-32 -> polyphase window -> PCM ====================================
+        const int bt_ = tid - 128;
+        // polyphase window step: thread (ch, half, j) keeps its 16 window coefficients in registers
+        const int w_ch = bt_ >> 6, w_j = bt_ & 31, w_half = (bt_ >> 5) & 1;
+        float wa[8], wb[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][w_j]; wb[p] = S.wb[p][w_j]; }
+        const int w_ia = S.ia[w_j], w_ib = S.ib[w_j];
+        // DCT step: thread (d, br): d = (channel, slot), br = 0 even outputs (sum branch) / 1 odd outputs (difference branch)
+        const int d_br = (bt_ >> 5) & 1, d_idx = (bt_ & 31) + 32 * (bt_ >> 6);
+        const bool d_on = d_idx < 18 * nch && d_idx < 36 && (bt_ & 31) < (bt_ < 64 ? 32 : 4);
+        const int d_ch = d_idx / 18, d_t = d_idx - 18 * d_ch;
 
-        // ---- G: 32-point DCT-II per time slot (Lee).  Ring rows: this granule's slots at ring_base + t; when the granule
-        // sits in the upper position its slots 3..17 are mirrored into rows 0..14 so the next granule (lower position) finds
-        // its 15 predecessors at negative offsets without any modular arithmetic.
-        if (tid < nch * 18) {
-            const int ch = tid / 18, t = tid % 18;
-            float x[32];
-#pragma unroll
-            for (int k = 0; k < 32; k++) x[k] = S.sb[ch][t][k];
-            Dct2<32, 0>::run(x);
-            float* dstrow = S.ring[ch][ring_base + t];
-#pragma unroll
-            for (int k = 0; k < 32; k++) dstrow[k] = x[k];
-            if ((gl & 1) && t >= 3) {
-                float* mir = S.ring[ch][t - 3];
-#pragma unroll
-                for (int k = 0; k < 32; k++) mir[k] = x[k];
-            }
-        }
-        __syncthreads();
+        for (uint32_t gl = 0; gl < gcount; gl++) {
+            const uint32_t g = gfirst + gl;
+            const int par = (int)(gl & 1);
+            const int ring_base = 15 + 18 * par;   // row of slot 0: granules alternate between rows 15.. and 33..
+            bar_sync(3 + par, 256);                // wait for the front half to fill sb[par]
 
-        // ---- H: polyphase window.  Thread (ch, half, j) produces 9 consecutive slots of output column j, sliding a
-        // register window over the ring: out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain)
-        if (g >= run.g0 && w_ch < nch) {
-            const float* colA = &S.ring[w_ch][ring_base + 9 * w_half][w_ia];
-            const float* colB = &S.ring[w_ch][ring_base + 9 * w_half][w_ib];
-            float A[24], B[24];   // rows t0-15 .. t0+8 relative to this thread's first slot t0
+            // ---- G: 32-point DCT-II per time slot (Lee), two threads per transform.  Ring rows: this granule's slots at
+            // ring_base + t; in the upper position slots 3..17 are mirrored into rows 0..14 so the next granule (lower
+            // position) finds its 15 predecessors at negative offsets without any modular arithmetic.
+            if (d_on) {
+                const float* x = S.sb[par][d_ch][d_t];
+                float z[16];
+                if (d_br == 0) {
 #pragma unroll
-            for (int r = 0; r < 15; r++) { A[r] = colA[(r - 15) * SB_STRIDE]; B[r] = colB[(r - 15) * SB_STRIDE]; }
-            float* dst = pcm + tr.pcm_off + (size_t)w_ch * tr.pcm_plane + (size_t)g * 576 + 32 * (9 * w_half) + w_j;
+                    for (int i = 0; i < 16; i++) z[i] = __fadd_rn(x[i], x[31 - i]);
+                } else {
 #pragma unroll
-            for (int t = 0; t < 9; t++) {
-                A[15 + t] = colA[t * SB_STRIDE];
-                B[15 + t] = colB[t * SB_STRIDE];
-                float a = 0.0f;
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    a = fmaf(A[15 + t - 2 * p], wa[p], a);
-                    a = fmaf(B[15 + t - 2 * p - 1], wb[p], a);
+                    for (int i = 0; i < 16; i++) z[i] = __fmul_rn(__fsub_rn(x[i], x[31 - i]), c_dct_sec[i]);
                 }
-                if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
-                dst[32 * t] = a;
+                Dct2<16, 16>::run(z);
+                float* dstrow = S.ring[d_ch][ring_base + d_t];
+                float* mir = S.ring[d_ch][d_t >= 3 ? d_t - 3 : 0];
+                const bool do_mir = par && d_t >= 3;
+                if (d_br == 0) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) { dstrow[2 * k] = z[k]; if (do_mir) mir[2 * k] = z[k]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const float v = k < 15 ? __fadd_rn(z[k], z[k + 1]) : z[15];
+                        dstrow[2 * k + 1] = v;
+                        if (do_mir) mir[2 * k + 1] = v;
+                    }
+                }
             }
+            __threadfence_block();
+            if (gl + 2 < gcount) bar_arrive(5 + par, 256);   // sb[par] may be overwritten (by granule gl+2)
+            bar_sync(2, 128);                                // ring rows of this granule are complete
+
+            // ---- H: polyphase window.  Thread (ch, half, j) produces 9 consecutive slots of output column j, sliding a
+            // register window over the ring: out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain)
+            if (g >= run.g0 && w_ch < nch) {
+                const float* colA = &S.ring[w_ch][ring_base + 9 * w_half][w_ia];
+                const float* colB = &S.ring[w_ch][ring_base + 9 * w_half][w_ib];
+                float A[24], B[24];   // rows t0-15 .. t0+8 relative to this thread's first slot t0
+#pragma unroll
+                for (int r = 0; r < 15; r++) { A[r] = colA[(r - 15) * SB_STRIDE]; B[r] = colB[(r - 15) * SB_STRIDE]; }
+                float* dst = pcm + tr.pcm_off + (size_t)w_ch * tr.pcm_plane + (size_t)g * 576 + 32 * (9 * w_half) + w_j;
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    A[15 + t] = colA[t * SB_STRIDE];
+                    B[15 + t] = colB[t * SB_STRIDE];
+                    float a = 0.0f;
+#pragma unroll
+                    for (int p = 0; p < 8; p++) {
+                        a = fmaf(A[15 + t - 2 * p], wa[p], a);
+                        a = fmaf(B[15 + t - 2 * p - 1], wb[p], a);
+                    }
+                    if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
+                    dst[32 * t] = a;
+                }
+            }
+            bar_sync(2, 128);   // ring reads done before the next granule's DCT overwrites the other position / mirror rows
         }
-        // no barrier here: the next granule's steps C..E do not touch the ring and its step G (other ring position, plus
-        // the mirror rows) runs only after three more barriers
     }
 }
