@@ -13,63 +13,79 @@
 //   (2^15*b_i)*x is bit-identical to b_i*(2^15*x).  The leading "0.0 +" of Rust's iterator sum is dropped:
 //   it can only change the sign of an all-zero partial sum, which the final add of a non-negative-zero
 //   term erases.
-//   FAST mode: same recurrence evaluated with FMAs and with the y[n-1] term added last (1-FMA recurrence
-//   latency); chains start from zero state n_warm samples early.  Not bit-identical to the reference;
-//   K5 flags every window whose bin decision is within `edge_tol` of flipping and the host re-runs those
-//   tracks through the EXACT kernel.
+//   FAST mode: the cascade as a linear transposed-direct-form-II filter evaluated with FMAs (see iir_step_fast);
+//   chains start from zero state n_warm samples early.  Not bit-identical to the reference; K5 flags every
+//   window whose bin decision is within `edge_tol` of flipping and the host re-runs those tracks through the
+//   EXACT kernel.
 #pragma once
 #include "rg_internal.h"
 
-// [rate][0..9]  = a_1..a_10 (Yule)      [rate][10..20] = 32768*b_0..b_10 (Yule)
-// [rate][21..22]= a_1,a_2 (Butter)      [rate][23..25] = b_0..b_2 (Butter)
-#define RG_CC_STRIDE 26
-__constant__ double c_rg_coef[12][RG_CC_STRIDE];
+// Coefficients travel as a by-value kernel parameter (constant bank 0), so every coefficient is a uniform operand at a
+// compile-time offset -- no coefficient registers, no shared device symbol between engines.
+struct RgCoefExact {      // reference order, direct form I
+    double a[10];         // a_1..a_10 (Yule)
+    double b[11];         // 32768*b_0..b_10 (Yule; the *32768 input scale of src/replaygain.rs:969 folded in)
+    double A[2];          // a_1,a_2 (Butterworth)
+    double B[3];          // b_0..b_2 (Butterworth)
+};
+struct RgCoefFast {       // transposed direct form II of the same cascade
+    double a[10], b[11], A[2], B[3];
+    double c2;            // steady-state output offset produced by the two "+1e-10" terms of the reference
+    double s0[10], u0[2]; // filter states equivalent to the reference's all-zero histories at the start of a track
+};
 
 struct IirState {
     double xh[10], yh[10];  // Yule histories: xh[i] = x[n-1-i], yh[i] = y[n-1-i]
     double bx[2], by[2];    // Butterworth histories
 };
 
-template <bool FAST>
-__device__ __forceinline__ double iir_step(IirState& s, const double* __restrict__ c, float xf) {
+// EXACT: per sample, t_i = b_i*x[n-i] - a_i*y[n-i] (two products, one subtract), S = t_1+...+t_10 left to right,
+// y = (1e-10 + b_0*x[n]) + S -- the reference's order (src/replaygain.rs:595-599, 608-612), nothing fused.
+__device__ __forceinline__ double iir_step_exact(IirState& s, const RgCoefExact& c, float xf) {
     const double x0 = (double)xf;
-    double y0;
-    if (!FAST) {
-        double S = __dsub_rn(__dmul_rn(c[11], s.xh[0]), __dmul_rn(c[0], s.yh[0]));
+    double S = __dsub_rn(__dmul_rn(c.b[1], s.xh[0]), __dmul_rn(c.a[0], s.yh[0]));
 #pragma unroll
-        for (int i = 1; i < 10; i++) {
-            double t = __dsub_rn(__dmul_rn(c[11 + i], s.xh[i]), __dmul_rn(c[i], s.yh[i]));
-            S = __dadd_rn(S, t);
-        }
-        y0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c[10], x0)), S);
-    } else {
-        double acc = __fma_rn(c[10], x0, 1e-10);
-#pragma unroll
-        for (int i = 9; i >= 0; i--) acc = __fma_rn(c[11 + i], s.xh[i], acc);
-#pragma unroll
-        for (int i = 9; i >= 1; i--) acc = __fma_rn(-c[i], s.yh[i], acc);
-        y0 = __fma_rn(-c[0], s.yh[0], acc);
+    for (int i = 1; i < 10; i++) {
+        double t = __dsub_rn(__dmul_rn(c.b[1 + i], s.xh[i]), __dmul_rn(c.a[i], s.yh[i]));
+        S = __dadd_rn(S, t);
     }
+    const double y0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c.b[0], x0)), S);
 #pragma unroll
     for (int i = 9; i >= 1; i--) { s.xh[i] = s.xh[i - 1]; s.yh[i] = s.yh[i - 1]; }
     s.xh[0] = x0;
     s.yh[0] = y0;
-
-    double z0;
-    if (!FAST) {
-        double t1 = __dsub_rn(__dmul_rn(c[24], s.bx[0]), __dmul_rn(c[21], s.by[0]));
-        double t2 = __dsub_rn(__dmul_rn(c[25], s.bx[1]), __dmul_rn(c[22], s.by[1]));
-        z0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c[23], y0)), __dadd_rn(t1, t2));
-    } else {
-        double acc = __fma_rn(c[23], y0, 1e-10);
-        acc = __fma_rn(c[25], s.bx[1], acc);
-        acc = __fma_rn(c[24], s.bx[0], acc);
-        acc = __fma_rn(-c[22], s.by[1], acc);
-        z0 = __fma_rn(-c[21], s.by[0], acc);
-    }
+    const double t1 = __dsub_rn(__dmul_rn(c.B[1], s.bx[0]), __dmul_rn(c.A[0], s.by[0]));
+    const double t2 = __dsub_rn(__dmul_rn(c.B[2], s.bx[1]), __dmul_rn(c.A[1], s.by[1]));
+    const double z0 = __dadd_rn(__dadd_rn(1e-10, __dmul_rn(c.B[0], y0)), __dadd_rn(t1, t2));
     s.bx[1] = s.bx[0]; s.bx[0] = y0;
     s.by[1] = s.by[0]; s.by[0] = z0;
     return z0;
+}
+
+// FAST: the same cascade as a *linear* filter in transposed direct form II, evaluated with FMAs:
+//     y = b0*x + s1;   s_k' = (b_k*x + s_{k+1}) - a_k*y   (k = 1..10, s_11 = 0)
+// Every state update is an independent 2-FMA chain and only y -> s1' -> y is loop-carried, so a single warp keeps ~10
+// DFMAs in flight, and the state is 12 doubles instead of 24.  The reference's two "+1e-10" terms make its filter affine;
+// an affine filter equals the linear one plus a constant (c2 at the output, once transients have died -- the same
+// argument that lets a chain start from zero state one window early) and, at the start of a track, the linear filter
+// started from the non-zero state {s0,u0} that corresponds to the reference's all-zero histories.  Not bit-identical
+// arithmetic: K5 flags every window whose bin decision is within edge_tol of flipping and those tracks are re-run EXACT.
+struct TdfState { double s[10], u[2]; };
+__device__ __forceinline__ double iir_step_fast(TdfState& st, const RgCoefFast& c, float xf) {
+    const double x = (double)xf;
+    double t[10];
+#pragma unroll
+    for (int k = 1; k <= 9; k++) t[k - 1] = __fma_rn(c.b[k], x, st.s[k]);
+    t[9] = __dmul_rn(c.b[10], x);
+    const double y = __fma_rn(c.b[0], x, st.s[0]);
+#pragma unroll
+    for (int k = 1; k <= 10; k++) st.s[k - 1] = __fma_rn(-c.a[k - 1], y, t[k - 1]);
+    const double v1 = __fma_rn(c.B[1], y, st.u[1]);
+    const double v2 = __dmul_rn(c.B[2], y);
+    const double z = __fma_rn(c.B[0], y, st.u[0]);
+    st.u[0] = __fma_rn(-c.A[0], z, v1);
+    st.u[1] = __fma_rn(-c.A[1], z, v2);
+    return __dadd_rn(z, c.c2);
 }
 
 // Per-chain window accounting.
@@ -81,9 +97,11 @@ struct WinAcc {
     uint32_t tot, win;
 };
 
-template <bool FAST, bool ACCUM>
-__device__ __forceinline__ void iir_sample(IirState& s, const double* __restrict__ c, WinAcc& w, float& peak, float xf) {
-    double z = iir_step<FAST>(s, c, xf);
+template <bool FAST, bool ACCUM, class State, class Coef>
+__device__ __forceinline__ void iir_sample(State& s, const Coef& c, WinAcc& w, float& peak, float xf) {
+    double z;
+    if constexpr (FAST) z = iir_step_fast(s, c, xf);
+    else z = iir_step_exact(s, c, xf);
     if (ACCUM) {
         w.wmax = fmaxf(w.wmax, fabsf(xf));
         if (FAST) w.sum = __fma_rn(z, z, w.sum);
@@ -99,31 +117,31 @@ __device__ __forceinline__ void iir_sample(IirState& s, const double* __restrict
     }
 }
 
-// Feed n consecutive samples starting at p: scalar head up to 16-byte alignment, float4 body, scalar tail.
-template <bool FAST, bool ACCUM>
-__device__ __forceinline__ void iir_run(IirState& s, const double* __restrict__ c, WinAcc& w, float& peak,
-                                        const float* __restrict__ p, uint32_t n) {
+// Feed n consecutive samples starting at p: scalar head up to 16-byte alignment, float4 body (NV float4 per iteration,
+// the next iteration's loads issued before this iteration's arithmetic), scalar tail.
+template <bool FAST, bool ACCUM, int NV, class State, class Coef>
+__device__ __forceinline__ void iir_run(State& s, const Coef& c, WinAcc& w, float& peak, const float* __restrict__ p, uint32_t n) {
     while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 15u)) {
         iir_sample<FAST, ACCUM>(s, c, w, peak, __ldg(p));
         p++; n--;
     }
     const float4* p4 = reinterpret_cast<const float4*>(p);
-    uint32_t n20 = n / 20;
-    if (n20) {
-        float4 buf[5];
+    uint32_t nit = n / (4 * NV);
+    if (nit) {
+        float4 buf[NV];
 #pragma unroll
-        for (int k = 0; k < 5; k++) buf[k] = __ldg(p4 + k);
-        for (uint32_t it = 0; it < n20; it++) {
-            float4 cur[5];
+        for (int k = 0; k < NV; k++) buf[k] = __ldg(p4 + k);
+        for (uint32_t it = 0; it < nit; it++) {
+            float4 cur[NV];
 #pragma unroll
-            for (int k = 0; k < 5; k++) cur[k] = buf[k];
-            p4 += 5;
-            if (it + 1 < n20) {
+            for (int k = 0; k < NV; k++) cur[k] = buf[k];
+            p4 += NV;
+            if (it + 1 < nit) {
 #pragma unroll
-                for (int k = 0; k < 5; k++) buf[k] = __ldg(p4 + k);
+                for (int k = 0; k < NV; k++) buf[k] = __ldg(p4 + k);
             }
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
+            for (int k = 0; k < NV; k++) {
                 iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].x);
                 iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].y);
                 iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].z);
@@ -132,22 +150,21 @@ __device__ __forceinline__ void iir_run(IirState& s, const double* __restrict__ 
         }
     }
     p = reinterpret_cast<const float*>(p4);
-    n -= n20 * 20;
+    n -= nit * (4 * NV);
     while (n > 0) {
         iir_sample<FAST, ACCUM>(s, c, w, peak, __ldg(p));
         p++; n--;
     }
 }
 
-// K4: one thread per chain.  All chains of one launch share a sample rate (rate_idx is a kernel argument so the
-// coefficient reads are uniform constant-bank operands).
-template <bool FAST>
-__global__ void __launch_bounds__(128)
-k_iir(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base, int rate_idx) {
+// K4: one thread per chain; all chains of one launch share a sample rate.
+#define K4_EXACT_THREADS 32
+__global__ void __launch_bounds__(K4_EXACT_THREADS)
+k_iir_exact(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base,
+            const __grid_constant__ RgCoefExact c) {
     uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
     if (ci >= n_chains) return;
     const RgChain ch = chains[ci];
-    const double* c = c_rg_coef[rate_idx];
     IirState s;
 #pragma unroll
     for (int i = 0; i < 10; i++) { s.xh[i] = 0.0; s.yh[i] = 0.0; }
@@ -155,8 +172,7 @@ k_iir(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__
     WinAcc w;
     w.sum = 0.0; w.out = ch.wsum; w.mout = ch.wmax; w.wmax = 0.0f; w.tot = 0; w.win = ch.win;
     float peak = 0.0f;
-    if (FAST && ch.n_warm) iir_run<FAST, false>(s, c, w, peak, ch.src, ch.n_warm);
-    iir_run<FAST, true>(s, c, w, peak, ch.src + ch.n_warm, ch.n_main);
+    iir_run<false, true, 5>(s, c, w, peak, ch.src, ch.n_main);
     if (w.tot) {  // the track's final partial window (src/replaygain.rs:907)
         *w.out = w.sum;
         *w.mout = w.wmax;
@@ -164,6 +180,36 @@ k_iir(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__
     }
     peaks[chain_base + ci] = peak;
 }
+
+template <int NV, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base,
+             const __grid_constant__ RgCoefFast c) {
+    uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chains) return;
+    const RgChain ch = chains[ci];
+    TdfState s;
+    const bool head = ch.flags & 1u;   // chain starts at the first sample of the track
+#pragma unroll
+    for (int i = 0; i < 10; i++) s.s[i] = head ? c.s0[i] : 0.0;
+    s.u[0] = head ? c.u0[0] : 0.0;
+    s.u[1] = head ? c.u0[1] : 0.0;
+    WinAcc w;
+    w.sum = 0.0; w.out = ch.wsum; w.mout = ch.wmax; w.wmax = 0.0f; w.tot = 0; w.win = ch.win;
+    float peak = 0.0f;
+    if (ch.n_warm) iir_run<true, false, NV>(s, c, w, peak, ch.src, ch.n_warm);
+    iir_run<true, true, NV>(s, c, w, peak, ch.src + ch.n_warm, ch.n_main);
+    if (w.tot) {
+        *w.out = w.sum;
+        *w.mout = w.wmax;
+        peak = fmaxf(peak, w.wmax);
+    }
+    peaks[chain_base + ci] = peak;
+}
+
+// the instantiation the engine launches (tools/iir_bench.cu times the alternatives)
+#define K4_FAST_THREADS 128
+#define k_iir_fast k_iir_fast_t<5, K4_FAST_THREADS, 3>
 
 // ------------------------------------------------------------------------------------------------------------
 // K5: one CTA per track.  Window sums -> bin index -> shared 12000-bin histogram (warp-aggregated atomics)
@@ -220,7 +266,10 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
             if (val > -2002.0 && val < 10001.0) {
                 double tol = edge_tol;
                 if (scale_tol) {
-                    const double amp = 32768.0 * (double)fmaxf(t.wmax0[w], t.wmax1[w]);
+                    // the filter state entering a window carries the previous window's level, so take the louder of the two
+                    float a = fmaxf(t.wmax0[w], t.wmax1[w]);
+                    if (w > 0) a = fmaxf(a, fmaxf(t.wmax0[w - 1], t.wmax1[w - 1]));
+                    const double amp = 32768.0 * (double)a;
                     const double ratio = amp / sqrt(ms + 1e-300);
                     tol = edge_tol * fmax(1.0, 0.1 * ratio);
                 }

@@ -48,6 +48,9 @@ struct L3Dev {
 };
 
 __constant__ float c_dct_sec[31];   // Lee DCT-II secants: compile-time indices only -> constant-bank operands
+__constant__ float c_alias_cs[8], c_alias_ca[8];   // alias-reduction butterflies, same access pattern
+#define L3_CS(i) c_alias_cs[i]
+#define L3_CA(i) c_alias_ca[i]
 
 struct TrackIn { uint64_t off, len; };            // byte range of one file image inside the device corpus buffer
 struct TrackMeta {                                 // K0 output
@@ -181,5 +184,7 @@ static int decode_init_tables(DecodeScratch& ds) {
     if (cudaMalloc(&ds.d_tab, sizeof(L3Dev)) != cudaSuccess) return -3;
     if (cudaMemcpy(ds.d_tab, &T, sizeof(L3Dev), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
     if (cudaMemcpyToSymbol(c_dct_sec, L3_DCT_SEC, sizeof(float) * 31) != cudaSuccess) return -3;
+    if (cudaMemcpyToSymbol(c_alias_cs, L3_ALIAS_CS, sizeof(float) * 8) != cudaSuccess) return -3;
+    if (cudaMemcpyToSymbol(c_alias_ca, L3_ALIAS_CA, sizeof(float) * 8) != cudaSuccess) return -3;
     return 0;
 }

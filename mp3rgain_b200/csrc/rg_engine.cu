@@ -77,6 +77,8 @@ struct rg_engine {
     cudaEvent_t ev[8] = {};
     // options
     uint32_t block_windows = 16, warm_windows = 1;
+    RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
+    RgCoefFast coef_fast[12];
     double edge_tol = 1e-9;
     // device scratch
     DevBuf d_pcm_in, d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_album, d_album_peak, d_misc;
@@ -154,16 +156,26 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (24ull << 30);
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
-    // coefficient table -> constant memory, b's of the Yule stage pre-scaled by 2^15 (see k_analysis.cuh)
-    static double cc[12][RG_CC_STRIDE];
+    // coefficient rows as K4 wants them, b's of the Yule stage pre-scaled by 2^15 (see k_analysis.cuh)
     for (int r = 0; r < 12; r++) {
-        const double* row = RG_COEFS[r];
-        for (int i = 1; i <= 10; i++) cc[r][i - 1] = row[i];
-        for (int i = 0; i <= 10; i++) cc[r][10 + i] = row[11 + i] * 32768.0;
-        cc[r][21] = row[23]; cc[r][22] = row[24];
-        cc[r][23] = row[25]; cc[r][24] = row[26]; cc[r][25] = row[27];
+        const double* row = RG_COEFS[r];   // [0..10] yule_a, [11..21] yule_b, [22..24] butter_a, [25..27] butter_b
+        RgCoefExact& x = e->coef_exact[r];
+        RgCoefFast& f = e->coef_fast[r];
+        for (int i = 1; i <= 10; i++) x.a[i - 1] = f.a[i - 1] = row[i];
+        for (int i = 0; i <= 10; i++) x.b[i] = f.b[i] = row[11 + i] * 32768.0;
+        x.A[0] = f.A[0] = row[23]; x.A[1] = f.A[1] = row[24];
+        for (int i = 0; i < 3; i++) x.B[i] = f.B[i] = row[25 + i];
+        // the affine reference filter = linear filter + constants: c after the Yule stage, c2 after the Butterworth stage
+        double sa = 1.0, sA = 1.0, sB = 0.0;
+        for (int i = 1; i <= 10; i++) sa += row[i];
+        sA += row[23] + row[24];
+        for (int i = 0; i < 3; i++) sB += row[25 + i];
+        const double c = 1e-10 / sa;
+        f.c2 = (1e-10 + sB * c) / sA;
+        // linear-filter states equivalent to the reference's all-zero histories: y'(-k) = -c, z'(-k) = -c2
+        for (int k = 1; k <= 10; k++) { double t = 0; for (int j = k; j <= 10; j++) t += row[j]; f.s0[k - 1] = c * t; }
+        for (int k = 1; k <= 2; k++) { double t = 0; for (int j = k; j <= 2; j++) t += -c * row[25 + j] + f.c2 * row[22 + j]; f.u0[k - 1] = t; }
     }
-    CK(cudaMemcpyToSymbol(c_rg_coef, cc, sizeof cc));
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
     int rc = decode_init_tables(e->dec);
     if (rc != RG_OK) { delete e; return rc; }
@@ -238,7 +250,7 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
                 if (exact) {
                     RgChain ch{};
                     ch.src = t.d_ch[c]; ch.wsum = wbase; ch.wmax = mbase; ch.n_warm = 0; ch.n_main = (uint32_t)t.frames;
-                    ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
+                    ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx; ch.flags = 1;
                     chains.push_back(ch);
                 } else {
                     const uint32_t bw = e->block_windows, ww = e->warm_windows;
@@ -253,7 +265,7 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
                         ch.wmax = mbase + w0;
                         ch.n_warm = (uint32_t)warm;
                         ch.n_main = (uint32_t)(s1 - s0);
-                        ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx;
+                        ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx; ch.flags = s0 == 0 ? 1u : 0u;
                         chains.push_back(ch);
                     }
                 }
@@ -323,12 +335,12 @@ static int launch_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, con
         uint32_t r = launch_chains[i0].rate_idx;
         while (i1 < launch_chains.size() && launch_chains[i1].rate_idx == r) i1++;
         uint32_t cnt = (uint32_t)(i1 - i0);
-        const int T = exact ? 32 : 128;
+        const int T = exact ? K4_EXACT_THREADS : K4_FAST_THREADS;
         uint32_t blocks = (cnt + T - 1) / T;
         if (exact)
-            k_iir<false><<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, (int)r);
+            k_iir_exact<<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_exact[r]);
         else
-            k_iir<true><<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, (int)r);
+            k_iir_fast<<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         // note: chain_base passed as i0 but the kernel indexes peaks[chain_base + ci] with ci relative to the sub-array
         e->stats.kernel_launches++;
         i0 = i1;

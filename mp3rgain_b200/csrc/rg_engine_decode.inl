@@ -1,7 +1,7 @@
 // rg_engine_decode.inl -- entry points that run the MP3 decode kernels (stage A) and feed stage B.
 // Included at the end of rg_engine.cu.
 
-#define RUN_GRANULES 64   // granules per K2 CTA (even: runs always start on granule 0 of a frame)
+#define RUN_GRANULES 62   // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
 
 static const uint32_t MPEG1_RATES[3] = {44100, 48000, 32000};
 

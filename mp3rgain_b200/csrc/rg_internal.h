@@ -15,6 +15,8 @@ struct RgChain {
     uint32_t n_main;    // samples accumulated (whole windows, plus the track's final partial one)
     uint32_t win;       // window length in samples (sample_rate*50/1000, src/replaygain.rs:704)
     uint32_t rate_idx;  // row of the coefficient table
+    uint32_t flags;     // bit0: the chain starts at the first sample of its track (reference state: all-zero histories)
+    uint32_t pad;
 };
 
 // One track as the histogram / percentile kernel sees it.
