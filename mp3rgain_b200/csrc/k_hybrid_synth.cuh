@@ -1,20 +1,22 @@
 // k_hybrid_synth.cuh -- K2: requantise -> MS stereo -> reorder -> alias reduction -> IMDCT/overlap -> polyphase -> PCM.
 //
-// One CTA owns a run of consecutive granules of one track (both channels) and walks it in time order in BATCHES of K2_G
-// granules.  Inside a batch every stage is data-parallel over (granule, channel, subband | slot | column), so each stage is
-// one phase in which all warps do the same kind of work, separated by one CTA barrier:
+// One CTA (8 warps) owns a run of consecutive granules of one track and walks it in time order in BATCHES of 8
+// granule-channels (4 stereo granules or 8 mono granules): one granule-channel per warp.  Every stage uses the mapping in
+// which its natural index is the lane, so there is no index arithmetic in the inner loops:
 //
-//   P0  side info + scalefactors -> per-band gain-table index      one warp per granule-channel (runs one batch ahead,
-//                                                                   on the two warps that have no P4 work)
-//   P1  requantise + MS + short-block reorder -> xr                one line pair (both channels) per thread-iteration
-//   P2  alias butterflies + IMDCT + window -> F (first 18 outputs) one (granule, channel, subband) per thread
-//                                            S2 (last 18 outputs = the overlap the NEXT granule adds)
-//   P3  x = F + S2(prev granule); 32-point DCT-II (Lee) -> ring    two threads per transform (sum / difference branch),
-//                                                                   the two branches on different warps
-//   P4  16-tap polyphase window over the ring -> PCM               one (granule, channel, output column) per thread, 18 slots
+//   TMA  the batch's int16 spectra (8 x 1152 B, contiguous in HBM) arrive in shared memory as ONE bulk copy
+//        (cp.async.bulk + mbarrier), issued a batch ahead by one thread
+//   P0   side info + scalefactors -> gain of every scalefactor band     warp per granule-channel, lane = band; runs one
+//                                                                        batch ahead on the three warps idle during P3
+//   P1   requantise + MS + short-block reorder -> xr (slot A)            the warps of one granule, lane = line pair;
+//                                                                        handed to P2 by a 64-thread named barrier
+//   P2   alias butterflies + IMDCT + window + frequency inversion        warp = granule-channel, lane = SUBBAND: the 18
+//        -> F (outputs 0..17, slot A in place), S2 (outputs 18..35)      lines live in registers, the matrices are
+//                                                                        constant-bank operands of the FFMAs
+//   P3   x = F + S2(previous granule); 32-point DCT-II (Lee) in place    thread = (granule-channel, time slot)
+//   P4   16-tap polyphase window over the DCT rows -> PCM                warp = granule-channel, lane = output column
 //
-// The overlap-add is performed by the reader (P3), so P2 has no dependency between granules; the overlap and the
-// filterbank history travel between batches in 5-slot rings (S2, ring) indexed by granule number modulo 5, so nothing is
+// The overlap (S2) and the DCT rows travel between batches in slots indexed by granule number modulo (G+1), so nothing is
 // copied.  Both are finite-memory: a run that does not start at the head of the track first replays the two granules
 // before it (PCM writes suppressed) to rebuild that state exactly, so runs are independent and the corpus decodes in
 // parallel.
@@ -23,13 +25,14 @@
 // addends instead of the sum: -(a+b) == (-a)+(-b) in IEEE arithmetic).
 #pragma once
 
-#define K2_THREADS 192
-#define K2_G 2             // granules per batch
-#define K2_RING (K2_G + 1) // slots of the S2 / DCT rings
+#define K2_THREADS 256
+#define K2_GC 8            // granule-channels per batch, one per warp
+#define K2_SLOTS 10        // slots of A / S2: (G+1) granules x channels = 5x2 (stereo) or 9x1 (mono)
 #define K2_MAX_G 64        // granules per run, including the two replayed ones
 #define ROW 33             // padded row of 32 values
+#define SLOTF (18 * ROW)   // floats per slot
 
-struct __align__(8) GranInfo {
+struct __align__(4) GranInfo {
     uint32_t part2_bit;   // absolute bit position of part 2 in the main-data stream
     uint32_t md_lim;      // bytes readable (later bytes read as zero)
     uint16_t nz;          // lines decoded by K1 (0 = silent)
@@ -38,22 +41,22 @@ struct __align__(8) GranInfo {
 };
 
 struct K2Smem {
-    // DCT-32 output rows; granule n owns rows 18*(n%3) .. +17 of each channel.  The same slot first holds the granule's
-    // requantised spectrum xr (576 floats per channel): xr is dead once P2 has read it, before P3 writes the rows.
-    alignas(16) float ring[2][K2_RING * 18][ROW];
-    float F[K2_G][2][18][ROW];                // IMDCT outputs 0..17  [slot][subband]
-    float S2[K2_RING][2][18][ROW];            // IMDCT outputs 18..35 of granule n live in slot (n+1)%3
-    alignas(16) float dct4[18][20];           // 18-point DCT-IV matrix, rows padded to 5 float4
-    float win[4][36];
-    alignas(16) float im12[12][8];            // 12-point IMDCT matrix, rows padded to 2 float4
+    alignas(16) float A[K2_SLOTS][SLOTF];     // per granule-channel: xr[576] -> F[18][ROW] -> DCT rows [18][ROW], in place
+    float S2[K2_SLOTS][SLOTF];                // IMDCT outputs 18..35 of the granule-channel (added by the NEXT granule)
+    alignas(16) uint32_t stage[K2_GC][288];   // the batch's int16 line pairs, written by the TMA unit
+    float bandgain[K2_GC][64];                // per band: 2^(exponent/4) ([0..21] long sfb, [22..60] short sfb*3+win)
+    uint32_t p1w[K2_GC];                      // tsel | ms<<2 | (nz!=0)<<3 | (9*max sb_limit of the granule)<<8
     float wa[8][32], wb[8][32];
-    float gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
     GranInfo gi[K2_MAX_G][2];                 // side info of every granule-channel of the run
-    uint16_t eidx[2][K2_G][2][64];            // [batch parity] per band: index into gain[] ([0..21] long, [22..60] short sfb*3+win)
     uint16_t scat[2][576];                    // bitstream-order line -> reordered line: [0] pure short, [1] mixed
     uint8_t code[3][576];                     // line -> band code: [0] long, [1] pure short, [2] mixed
     uint8_t ia[32], ib[32];
+    alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
 };
+
+__constant__ float c_dct4[18][18];   // 18-point DCT-IV matrix (compile-time indices only -> constant-bank FFMA operands)
+__constant__ float c_im12[12][6];    // 12-point IMDCT matrix
+__constant__ float c_win[4][36];     // block-type windows with the IMDCT sign folded in
 
 template <int N, int OFF>
 struct Dct2 {
@@ -144,29 +147,61 @@ __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corp
     return gi;
 }
 
-__global__ void __launch_bounds__(K2_THREADS, 4)
-k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
-               const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
-               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
-    extern __shared__ __align__(16) unsigned char k2_raw[];
-    K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+)
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k2_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void k2_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(k2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "K2_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra K2_DONE;\n"
+        "bra K2_WAIT;\n"
+        "K2_DONE:\n"
+        "}" ::"r"(k2_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void k2_pair_sync(int pair) {   // immediate ids, so that ptxas reserves 5 barriers and not 16
+    switch (pair) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
 
+// long-block window: o[i] = u[idx36(i)] * win[BT][i]
+template <int BT>
+__device__ __forceinline__ void k2_window36(const float (&u)[18], float (&o)[36]) {
+#pragma unroll
+    for (int i = 0; i < 36; i++) o[i] = __fmul_rn(u[idx36(i)], c_win[BT][i]);
+}
+
+template <int NCH>
+__device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md,
+                                        const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
+                                        const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
+                                        const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
+    constexpr int G = K2_GC / NCH;      // granules per batch
+    constexpr int NS = G + 1;           // granule slots
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const RunDesc run = runs[blockIdx.x];
-    const DecTrack tr = tracks[run.track];
-    const int nch = (int)tr.channels;
     const int sr = (int)tr.sr_idx;
     const uint8_t* mdp = md + tr.md_off;
     const uint32_t warm = run.g0 < 2 ? run.g0 : 2;
     const uint32_t gfirst = run.g0 - warm, gcount = run.ng + warm;   // gcount <= K2_MAX_G
-    const uint32_t n_batches = (gcount + K2_G - 1) / K2_G;
+    const uint32_t n_batches = (gcount + G - 1) / G;
+    const int my_gi = warp / NCH, my_ch = warp % NCH;                // this warp's granule-channel within a batch
 
     // ---- one-time table staging and state reset
-    for (int i = tid; i < 18 * 20; i += K2_THREADS) { const int m = i / 20, k = i - 20 * m; S.dct4[m][k] = k < 18 ? T->dct4_18[m][k] : 0.0f; }
-    for (int i = tid; i < 4 * 36; i += K2_THREADS) (&S.win[0][0])[i] = (&T->winsgn[0][0])[i];
-    for (int i = tid; i < 12 * 8; i += K2_THREADS) { const int r = i >> 3, k = i & 7; S.im12[r][k] = k < 6 ? T->imdct12[r][k] : 0.0f; }
     for (int i = tid; i < 256; i += K2_THREADS) { (&S.wa[0][0])[i] = (&T->synth_wa[0][0])[i]; (&S.wb[0][0])[i] = (&T->synth_wb[0][0])[i]; }
-    for (int i = tid; i < L3_GAIN_MAX - L3_GAIN_MIN + 1; i += K2_THREADS) S.gain[i] = T->gain[i];
     for (int i = tid; i < 576; i += K2_THREADS) {
         S.code[0][i] = T->line_sfb_long[sr][i];
         S.code[1][i] = 22 + T->line_sfb_short[sr][i];
@@ -176,25 +211,34 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
         S.scat[1][i] = T->scatter_mixed[sr][i];
     }
     if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
-    for (int i = tid; i < K2_RING * 2 * 18 * ROW; i += K2_THREADS) { (&S.S2[0][0][0][0])[i] = 0.0f; (&S.ring[0][0][0])[i] = 0.0f; }
+    for (int i = tid; i < K2_SLOTS * SLOTF; i += K2_THREADS) { (&S.A[0][0])[i] = 0.0f; (&S.S2[0][0])[i] = 0.0f; }
+    if (tid == 0) k2_mbar_init(&S.mbar, 1);
     // side info of every granule-channel of the run, one thread each
-    for (uint32_t it = tid; it < gcount * nch; it += K2_THREADS) {
-        const uint32_t gl = it / nch, ch = it - gl * nch;
-        S.gi[gl][ch] = k2_parse_gi(corpus, tr, frames, nz_in, gfirst + gl, ch, nch);
+    for (uint32_t it = tid; it < gcount * NCH; it += K2_THREADS) {
+        const uint32_t gl = it / NCH, ch = it % NCH;
+        S.gi[gl][ch] = k2_parse_gi(corpus, tr, frames, nz_in, gfirst + gl, ch, NCH);
     }
     __syncthreads();
 
-    // ---- P0: scalefactors of granule-channel q of batch b -> eidx[b&1].  One warp per granule-channel; every branch on the
-    // block type is warp-uniform.  Part 2 of the main data has a closed-form layout, so each lane reads its own band's
-    // scalefactor straight from the bitstream.
+    // spectra of batch b: granule-channels are contiguous in HBM, 1152 bytes each
+    auto issue_copy = [&](uint32_t b) {
+        const uint32_t gl0 = b * G;
+        const uint32_t ng = min((uint32_t)G, gcount - gl0);
+        const int16_t* src = spectra + ((size_t)tr.gc_base + (size_t)(gfirst + gl0) * NCH) * 576;
+        k2_bulk_load(&S.stage[0][0], src, ng * NCH * 1152u, &S.mbar);
+    };
+
+    // ---- P0: scalefactors of granule-channel q of batch b -> bandgain[q], p1w[q].  One warp per granule-channel; every
+    // branch on the block type is warp-uniform.  Part 2 of the main data has a closed-form layout, so each lane reads its
+    // own band's scalefactor straight from the bitstream.
     auto p0_gc = [&](uint32_t b, int q) {
-        const int gi_ = q / nch, ch = q - gi_ * nch;
-        const uint32_t gl = b * K2_G + gi_;
+        const int gi_ = q / NCH, ch = q % NCH;
+        const uint32_t gl = b * G + gi_;
         if (gl >= gcount) return;
         const GranInfo gi = S.gi[gl][ch];
         const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
         const int base_e = (int)gi.global_gain - 210 - L3_GAIN_MIN;
-        uint16_t* eidx = S.eidx[b & 1][gi_][ch];
+        float* bg = S.bandgain[q];
         if (gi.bt != 2) {
             if (lane < 22) {
                 int v = 0;
@@ -211,13 +255,13 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
                         else if (g0.mixed && lane < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + lane * a1, a1);
                     }
                 }
-                eidx[lane] = (uint16_t)(base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0)));
+                bg[lane] = __ldg(&T->gain[base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0))]);
             }
         } else {
             if (lane < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors
                 int v = 0;
                 if (gi.mixed && lane < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + lane * slen1, slen1);
-                eidx[lane] = (uint16_t)(base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0)));
+                bg[lane] = __ldg(&T->gain[base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0))]);
             }
             for (int q2 = lane; q2 < 39; q2 += 32) {
                 const int sfb = q2 / 3, win = q2 - 3 * sfb;
@@ -228,276 +272,221 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
                     else off = (sfb < 6) ? q2 * slen1 : 18 * slen1 + (q2 - 18) * slen2;
                     v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
                 }
-                eidx[22 + q2] = (uint16_t)(base_e - 8 * gi.sbg[win] - gi.sf_shift * v);
+                bg[22 + q2] = __ldg(&T->gain[base_e - 8 * gi.sbg[win] - gi.sf_shift * v]);
             }
         }
-    };
-    // The requantiser's input (packed int16 line pairs, K2_G*288 pairs per channel) is fetched one batch ahead into
-    // registers, so its HBM latency overlaps a whole batch of compute.  Pairs at or above nz are zero and are not read.
-    constexpr int P1_IT = K2_G * 288 / K2_THREADS;   // 3
-    uint32_t pre[P1_IT][2];
-    auto fetch = [&](uint32_t b) {
-#pragma unroll
-        for (int r = 0; r < P1_IT; r++) {
-            const int it = tid + K2_THREADS * r;
-            const int gi_ = it / 288, pr = it - 288 * gi_;
-            const uint32_t gl = b * K2_G + gi_;
-            pre[r][0] = pre[r][1] = 0;
-            if (gl < gcount) {
-                const uint32_t g = gfirst + gl;
-                const size_t gcf = (size_t)tr.gc_base + (size_t)(g >> 1) * 2 * nch + (g & 1) * nch;
-#pragma unroll
-                for (int ch = 0; ch < 2; ch++)
-                    if (ch < nch && (uint32_t)(2 * pr) < S.gi[gl][ch].nz)
-                        pre[r][ch] = __ldg(reinterpret_cast<const uint32_t*>(spectra + (gcf + ch) * 576 + 2 * pr));
-            }
+        if (lane == 0) {
+            const int lim = max((int)gi.sb_limit, (int)S.gi[gl][NCH - 1 - ch].sb_limit);
+            const uint32_t tsel = gi.bt != 2 ? 0u : (gi.mixed ? 2u : 1u);
+            S.p1w[q] = tsel | ((uint32_t)gi.ms << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(9 * lim) << 8);
         }
     };
-    fetch(0);
-    for (int q = warp; q < K2_G * nch; q += K2_THREADS / 32) p0_gc(0, q);
+
+    if (tid == 0) issue_copy(0);
+    p0_gc(0, warp);
     __syncthreads();
 
     for (uint32_t b = 0; b < n_batches; b++) {
-        const int par = (int)(b & 1);
-        const uint32_t gl0 = b * K2_G;   // first granule of the batch, relative to gfirst
+        const uint32_t gl0 = b * G;
+        const uint32_t gl = gl0 + my_gi;          // this warp's granule (relative to gfirst)
+        const bool have = gl < gcount;
+        const int slot = (int)(gl % NS) * NCH + my_ch;
+        const int slot_prev = (int)((gl + NS - 1) % NS) * NCH + my_ch;
 
         // ================= P1: requantise (+ MS stereo, + short-block reorder folded into the store index) =================
-        // One line pair of both channels per iteration; scalefactor bands start on even lines, so a pair shares its band.
+        // The warps of one granule share its line pairs; scalefactor bands start on even lines, so a pair shares its band.
+        k2_mbar_wait(&S.mbar, b & 1);
+        if (have) {
+            const uint32_t w0 = S.p1w[my_gi * NCH], w1 = S.p1w[my_gi * NCH + NCH - 1];
+            const int lim9 = (int)(w0 >> 8);
+            const int tsel0 = w0 & 3, tsel1 = w1 & 3;
+            const bool ms = (w0 >> 2) & 1;
+            const bool nzf0 = (w0 >> 3) & 1, nzf1 = (w1 >> 3) & 1;
+            const uint32_t* st0 = S.stage[my_gi * NCH];
+            const uint32_t* st1 = S.stage[my_gi * NCH + NCH - 1];
+            const float* bg0 = S.bandgain[my_gi * NCH];
+            const float* bg1 = S.bandgain[my_gi * NCH + NCH - 1];
+            float* x0 = S.A[(gl % NS) * NCH];
+            float* x1 = S.A[(gl % NS) * NCH + NCH - 1];
+            for (int pr = lane + 32 * my_ch; pr < lim9; pr += 32 * NCH) {
+                float v[2][2];
 #pragma unroll
-        for (int r = 0; r < P1_IT; r++) {
-            const int it = tid + K2_THREADS * r;
-            const int gi_ = it / 288, pr = it - 288 * gi_;
-            const uint32_t gl = gl0 + gi_;
-            if (gl >= gcount) continue;
-            const GranInfo& ga = S.gi[gl][0];
-            const GranInfo& gb = S.gi[gl][nch - 1];
-            if (pr >= 9 * max((int)ga.sb_limit, (int)gb.sb_limit)) continue;   // no active subband reads these lines
-            const int slot = (int)(gl % K2_RING);
-            float v[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
-            int dst[2][2] = {{2 * pr, 2 * pr + 1}, {2 * pr, 2 * pr + 1}};
+                for (int ch = 0; ch < NCH; ch++) {
+                    const uint32_t packed = (ch ? nzf1 : nzf0) ? (ch ? st1 : st0)[pr] : 0u;
+                    const float gn = (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]];
+                    const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
+                    const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
+                    const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
+                    v[ch][0] = q0 < 0 ? -m0 : m0;
+                    v[ch][1] = q1 < 0 ? -m1 : m1;
+                }
+                if (NCH == 2 && ms) {
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                if (ch >= nch) break;
-                const GranInfo& gi = S.gi[gl][ch];
-                const uint32_t packed = pre[r][ch];
-                const int tsel = gi.bt != 2 ? 0 : (gi.mixed ? 2 : 1);
-                const float gn = S.gain[S.eidx[par][gi_][ch][S.code[tsel][2 * pr]]];
+                    for (int h = 0; h < 2; h++) {
+                        const float a = v[0][h], c = v[NCH - 1][h];
+                        v[0][h] = __fmul_rn(__fadd_rn(a, c), L3_INV_SQRT2);
+                        v[NCH - 1][h] = __fmul_rn(__fsub_rn(a, c), L3_INV_SQRT2);
+                    }
+                }
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int q = (int)(int16_t)(h ? (packed >> 16) : (packed & 0xFFFFu));
-                    const int aq = q < 0 ? -q : q;
-                    const float m = __fmul_rn(__ldg(&T->pow43[aq]), gn);
-                    v[ch][h] = q < 0 ? -m : m;
-                    if (tsel) dst[ch][h] = S.scat[tsel - 1][2 * pr + h];
+                for (int ch = 0; ch < NCH; ch++) {
+                    float* x = ch ? x1 : x0;
+                    const int tsel = ch ? tsel1 : tsel0;
+                    if (tsel == 0) *reinterpret_cast<float2*>(x + 2 * pr) = make_float2(v[ch][0], v[ch][1]);
+                    else { x[S.scat[tsel - 1][2 * pr]] = v[ch][0]; x[S.scat[tsel - 1][2 * pr + 1]] = v[ch][1]; }
                 }
             }
-            if (ga.ms) {
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float a = v[0][h], c = v[1][h];
-                    v[0][h] = __fmul_rn(__fadd_rn(a, c), L3_INV_SQRT2);
-                    v[1][h] = __fmul_rn(__fsub_rn(a, c), L3_INV_SQRT2);
-                }
-            }
-            float* x0 = &S.ring[0][18 * slot][0];
-            x0[dst[0][0]] = v[0][0];
-            x0[dst[0][1]] = v[0][1];
-            if (nch == 2) { float* x1 = &S.ring[1][18 * slot][0]; x1[dst[1][0]] = v[1][0]; x1[dst[1][1]] = v[1][1]; }
         }
-        __syncthreads();
-        if (b + 1 < n_batches) fetch(b + 1);
+        if (NCH == 2) k2_pair_sync(my_gi); else __syncwarp();
 
-        // ================= P2: alias butterflies + IMDCT + window ==========================================================
-        // Tasks = (granule-channel q, half, subband) for the ACTIVE subbands only, compacted so that warps stay full:
-        // half 1 evaluates DCT-IV rows 9..17 = the 18 outputs of this granule (F), half 0 rows 0..8 = the 18 outputs the next
-        // granule adds (S2).  Inactive subbands are zero-filled by all threads.
-        {
-            int lim[2 * K2_G], base[2 * K2_G + 1];
-            base[0] = 0;
+        // ================= P2: alias butterflies + IMDCT + window, lane = subband ==========================================
+        if (have) {
+            const GranInfo gi = S.gi[gl][my_ch];
+            float* Aq = S.A[slot];
+            float* Sq = S.S2[slot];
+            const int sb = lane, limit = (int)gi.sb_limit;
+            if (limit == 0) {
 #pragma unroll
-            for (int q = 0; q < 2 * K2_G; q++) {
-                const int gi_ = q >> 1, ch = q & 1;
-                lim[q] = (ch < nch && gl0 + gi_ < gcount) ? (int)S.gi[gl0 + gi_][ch].sb_limit : -1;   // -1: no such granule-channel
-                base[q + 1] = base[q] + (lim[q] > 0 ? lim[q] : 0);
-            }
-            const int total = base[2 * K2_G];
+                for (int i = 0; i < 18; i++) { Aq[i * ROW + sb] = 0.0f; Sq[i * ROW + sb] = 0.0f; }
+            } else {
+                float X[18], lo[8], hi[8];
+                const bool act = sb < limit;
+                {
+                    const float2* X2 = reinterpret_cast<const float2*>(Aq + 18 * sb);
 #pragma unroll
-            for (int q = 0; q < 2 * K2_G; q++) {
-                if (lim[q] < 0 || lim[q] >= 32) continue;
-                const int gi_ = q >> 1, ch = q & 1, nsb = 32 - lim[q];
-                float* Fq = &S.F[gi_][ch][0][0];
-                float* Sq = &S.S2[(gl0 + gi_ + 1) % K2_RING][ch][0][0];
-                for (int idx = tid; idx < 18 * nsb; idx += K2_THREADS) {
-                    const int i = idx / nsb, sb = lim[q] + (idx - i * nsb);
-                    Fq[i * ROW + sb] = 0.0f;
-                    Sq[i * ROW + sb] = 0.0f;
+                    for (int k = 0; k < 9; k++) { const float2 x = X2[k]; X[2 * k] = act ? x.x : 0.0f; X[2 * k + 1] = act ? x.y : 0.0f; }
+                    const float* pl = Aq + 18 * max(sb, 1) - 1;
+                    const float* ph = Aq + 18 * min(sb + 1, 31);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { lo[i] = pl[-i]; hi[i] = ph[i]; }
                 }
-            }
-            for (int t = tid; t < 2 * total; t += K2_THREADS) {
-                const int half = t >= total ? 0 : 1;       // F producers first
-                const int rr = t >= total ? t - total : t;
-                int q = 0;
-#pragma unroll
-                for (int k = 1; k < 2 * K2_G; k++) q += rr >= base[k] ? 1 : 0;
-                int bq = 0;
-#pragma unroll
-                for (int k = 1; k < 2 * K2_G; k++) bq = (q >= k) ? base[k] : bq;
-                const int sb = rr - bq;
-                const int gi_ = q >> 1, ch = q & 1;
-                const uint32_t gl = gl0 + gi_;
-                const GranInfo& gi = S.gi[gl][ch];
-                const int limit = (int)gi.sb_limit;
-                const float* xr = &S.ring[ch][18 * (gl % K2_RING)][0];
-                float X[18];
-                const float2* X2 = reinterpret_cast<const float2*>(&xr[18 * sb]);
-#pragma unroll
-                for (int k = 0; k < 9; k++) { const float2 x = X2[k]; X[2 * k] = x.x; X[2 * k + 1] = x.y; }
+                __syncwarp();   // every lane holds its inputs: the slot may now be overwritten in place
                 // alias reduction: boundary s (between subbands s-1 and s) is processed when s < limit and the block is long
                 // (or s == 1 of a mixed block).  The butterflies of neighbouring boundaries touch disjoint lines, so both of
-                // this subband's boundaries use the un-aliased neighbour lines still in xr.
-                const bool lo_b = sb >= 1 && (gi.bt != 2 || (gi.mixed && sb == 1));
+                // this subband's boundaries use the un-aliased neighbour lines loaded above.
+                const bool lo_b = act && sb >= 1 && (gi.bt != 2 || (gi.mixed && sb == 1));
                 const bool hi_b = sb + 1 < limit && (gi.bt != 2 || (gi.mixed && sb == 0));
                 if (lo_b) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float lo = xr[18 * sb - 1 - i], hi = X[i];
-                        X[i] = __fadd_rn(__fmul_rn(hi, L3_CS(i)), __fmul_rn(lo, L3_CA(i)));
-                    }
+                    for (int i = 0; i < 8; i++) X[i] = __fadd_rn(__fmul_rn(X[i], L3_CS(i)), __fmul_rn(lo[i], L3_CA(i)));
                 }
                 if (hi_b) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float lo = X[17 - i], hi = xr[18 * (sb + 1) + i];
-                        X[17 - i] = __fsub_rn(__fmul_rn(lo, L3_CS(i)), __fmul_rn(hi, L3_CA(i)));
-                    }
+                    for (int i = 0; i < 8; i++) X[17 - i] = __fsub_rn(__fmul_rn(X[17 - i], L3_CS(i)), __fmul_rn(hi[i], L3_CA(i)));
                 }
                 const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
-                float o[18];   // half 1: raw[0..17]; half 0: raw[18..35]
+                float o[36];
                 if (!is_short) {
+                    float u[18];
+#pragma unroll
+                    for (int m = 0; m < 18; m++) {
+                        float a = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 18; k++) a = fmaf(X[k], c_dct4[m][k], a);
+                        u[m] = a;
+                    }
                     const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
-                    float u[9];
+                    if (bt == 0) k2_window36<0>(u, o);
+                    else if (bt == 1) k2_window36<1>(u, o);
+                    else k2_window36<3>(u, o);
+                } else {
+                    // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window order
+                    float y[3][12];
 #pragma unroll
-                    for (int mm = 0; mm < 9; mm++) {
-                        const float4* C4 = reinterpret_cast<const float4*>(S.dct4[9 * half + mm]);
-                        float a = 0.0f;
+                    for (int w = 0; w < 3; w++)
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; k4++) {
-                            const float4 c = C4[k4];
-                            a = fmaf(X[4 * k4], c.x, a); a = fmaf(X[4 * k4 + 1], c.y, a);
-                            a = fmaf(X[4 * k4 + 2], c.z, a); a = fmaf(X[4 * k4 + 3], c.w, a);
+                        for (int i = 0; i < 12; i++) {
+                            float a = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], c_im12[i][k], a);
+                            y[w][i] = __fmul_rn(a, c_win[2][i]);
                         }
-                        const float4 c = C4[4];
-                        a = fmaf(X[16], c.x, a); a = fmaf(X[17], c.y, a);
-                        u[mm] = a;
-                    }
-                    const float* wrow = &S.win[bt][18 * (1 - half)];
 #pragma unroll
-                    for (int i = 0; i < 18; i++) {
-                        // half 1: output i uses u[idx36(i)] (9..17); half 0: output 18+i uses u[idx36(18+i)] (0..8)
-                        const float uv = half ? u[idx36(i) - 9] : u[idx36(18 + i)];
-                        o[i] = __fmul_rn(uv, wrow[i]);
-                    }
-                } else {
-                    // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window
-                    // order.  half 1 needs y0[0..11], y1[0..5]; half 0 needs y1[6..11], y2[0..11]: 18 dot products each.
-                    float y[18];
-#pragma unroll
-                    for (int d = 0; d < 18; d++) {
-                        const int w = half ? (d < 12 ? 0 : 1) : (d < 6 ? 1 : 2);
-                        const int i = half ? (d < 12 ? d : d - 12) : (d < 6 ? d + 6 : d - 6);
-                        const float4 c0 = *reinterpret_cast<const float4*>(&S.im12[i][0]);
-                        const float2 c1 = *reinterpret_cast<const float2*>(&S.im12[i][4]);
-                        float a = 0.0f;
-                        a = fmaf(X[w], c0.x, a); a = fmaf(X[3 + w], c0.y, a); a = fmaf(X[6 + w], c0.z, a);
-                        a = fmaf(X[9 + w], c0.w, a); a = fmaf(X[12 + w], c1.x, a); a = fmaf(X[15 + w], c1.y, a);
-                        y[d] = __fmul_rn(a, S.win[2][i]);
-                    }
-                    if (half) {
-#pragma unroll
-                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? 0.0f : (i < 12 ? y[i - 6] : __fadd_rn(y[i - 6], y[12 + (i - 12)]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 18; i++) o[i] = i < 6 ? __fadd_rn(y[i], y[6 + i]) : (i < 12 ? y[6 + i] : 0.0f);
+                    for (int i = 0; i < 6; i++) {
+                        o[i] = 0.0f;
+                        o[6 + i] = y[0][i];
+                        o[12 + i] = __fadd_rn(y[0][6 + i], y[1][i]);
+                        o[18 + i] = __fadd_rn(y[1][6 + i], y[2][i]);
+                        o[24 + i] = y[2][6 + i];
+                        o[30 + i] = 0.0f;
                     }
                 }
-                // frequency inversion is applied to both addends of the overlap-add: -(a+b) == (-a)+(-b)
-                float* dstp = half ? &S.F[gi_][ch][0][sb] : &S.S2[(gl + 1) % K2_RING][ch][0][sb];
-                const bool odd = sb & 1;
+                // frequency inversion (odd samples of odd subbands), applied to both addends of the overlap-add
+                const uint32_t sgn = (sb & 1) ? 0x80000000u : 0u;
 #pragma unroll
-                for (int i = 0; i < 18; i++) dstp[i * ROW] = (odd && (i & 1)) ? -o[i] : o[i];
-            }
-        }
-        __syncthreads();
-
-        // ================= P3: overlap-add + 32-point DCT-II per time slot (Lee), two threads per transform ================
-        // Warps 0..2 take the sum branch (even outputs), warps 3..5 the difference branch (odd outputs).
-        {
-            const int br = tid >= K2_THREADS / 2;
-            const int task = br ? tid - K2_THREADS / 2 : tid;     // (granule, channel, slot)
-            const int per_g = 18 * nch;
-            const int gi_ = task / per_g, rem = task - gi_ * per_g;
-            const int ch = rem / 18, t = rem - 18 * ch;
-            const uint32_t gl = gl0 + gi_;
-            if (gi_ < K2_G && gl < gcount) {
-                const float* xa = S.F[gi_][ch][t];
-                const float* xb = S.S2[gl % K2_RING][ch][t];
-                float z[16];
-                if (br == 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) z[i] = __fadd_rn(__fadd_rn(xa[i], xb[i]), __fadd_rn(xa[31 - i], xb[31 - i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        z[i] = __fmul_rn(__fsub_rn(__fadd_rn(xa[i], xb[i]), __fadd_rn(xa[31 - i], xb[31 - i])), c_dct_sec[i]);
-                }
-                Dct2<16, 16>::run(z);
-                float* dstrow = S.ring[ch][18 * (gl % K2_RING) + t];
-                if (br == 0) {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) dstrow[2 * k] = z[k];
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; k++) dstrow[2 * k + 1] = k < 15 ? __fadd_rn(z[k], z[k + 1]) : z[15];
+                for (int i = 0; i < 18; i++) {
+                    const float f = (i & 1) ? __uint_as_float(__float_as_uint(o[i]) ^ sgn) : o[i];
+                    const float s = (i & 1) ? __uint_as_float(__float_as_uint(o[18 + i]) ^ sgn) : o[18 + i];
+                    Aq[i * ROW + sb] = f;
+                    Sq[i * ROW + sb] = s;
                 }
             }
         }
         __syncthreads();
 
-        // ================= P4: polyphase window -> PCM; the two spare warps run P0 of the next batch ======================
-        if (tid < K2_G * 64) {
-            const int gi_ = tid >> 6, ch = (tid >> 5) & 1, j = lane;
-            const uint32_t gl = gl0 + gi_;
+        // ================= P3: overlap-add + 32-point DCT-II per time slot (Lee), in place ================================
+        // Threads 0..143 take one (granule-channel, slot) each; the idle warps prepare the next batch.
+        if (tid < 18 * K2_GC) {
+            const int q = tid / 18, t = tid - 18 * q;
+            const uint32_t g3 = gl0 + q / NCH;
+            if (g3 < gcount) {
+                float* a = S.A[(g3 % NS) * NCH + q % NCH] + t * ROW;
+                const float* s = S.S2[((g3 + NS - 1) % NS) * NCH + q % NCH] + t * ROW;
+                float x[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) x[i] = __fadd_rn(a[i], s[i]);
+                Dct2<32, 0>::run(x);
+#pragma unroll
+                for (int i = 0; i < 32; i++) a[i] = x[i];
+            }
+        } else if (warp >= 5 && b + 1 < n_batches) {
+            if (tid == 5 * 32) issue_copy(b + 1);   // P1 of this batch has consumed the staging buffer (barrier above)
+            for (int q = warp - 5; q < K2_GC; q += 3) p0_gc(b + 1, q);
+        }
+        __syncthreads();
+
+        // ================= P4: polyphase window -> PCM, lane = output column ==============================================
+        if (have && gfirst + gl >= run.g0) {
             const uint32_t g = gfirst + gl;
-            if (ch < nch && gl < gcount && g >= run.g0) {
-                // out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain); rows t-15..t-1 of slot 0
-                // live in the previous granule's ring slot (rows 3..17)
-                float wa[8], wb[8];
+            const int j = lane;
+            // out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain); rows t-15..t-1 of slot 0
+            // live in the previous granule's slot (rows 3..17)
+            float wa[8], wb[8];
 #pragma unroll
-                for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][j]; wb[p] = S.wb[p][j]; }
-                const int ia = S.ia[j], ib = S.ib[j];
-                const float* cur = S.ring[ch][18 * (gl % K2_RING)];
-                const float* prv = S.ring[ch][18 * ((gl + K2_RING - 1) % K2_RING) + 3];
-                float A[33], B[33];   // rows -15 .. 17 relative to this granule's slot 0
+            for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][j]; wb[p] = S.wb[p][j]; }
+            const int ia = S.ia[j], ib = S.ib[j];
+            const float* cur = S.A[slot];
+            const float* prv = S.A[slot_prev] + 3 * ROW;
+            float Av[33], Bv[33];   // rows -15 .. 17 relative to this granule's slot 0
 #pragma unroll
-                for (int r = 0; r < 15; r++) { A[r] = prv[r * ROW + ia]; B[r] = prv[r * ROW + ib]; }
-                float* dst = pcm + tr.pcm_off + (size_t)ch * tr.pcm_plane + (size_t)g * 576 + j;
+            for (int r = 0; r < 15; r++) { Av[r] = prv[r * ROW + ia]; Bv[r] = prv[r * ROW + ib]; }
+            float* dst = pcm + tr.pcm_off + (size_t)my_ch * tr.pcm_plane + (size_t)g * 576 + j;
 #pragma unroll
-                for (int t = 0; t < 18; t++) {
-                    A[15 + t] = cur[t * ROW + ia];
-                    B[15 + t] = cur[t * ROW + ib];
-                    float a = 0.0f;
+            for (int t = 0; t < 18; t++) {
+                Av[15 + t] = cur[t * ROW + ia];
+                Bv[15 + t] = cur[t * ROW + ib];
+                float a = 0.0f;
 #pragma unroll
-                    for (int p = 0; p < 8; p++) {
-                        a = fmaf(A[15 + t - 2 * p], wa[p], a);
-                        a = fmaf(B[15 + t - 2 * p - 1], wb[p], a);
-                    }
-                    if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
-                    dst[32 * t] = a;
+                for (int p = 0; p < 8; p++) {
+                    a = fmaf(Av[15 + t - 2 * p], wa[p], a);
+                    a = fmaf(Bv[15 + t - 2 * p - 1], wb[p], a);
                 }
+                if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
+                dst[32 * t] = a;
             }
-        } else if (b + 1 < n_batches) {
-            for (int q = warp - K2_G * 2; q < K2_G * nch; q += K2_THREADS / 32 - K2_G * 2) p0_gc(b + 1, q);
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 3)
+k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
+               const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
+               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
+    extern __shared__ __align__(16) unsigned char k2_raw[];
+    K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
+    const RunDesc run = runs[blockIdx.x];
+    const DecTrack tr = tracks[run.track];
+    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, pcm, flags);
+    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, pcm, flags);
 }

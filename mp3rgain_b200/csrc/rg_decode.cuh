@@ -186,5 +186,8 @@ static int decode_init_tables(DecodeScratch& ds) {
     if (cudaMemcpyToSymbol(c_dct_sec, L3_DCT_SEC, sizeof(float) * 31) != cudaSuccess) return -3;
     if (cudaMemcpyToSymbol(c_alias_cs, L3_ALIAS_CS, sizeof(float) * 8) != cudaSuccess) return -3;
     if (cudaMemcpyToSymbol(c_alias_ca, L3_ALIAS_CA, sizeof(float) * 8) != cudaSuccess) return -3;
+    if (cudaMemcpyToSymbol(c_dct4, L3_DCT4_18, sizeof(float) * 18 * 18) != cudaSuccess) return -3;
+    if (cudaMemcpyToSymbol(c_im12, L3_IMDCT12, sizeof(float) * 12 * 6) != cudaSuccess) return -3;
+    if (cudaMemcpyToSymbol(c_win, L3_WINSGN, sizeof(float) * 4 * 36) != cudaSuccess) return -3;
     return 0;
 }
