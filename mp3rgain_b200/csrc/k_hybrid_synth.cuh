@@ -54,19 +54,27 @@ struct K2Smem {
     alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
 };
 
-__constant__ float c_dct4[18][18];   // 18-point DCT-IV matrix (compile-time indices only -> constant-bank FFMA operands)
-__constant__ float c_im12[12][6];    // 12-point IMDCT matrix
-__constant__ float c_win[4][36];     // block-type windows with the IMDCT sign folded in
+// Compile-time loop: the body receives its index as an integral_constant, so table entries indexed with it are constant
+// expressions and reach the SASS as instruction immediates (FFMA/FMUL imm32) -- no constant-bank or uniform-register
+// traffic for the 324 matrix entries of the IMDCT, the window shapes or the DCT secants.
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
 
 template <int N, int OFF>
 struct Dct2 {
     static __device__ __forceinline__ void run(float (&x)[N]) {
         float g[N / 2], h[N / 2];
-#pragma unroll
-        for (int i = 0; i < N / 2; i++) {
+        static_for<0, N / 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr float sec = L3_DCT_SEC[OFF + i];
             g[i] = __fadd_rn(x[i], x[N - 1 - i]);
-            h[i] = __fmul_rn(__fsub_rn(x[i], x[N - 1 - i]), c_dct_sec[OFF + i]);
-        }
+            h[i] = __fmul_rn(__fsub_rn(x[i], x[N - 1 - i]), sec);
+        });
         Dct2<N / 2, OFF + N / 2>::run(g);
         Dct2<N / 2, OFF + N / 2>::run(h);
 #pragma unroll
@@ -181,8 +189,11 @@ __device__ __forceinline__ void k2_pair_sync(int pair) {   // immediate ids, so 
 // long-block window: o[i] = u[idx36(i)] * win[BT][i]
 template <int BT>
 __device__ __forceinline__ void k2_window36(const float (&u)[18], float (&o)[36]) {
-#pragma unroll
-    for (int i = 0; i < 36; i++) o[i] = __fmul_rn(u[idx36(i)], c_win[BT][i]);
+    static_for<0, 36>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr float w = L3_WINSGN[BT][i];
+        o[i] = __fmul_rn(u[idx36(i)], w);
+    });
 }
 
 template <int NCH>
@@ -367,24 +378,33 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 const bool lo_b = act && sb >= 1 && (gi.bt != 2 || (gi.mixed && sb == 1));
                 const bool hi_b = sb + 1 < limit && (gi.bt != 2 || (gi.mixed && sb == 0));
                 if (lo_b) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) X[i] = __fadd_rn(__fmul_rn(X[i], L3_CS(i)), __fmul_rn(lo[i], L3_CA(i)));
+                    static_for<0, 8>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr float cs = L3_ALIAS_CS[i], ca = L3_ALIAS_CA[i];
+                        X[i] = __fadd_rn(__fmul_rn(X[i], cs), __fmul_rn(lo[i], ca));
+                    });
                 }
                 if (hi_b) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) X[17 - i] = __fsub_rn(__fmul_rn(X[17 - i], L3_CS(i)), __fmul_rn(hi[i], L3_CA(i)));
+                    static_for<0, 8>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr float cs = L3_ALIAS_CS[i], ca = L3_ALIAS_CA[i];
+                        X[17 - i] = __fsub_rn(__fmul_rn(X[17 - i], cs), __fmul_rn(hi[i], ca));
+                    });
                 }
                 const bool is_short = gi.bt == 2 && !(gi.mixed && sb < 2);
                 float o[36];
                 if (!is_short) {
                     float u[18];
-#pragma unroll
-                    for (int m = 0; m < 18; m++) {
+                    static_for<0, 18>([&](auto mc) {
+                        constexpr int m = decltype(mc)::value;
                         float a = 0.0f;
-#pragma unroll
-                        for (int k = 0; k < 18; k++) a = fmaf(X[k], c_dct4[m][k], a);
+                        static_for<0, 18>([&](auto kc) {
+                            constexpr int k = decltype(kc)::value;
+                            constexpr float c = L3_DCT4_18[m][k];
+                            a = fmaf(X[k], c, a);
+                        });
                         u[m] = a;
-                    }
+                    });
                     const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
                     if (bt == 0) k2_window36<0>(u, o);
                     else if (bt == 1) k2_window36<1>(u, o);
@@ -392,15 +412,17 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 } else {
                     // three 12-point IMDCTs y_w (w = 0,1,2) placed at raw[6+6w ..]; overlaps added in ascending window order
                     float y[3][12];
-#pragma unroll
-                    for (int w = 0; w < 3; w++)
-#pragma unroll
-                        for (int i = 0; i < 12; i++) {
-                            float a = 0.0f;
-#pragma unroll
-                            for (int k = 0; k < 6; k++) a = fmaf(X[3 * k + w], c_im12[i][k], a);
-                            y[w][i] = __fmul_rn(a, c_win[2][i]);
-                        }
+                    static_for<0, 36>([&](auto wc) {
+                        constexpr int w = decltype(wc)::value / 12, i = decltype(wc)::value % 12;
+                        constexpr float win = L3_WINSGN[2][i];
+                        float a = 0.0f;
+                        static_for<0, 6>([&](auto kc) {
+                            constexpr int k = decltype(kc)::value;
+                            constexpr float c = L3_IMDCT12[i][k];
+                            a = fmaf(X[3 * k + w], c, a);
+                        });
+                        y[w][i] = __fmul_rn(a, win);
+                    });
 #pragma unroll
                     for (int i = 0; i < 6; i++) {
                         o[i] = 0.0f;

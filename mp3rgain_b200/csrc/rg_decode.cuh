@@ -13,6 +13,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 #include "rg_internal.h"
 #include "l3_tables.h"
@@ -47,10 +48,6 @@ struct L3Dev {
     uint8_t synth_ia[32], synth_ib[32];
 };
 
-__constant__ float c_dct_sec[31];   // Lee DCT-II secants: compile-time indices only -> constant-bank operands
-__constant__ float c_alias_cs[8], c_alias_ca[8];   // alias-reduction butterflies, same access pattern
-#define L3_CS(i) c_alias_cs[i]
-#define L3_CA(i) c_alias_ca[i]
 
 struct TrackIn { uint64_t off, len; };            // byte range of one file image inside the device corpus buffer
 struct TrackMeta {                                 // K0 output
@@ -183,11 +180,5 @@ static int decode_init_tables(DecodeScratch& ds) {
     memcpy(T.synth_ib, L3_SYNTH_IB, sizeof T.synth_ib);
     if (cudaMalloc(&ds.d_tab, sizeof(L3Dev)) != cudaSuccess) return -3;
     if (cudaMemcpy(ds.d_tab, &T, sizeof(L3Dev), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_dct_sec, L3_DCT_SEC, sizeof(float) * 31) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_alias_cs, L3_ALIAS_CS, sizeof(float) * 8) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_alias_ca, L3_ALIAS_CA, sizeof(float) * 8) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_dct4, L3_DCT4_18, sizeof(float) * 18 * 18) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_im12, L3_IMDCT12, sizeof(float) * 12 * 6) != cudaSuccess) return -3;
-    if (cudaMemcpyToSymbol(c_win, L3_WINSGN, sizeof(float) * 4 * 36) != cudaSuccess) return -3;
     return 0;
 }

@@ -139,7 +139,7 @@ def carr_f32(name, a, per=8):
     a = np.asarray(a, np.float32)
     flat = a.reshape(-1).tolist()
     shape = "".join(f"[{s}]" for s in a.shape)
-    lines = [f"static const float {name}{shape} = {{"]
+    lines = [f"L3_FCONST float {name}{shape} = {{"]
     for i in range(0, len(flat), per):
         lines.append("  " + ", ".join(float(v).hex() + "f" for v in flat[i:i + per]) + ",")
     lines.append("};")
@@ -152,6 +152,8 @@ def emit(path, guard, note):
              " * symbols, band widths sum to 576); float tables are float64 results frozen as float32 hex literals.\n"
              f" * {note}\n */")
     o.append(f"#ifndef {guard}\n#define {guard}\n#include <stdint.h>\n")
+    o.append("/* float tables are constexpr under C++ so that kernels can fold single entries into instruction immediates */\n"
+             "#ifdef __cplusplus\n#define L3_FCONST static constexpr\n#else\n#define L3_FCONST static const\n#endif")
     o.append("#define L3_NUM_HUFF 15")
     o.append(f"#define L3_HUFF_TOTAL {NH}")
     o.append("/* ISO table numbers of the 15 code books, their sizes and offsets into L3_HUFF_LEN/SYM */")

@@ -30,7 +30,8 @@ for r in rows:
         inst = int(rec["Instructions Executed"])
     except ValueError:
         continue
-    out.append((cur_file, int(r[0]), r[1].strip(), inst, int(rec["# Samples"]), rec))
+    smp = int(rec["# Samples"]) if rec["# Samples"].isdigit() else 0
+    out.append((cur_file, int(r[0]), r[1].strip(), inst, smp, rec))
 tot_i = sum(o[3] for o in out) or 1
 tot_s = sum(o[4] for o in out) or 1
 print(f"total warp-instructions {tot_i:,}   samples {tot_s:,}")
