@@ -39,6 +39,12 @@ k_frame_index(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
               const uint64_t* __restrict__ md_base, FrameRec* __restrict__ frames, uint8_t* __restrict__ md,
               TrackMeta* __restrict__ meta, uint32_t n_tracks, uint32_t flags) {
     __shared__ __align__(16) uint8_t s_chunk[K0_WARPS][K0_CHUNK + 16];
+    __shared__ uint16_t s_flen[3][16];   // MPEG-1 Layer III frame length without padding, by sample-rate and bitrate index
+    if (threadIdx.x < 48) {
+        const int sr = threadIdx.x >> 4, br = threadIdx.x & 15;
+        s_flen[sr][br] = (br == 0 || br == 15) ? 0 : (uint16_t)k0_frame_len(0xFFFA0000u | (br << 12) | (sr << 10));
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * K0_WARPS + warp;
     if (t >= n_tracks) return;
@@ -64,11 +70,13 @@ k_frame_index(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
     bool have_ref = false, in_sync = false, first = true;
     int status = -5;  // RG_ERR_PROBE until a frame is found
     uint32_t n_frames = 0, n_dropped = 0, skipped_info = 0, n_total = 0;
-    uint32_t M = 0;   // main-data bytes appended so far
+    uint32_t M = 0;   // main-data bytes accounted for so far
     uint64_t chunk_start = ~0ull, chunk_end = 0;
-    const bool done = false;
 
-    while (!done && pos + 4 <= len) {
+    // The walk itself only touches the 4 header bytes and the side info of each frame; the main data of every indexed frame
+    // is gathered into the track's contiguous stream afterwards by k_md_gather (fully parallel).  Only frames that are
+    // dropped from the index (they still feed the bit reservoir) are copied here, inline.
+    while (pos + 4 <= len) {
         // keep [pos, pos + 1448) inside the window (largest frame 1441 B + the next header), or up to EOF
         const uint64_t avail_end0 = chunk_end < len ? chunk_end : len;
         if (pos < chunk_start || pos >= chunk_end || (pos + 1448 > avail_end0 && avail_end0 < len)) {
@@ -93,7 +101,7 @@ k_frame_index(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
         bool ok = k0_hdr_valid(h) && (!have_ref || k0_compatible(h, ref));
         int flen = 0;
         if (ok) {
-            flen = k0_frame_len(h);
+            flen = (((h >> 19) & 3) == 3) ? (int)s_flen[(h >> 10) & 3][(h >> 12) & 15] + (int)((h >> 9) & 1) : k0_frame_len(h);
             if (pos + flen > len) break;  // truncated final frame = EOF (src/replaygain.rs:884-888)
         }
         if (ok && !in_sync) {  // (re)sync: the next header must confirm
@@ -126,36 +134,38 @@ k_frame_index(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
                 if (tag) { skipped_info = 1; continue; }
             }
         }
-        // side info: main_data_begin + validity (big_values <= 288, block_type != 0 when window switching)
+        // side info: main_data_begin + validity (big_values <= 288, block_type != 0 when window switching); lane = granule-channel
         const uint8_t* s = p + so;
         const int mdb = ((int)s[0] << 1) | (s[1] >> 7);
-        bool valid = true;
-        const int nch = mono ? 1 : 2;
-        for (int gc = 0; gc < 2 * nch; gc++) {
-            const int b0 = (mono ? 18 : 20) + 59 * gc;
+        bool bad = false;
+        if (lane < (mono ? 2 : 4)) {
+            const int b0 = (mono ? 18 : 20) + 59 * lane;
             const int bb = b0 + 12;  // big_values: 9 bits
             const uint32_t w = ((uint32_t)s[bb >> 3] << 16) | ((uint32_t)s[(bb >> 3) + 1] << 8) | s[(bb >> 3) + 2];
             const int bv = (w >> (24 - 9 - (bb & 7))) & 0x1FF;
             const int wb = b0 + 33;  // window_switching, block_type(2)
             const uint32_t w2 = ((uint32_t)s[wb >> 3] << 8) | s[(wb >> 3) + 1];
             const int ws_bt = (w2 >> (16 - 3 - (wb & 7))) & 7;
-            if (bv > 288) valid = false;
-            if ((ws_bt & 4) && !(ws_bt & 3)) valid = false;
+            bad = bv > 288 || ((ws_bt & 4) && !(ws_bt & 3));
         }
+        const bool valid = !__any_sync(0xffffffffu, bad);
         const int mdo_off = so + side_len;
         const int cap = flen > mdo_off ? flen - mdo_off : 0;
         const bool start_ok = (uint32_t)mdb <= M;
         const uint32_t start = M - (start_ok ? mdb : 0);
-        for (int b = lane; b < cap; b += 32) mdo[M + b] = p[mdo_off + b];  // all lanes: append the main data
-        M += cap;
         if (valid && start_ok) {
+            M += cap;
             if (lane == 0) {
                 FrameRec r;
                 r.file_off = fpos; r.md_start = start; r.hdr = h; r.md_end = M;
                 fr[n_frames] = r;
             }
             n_frames++;
-        } else n_dropped++;
+        } else {
+            for (int b = lane; b < cap; b += 32) mdo[M + b] = p[mdo_off + b];  // dropped frame: its main data still enters the reservoir
+            M += cap;
+            n_dropped++;
+        }
     }
     // zero padding after the stream so bit readers may over-read
     for (int b = lane; b < 16; b += 32) mdo[M + b] = 0;
@@ -169,5 +179,39 @@ k_frame_index(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
         }
         m.n_frames = n_frames; m.md_bytes = M; m.n_dropped = n_dropped; m.skipped_info = skipped_info; m.n_total = n_total;
         meta[t] = m;
+    }
+}
+
+// K0b: gathers the main data of every indexed frame into the track's contiguous stream (the bit reservoir unrolled).
+// One CTA per run of frames (the K2 run descriptors are reused: granules g0 .. g0+ng of a track), one warp per frame.
+#define K0B_THREADS 128
+__global__ void __launch_bounds__(K0B_THREADS)
+k_md_gather(const uint8_t* __restrict__ corpus, uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
+            const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs) {
+    const RunDesc run = runs[blockIdx.x];
+    const DecTrack tr = tracks[run.track];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t f0 = run.g0 >> 1, f1 = (run.g0 + run.ng + 1) >> 1;
+    for (uint32_t f = f0 + warp; f < f1; f += K0B_THREADS / 32) {
+        const FrameRec rec = frames[tr.frame_base + f];
+        const uint32_t h = rec.hdr;
+        const int off = 4 + ((h & 0x10000u) ? 0 : 2) + ((((h >> 6) & 3) == 3) ? 17 : 32);
+        const int flen = k0_frame_len(h);
+        const int cap = flen > off ? flen - off : 0;
+        const uint8_t* src = corpus + tr.corpus_off + rec.file_off + off;
+        uint8_t* dst = md + tr.md_off + rec.md_end - cap;
+        // head bytes up to the first 4-byte boundary of dst, aligned words, tail bytes; the source is read bytewise
+        // through L1 (each sector is reused by neighbouring lanes)
+        const int head = min(cap, (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3));
+        if (lane < head) dst[lane] = __ldg(src + lane);
+        const int nw = (cap - head) >> 2;
+        const uint8_t* s4 = src + head;
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+        for (int w = lane; w < nw; w += 32) {
+            const uint8_t* q = s4 + 4 * w;
+            d4[w] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+        }
+        const int tail0 = head + 4 * nw;
+        if (tail0 + lane < cap) dst[tail0 + lane] = __ldg(src + tail0 + lane);
     }
 }

@@ -69,37 +69,70 @@ struct PcmTrack {
     int status = RG_OK;
 };
 
+// Everything one in-flight batch of tracks owns.  Two of these alternate, so that the decode kernels of batch k+1
+// (integer / f32 work) run while the IIR of batch k keeps the FP64 pipe busy, and the host plans batch k+1 meanwhile.
+struct BatchCtx {
+    // stage A scratch
+    DevBuf d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_pcm;
+    // stage B scratch
+    DevBuf d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_perm;
+    HostBuf h_desc_a, h_desc, h_tout;      // pinned: descriptor staging (decode / analysis), results
+    cudaEvent_t ev_a[4] = {};              // decode stream: gather start, K1 end = K2 start, K2 end, gather end = K1 start
+    cudaEvent_t ev_b[4] = {};              // analysis stream: K4 start, K4 end = K5 start, K5 end, results on the host
+    // host bookkeeping of the batch in flight
+    bool busy = false, decoded = false, exact = false;
+    std::vector<uint32_t> ids;             // caller-side index of every track of the batch
+    std::vector<PcmTrack> pt;
+    size_t n_chains = 0;
+    uint32_t* hist_host = nullptr;         // where this batch's per-track histograms go (n x 12000), or null
+    std::vector<DevBuf*> bufs() {
+        return {&d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_pcm, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_perm};
+    }
+};
+
 struct rg_engine {
     int device = 0;
     uint32_t flags = 0;
     uint64_t scratch_bytes = 0;
-    cudaStream_t stream = nullptr;
+    // streams: file images in (copy), frame index (index), Huffman + hybrid (decode), IIR + histogram (stream)
+    cudaStream_t stream = nullptr, s_copy = nullptr, s_index = nullptr, s_dec = nullptr;
+    cudaStream_t s_index_x[3] = {};       // more index streams: K0 is latency-bound, so groups overlap each other
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> ev_pool;     // per-group events of the pipelined path (grown on demand)
     // options
     uint32_t block_windows = 16, warm_windows = 1;
+    bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
     RgCoefFast coef_fast[12];
     double edge_tol = 1e-9;
-    // device scratch
-    DevBuf d_pcm_in, d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_album, d_album_peak, d_misc;
-    // stage A scratch
-    DevBuf d_tin, d_fbase, d_frames, d_md, d_meta, d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_pcm;
-    HostBuf h_stage, h_tout;
+    BatchCtx ctx[2];
+    // device scratch that lives across batches
+    DevBuf d_pcm_in, d_album, d_album_peak, d_misc;
+    DevBuf d_tin, d_fbase, d_frames, d_md, d_meta;
+    DevBuf d_corpus;                      // file images of rg_analyze_tracks / rg_analyze_album (kept between calls)
+    HostBuf h_meta;
     rg_stats stats = {};
     DecodeScratch dec;
-    bool pending_decode_timing = false;
     std::vector<DevBuf*> all_bufs() {
-        return {&d_pcm_in, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_album, &d_album_peak, &d_misc,
-                &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_pcm};
+        std::vector<DevBuf*> v = {&d_pcm_in, &d_album, &d_album_peak, &d_misc, &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_corpus};
+        for (auto& c : ctx) for (DevBuf* b : c.bufs()) v.push_back(b);
+        return v;
+    }
+    cudaEvent_t pool_event(size_t i) {
+        while (ev_pool.size() <= i) { cudaEvent_t x = nullptr; cudaEventCreate(&x); ev_pool.push_back(x); }
+        return ev_pool[i];
     }
 };
 
 struct rg_corpus {
-    DevBuf d_bytes;
+    DevBuf d_own;                          // owned storage (rg_corpus_upload); empty when the corpus borrows e->d_corpus
+    uint8_t* d_bytes = nullptr;
     std::vector<uint64_t> off, len;
     std::vector<int32_t> track_index;
     std::vector<uint8_t> is_mp4;
     uint64_t total = 0;
+    // host sources still being copied in (the end-to-end path): group g of tracks is resident once ev_copied[g] fires
+    const rg_input* pending_in = nullptr;
 };
 
 static int rate_index(uint32_t sr) {
@@ -155,7 +188,15 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     e->flags = cfg ? cfg->flags : 0;
     e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (24ull << 30);
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_index, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->s_dec, cudaStreamNonBlocking));
+    for (auto& st : e->s_index_x) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
+    for (auto& c : e->ctx) {
+        for (auto& ev : c.ev_a) CK(cudaEventCreate(&ev));
+        for (auto& ev : c.ev_b) CK(cudaEventCreate(&ev));
+    }
     // coefficient rows as K4 wants them, b's of the Yule stage pre-scaled by 2^15 (see k_analysis.cuh)
     for (int r = 0; r < 12; r++) {
         const double* row = RG_COEFS[r];   // [0..10] yule_a, [11..21] yule_b, [22..24] butter_a, [25..27] butter_b
@@ -186,13 +227,20 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
 extern "C" void rg_engine_destroy(rg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    cudaDeviceSynchronize();
     for (DevBuf* b : e->all_bufs()) b->release();
-    e->h_stage.release();
-    e->h_tout.release();
+    e->h_meta.release();
     e->dec.release();
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    for (auto& ev : e->ev_pool) if (ev) cudaEventDestroy(ev);
+    for (auto& c : e->ctx) {
+        c.h_desc.release();
+        c.h_desc_a.release();
+        c.h_tout.release();
+        for (auto& ev : c.ev_a) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : c.ev_b) if (ev) cudaEventDestroy(ev);
+    }
+    for (cudaStream_t st : {e->stream, e->s_copy, e->s_index, e->s_dec, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2]}) if (st) cudaStreamDestroy(st);
     delete e;
 }
 
@@ -201,6 +249,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_block_windows")) { if (value < 1) return RG_ERR_INVALID_ARG; e->block_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
+    if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "exact_iir")) { if (value != 0) e->flags |= RG_FLAG_EXACT_IIR; else e->flags &= ~RG_FLAG_EXACT_IIR; return RG_OK; }
     return RG_ERR_INVALID_ARG;
 }
@@ -212,22 +261,33 @@ extern "C" int rg_engine_stats(rg_engine* e, rg_stats* out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stage B over device-resident PCM.  `tracks` entries with status != RG_OK or frames == 0 are skipped
+// Stage B over device-resident PCM.  Tracks with status != RG_OK or frames == 0 contribute no windows
 // (frames == 0 yields the reference's empty-histogram answer: -20 dB).
-struct StageBOut {
-    std::vector<RgTrackOut> res;     // per track
-    std::vector<uint8_t> rerun;      // per track: exact kernel re-ran it
-};
+// Descriptor tables reach the device through a tiny kernel that reads the batch's pinned staging buffer over the bus, not
+// through cudaMemcpyAsync: the H2D copy engine is a FIFO that the end-to-end path keeps full of file images, and a
+// descriptor copy queued behind them would stall the kernels of the batches that are already resident.
+__global__ void k_fetch_desc(uint4* __restrict__ dst, const uint4* __restrict__ src_pinned, uint32_t n16) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16) dst[i] = src_pinned[i];
+}
+static int fetch_desc(rg_engine* e, cudaStream_t st, void* dst, const void* src_pinned, size_t bytes) {
+    if (!bytes) return RG_OK;
+    const uint32_t n16 = (uint32_t)((bytes + 15) / 16);
+    k_fetch_desc<<<(n16 + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(src_pinned), n16);
+    e->stats.kernel_launches++;
+    e->stats.h2d_bytes += bytes;
+    CK(cudaGetLastError());
+    return RG_OK;
+}
+static inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, const std::vector<uint32_t>& which,
-                         bool exact, double* d_wsum_base, float* d_wmax_base, std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin,
-                         size_t& wsum_doubles) {
-    // wsum layout: for each selected track, channel 0 windows then channel 1 windows
+static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, bool exact, double* d_wsum_base, float* d_wmax_base,
+                         std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin, size_t& wsum_doubles) {
+    // wsum layout: for each track, channel 0 windows then channel 1 windows
     chains.clear();
     twin.clear();
     size_t woff = 0;
-    for (uint32_t ti : which) {
-        const PcmTrack& t = tracks[ti];
+    for (const PcmTrack& t : tracks) {
         RgTrackWin tw{};
         uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
         uint32_t n_full = 0, rem = 0;
@@ -278,138 +338,116 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
     wsum_doubles = woff;
 }
 
-// Runs K4 (+K5) for the selected tracks.  Outputs land in d_tout[slot] / d_hist[slot] where slot = position in `which`.
-static int launch_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, const std::vector<uint32_t>& which, bool exact,
-                          bool want_hist, unsigned long long* d_album_hist, unsigned long long* d_album_peak,
-                          bool defer_album_on_edge, std::vector<RgTrackOut>& h_out, uint32_t* hist_host, size_t hist_stride_tracks) {
-    (void)hist_stride_tracks;
-    const size_t n = which.size();
+// Enqueues K4 (+K5) for the tracks in c.pt on the analysis stream and the copy of their results back to pinned memory.
+// Nothing here waits for the device: stage_b_collect() does.
+static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist, unsigned long long* d_album_hist,
+                           unsigned long long* d_album_peak, bool defer_album_on_edge, bool after_decode) {
+    const size_t n = c.pt.size();
+    c.exact = exact;
+    c.n_chains = 0;
     if (!n) return RG_OK;
-    // size the window-sum buffer first
     size_t total_w = 0;
-    for (uint32_t ti : which) {
-        const PcmTrack& t = tracks[ti];
+    for (const PcmTrack& t : c.pt) {
         uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
         if (t.status == RG_OK && t.frames > 0 && win > 0) total_w += (size_t)((t.frames + win - 1) / win) * (t.nch >= 2 ? 2 : 1);
     }
-    CK(e->d_wsum.ensure(std::max<size_t>(total_w, 1) * sizeof(double)));
-    CK(e->d_wmax.ensure(std::max<size_t>(total_w, 1) * sizeof(float)));
+    CK(c.d_wsum.ensure(std::max<size_t>(total_w, 1) * sizeof(double)));
+    CK(c.d_wmax.ensure(std::max<size_t>(total_w, 1) * sizeof(float)));
     std::vector<RgChain> chains;
     std::vector<RgTrackWin> twin;
     size_t wd = 0;
-    build_chains(e, tracks, which, exact, e->d_wsum.as<double>(), e->d_wmax.as<float>(), chains, twin, wd);
+    build_chains(e, c.pt, exact, c.d_wsum.as<double>(), c.d_wmax.as<float>(), chains, twin, wd);
     for (auto& tw : twin) tw.flags = (d_album_hist != nullptr) ? 1u : 0u;
+    c.n_chains = chains.size();
 
     // group chains by sample rate so each launch reads one coefficient row through uniform constant operands
-    std::vector<uint32_t> order(chains.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
     bool mixed = false;
     for (size_t i = 1; i < chains.size(); i++) if (chains[i].rate_idx != chains[0].rate_idx) { mixed = true; break; }
-    std::vector<RgChain> sorted;
-    std::vector<uint32_t> newpos;
+    std::vector<uint32_t> order;
     if (mixed) {
+        order.resize(chains.size());
+        for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return chains[a].rate_idx < chains[b].rate_idx; });
-        // peaks are indexed by ORIGINAL chain id (the K5 track ranges), so keep a per-chain slot in the sorted copy
-        sorted.resize(chains.size());
-        newpos.resize(chains.size());
-        for (uint32_t i = 0; i < order.size(); i++) { sorted[i] = chains[order[i]]; newpos[i] = order[i]; }
     }
-    const std::vector<RgChain>& launch_chains = mixed ? sorted : chains;
 
-    CK(e->d_chains.ensure(std::max<size_t>(chains.size(), 1) * sizeof(RgChain)));
-    CK(e->d_peaks.ensure(std::max<size_t>(chains.size(), 1) * sizeof(float) * 2));
-    CK(e->d_twin.ensure(n * sizeof(RgTrackWin)));
-    CK(e->d_tout.ensure(n * sizeof(RgTrackOut)));
-    if (want_hist) CK(e->d_hist.ensure(n * RG_HIST_BINS * sizeof(uint32_t)));
-    if (!chains.empty())
-        CK(cudaMemcpyAsync(e->d_chains.p, launch_chains.data(), chains.size() * sizeof(RgChain), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_twin.p, twin.data(), n * sizeof(RgTrackWin), cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += chains.size() * sizeof(RgChain) + n * sizeof(RgTrackWin);
+    // descriptors travel through this batch's pinned staging buffer: [chains (launch order)] [twin] [perm]
+    const size_t b_ch = up16(chains.size() * sizeof(RgChain)), b_tw = up16(n * sizeof(RgTrackWin)), b_pm = mixed ? up16(chains.size() * sizeof(uint32_t)) : 0;
+    CK(c.h_desc.ensure(b_ch + b_tw + b_pm + 64));
+    uint8_t* hd = c.h_desc.as<uint8_t>();
+    RgChain* h_ch = reinterpret_cast<RgChain*>(hd);
+    if (mixed) for (size_t i = 0; i < order.size(); i++) h_ch[i] = chains[order[i]];
+    else if (b_ch) memcpy(h_ch, chains.data(), chains.size() * sizeof(RgChain));
+    memcpy(hd + b_ch, twin.data(), n * sizeof(RgTrackWin));
+    if (mixed) memcpy(hd + b_ch + b_tw, order.data(), chains.size() * sizeof(uint32_t));   // peaks are indexed by ORIGINAL chain id (the K5 track ranges)
 
-    float* d_peaks_sorted = e->d_peaks.as<float>();                      // written by K4 in launch order
-    float* d_peaks_orig = e->d_peaks.as<float>() + chains.size();        // original order (only when mixed)
-    CK(cudaEventRecord(e->ev[4], e->stream));
+    CK(c.d_chains.ensure(std::max<size_t>(chains.size(), 1) * sizeof(RgChain)));
+    CK(c.d_peaks.ensure(std::max<size_t>(chains.size(), 1) * sizeof(float) * 2));
+    CK(c.d_twin.ensure(up16(n * sizeof(RgTrackWin))));
+    CK(c.d_tout.ensure(n * sizeof(RgTrackOut)));
+    CK(c.h_tout.ensure(n * sizeof(RgTrackOut)));
+    if (want_hist) CK(c.d_hist.ensure(n * RG_HIST_BINS * sizeof(uint32_t)));
+    if (mixed) CK(c.d_perm.ensure(b_pm));   // (all DevBufs carry >= 256 bytes of slack, so 16-byte granular fetches stay inside)
+    cudaStream_t st = e->stream;
+    if (int r = fetch_desc(e, st, c.d_chains.p, h_ch, b_ch)) return r;
+    if (int r = fetch_desc(e, st, c.d_twin.p, hd + b_ch, b_tw)) return r;
+    if (mixed) if (int r = fetch_desc(e, st, c.d_perm.p, hd + b_ch + b_tw, b_pm)) return r;
+    if (after_decode) CK(cudaStreamWaitEvent(st, c.ev_a[2], 0));
+
+    float* d_peaks_sorted = c.d_peaks.as<float>();                      // written by K4 in launch order
+    float* d_peaks_orig = c.d_peaks.as<float>() + chains.size();        // original order (only when mixed)
+    CK(cudaEventRecord(c.ev_b[0], st));
     size_t i0 = 0;
-    while (i0 < launch_chains.size()) {
+    while (i0 < chains.size()) {
         size_t i1 = i0;
-        uint32_t r = launch_chains[i0].rate_idx;
-        while (i1 < launch_chains.size() && launch_chains[i1].rate_idx == r) i1++;
-        uint32_t cnt = (uint32_t)(i1 - i0);
+        const uint32_t r = h_ch[i0].rate_idx;
+        while (i1 < chains.size() && h_ch[i1].rate_idx == r) i1++;
+        const uint32_t cnt = (uint32_t)(i1 - i0);
         const int T = exact ? K4_EXACT_THREADS : K4_FAST_THREADS;
-        uint32_t blocks = (cnt + T - 1) / T;
+        const uint32_t blocks = (cnt + T - 1) / T;
+        // peaks[chain_base + ci], ci relative to the sub-array of this launch
         if (exact)
-            k_iir_exact<<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_exact[r]);
+            k_iir_exact<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_exact[r]);
         else
-            k_iir_fast<<<blocks, T, 0, e->stream>>>(e->d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
-        // note: chain_base passed as i0 but the kernel indexes peaks[chain_base + ci] with ci relative to the sub-array
+            k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         e->stats.kernel_launches++;
         i0 = i1;
     }
     CK(cudaGetLastError());
     const float* d_peaks_for_k5 = d_peaks_sorted;
     if (mixed) {
-        // scatter peaks back to original chain order with a tiny gather on the host-provided permutation
-        CK(e->d_misc.ensure(chains.size() * sizeof(uint32_t)));
-        CK(cudaMemcpyAsync(e->d_misc.p, newpos.data(), chains.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-        k_scatter_f32<<<(unsigned)((chains.size() + 255) / 256), 256, 0, e->stream>>>(d_peaks_sorted, e->d_misc.as<uint32_t>(), d_peaks_orig,
-                                                                                      (uint32_t)chains.size());
+        k_scatter_f32<<<(unsigned)((chains.size() + 255) / 256), 256, 0, st>>>(d_peaks_sorted, c.d_perm.as<uint32_t>(), d_peaks_orig,
+                                                                            (uint32_t)chains.size());
         e->stats.kernel_launches++;
         d_peaks_for_k5 = d_peaks_orig;
     }
-    CK(cudaEventRecord(e->ev[5], e->stream));
+    CK(cudaEventRecord(c.ev_b[1], st));
     const double tol = exact ? 1e-9 : e->edge_tol;
-    k_hist_percentile<<<(unsigned)n, K5_THREADS, 0, e->stream>>>(e->d_twin.as<RgTrackWin>(), d_peaks_for_k5, e->d_tout.as<RgTrackOut>(),
-                                                               want_hist ? e->d_hist.as<uint32_t>() : nullptr, d_album_hist,
-                                                               d_album_peak, tol, defer_album_on_edge ? 1 : 0, exact ? 0 : 1);
+    k_hist_percentile<<<(unsigned)n, K5_THREADS, 0, st>>>(c.d_twin.as<RgTrackWin>(), d_peaks_for_k5, c.d_tout.as<RgTrackOut>(),
+                                                        want_hist ? c.d_hist.as<uint32_t>() : nullptr, d_album_hist, d_album_peak, tol,
+                                                        defer_album_on_edge ? 1 : 0, exact ? 0 : 1);
     e->stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev[6], e->stream));
-    h_out.resize(n);
-    CK(e->h_tout.ensure(n * sizeof(RgTrackOut)));
-    CK(cudaMemcpyAsync(e->h_tout.p, e->d_tout.p, n * sizeof(RgTrackOut), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(c.ev_b[2], st));
+    CK(cudaMemcpyAsync(c.h_tout.p, c.d_tout.p, n * sizeof(RgTrackOut), cudaMemcpyDeviceToHost, st));
     e->stats.d2h_bytes += n * sizeof(RgTrackOut);
-    if (hist_host && want_hist) {
-        CK(cudaMemcpyAsync(hist_host, e->d_hist.p, n * RG_HIST_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (c.hist_host && want_hist) {
+        CK(cudaMemcpyAsync(c.hist_host, c.d_hist.p, n * RG_HIST_BINS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         e->stats.d2h_bytes += n * RG_HIST_BINS * sizeof(uint32_t);
     }
-    CK(cudaStreamSynchronize(e->stream));
-    memcpy(h_out.data(), e->h_tout.p, n * sizeof(RgTrackOut));
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]) == cudaSuccess) e->stats.last_ms_iir += ms;
-    if (cudaEventElapsedTime(&ms, e->ev[5], e->ev[6]) == cudaSuccess) e->stats.last_ms_hist += ms;
+    CK(cudaEventRecord(c.ev_b[3], st));
     return RG_OK;
 }
 
-// Full stage B with the time-blocked pass + exact re-run of edge-flagged tracks (or exact for all when RG_FLAG_EXACT_IIR).
-// hist_host: null or tracks.size()*12000 u32.  d_album_*: device accumulators or null.
-static int run_stage_b(rg_engine* e, const std::vector<PcmTrack>& tracks, std::vector<RgTrackOut>& res, std::vector<uint8_t>& rerun,
-                       uint32_t* hist_host, unsigned long long* d_album_hist, unsigned long long* d_album_peak) {
-    const size_t n = tracks.size();
-    res.assign(n, RgTrackOut{});
-    rerun.assign(n, 0);
-    std::vector<uint32_t> all(n);
-    for (uint32_t i = 0; i < n; i++) all[i] = i;
-    const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0;
-    std::vector<RgTrackOut> out;
-    int rc = launch_stage_b(e, tracks, all, exact, hist_host != nullptr, d_album_hist, d_album_peak, !exact, out, hist_host, n);
-    if (rc != RG_OK) return rc;
-    for (size_t i = 0; i < n; i++) res[i] = out[i];
-    if (exact) return RG_OK;
-    std::vector<uint32_t> flagged;
-    for (uint32_t i = 0; i < n; i++) if (res[i].n_edge > 0) flagged.push_back(i);
-    if (flagged.empty()) return RG_OK;
-    std::vector<uint32_t> hist_tmp;
-    if (hist_host) hist_tmp.resize(flagged.size() * RG_HIST_BINS);
-    rc = launch_stage_b(e, tracks, flagged, true, hist_host != nullptr, d_album_hist, d_album_peak, false, out,
-                        hist_host ? hist_tmp.data() : nullptr, flagged.size());
-    if (rc != RG_OK) return rc;
-    for (size_t k = 0; k < flagged.size(); k++) {
-        uint32_t i = flagged[k];
-        res[i] = out[k];
-        rerun[i] = 1;
-        if (hist_host) memcpy(hist_host + (size_t)i * RG_HIST_BINS, hist_tmp.data() + k * RG_HIST_BINS, RG_HIST_BINS * sizeof(uint32_t));
-    }
-    e->stats.exact_reruns += flagged.size();
+// Waits for the batch's results and returns them (one RgTrackOut per track of c.pt).
+static int stage_b_collect(rg_engine* e, BatchCtx& c, std::vector<RgTrackOut>& out) {
+    const size_t n = c.pt.size();
+    out.assign(n, RgTrackOut{});
+    if (!n) return RG_OK;
+    CK(cudaEventSynchronize(c.ev_b[3]));
+    memcpy(out.data(), c.h_tout.p, n * sizeof(RgTrackOut));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c.ev_b[0], c.ev_b[1]) == cudaSuccess) e->stats.last_ms_iir += ms;
+    if (cudaEventElapsedTime(&ms, c.ev_b[1], c.ev_b[2]) == cudaSuccess) e->stats.last_ms_hist += ms;
     return RG_OK;
 }
 
@@ -455,12 +493,24 @@ extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int 
         t.d_ch[c] = d;
         e->stats.h2d_bytes += frames * sizeof(float);
     }
-    std::vector<PcmTrack> tracks{t};
+    // time-blocked pass, then the exact kernel if any window sat on a bin edge (or exact straight away in parity mode)
+    BatchCtx& c = e->ctx[0];
+    c.pt.assign(1, t);
+    c.hist_host = hist_out;
+    const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0;
     std::vector<RgTrackOut> res;
-    std::vector<uint8_t> rerun;
-    int rc = run_stage_b(e, tracks, res, rerun, hist_out, nullptr, nullptr);
+    int rc = stage_b_enqueue(e, c, exact, hist_out != nullptr, nullptr, nullptr, false, false);
+    if (rc == RG_OK) rc = stage_b_collect(e, c, res);
+    uint8_t rerun = 0;
+    if (rc == RG_OK && !exact && res[0].n_edge > 0) {
+        rc = stage_b_enqueue(e, c, true, hist_out != nullptr, nullptr, nullptr, false, false);
+        if (rc == RG_OK) rc = stage_b_collect(e, c, res);
+        rerun = 1;
+        e->stats.exact_reruns++;
+    }
+    c.hist_host = nullptr;
     if (rc != RG_OK) return rc;
-    fill_result(out, t, res[0], rerun[0], 0);
+    fill_result(out, t, res[0], rerun, 0);
     e->stats.tracks += 1;
     return RG_OK;
 }

@@ -1,5 +1,13 @@
 // rg_engine_decode.inl -- entry points that run the MP3 decode kernels (stage A) and feed stage B.
 // Included at the end of rg_engine.cu.
+//
+// The whole path is a pipeline over four streams:
+//   copy    file images host -> HBM, group by group                       (end-to-end entry points only)
+//   index   K0 per group as soon as its bytes are resident; frame counts back to pinned memory
+//   decode  K1 + K2 of batch k+1                                           (integer + f32 pipes)
+//   main    K4 + K5 of batch k, results back to pinned memory              (FP64 pipe)
+// The host plans batch k+1 (run / chain descriptors need K0's frame counts) while the device works on batch k; two
+// BatchCtx alternate, each with half of the scratch budget.
 
 #define RUN_GRANULES 62   // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
 
@@ -15,32 +23,40 @@ static bool sniff_mp4(const uint8_t* d, uint64_t len) {
     return false;
 }
 
+// Host-side description of n file images laid out back to back (16-byte aligned starts, >= 16 bytes of slack)
+static int corpus_describe(rg_corpus* c, const rg_input* in, size_t n) {
+    c->off.resize(n); c->len.resize(n); c->track_index.resize(n); c->is_mp4.resize(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (in[i].len && !in[i].data) return RG_ERR_INVALID_ARG;
+        c->off[i] = total;
+        c->len[i] = in[i].len;
+        c->track_index[i] = in[i].track_index;
+        c->is_mp4[i] = sniff_mp4(in[i].data, in[i].len) ? 1 : 0;
+        total += (in[i].len + 16 + 15) & ~15ull;
+    }
+    c->total = total;
+    return RG_OK;
+}
+
 extern "C" int rg_corpus_upload(rg_engine* e, const rg_input* in, size_t n, rg_corpus** out) {
     if (!e || !out || (n && !in)) return RG_ERR_INVALID_ARG;
     *out = nullptr;
     CK(cudaSetDevice(e->device));
     rg_corpus* c = new rg_corpus();
-    c->off.resize(n); c->len.resize(n); c->track_index.resize(n); c->is_mp4.resize(n);
-    uint64_t total = 0;
-    for (size_t i = 0; i < n; i++) {
-        if (in[i].len && !in[i].data) { delete c; return RG_ERR_INVALID_ARG; }
-        c->off[i] = total;
-        c->len[i] = in[i].len;
-        c->track_index[i] = in[i].track_index;
-        c->is_mp4[i] = sniff_mp4(in[i].data, in[i].len) ? 1 : 0;
-        total += (in[i].len + 16 + 15) & ~15ull;   // 16-byte aligned start, >= 16 bytes of slack
-    }
-    c->total = total;
-    cudaError_t err = c->d_bytes.ensure(total + 64);
+    int rc = corpus_describe(c, in, n);
+    if (rc != RG_OK) { delete c; return rc; }
+    cudaError_t err = c->d_own.ensure(c->total + 64);
     if (err != cudaSuccess) { delete c; return fail_cuda(err, "cudaMalloc(corpus)", __LINE__); }
+    c->d_bytes = c->d_own.as<uint8_t>();
     for (size_t i = 0; i < n; i++) {
         if (!in[i].len) continue;
-        err = cudaMemcpyAsync(c->d_bytes.as<uint8_t>() + c->off[i], in[i].data, in[i].len, cudaMemcpyHostToDevice, e->stream);
-        if (err != cudaSuccess) { c->d_bytes.release(); delete c; return fail_cuda(err, "cudaMemcpyAsync(corpus)", __LINE__); }
+        err = cudaMemcpyAsync(c->d_bytes + c->off[i], in[i].data, in[i].len, cudaMemcpyHostToDevice, e->stream);
+        if (err != cudaSuccess) { c->d_own.release(); delete c; return fail_cuda(err, "cudaMemcpyAsync(corpus)", __LINE__); }
         e->stats.h2d_bytes += in[i].len;
     }
     err = cudaStreamSynchronize(e->stream);
-    if (err != cudaSuccess) { c->d_bytes.release(); delete c; return fail_cuda(err, "cudaStreamSynchronize", __LINE__); }
+    if (err != cudaSuccess) { c->d_own.release(); delete c; return fail_cuda(err, "cudaStreamSynchronize", __LINE__); }
     *out = c;
     return RG_OK;
 }
@@ -48,7 +64,7 @@ extern "C" int rg_corpus_upload(rg_engine* e, const rg_input* in, size_t n, rg_c
 extern "C" void rg_corpus_free(rg_engine* e, rg_corpus* c) {
     if (!c) return;
     if (e) cudaSetDevice(e->device);
-    c->d_bytes.release();
+    c->d_own.release();
     delete c;
 }
 
@@ -59,92 +75,146 @@ extern "C" uint64_t rg_corpus_bytes(const rg_corpus* c) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-struct DecodeOut {          // what a decode pass leaves behind for its caller
-    std::vector<TrackMeta> meta;
-    std::vector<int> status;            // rg_status per track after host-side checks
+struct IndexPlan {                      // K0 bookkeeping of one analyse call
+    std::vector<uint64_t> frame_base, md_base;
+    std::vector<size_t> group_begin;    // tracks [group_begin[g], group_begin[g+1]) form index group g
+    std::vector<int> status;            // rg_status per track after host-side checks (valid once its group is absorbed)
     std::vector<uint32_t> sample_rate;
+    size_t groups_absorbed = 0;
+    const TrackMeta* meta = nullptr;    // pinned, written by the index stream
 };
 
-// K0 over the whole corpus.  Leaves FrameRec / main-data / meta on the device (e->dec_*), meta on the host.
-static int run_frame_index(rg_engine* e, rg_corpus* c, DecodeOut& d, std::vector<uint64_t>& frame_base, std::vector<uint64_t>& md_base) {
+// Enqueues the copy (if the corpus still lives in host memory) and K0 of every group.  Returns without waiting.
+static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     const size_t n = c->len.size();
-    d.meta.assign(n, TrackMeta{});
-    d.status.assign(n, RG_OK);
-    d.sample_rate.assign(n, 0);
-    frame_base.resize(n + 1);
-    md_base.resize(n + 1);
+    ip.status.assign(n, RG_OK);
+    ip.sample_rate.assign(n, 0);
+    ip.frame_base.resize(n + 1);
+    ip.md_base.resize(n + 1);
+    ip.group_begin.clear();
+    ip.groups_absorbed = 0;
     std::vector<TrackIn> tin(n);
-    uint64_t fb = 0, mb = 0;
+    uint64_t fb = 0, mb = 0, bytes = 0;
     for (size_t i = 0; i < n; i++) {
         tin[i].off = c->off[i]; tin[i].len = c->len[i];
-        frame_base[i] = fb; md_base[i] = mb;
+        ip.frame_base[i] = fb; ip.md_base[i] = mb;
         fb += c->len[i] / 96 + 2;                      // smallest MPEG-1 Layer III frame is 96 bytes
         mb += (c->len[i] + 32 + 15) & ~15ull;
+        bytes += c->len[i];
     }
-    frame_base[n] = fb; md_base[n] = mb;
+    ip.frame_base[n] = fb; ip.md_base[n] = mb;
+    // index groups: one when the corpus is already resident (K0 is a serial walk per track, so its time does not depend on
+    // the number of tracks); about eight, never smaller than 32 MiB, when the bytes are still arriving from the host, so
+    // that indexing starts as soon as the first group has landed
+    const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, 32ull << 20) : ~0ull;
+    uint64_t acc = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (i == 0 || acc >= gbytes) { ip.group_begin.push_back(i); acc = 0; }
+        acc += c->len[i];
+    }
+    ip.group_begin.push_back(n);
     if (!n) return RG_OK;
     CK(e->d_tin.ensure(n * sizeof(TrackIn)));
     CK(e->d_fbase.ensure((n + 1) * sizeof(uint64_t) * 2));
     CK(e->d_frames.ensure(fb * sizeof(FrameRec)));
     CK(e->d_md.ensure(mb + 64));
     CK(e->d_meta.ensure(n * sizeof(TrackMeta)));
-    CK(cudaMemcpyAsync(e->d_tin.p, tin.data(), n * sizeof(TrackIn), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_fbase.p, frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_fbase.as<uint64_t>() + (n + 1), md_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    CK(e->h_meta.ensure(n * sizeof(TrackMeta)));
+    ip.meta = e->h_meta.as<TrackMeta>();
+    CK(cudaMemcpyAsync(e->d_tin.p, tin.data(), n * sizeof(TrackIn), cudaMemcpyHostToDevice, e->s_index));
+    CK(cudaMemcpyAsync(e->d_fbase.p, ip.frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->s_index));
+    CK(cudaMemcpyAsync(e->d_fbase.as<uint64_t>() + (n + 1), ip.md_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->s_index));
+    CK(cudaStreamSynchronize(e->s_index));   // the three sources above are stack / heap temporaries
     e->stats.h2d_bytes += n * sizeof(TrackIn) + 2 * (n + 1) * sizeof(uint64_t);
-    CK(cudaEventRecord(e->ev[0], e->stream));
-    k_frame_index<<<(unsigned)((n + K0_WARPS - 1) / K0_WARPS), 32 * K0_WARPS, 0, e->stream>>>(
-        c->d_bytes.as<uint8_t>(), e->d_tin.as<TrackIn>(), e->d_fbase.as<uint64_t>(), e->d_fbase.as<uint64_t>() + (n + 1),
-        e->d_frames.as<FrameRec>(), e->d_md.as<uint8_t>(), e->d_meta.as<TrackMeta>(), (uint32_t)n, e->flags);
-    e->stats.kernel_launches++;
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(e->ev[1], e->stream));
-    CK(cudaMemcpyAsync(d.meta.data(), e->d_meta.p, n * sizeof(TrackMeta), cudaMemcpyDeviceToHost, e->stream));
-    e->stats.d2h_bytes += n * sizeof(TrackMeta);
-    CK(cudaStreamSynchronize(e->stream));
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]) == cudaSuccess) e->stats.last_ms_index += ms;
-    for (size_t i = 0; i < n; i++) {
-        const TrackMeta& m = d.meta[i];
-        int st = m.status;
-        if (c->is_mp4[i]) st = RG_ERR_UNSUPPORTED_FORMAT;          // AAC/M4A: out of scope for this engine
-        else if (st == RG_OK) {
-            d.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3];
-            // MP3 carries exactly one audio track (src/replaygain.rs:838-851)
-            if (c->track_index[i] > 0) st = RG_ERR_TRACK_INDEX;
-            else if (c->track_index[i] < -1) st = RG_ERR_INVALID_ARG;
-        } else if (st == RG_ERR_UNSUPPORTED_FORMAT) {
-            const uint32_t ver = (m.sr_idx >> 4) & 3;
-            d.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3] >> (ver == 2 ? 1 : 2);
+    const size_t ng = ip.group_begin.size() - 1;
+    CK(cudaEventRecord(e->ev[1], e->s_index));   // the descriptor tables above are in place
+    for (size_t g = 0; g < ng; g++) {
+        const size_t t0 = ip.group_begin[g], t1 = ip.group_begin[g + 1];
+        cudaStream_t si = (g & 3) == 0 ? e->s_index : e->s_index_x[(g & 3) - 1];
+        if (si != e->s_index) CK(cudaStreamWaitEvent(si, e->ev[1], 0));
+        cudaEvent_t ev_copied = e->pool_event(4 * g), ev_k0a = e->pool_event(4 * g + 1), ev_k0b = e->pool_event(4 * g + 2),
+                    ev_done = e->pool_event(4 * g + 3);
+        if (c->pending_in) {
+            for (size_t i = t0; i < t1; i++) {
+                if (!c->len[i]) continue;
+                CK(cudaMemcpyAsync(c->d_bytes + c->off[i], c->pending_in[i].data, c->len[i], cudaMemcpyHostToDevice, e->s_copy));
+                e->stats.h2d_bytes += c->len[i];
+            }
+            CK(cudaEventRecord(ev_copied, e->s_copy));
+            CK(cudaStreamWaitEvent(si, ev_copied, 0));
         }
-        d.status[i] = st;
+        CK(cudaEventRecord(ev_k0a, si));
+        k_frame_index<<<(unsigned)((t1 - t0 + K0_WARPS - 1) / K0_WARPS), 32 * K0_WARPS, 0, si>>>(
+            c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_fbase.as<uint64_t>() + t0, e->d_fbase.as<uint64_t>() + (n + 1) + t0,
+            e->d_frames.as<FrameRec>(), e->d_md.as<uint8_t>(), e->d_meta.as<TrackMeta>() + t0, (uint32_t)(t1 - t0), e->flags);
+        e->stats.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ev_k0b, si));
+        CK(cudaMemcpyAsync(e->h_meta.as<TrackMeta>() + t0, e->d_meta.as<TrackMeta>() + t0, (t1 - t0) * sizeof(TrackMeta),
+                           cudaMemcpyDeviceToHost, si));
+        e->stats.d2h_bytes += (t1 - t0) * sizeof(TrackMeta);
+        CK(cudaEventRecord(ev_done, si));
     }
     return RG_OK;
 }
 
-// Decode tracks [t0,t1) of the corpus (K1+K2) into e->d_pcm; fills `pt` with the PCM views.
-static int run_decode_batch(rg_engine* e, rg_corpus* c, const DecodeOut& d, const std::vector<uint64_t>& frame_base,
-                            const std::vector<uint64_t>& md_base, size_t t0, size_t t1, std::vector<PcmTrack>& pt) {
-    const size_t nb = t1 - t0;
-    pt.assign(nb, PcmTrack{});
+// Waits until track `upto - 1` has been indexed and derives the per-track status of every newly finished group.
+// With `opportunistic`, also absorbs later groups that happen to be finished already.
+static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, bool opportunistic) {
+    const size_t ng = ip.group_begin.size() - 1;
+    while (ip.groups_absorbed < ng) {
+        const size_t g = ip.groups_absorbed;
+        const bool needed = ip.group_begin[g] < upto;
+        if (!needed) {
+            if (!opportunistic || cudaEventQuery(e->pool_event(4 * g + 3)) != cudaSuccess) break;
+        }
+        CK(cudaEventSynchronize(e->pool_event(4 * g + 3)));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, e->pool_event(4 * g + 1), e->pool_event(4 * g + 2)) == cudaSuccess) e->stats.last_ms_index += ms;
+        for (size_t i = ip.group_begin[g]; i < ip.group_begin[g + 1]; i++) {
+            const TrackMeta& m = ip.meta[i];
+            int st = m.status;
+            if (c->is_mp4[i]) st = RG_ERR_UNSUPPORTED_FORMAT;          // AAC/M4A: out of scope for this engine
+            else if (st == RG_OK) {
+                ip.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3];
+                // MP3 carries exactly one audio track (src/replaygain.rs:838-851)
+                if (c->track_index[i] > 0) st = RG_ERR_TRACK_INDEX;
+                else if (c->track_index[i] < -1) st = RG_ERR_INVALID_ARG;
+                else if (rate_index(ip.sample_rate[i]) < 0) st = RG_ERR_UNSUPPORTED_RATE;
+            } else if (st == RG_ERR_UNSUPPORTED_FORMAT) {
+                const uint32_t ver = (m.sr_idx >> 4) & 3;
+                ip.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3] >> (ver == 2 ? 1 : 2);
+            }
+            ip.status[i] = st;
+        }
+        ip.groups_absorbed++;
+    }
+    return RG_OK;
+}
+
+// Enqueues K1 + K2 for the tracks `x.ids` of the corpus on the decode stream; fills x.pt with the PCM views.
+static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, BatchCtx& x) {
+    const size_t nb = x.ids.size();
+    x.pt.assign(nb, PcmTrack{});
+    x.decoded = false;
     std::vector<DecTrack> dt(nb);
     std::vector<HuffBlock> hb;
     std::vector<RunDesc> runs;
     uint64_t gc_total = 0, pcm_total = 0;
     for (size_t k = 0; k < nb; k++) {
-        const size_t i = t0 + k;
-        const TrackMeta& m = d.meta[i];
+        const size_t i = x.ids[k];
+        const TrackMeta& m = ip.meta[i];
         DecTrack& t = dt[k];
         memset(&t, 0, sizeof t);
-        PcmTrack& p = pt[k];
-        p.status = d.status[i];
-        p.sample_rate = d.sample_rate[i];
+        PcmTrack& p = x.pt[k];
+        p.status = ip.status[i];
+        p.sample_rate = ip.sample_rate[i];
         p.rate_idx = rate_index(p.sample_rate);
         p.nch = (int)m.channels;
         if (p.status != RG_OK) continue;
         t.corpus_off = c->off[i];
-        t.md_off = md_base[i];
-        t.frame_base = frame_base[i];
+        t.md_off = ip.md_base[i];
+        t.frame_base = ip.frame_base[i];
         t.gc_base = gc_total;
         t.n_frames = m.n_frames; t.channels = m.channels; t.sr_idx = m.sr_idx & 3; t.md_bytes = m.md_bytes;
         const uint64_t plane = (uint64_t)m.n_frames * 1152;
@@ -157,48 +227,64 @@ static int run_decode_batch(rg_engine* e, rg_corpus* c, const DecodeOut& d, cons
         pcm_total += plane * m.channels;
         p.frames = plane;
     }
-    CK(e->d_dtracks.ensure(std::max<size_t>(nb, 1) * sizeof(DecTrack)));
-    CK(e->d_hblocks.ensure(std::max<size_t>(hb.size(), 1) * sizeof(HuffBlock)));
-    CK(e->d_runs.ensure(std::max<size_t>(runs.size(), 1) * sizeof(RunDesc)));
-    CK(e->d_spectra.ensure(std::max<uint64_t>(gc_total, 1) * 576 * sizeof(int16_t) + 64));
-    CK(e->d_nz.ensure(std::max<uint64_t>(gc_total, 1) * sizeof(uint16_t) + 64));
-    CK(e->d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
+    CK(x.d_dtracks.ensure(std::max<size_t>(nb, 1) * sizeof(DecTrack)));
+    CK(x.d_hblocks.ensure(std::max<size_t>(hb.size(), 1) * sizeof(HuffBlock)));
+    CK(x.d_runs.ensure(std::max<size_t>(runs.size(), 1) * sizeof(RunDesc)));
+    CK(x.d_spectra.ensure(std::max<uint64_t>(gc_total, 1) * 576 * sizeof(int16_t) + 64));
+    CK(x.d_nz.ensure(std::max<uint64_t>(gc_total, 1) * sizeof(uint16_t) + 64));
+    CK(x.d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
     for (size_t k = 0; k < nb; k++) {
-        if (pt[k].status != RG_OK) continue;
-        pt[k].d_ch[0] = e->d_pcm.as<float>() + dt[k].pcm_off;
-        pt[k].d_ch[1] = pt[k].nch >= 2 ? pt[k].d_ch[0] + dt[k].pcm_plane : nullptr;
+        if (x.pt[k].status != RG_OK) continue;
+        x.pt[k].d_ch[0] = x.d_pcm.as<float>() + dt[k].pcm_off;
+        x.pt[k].d_ch[1] = x.pt[k].nch >= 2 ? x.pt[k].d_ch[0] + dt[k].pcm_plane : nullptr;
     }
-    CK(cudaMemcpyAsync(e->d_dtracks.p, dt.data(), nb * sizeof(DecTrack), cudaMemcpyHostToDevice, e->stream));
-    if (!hb.empty()) CK(cudaMemcpyAsync(e->d_hblocks.p, hb.data(), hb.size() * sizeof(HuffBlock), cudaMemcpyHostToDevice, e->stream));
-    if (!runs.empty()) CK(cudaMemcpyAsync(e->d_runs.p, runs.data(), runs.size() * sizeof(RunDesc), cudaMemcpyHostToDevice, e->stream));
-    e->stats.h2d_bytes += nb * sizeof(DecTrack) + hb.size() * sizeof(HuffBlock) + runs.size() * sizeof(RunDesc);
-    CK(cudaEventRecord(e->ev[1], e->stream));
-    if (!hb.empty()) {
-        k_huffman<<<(unsigned)hb.size(), K1_THREADS, 0, e->stream>>>(c->d_bytes.as<uint8_t>(), e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
-                                                                  e->d_dtracks.as<DecTrack>(), e->d_hblocks.as<HuffBlock>(), e->dec.d_tab,
-                                                                  e->d_spectra.as<int16_t>(), e->d_nz.as<uint16_t>());
-        e->stats.kernel_launches++;
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(e->ev[2], e->stream));
+    // descriptors through pinned staging: [dtracks] [hblocks] [runs]
+    const size_t b_dt = up16(nb * sizeof(DecTrack)), b_hb = up16(hb.size() * sizeof(HuffBlock)), b_rn = up16(runs.size() * sizeof(RunDesc));
+    CK(x.h_desc_a.ensure(b_dt + b_hb + b_rn + 64));
+    uint8_t* hd = x.h_desc_a.as<uint8_t>();
+    memcpy(hd, dt.data(), nb * sizeof(DecTrack));
+    if (b_hb) memcpy(hd + b_dt, hb.data(), hb.size() * sizeof(HuffBlock));
+    if (b_rn) memcpy(hd + b_dt + b_hb, runs.data(), runs.size() * sizeof(RunDesc));
+    cudaStream_t st = e->s_dec;
+    if (int r = fetch_desc(e, st, x.d_dtracks.p, hd, b_dt)) return r;
+    if (int r = fetch_desc(e, st, x.d_hblocks.p, hd + b_dt, b_hb)) return r;
+    if (int r = fetch_desc(e, st, x.d_runs.p, hd + b_dt + b_hb, b_rn)) return r;
+    CK(cudaEventRecord(x.ev_a[0], st));
     if (!runs.empty()) {
-        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), e->stream>>>(c->d_bytes.as<uint8_t>(), e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
-                                                                         e->d_dtracks.as<DecTrack>(), e->d_runs.as<RunDesc>(), e->dec.d_tab,
-                                                                         e->d_spectra.as<int16_t>(), e->d_nz.as<uint16_t>(), e->d_pcm.as<float>(), e->flags);
+        k_md_gather<<<(unsigned)runs.size(), K0B_THREADS, 0, st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
+                                                                 x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>());
         e->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(e->ev[3], e->stream));
-    e->pending_decode_timing = true;
+    CK(cudaEventRecord(x.ev_a[3], st));
+    if (!hb.empty()) {
+        k_huffman<<<(unsigned)hb.size(), K1_THREADS, 0, st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
+                                                           x.d_dtracks.as<DecTrack>(), x.d_hblocks.as<HuffBlock>(), e->dec.d_tab,
+                                                           x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>());
+        e->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(x.ev_a[1], st));
+    if (!runs.empty()) {
+        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
+                                                                               x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>(), e->dec.d_tab,
+                                                                               x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(),
+                                                                               x.d_pcm.as<float>(), e->flags);
+        e->stats.kernel_launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(x.ev_a[2], st));
+    x.decoded = true;
     return RG_OK;
 }
 
-static void collect_decode_timing(rg_engine* e) {
-    if (!e->pending_decode_timing) return;
-    e->pending_decode_timing = false;
+static void collect_decode_timing(rg_engine* e, BatchCtx& x) {
+    if (!x.decoded) return;
+    x.decoded = false;
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]) == cudaSuccess) e->stats.last_ms_huffman += ms;
-    if (cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]) == cudaSuccess) e->stats.last_ms_hybrid += ms;
+    if (cudaEventElapsedTime(&ms, x.ev_a[0], x.ev_a[3]) == cudaSuccess) e->stats.last_ms_index += ms;
+    if (cudaEventElapsedTime(&ms, x.ev_a[3], x.ev_a[1]) == cudaSuccess) e->stats.last_ms_huffman += ms;
+    if (cudaEventElapsedTime(&ms, x.ev_a[1], x.ev_a[2]) == cudaSuccess) e->stats.last_ms_hybrid += ms;
 }
 
 // Bytes of device scratch one track needs in a batch (spectra + nz + PCM)
@@ -206,7 +292,12 @@ static uint64_t track_scratch_bytes(const TrackMeta& m) {
     return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2) + 1152ull * 4) + 4096;
 }
 
-// The whole pipeline over a device-resident corpus.
+static void drain_streams(rg_engine* e) {
+    for (cudaStream_t st : {e->s_copy, e->s_index, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2], e->s_dec, e->stream}) cudaStreamSynchronize(st);
+    for (auto& x : e->ctx) { x.busy = false; x.decoded = false; x.hist_host = nullptr; }
+}
+
+// The whole pipeline over a corpus (resident, or still arriving from c->pending_in).
 static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out, uint32_t* hist_out,
                                unsigned long long* d_album_hist, unsigned long long* d_album_peak, bool album_fail_fast,
                                int* first_bad) {
@@ -217,48 +308,105 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
     if (first_bad) *first_bad = -1;
     if (!n) return RG_OK;
     CK(cudaEventRecord(e->ev[7], e->stream));
-    DecodeOut d;
-    std::vector<uint64_t> frame_base, md_base;
-    int rc = run_frame_index(e, c, d, frame_base, md_base);
-    if (rc != RG_OK) return rc;
-    for (size_t i = 0; i < n; i++) {
-        if (d.status[i] == RG_OK && rate_index(d.sample_rate[i]) < 0) d.status[i] = RG_ERR_UNSUPPORTED_RATE;
-        if (d.status[i] != RG_OK && first_bad && *first_bad < 0) *first_bad = (int)i;
-    }
-    if (album_fail_fast && first_bad && *first_bad >= 0) {
-        // album mode: the first failing file aborts everything (src/replaygain.rs:1055)
-        for (size_t i = 0; i < n; i++) {
-            memset(&out[i], 0, sizeof out[i]);
-            out[i].status = d.status[i];
-            out[i].sample_rate = d.sample_rate[i];
-            out[i].file_type = c->is_mp4[i] ? 1 : 0;
+    const bool exact_all = (e->flags & RG_FLAG_EXACT_IIR) != 0;
+    IndexPlan ip;
+    int rc = index_enqueue(e, c, ip);
+    if (rc != RG_OK) { drain_streams(e); return rc; }
+    if (album_fail_fast) {
+        // album mode: the first failing file aborts everything (src/replaygain.rs:1055), before any histogram is merged
+        rc = index_absorb(e, c, ip, n, false);
+        if (rc != RG_OK) { drain_streams(e); return rc; }
+        int bad = -1;
+        for (size_t i = 0; i < n && bad < 0; i++) if (ip.status[i] != RG_OK) bad = (int)i;
+        if (first_bad) *first_bad = bad;
+        if (bad >= 0) {
+            for (size_t i = 0; i < n; i++) {
+                memset(&out[i], 0, sizeof out[i]);
+                out[i].status = ip.status[i];
+                out[i].sample_rate = ip.sample_rate[i];
+                out[i].file_type = c->is_mp4[i] ? 1 : 0;
+            }
+            drain_streams(e);
+            return ip.status[bad];
         }
-        return d.status[*first_bad];
     }
-    size_t t0 = 0;
-    while (t0 < n) {
-        size_t t1 = t0;
+    const uint64_t budget = e->pipeline ? e->scratch_bytes / 2 : e->scratch_bytes;
+    std::vector<uint32_t> flagged;
+    std::vector<uint32_t> hist_tmp;   // histograms of a re-run batch, scattered back to the caller's rows afterwards
+
+    auto collect = [&](BatchCtx& x, bool rerun_batch) -> int {
+        if (!x.busy) return RG_OK;
+        std::vector<RgTrackOut> res;
+        int r = stage_b_collect(e, x, res);
+        if (r != RG_OK) return r;
+        collect_decode_timing(e, x);
+        for (size_t k = 0; k < x.ids.size(); k++) {
+            const uint32_t i = x.ids[k];
+            if (!x.exact && x.pt[k].status == RG_OK && res[k].n_edge > 0) { flagged.push_back(i); }
+            fill_result(&out[i], x.pt[k], res[k], rerun_batch ? 1 : 0, ip.meta[i].n_frames);
+            out[i].file_type = c->is_mp4[i] ? 1 : 0;
+            if (rerun_batch && hist_out) memcpy(hist_out + (size_t)i * RG_HIST_BINS, hist_tmp.data() + k * RG_HIST_BINS, RG_HIST_BINS * sizeof(uint32_t));
+            if (!rerun_batch && x.pt[k].status == RG_OK) { e->stats.tracks++; e->stats.frames += ip.meta[i].n_frames; }
+        }
+        x.busy = false;
+        x.hist_host = nullptr;
+        return RG_OK;
+    };
+    auto fail = [&](int r) { drain_streams(e); return r; };
+
+    size_t next = 0, k = 0;
+    while (next < n) {
+        rc = index_absorb(e, c, ip, next + 1, true);
+        if (rc != RG_OK) return fail(rc);
+        const size_t indexed_end = ip.group_begin[ip.groups_absorbed];
+        size_t t1 = next;
         uint64_t bytes = 0;
-        while (t1 < n) {
-            const uint64_t b = d.status[t1] == RG_OK ? track_scratch_bytes(d.meta[t1]) : 0;
-            if (t1 > t0 && bytes + b > e->scratch_bytes) break;
+        while (t1 < indexed_end) {
+            const uint64_t b = ip.status[t1] == RG_OK ? track_scratch_bytes(ip.meta[t1]) : 0;
+            if (t1 > next && bytes + b > budget) break;
             bytes += b;
             t1++;
         }
-        std::vector<PcmTrack> pt;
-        rc = run_decode_batch(e, c, d, frame_base, md_base, t0, t1, pt);
-        if (rc != RG_OK) return rc;
-        std::vector<RgTrackOut> res;
-        std::vector<uint8_t> rerun;
-        rc = run_stage_b(e, pt, res, rerun, hist_out ? hist_out + t0 * RG_HIST_BINS : nullptr, d_album_hist, d_album_peak);
-        if (rc != RG_OK) return rc;
-        collect_decode_timing(e);
-        for (size_t k = 0; k < pt.size(); k++) {
-            fill_result(&out[t0 + k], pt[k], res[k], rerun[k], d.meta[t0 + k].n_frames);
-            out[t0 + k].file_type = c->is_mp4[t0 + k] ? 1 : 0;
-            if (pt[k].status == RG_OK) { e->stats.tracks++; e->stats.frames += d.meta[t0 + k].n_frames; }
+        BatchCtx& x = e->ctx[e->pipeline ? (k & 1) : 0];
+        rc = collect(x, false);
+        if (rc != RG_OK) return fail(rc);
+        x.ids.resize(t1 - next);
+        for (size_t i = next; i < t1; i++) x.ids[i - next] = (uint32_t)i;
+        x.hist_host = hist_out ? hist_out + next * RG_HIST_BINS : nullptr;
+        rc = decode_enqueue(e, c, ip, x);
+        if (rc == RG_OK) rc = stage_b_enqueue(e, x, exact_all, hist_out != nullptr, d_album_hist, d_album_peak, !exact_all, true);
+        if (rc != RG_OK) return fail(rc);
+        x.busy = true;
+        if (!e->pipeline) { rc = collect(x, false); if (rc != RG_OK) return fail(rc); }
+        next = t1;
+        k++;
+    }
+    for (size_t j = 0; j < 2; j++) {   // oldest first
+        rc = collect(e->ctx[(k + j) & 1], false);
+        if (rc != RG_OK) return fail(rc);
+    }
+    // tracks whose time-blocked pass left a window on a bin edge: decode again, exact kernel (rare: ~1e-5 of tracks)
+    size_t f0 = 0;
+    while (f0 < flagged.size()) {
+        size_t f1 = f0;
+        uint64_t bytes = 0;
+        while (f1 < flagged.size()) {
+            const uint64_t b = track_scratch_bytes(ip.meta[flagged[f1]]);
+            if (f1 > f0 && bytes + b > budget) break;
+            bytes += b;
+            f1++;
         }
-        t0 = t1;
+        BatchCtx& x = e->ctx[0];
+        x.ids.assign(flagged.begin() + f0, flagged.begin() + f1);
+        if (hist_out) { hist_tmp.resize((f1 - f0) * RG_HIST_BINS); x.hist_host = hist_tmp.data(); }
+        rc = decode_enqueue(e, c, ip, x);
+        if (rc == RG_OK) rc = stage_b_enqueue(e, x, true, hist_out != nullptr, d_album_hist, d_album_peak, false, true);
+        if (rc != RG_OK) return fail(rc);
+        x.busy = true;
+        rc = collect(x, true);
+        if (rc != RG_OK) return fail(rc);
+        e->stats.exact_reruns += f1 - f0;
+        f0 = f1;
     }
     CK(cudaEventRecord(e->ev[0], e->stream));
     CK(cudaEventSynchronize(e->ev[0]));
@@ -272,14 +420,24 @@ extern "C" int rg_analyze_corpus(rg_engine* e, rg_corpus* c, rg_track_result* ou
     return analyze_corpus_impl(e, c, out, hist_out, nullptr, nullptr, false, nullptr);
 }
 
+// A corpus whose bytes are still in the caller's (ideally pinned) buffers: the copy into the engine's own device buffer is
+// part of the pipeline, group by group, so decoding starts while later files are still crossing the bus.
+static int host_corpus(rg_engine* e, const rg_input* in, size_t n, rg_corpus& c) {
+    CK(cudaSetDevice(e->device));
+    int rc = corpus_describe(&c, in, n);
+    if (rc != RG_OK) return rc;
+    CK(e->d_corpus.ensure(c.total + 64));
+    c.d_bytes = e->d_corpus.as<uint8_t>();
+    c.pending_in = in;
+    return RG_OK;
+}
+
 extern "C" int rg_analyze_tracks(rg_engine* e, const rg_input* in, size_t n, rg_track_result* out, uint32_t* hist_out) {
     if (!e || (n && (!in || !out))) return RG_ERR_INVALID_ARG;
-    rg_corpus* c = nullptr;
-    int rc = rg_corpus_upload(e, in, n, &c);
+    rg_corpus c;
+    int rc = host_corpus(e, in, n, c);
     if (rc != RG_OK) return rc;
-    rc = analyze_corpus_impl(e, c, out, hist_out, nullptr, nullptr, false, nullptr);
-    rg_corpus_free(e, c);
-    return rc;
+    return analyze_corpus_impl(e, &c, out, hist_out, nullptr, nullptr, false, nullptr);
 }
 
 static int album_buffers(rg_engine* e) {
@@ -322,12 +480,11 @@ extern "C" int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_t
     unsigned long long* d_peak = e->d_album_peak.as<unsigned long long>();
     CK(cudaMemsetAsync(d_hist, 0, RG_HIST_BINS * sizeof(unsigned long long), e->stream));
     CK(cudaMemsetAsync(d_peak, 0, sizeof(unsigned long long), e->stream));
-    rg_corpus* c = nullptr;
-    rc = rg_corpus_upload(e, in, n, &c);
+    rg_corpus c;
+    rc = host_corpus(e, in, n, c);
     if (rc != RG_OK) return rc;
     int bad = -1;
-    rc = analyze_corpus_impl(e, c, out, nullptr, d_hist, d_peak, true, &bad);
-    rg_corpus_free(e, c);
+    rc = analyze_corpus_impl(e, &c, out, nullptr, d_hist, d_peak, true, &bad);
     if (rc != RG_OK) return rc;
     rc = rg_album_finish(e, reinterpret_cast<const uint64_t*>(d_hist), reinterpret_cast<const double*>(d_peak), album);
     if (rc != RG_OK) return rc;
@@ -358,27 +515,28 @@ extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_
 extern "C" int rg_decode_pcm(rg_engine* e, const rg_input* in, float* pcm, size_t max_frames, size_t* frames_out,
                              uint32_t* channels_out, uint32_t* sample_rate_out) {
     if (!e || !in || !pcm || !frames_out) return RG_ERR_INVALID_ARG;
-    rg_corpus* c = nullptr;
-    int rc = rg_corpus_upload(e, in, 1, &c);
+    rg_corpus c;
+    int rc = host_corpus(e, in, 1, c);
     if (rc != RG_OK) return rc;
-    DecodeOut d;
-    std::vector<uint64_t> frame_base, md_base;
-    rc = run_frame_index(e, c, d, frame_base, md_base);
-    if (rc == RG_OK && d.status[0] != RG_OK) rc = d.status[0];
-    std::vector<PcmTrack> pt;
-    if (rc == RG_OK) rc = run_decode_batch(e, c, d, frame_base, md_base, 0, 1, pt);
+    e->stats.last_ms_index = e->stats.last_ms_huffman = e->stats.last_ms_hybrid = 0;
+    IndexPlan ip;
+    rc = index_enqueue(e, &c, ip);
+    if (rc == RG_OK) rc = index_absorb(e, &c, ip, 1, false);
+    if (rc == RG_OK && ip.status[0] != RG_OK) rc = ip.status[0];
+    BatchCtx& x = e->ctx[0];
+    if (rc == RG_OK) { x.ids.assign(1, 0u); rc = decode_enqueue(e, &c, ip, x); }
     if (rc == RG_OK) {
-        const size_t frames = pt[0].frames, ncopy = std::min(frames, max_frames);
-        for (int ch = 0; ch < pt[0].nch && rc == RG_OK; ch++)
-            if (ncopy && cudaMemcpyAsync(pcm + (size_t)ch * max_frames, pt[0].d_ch[ch], ncopy * sizeof(float), cudaMemcpyDeviceToHost, e->stream) != cudaSuccess)
+        const size_t frames = x.pt[0].frames, ncopy = std::min(frames, max_frames);
+        for (int ch = 0; ch < x.pt[0].nch && rc == RG_OK; ch++)
+            if (ncopy && cudaMemcpyAsync(pcm + (size_t)ch * max_frames, x.pt[0].d_ch[ch], ncopy * sizeof(float), cudaMemcpyDeviceToHost, e->s_dec) != cudaSuccess)
                 rc = RG_ERR_CUDA;
-        if (cudaStreamSynchronize(e->stream) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "rg_decode_pcm sync", __LINE__);
-        collect_decode_timing(e);
+        if (cudaStreamSynchronize(e->s_dec) != cudaSuccess) rc = fail_cuda(cudaGetLastError(), "rg_decode_pcm sync", __LINE__);
+        collect_decode_timing(e, x);
         *frames_out = frames;
-        if (channels_out) *channels_out = (uint32_t)pt[0].nch;
-        if (sample_rate_out) *sample_rate_out = pt[0].sample_rate;
-        e->stats.d2h_bytes += ncopy * sizeof(float) * pt[0].nch;
+        if (channels_out) *channels_out = (uint32_t)x.pt[0].nch;
+        if (sample_rate_out) *sample_rate_out = x.pt[0].sample_rate;
+        e->stats.d2h_bytes += ncopy * sizeof(float) * x.pt[0].nch;
     }
-    rg_corpus_free(e, c);
+    drain_streams(e);
     return rc;
 }

@@ -39,3 +39,29 @@ for it in range(3):
         dt, st.last_ms_total, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist,
         audio_s / 3600.0 / dt, st.exact_reruns, st.kernel_launches), flush=True)
 print("sample result", out[0].loudness_db, out[0].peak, out[0].n_windows, out[0].n_edge_windows, out[0].exact_rerun)
+
+if len(sys.argv) > 4 and sys.argv[4] == "e2e":
+    # host buffers (pinned) -> rg_analyze_tracks, plus the raw H2D rate of the same bytes for reference
+    import torch
+    offs = np.zeros(n_tracks + 1, np.int64)
+    for i, im in enumerate(imgs):
+        offs[i + 1] = offs[i] + ((len(im) + 63) & ~63)
+    pinned = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
+    pnp = pinned.numpy()
+    arr2 = (_lib.RgInput * n_tracks)()
+    for i, im in enumerate(imgs):
+        pnp[offs[i]: offs[i] + len(im)] = np.frombuffer(im, np.uint8)
+        arr2[i].data = pnp.ctypes.data + int(offs[i])
+        arr2[i].len = len(im)
+        arr2[i].track_index = -1
+    dev = torch.empty(int(offs[-1]), dtype=torch.uint8, device="cuda")
+    for it in range(3):
+        torch.cuda.synchronize(); t = time.time(); dev.copy_(pinned, non_blocking=True); torch.cuda.synchronize(); dt = time.time() - t
+        print("raw H2D %.1f ms  %.1f GB/s" % (dt * 1e3, offs[-1] / dt / 1e9), flush=True)
+    for it in range(4):
+        t = time.time()
+        rc = lib.rg_analyze_tracks(eng._h, arr2, n_tracks, out, None)
+        dt = time.time() - t
+        st = eng.stats()
+        print("e2e rc", rc, "wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f" % (
+            dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt), flush=True)
