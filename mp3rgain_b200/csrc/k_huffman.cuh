@@ -1,46 +1,63 @@
-// k_huffman.cuh -- K1: Layer III part-3 (Huffman) decode, one thread per granule-channel.
+// k_huffman.cuh -- K1: Layer III part 2 (scalefactors) and part 3 (Huffman) decode, one thread per granule-channel.
 //
 // The bit offset of every granule-channel is known without decoding anything: frame f's data starts md_start bytes into the
 // track's compacted main-data stream (K0) and granule-channels follow each other at part2_3_length strides, so all
-// granule-channels of all frames decode in parallel.  Scalefactor bits (part 2) are skipped here -- their length follows
-// from the side info -- and extracted directly by K2.
+// granule-channels of all frames decode in parallel.
 //
-// All lanes of a warp advance through the 288 line pairs in lockstep; each lane parks its pair in a 16-pair shared-memory
-// row and every 16 pairs the warp flushes 32 rows with coalesced 64-byte segments, so the int16 spectra reach HBM as full
-// sectors although every lane owns a different 1152-byte row.
+// Part 2: the thread reads its scalefactors (an irregular, serial bit-field walk that this mapping runs 32-wide), resolves
+// scfsi against granule 0's thread in the same warp, and writes the GAIN of every scalefactor band -- 2^((global_gain-210
+// - ...)/4) looked up in the frozen table -- as 64 floats per granule-channel, so that K2 receives them with its bulk copy.
+//
+// Part 3: all lanes of a warp advance through the 288 line pairs in lockstep.  The bit reader is a 64-bit accumulator with
+// a one-word look-ahead: one refill + one table lookup per code word, and the linbits / sign bits of a pair (or the four
+// sign bits of a count1 quad) are peeled off a single 32-bit peek without branches.  Each lane parks its pair in a 16-pair
+// shared-memory row and every 16 pairs the warp flushes 32 rows with coalesced 64-byte segments, so the int16 spectra
+// reach HBM as full sectors although every lane owns a different 1152-byte row.
 #pragma once
 
 #define K1_THREADS 128
+#define K1_GAIN_ROW 64   // floats per granule-channel: [0..21] long sfb, [22..60] short sfb*3+win
 
-struct BitRd {
+struct BitBuf {
     const uint32_t* w;   // main-data stream as 32-bit words (16-byte aligned base)
     uint32_t lim;        // bytes readable for this frame (later bytes read as zero, like the oracle's reservoir)
-    uint32_t cw0, cw1;   // big-endian words at index wi, wi+1
-    uint32_t wi;
-    uint32_t pos;        // bit position
+    uint32_t wi;         // index of the look-ahead word
+    uint32_t nxt;        // look-ahead word (big-endian), not yet in acc
+    uint32_t pos;        // bit position of the next unread bit
+    unsigned long long acc;   // unread bits, left-aligned
+    int nb;              // valid bits in acc (>= 33 after refill())
     __device__ __forceinline__ uint32_t ld(uint32_t i) const {
         const uint32_t b = i * 4;
-        if (b >= lim) return 0;
         uint32_t v = __byte_perm(__ldg(w + i), 0, 0x0123);
-        if (b + 4 > lim) v &= 0xFFFFFFFFu << (8 * (b + 4 - lim));
+        if (b + 4 > lim) v = b >= lim ? 0u : (v & (0xFFFFFFFFu << (8 * (b + 4 - lim))));
         return v;
     }
     __device__ __forceinline__ void init(const uint8_t* base, uint32_t lim_bytes, uint32_t bitpos) {
         w = reinterpret_cast<const uint32_t*>(base);
         lim = lim_bytes;
         pos = bitpos;
-        wi = pos >> 5;
-        cw0 = ld(wi);
-        cw1 = ld(wi + 1);
+        wi = bitpos >> 5;
+        const uint32_t sh = bitpos & 31;
+        acc = ((((unsigned long long)ld(wi)) << 32) | ld(wi + 1)) << sh;
+        nb = 64 - (int)sh;
+        wi += 2;
+        nxt = ld(wi);
     }
-    __device__ __forceinline__ uint32_t peek() {
-        const uint32_t nwi = pos >> 5;
-        if (nwi != wi) {
-            if (nwi == wi + 1) { cw0 = cw1; cw1 = ld(nwi + 1); }
-            else { cw0 = ld(nwi); cw1 = ld(nwi + 1); }
-            wi = nwi;
+    __device__ __forceinline__ void refill() {
+        if (nb <= 32) {
+            acc |= (unsigned long long)nxt << (32 - nb);
+            nb += 32;
+            wi++;
+            nxt = ld(wi);
         }
-        return __funnelshift_l(cw1, cw0, pos & 31);
+    }
+    __device__ __forceinline__ uint32_t top() const { return (uint32_t)(acc >> 32); }
+    __device__ __forceinline__ void skip(int n) { acc <<= n; nb -= n; pos += n; }
+    __device__ __forceinline__ uint32_t get(int n) {   // n <= 16
+        refill();
+        const uint32_t v = (top() >> 1) >> (31 - n);
+        skip(n);
+        return v;
     }
 };
 
@@ -54,14 +71,21 @@ __device__ __forceinline__ uint32_t side_field(const uint8_t* __restrict__ s, in
 __global__ void __launch_bounds__(K1_THREADS)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
-          int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */) {
+          int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
+          float* __restrict__ gains /* [gc][K1_GAIN_ROW] */) {
     __shared__ uint16_t s_huff[8192];
     __shared__ uint32_t s_stage[K1_THREADS / 32][32][17];
+    __shared__ uint8_t s_sfl[K1_THREADS][24];     // long scalefactors of every thread's granule-channel (scfsi source)
+    __shared__ uint8_t s_c1[2][64];               // count1 tables A / B: 6-bit peek -> (len<<4)|quad
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const uint4* src = reinterpret_cast<const uint4*>(T->huff);
         uint4* dst = reinterpret_cast<uint4*>(s_huff);
         for (int i = tid; i < 8192 * 2 / 16; i += K1_THREADS) dst[i] = src[i];
+        if (tid < 64) {
+            s_c1[0][tid] = T->c1a_lut[tid];
+            s_c1[1][tid] = (uint8_t)((4u << 4) | (15u - (tid >> 2)));
+        }
     }
     const HuffBlock blk = blocks[blockIdx.x];
     const DecTrack tr = tracks[blk.track];
@@ -73,15 +97,22 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
 
     // ---- side info of my granule-channel
     int bv = 0, r0 = 0, r1 = 0, c1tab = 0;
-    int sel0 = 0, sel1 = 0, sel2 = 0;
-    int slot0 = 0, slot1 = 0, slot2 = 0, lb0 = 0, lb1 = 0, lb2 = 0;
+    uint32_t reg0 = 0, reg1 = 0, reg2 = 0;   // per region: first-level table base << 8 | linbits
     uint32_t end = 0;
     bool silent = true;
-    BitRd br;
+    BitBuf br;
     br.w = reinterpret_cast<const uint32_t*>(md + tr.md_off);
-    br.lim = 0; br.cw0 = br.cw1 = 0; br.wi = 0; br.pos = 0;
+    br.lim = 0; br.acc = 0; br.nxt = 0; br.wi = 0; br.pos = 0; br.nb = 64;
+    float* grow = gains + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
+    uint8_t* sfl = s_sfl[tid];
+#pragma unroll
+    for (int i = 0; i < 6; i++) reinterpret_cast<uint32_t*>(sfl)[i] = 0;
+    // part-2 parameters, kept for the gain pass below
+    int bt = 0, mixed = 0, slen1 = 0, slen2 = 0, scfsi = 0, base_e = 0, sf_shift = 2, preflag = 0, sbg0 = 0, sbg1 = 0, sbg2 = 0;
+    uint32_t gr = 0;
     if (active) {
-        const uint32_t frame = gc / (2 * nch), rem = gc % (2 * nch), gr = rem / nch, ch = rem % nch;
+        const uint32_t frame = gc / (2 * nch), rem = gc % (2 * nch), ch = rem % nch;
+        gr = rem / nch;
         const FrameRec rec = frames[tr.frame_base + frame];
         const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
         const int gbase = (nch == 1 ? 18 : 20);
@@ -90,14 +121,16 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         const int b0 = gbase + 59 * rem;
         const uint32_t p23 = side_field(s, b0, 12);
         bv = side_field(s, b0 + 12, 9);
+        base_e = (int)side_field(s, b0 + 21, 8) - 210 - L3_GAIN_MIN;
         const int sfc = side_field(s, b0 + 29, 4);
         const int ws = side_field(s, b0 + 33, 1);
-        int bt = 0, mixed = 0;
+        int sel0, sel1, sel2 = 0;
         if (ws) {
             bt = side_field(s, b0 + 34, 2);
             mixed = side_field(s, b0 + 36, 1);
             sel0 = side_field(s, b0 + 37, 5);
             sel1 = side_field(s, b0 + 42, 5);
+            sbg0 = side_field(s, b0 + 47, 3); sbg1 = side_field(s, b0 + 50, 3); sbg2 = side_field(s, b0 + 53, 3);
             r0 = 36; r1 = 576;
         } else {
             sel0 = side_field(s, b0 + 34, 5);
@@ -108,30 +141,70 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const int k = rc0 + rc1 + 2;
             r1 = T->long_start[tr.sr_idx][k > 22 ? 22 : k];
         }
+        if (bt != 2) mixed = 0;
+        preflag = side_field(s, b0 + 56, 1);
+        sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
         c1tab = side_field(s, b0 + 58, 1);
-        slot0 = T->tabsel[sel0][0]; lb0 = T->tabsel[sel0][1];
-        slot1 = T->tabsel[sel1][0]; lb1 = T->tabsel[sel1][1];
-        slot2 = T->tabsel[sel2][0]; lb2 = T->tabsel[sel2][1];
+        // slot 0 ("no data") reads the all-zero first-level table at huff_base[0]: length 0, x = y = 0
+        reg0 = ((uint32_t)T->huff_base[T->tabsel[sel0][0]] << 8) | T->tabsel[sel0][1];
+        reg1 = ((uint32_t)T->huff_base[T->tabsel[sel1][0]] << 8) | T->tabsel[sel1][1];
+        reg2 = ((uint32_t)T->huff_base[T->tabsel[sel2][0]] << 8) | T->tabsel[sel2][1];
         // part-2 length
-        const int slen1 = T->slen[0][sfc], slen2 = T->slen[1][sfc];
+        slen1 = T->slen[0][sfc]; slen2 = T->slen[1][sfc];
         int part2;
         if (bt == 2) part2 = (mixed ? 17 : 18) * slen1 + 18 * slen2;
         else {
+            scfsi = (gr == 1) ? (int)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;  // band group 0 first
             part2 = 0;
-            const int sc = (gr == 1) ? (int)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;  // scfsi bits, band group 0 first
-            part2 += (sc & 8) ? 0 : 6 * slen1;
-            part2 += (sc & 4) ? 0 : 5 * slen1;
-            part2 += (sc & 2) ? 0 : 5 * slen2;
-            part2 += (sc & 1) ? 0 : 5 * slen2;
+            part2 += (scfsi & 8) ? 0 : 6 * slen1;
+            part2 += (scfsi & 4) ? 0 : 5 * slen1;
+            part2 += (scfsi & 2) ? 0 : 5 * slen2;
+            part2 += (scfsi & 1) ? 0 : 5 * slen2;
         }
         end = bit + p23;
         silent = (uint32_t)part2 > p23;
-        br.init(md + tr.md_off, rec.md_end, bit + part2);
+        br.init(md + tr.md_off, rec.md_end, bit);
+
+        // ---- part 2 (ISO 11172-3 2.4.2.7): my own scalefactors.  Long ones go to shared memory (granule 1 may need them),
+        // short ones straight into their band gain.
+        if (bt == 2) {
+            if (mixed) for (int sfb = 0; sfb < 8; sfb++) sfl[sfb] = (uint8_t)br.get(slen1);
+            for (int q2 = mixed ? 9 : 0; q2 < 36; q2++) {
+                const int v = (int)br.get(q2 < 18 ? slen1 : slen2);
+                const int win = q2 % 3;
+                grow[22 + q2] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)) - sf_shift * v]);
+            }
+#pragma unroll
+            for (int win = 0; win < 3; win++)   // sfb 12 carries no scalefactor; a mixed block has no short sfb 0..2
+                grow[22 + 36 + win] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2))]);
+        } else {
+            for (int sfb = 0; sfb < 21; sfb++) {
+                const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+                if (!(scfsi & (8 >> grp))) sfl[sfb] = (uint8_t)br.get(grp < 2 ? slen1 : slen2);
+            }
+        }
+    }
+    __syncwarp();
+    if (active) {
+        // scfsi: granule 1 reuses granule 0's scalefactors of the same channel (thread lane - nch, same frame, same warp).
+        // A short granule 0 has no long scalefactors (zero) except the 8 of a mixed block -- exactly what its row holds.
+        if (bt != 2 && scfsi) {
+            const uint8_t* g0 = s_sfl[tid - nch];
+            for (int sfb = 0; sfb < 21; sfb++) {
+                const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
+                if (scfsi & (8 >> grp)) sfl[sfb] = g0[sfb];
+            }
+        }
+        if (bt != 2 || mixed) {
+            const int nl = bt != 2 ? 22 : 8;
+            for (int sfb = 0; sfb < nl; sfb++)
+                grow[sfb] = __ldg(&T->gain[base_e - sf_shift * ((int)sfl[sfb] + (preflag ? (int)T->pretab[sfb] : 0))]);
+        }
+        // part 3 starts where part 2 ends by the side info's arithmetic (not where the reads above stopped: scfsi)
     }
     if (silent) bv = 0;
 
     // ---- lockstep pair loop
-    const uint16_t* hb = T->huff_base;
     int16_t q2 = 0, q3 = 0;
     bool have_second = false;
     int state = silent ? 2 : 0;   // 0 big values, 1 count1, 2 zero tail
@@ -139,6 +212,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     uint32_t nz = 0;
     int16_t* my_rows = spectra + ((size_t)tr.gc_base + blk.gc0 + warp * 32) * 576;
     const uint32_t warp_gc0 = blk.gc0 + warp * 32;
+    const uint8_t* c1 = s_c1[c1tab];
 
     for (int p0 = 0; p0 < 288; p0 += 16) {
         if (__any_sync(0xffffffffu, state != 2)) {
@@ -153,38 +227,55 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 }
                 if (state == 0) {
                     const int line = 2 * p;
-                    const int slot = line < r0 ? slot0 : (line < r1 ? slot1 : slot2);
-                    const int linbits = line < r0 ? lb0 : (line < r1 ? lb1 : lb2);
-                    if (slot) {
-                        const uint32_t w = br.peek();
-                        uint32_t e = s_huff[hb[slot] + (w >> (32 - HUF_L1))];
-                        if (e & 0x8000u) {
-                            const uint32_t nb = (e >> 11) & 15;
-                            e = s_huff[((e & 0x7FFu) << 2) + ((w << HUF_L1) >> (32 - nb))];
-                        }
-                        br.pos += e >> 8;
-                        x = (e >> 4) & 15;
-                        y = e & 15;
-                        if (x == 15 && linbits) { x += br.peek() >> (32 - linbits); br.pos += linbits; }
-                        if (x) { if (br.peek() >> 31) x = -x; br.pos++; }
-                        if (y == 15 && linbits) { y += br.peek() >> (32 - linbits); br.pos += linbits; }
-                        if (y) { if (br.peek() >> 31) y = -y; br.pos++; }
+                    const uint32_t reg = line < r0 ? reg0 : (line < r1 ? reg1 : reg2);
+                    const int linbits = (int)(reg & 0xFFu);
+                    br.refill();
+                    uint32_t w = br.top();
+                    uint32_t e = s_huff[(reg >> 8) + (w >> (32 - HUF_L1))];
+                    if (e & 0x8000u) {
+                        const uint32_t nb2 = (e >> 11) & 15;
+                        e = s_huff[((e & 0x7FFu) << 2) + ((w << HUF_L1) >> (32 - nb2))];
                     }
+                    br.skip((int)(e >> 8));
+                    x = (e >> 4) & 15;
+                    y = e & 15;
+                    // linbits(x) sign(x) linbits(y) sign(y): at most 28 bits, peeled off one peek
+                    br.refill();
+                    w = br.top();
+                    const int lbx = (x == 15) ? linbits : 0;
+                    x += (int)((w >> 1) >> (31 - lbx));
+                    w <<= lbx;
+                    const int sx = x != 0;
+                    const bool negx = sx && (w >> 31);
+                    w <<= sx;
+                    const int lby = (y == 15) ? linbits : 0;
+                    y += (int)((w >> 1) >> (31 - lby));
+                    w <<= lby;
+                    const int sy = y != 0;
+                    const bool negy = sy && (w >> 31);
+                    br.skip(lbx + sx + lby + sy);
+                    x = negx ? -x : x;
+                    y = negy ? -y : y;
                 } else if (state == 1) {
                     if (have_second) { x = q2; y = q3; have_second = false; }
                     else if (br.pos < end && p <= 286) {
-                        const uint32_t w = br.peek();
-                        uint32_t e;
-                        if (c1tab) e = (4u << 4) | (15u - (w >> 28));
-                        else e = T->c1a_lut[w >> 26];
-                        br.pos += e >> 4;
-                        int v0 = (e >> 3) & 1, v1 = (e >> 2) & 1, v2 = (e >> 1) & 1, v3 = e & 1;
-                        if (v0) { if (br.peek() >> 31) v0 = -1; br.pos++; }
-                        if (v1) { if (br.peek() >> 31) v1 = -1; br.pos++; }
-                        if (v2) { if (br.peek() >> 31) v2 = -1; br.pos++; }
-                        if (v3) { if (br.peek() >> 31) v3 = -1; br.pos++; }
+                        br.refill();
+                        const uint32_t e = c1[br.top() >> 26];
+                        br.skip((int)(e >> 4));
+                        // four sign bits at most, present only for the non-zero values, in order v w x y
+                        uint32_t w = br.top();
+                        const int a0 = (e >> 3) & 1, a1 = (e >> 2) & 1, a2 = (e >> 1) & 1, a3 = e & 1;
+                        const int n0 = a0 & (int)(w >> 31); w <<= a0;
+                        const int n1 = a1 & (int)(w >> 31); w <<= a1;
+                        const int n2 = a2 & (int)(w >> 31); w <<= a2;
+                        const int n3 = a3 & (int)(w >> 31);
+                        br.skip(a0 + a1 + a2 + a3);
                         if (br.pos > end) state = 2;  // quad straddles the end: discarded
-                        else { x = v0; y = v1; q2 = (int16_t)v2; q3 = (int16_t)v3; have_second = true; nz += 4; }
+                        else {
+                            x = a0 - 2 * n0; y = a1 - 2 * n1;
+                            q2 = (int16_t)(a2 - 2 * n2); q3 = (int16_t)(a3 - 2 * n3);
+                            have_second = true; nz += 4;
+                        }
                     } else state = 2;
                 }
                 s_stage[warp][lane][pp] = ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);

@@ -5,9 +5,8 @@
 // which its natural index is the lane, so there is no index arithmetic in the inner loops:
 //
 //   TMA  the batch's int16 spectra (8 x 1152 B, contiguous in HBM) arrive in shared memory as ONE bulk copy
-//        (cp.async.bulk + mbarrier), issued a batch ahead by one thread
-//   P0   side info + scalefactors -> gain of every scalefactor band     warp per granule-channel, lane = band; runs one
-//                                                                        batch ahead on the three warps idle during P3
+//        (cp.async.bulk + mbarrier), issued a batch ahead by one thread,
+//        together with the gain of every scalefactor band that K1 derived from part 2 (8 x 256 B)
 //   P1   requantise + MS + short-block reorder -> xr (slot A)            the warps of one granule, lane = line pair;
 //                                                                        handed to P2 by a 64-thread named barrier
 //   P2   alias butterflies + IMDCT + window + frequency inversion        warp = granule-channel, lane = SUBBAND: the 18
@@ -32,22 +31,19 @@
 #define ROW 33             // padded row of 32 values
 #define SLOTF (18 * ROW)   // floats per slot
 
-struct __align__(4) GranInfo {
-    uint32_t part2_bit;   // absolute bit position of part 2 in the main-data stream
-    uint32_t md_lim;      // bytes readable (later bytes read as zero)
+struct __align__(2) GranInfo {
     uint16_t nz;          // lines decoded by K1 (0 = silent)
-    uint8_t global_gain, sfc, bt, mixed, preflag, sf_shift /* 2 or 4 */;
-    uint8_t sbg[3], scfsi, ms, sb_limit /* subbands with possibly non-zero IMDCT input */, pad[2];
+    uint8_t bt, mixed, ms, sb_limit /* subbands with possibly non-zero IMDCT input */;
 };
 
 struct K2Smem {
     alignas(16) float A[K2_SLOTS][SLOTF];     // per granule-channel: xr[576] -> F[18][ROW] -> DCT rows [18][ROW], in place
     float S2[K2_SLOTS][SLOTF];                // IMDCT outputs 18..35 of the granule-channel (added by the NEXT granule)
     alignas(16) uint32_t stage[K2_GC][288];   // the batch's int16 line pairs, written by the TMA unit
-    float bandgain[K2_GC][64];                // per band: 2^(exponent/4) ([0..21] long sfb, [22..60] short sfb*3+win)
-    uint32_t p1w[K2_GC];                      // tsel | ms<<2 | (nz!=0)<<3 | (9*max sb_limit of the granule)<<8
+    alignas(16) float bandgain[K2_GC][64];    // per band: 2^(exponent/4) ([0..21] long sfb, [22..60] short sfb*3+win), by TMA
     float wa[8][32], wb[8][32];
     GranInfo gi[K2_MAX_G][2];                 // side info of every granule-channel of the run
+    uint32_t p1w[K2_MAX_G][2];                // tsel | ms<<2 | (nz!=0)<<3 | (9*max sb_limit of the granule)<<8
     uint16_t scat[2][576];                    // bitstream-order line -> reordered line: [0] pure short, [1] mixed
     uint8_t code[3][576];                     // line -> band code: [0] long, [1] pure short, [2] mixed
     uint8_t ia[32], ib[32];
@@ -89,69 +85,28 @@ struct Dct2<1, OFF> {
     static __device__ __forceinline__ void run(float (&)[1]) {}
 };
 
-__device__ __forceinline__ uint32_t md_bits(const uint8_t* __restrict__ mdp, uint32_t lim, uint32_t bit, int n) {
-    // n <= 8 bits at absolute bit position `bit`; bytes at or beyond lim read as zero
-    if (n == 0) return 0;
-    const uint32_t by = bit >> 3;
-    const uint32_t b0 = by < lim ? __ldg(mdp + by) : 0u, b1 = by + 1 < lim ? __ldg(mdp + by + 1) : 0u;
-    const uint32_t w = (b0 << 8) | b1;
-    return (w >> (16 - n - (bit & 7))) & ((1u << n) - 1);
-}
-
-// long-block scalefactor `sfb` (0..20) of a granule-channel whose part 2 starts at gi.part2_bit; `scfsi` = bands skipped
-__device__ __forceinline__ int read_long_sf(const uint8_t* __restrict__ mdp, const GranInfo& gi, int scfsi, int sfb, int slen1, int slen2) {
-    const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
-    const int lo = grp == 0 ? 0 : (grp == 1 ? 6 : (grp == 2 ? 11 : 16));
-    uint32_t off = 0;
-    if (grp > 0 && !(scfsi & 8)) off += 6 * slen1;
-    if (grp > 1 && !(scfsi & 4)) off += 5 * slen1;
-    if (grp > 2 && !(scfsi & 2)) off += 5 * slen2;
-    const int sl = grp < 2 ? slen1 : slen2;
-    off += (sfb - lo) * sl;
-    return (int)md_bits(mdp, gi.md_lim, gi.part2_bit + off, sl);
-}
-
 // position of IMDCT-36 output i in the 18-point DCT-IV vector u: i<9: u[i+9]; 9..26: u[26-i]; 27..35: u[i-27]
 __device__ __forceinline__ constexpr int idx36(int i) { return i < 9 ? i + 9 : (i < 27 ? 26 - i : i - 27); }
 
-// side info of granule g (0 = first granule of the track), channel ch
+// the side-info fields K2 still needs of granule g (0 = first granule of the track), channel ch
 __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corpus, const DecTrack& tr, const FrameRec* __restrict__ frames,
                                                 const uint16_t* __restrict__ nz_in, uint32_t g, uint32_t ch, int nch) {
     const uint32_t frame = g >> 1, gr = g & 1;
     const FrameRec rec = frames[tr.frame_base + frame];
     const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-    const int gbase = (nch == 1 ? 18 : 20);
-    const int rem = gr * nch + ch;
-    uint32_t bit = rec.md_start * 8;
-    for (int k = 0; k < rem; k++) bit += side_field(s, gbase + 59 * k, 12);
-    const int b0 = gbase + 59 * rem;
+    const int b0 = (nch == 1 ? 18 : 20) + 59 * (gr * nch + ch);
     GranInfo gi;
-    gi.global_gain = (uint8_t)side_field(s, b0 + 21, 8);
-    gi.sfc = (uint8_t)side_field(s, b0 + 29, 4);
-    const int ws = side_field(s, b0 + 33, 1);
-    gi.bt = 0; gi.mixed = 0; gi.sbg[0] = gi.sbg[1] = gi.sbg[2] = 0;
-    if (ws) {
-        gi.bt = (uint8_t)side_field(s, b0 + 34, 2);
-        gi.mixed = (uint8_t)side_field(s, b0 + 36, 1);
-        gi.sbg[0] = (uint8_t)side_field(s, b0 + 47, 3);
-        gi.sbg[1] = (uint8_t)side_field(s, b0 + 50, 3);
-        gi.sbg[2] = (uint8_t)side_field(s, b0 + 53, 3);
-    }
-    if (gi.bt != 2) gi.mixed = 0;
-    gi.preflag = (uint8_t)side_field(s, b0 + 56, 1);
-    gi.sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
-    gi.part2_bit = bit;
-    gi.md_lim = rec.md_end;
+    const uint32_t f = side_field(s, b0 + 33, 4);   // window_switching(1) block_type(2) mixed(1)
+    gi.bt = (f & 8) ? (uint8_t)((f >> 1) & 3) : 0;
+    gi.mixed = (gi.bt == 2) ? (uint8_t)(f & 1) : 0;
     const size_t gcb = (size_t)tr.gc_base + (size_t)frame * 2 * nch + gr * nch;
     gi.nz = nz_in[gcb + ch];
-    gi.scfsi = (gr == 1) ? (uint8_t)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;
     gi.ms = (nch == 2 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 2)) ? 1 : 0;
     // subbands whose IMDCT input can be non-zero: the coded lines (of either channel under MS), one more subband for
     // the alias butterflies; short blocks scatter lines across the whole band, so they keep all 32
     uint32_t nzm = gi.nz;
     if (gi.ms) nzm = max(nzm, (uint32_t)nz_in[gcb + (ch ^ 1)]);
     gi.sb_limit = nzm == 0 ? 0 : (gi.bt == 2 ? 32 : (uint8_t)min(32u, (nzm + 17) / 18 + 1));
-    gi.pad[0] = gi.pad[1] = 0;
     return gi;
 }
 
@@ -161,8 +116,10 @@ __device__ __forceinline__ void k2_mbar_init(unsigned long long* bar, uint32_t c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void k2_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+__device__ __forceinline__ void k2_mbar_expect(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k2_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(k2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k2_smem_u32(bar)) : "memory");
 }
@@ -200,12 +157,12 @@ template <int NCH>
 __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md,
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
-                                        const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
+                                        const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
+                                        float* __restrict__ pcm, uint32_t flags) {
     constexpr int G = K2_GC / NCH;      // granules per batch
     constexpr int NS = G + 1;           // granule slots
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sr = (int)tr.sr_idx;
-    const uint8_t* mdp = md + tr.md_off;
     const uint32_t warm = run.g0 < 2 ? run.g0 : 2;
     const uint32_t gfirst = run.g0 - warm, gcount = run.ng + warm;   // gcount <= K2_MAX_G
     const uint32_t n_batches = (gcount + G - 1) / G;
@@ -230,71 +187,25 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         S.gi[gl][ch] = k2_parse_gi(corpus, tr, frames, nz_in, gfirst + gl, ch, NCH);
     }
     __syncthreads();
+    for (uint32_t it = tid; it < gcount * NCH; it += K2_THREADS) {
+        const uint32_t gl = it / NCH, ch = it % NCH;
+        const GranInfo gi = S.gi[gl][ch];
+        const int lim = max((int)gi.sb_limit, (int)S.gi[gl][NCH - 1 - ch].sb_limit);
+        const uint32_t tsel = gi.bt != 2 ? 0u : (gi.mixed ? 2u : 1u);
+        S.p1w[gl][ch] = tsel | ((uint32_t)gi.ms << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(9 * lim) << 8);
+    }
 
-    // spectra of batch b: granule-channels are contiguous in HBM, 1152 bytes each
+    // spectra and band gains of batch b: granule-channels are contiguous in HBM, 1152 + 256 bytes each
     auto issue_copy = [&](uint32_t b) {
         const uint32_t gl0 = b * G;
-        const uint32_t ng = min((uint32_t)G, gcount - gl0);
-        const int16_t* src = spectra + ((size_t)tr.gc_base + (size_t)(gfirst + gl0) * NCH) * 576;
-        k2_bulk_load(&S.stage[0][0], src, ng * NCH * 1152u, &S.mbar);
-    };
-
-    // ---- P0: scalefactors of granule-channel q of batch b -> bandgain[q], p1w[q].  One warp per granule-channel; every
-    // branch on the block type is warp-uniform.  Part 2 of the main data has a closed-form layout, so each lane reads its
-    // own band's scalefactor straight from the bitstream.
-    auto p0_gc = [&](uint32_t b, int q) {
-        const int gi_ = q / NCH, ch = q % NCH;
-        const uint32_t gl = b * G + gi_;
-        if (gl >= gcount) return;
-        const GranInfo gi = S.gi[gl][ch];
-        const int slen1 = T->slen[0][gi.sfc], slen2 = T->slen[1][gi.sfc];
-        const int base_e = (int)gi.global_gain - 210 - L3_GAIN_MIN;
-        float* bg = S.bandgain[q];
-        if (gi.bt != 2) {
-            if (lane < 22) {
-                int v = 0;
-                if (lane < 21) {
-                    const int grp = lane < 6 ? 0 : (lane < 11 ? 1 : (lane < 16 ? 2 : 3));
-                    if (!(gi.scfsi & (8 >> grp))) v = read_long_sf(mdp, gi, gi.scfsi, lane, slen1, slen2);
-                    else {
-                        // scfsi: reuse granule 0's scalefactor of the same frame (the previous granule of the run: runs start
-                        // on an even granule).  A short granule 0 has no long scalefactors (they read as 0) except the 8
-                        // of a mixed block.
-                        const GranInfo g0 = S.gi[gl - 1][ch];
-                        const int a1 = T->slen[0][g0.sfc], a2 = T->slen[1][g0.sfc];
-                        if (g0.bt != 2) v = read_long_sf(mdp, g0, 0, lane, a1, a2);
-                        else if (g0.mixed && lane < 8) v = md_bits(mdp, g0.md_lim, g0.part2_bit + lane * a1, a1);
-                    }
-                }
-                bg[lane] = __ldg(&T->gain[base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0))]);
-            }
-        } else {
-            if (lane < 22) {  // long part: only the first 8 bands of a mixed block carry scalefactors
-                int v = 0;
-                if (gi.mixed && lane < 8) v = md_bits(mdp, gi.md_lim, gi.part2_bit + lane * slen1, slen1);
-                bg[lane] = __ldg(&T->gain[base_e - gi.sf_shift * (v + (gi.preflag ? T->pretab[lane] : 0))]);
-            }
-            for (int q2 = lane; q2 < 39; q2 += 32) {
-                const int sfb = q2 / 3, win = q2 - 3 * sfb;
-                int v = 0;
-                if (sfb < 12 && !(gi.mixed && sfb < 3)) {
-                    uint32_t off;
-                    if (gi.mixed) off = (sfb < 6) ? (8 + (q2 - 9)) * slen1 : 17 * slen1 + (q2 - 18) * slen2;
-                    else off = (sfb < 6) ? q2 * slen1 : 18 * slen1 + (q2 - 18) * slen2;
-                    v = md_bits(mdp, gi.md_lim, gi.part2_bit + off, sfb < 6 ? slen1 : slen2);
-                }
-                bg[22 + q2] = __ldg(&T->gain[base_e - 8 * gi.sbg[win] - gi.sf_shift * v]);
-            }
-        }
-        if (lane == 0) {
-            const int lim = max((int)gi.sb_limit, (int)S.gi[gl][NCH - 1 - ch].sb_limit);
-            const uint32_t tsel = gi.bt != 2 ? 0u : (gi.mixed ? 2u : 1u);
-            S.p1w[q] = tsel | ((uint32_t)gi.ms << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(9 * lim) << 8);
-        }
+        const uint32_t ngc = min((uint32_t)G, gcount - gl0) * NCH;
+        const size_t gc0 = (size_t)tr.gc_base + (size_t)(gfirst + gl0) * NCH;
+        k2_mbar_expect(&S.mbar, ngc * (1152u + 4u * K1_GAIN_ROW));
+        k2_bulk_load(&S.stage[0][0], spectra + gc0 * 576, ngc * 1152u, &S.mbar);
+        k2_bulk_load(&S.bandgain[0][0], gains + gc0 * K1_GAIN_ROW, ngc * 4u * K1_GAIN_ROW, &S.mbar);
     };
 
     if (tid == 0) issue_copy(0);
-    p0_gc(0, warp);
     __syncthreads();
 
     for (uint32_t b = 0; b < n_batches; b++) {
@@ -308,7 +219,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         // The warps of one granule share its line pairs; scalefactor bands start on even lines, so a pair shares its band.
         k2_mbar_wait(&S.mbar, b & 1);
         if (have) {
-            const uint32_t w0 = S.p1w[my_gi * NCH], w1 = S.p1w[my_gi * NCH + NCH - 1];
+            const uint32_t w0 = S.p1w[gl][0], w1 = S.p1w[gl][NCH - 1];
             const int lim9 = (int)(w0 >> 8);
             const int tsel0 = w0 & 3, tsel1 = w1 & 3;
             const bool ms = (w0 >> 2) & 1;
@@ -324,7 +235,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++) {
                     const uint32_t packed = (ch ? nzf1 : nzf0) ? (ch ? st1 : st0)[pr] : 0u;
-                    const float gn = (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]];
+                    const float gn = (ch ? nzf1 : nzf0) ? (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]] : 0.0f;
                     const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
                     const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
                     const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
@@ -447,7 +358,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         __syncthreads();
 
         // ================= P3: overlap-add + 32-point DCT-II per time slot (Lee), in place ================================
-        // Threads 0..143 take one (granule-channel, slot) each; the idle warps prepare the next batch.
+        // Threads 0..143 take one (granule-channel, slot) each; one thread of an idle warp starts the next batch's copy.
         if (tid < 18 * K2_GC) {
             const int q = tid / 18, t = tid - 18 * q;
             const uint32_t g3 = gl0 + q / NCH;
@@ -461,9 +372,8 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 #pragma unroll
                 for (int i = 0; i < 32; i++) a[i] = x[i];
             }
-        } else if (warp >= 5 && b + 1 < n_batches) {
-            if (tid == 5 * 32) issue_copy(b + 1);   // P1 of this batch has consumed the staging buffer (barrier above)
-            for (int q = warp - 5; q < K2_GC; q += 3) p0_gc(b + 1, q);
+        } else if (tid == 5 * 32 && b + 1 < n_batches) {
+            issue_copy(b + 1);   // P1 of this batch has consumed the staging buffers (barrier above)
         }
         __syncthreads();
 
@@ -504,11 +414,12 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
-               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, float* __restrict__ pcm, uint32_t flags) {
+               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
+               float* __restrict__ pcm, uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
-    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, pcm, flags);
-    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, pcm, flags);
+    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, pcm, flags);
+    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, pcm, flags);
 }

@@ -23,7 +23,8 @@
 #define HUF_L1 8
 struct L3Dev {
     uint16_t huff[8192];        // two-level lookup, all 15 books in one array (see build_huff_lookup)
-    uint16_t huff_base[16];     // first-level base of book slot s (1..15)
+    uint16_t huff_base[16];     // first-level base of book slot s (1..15); [0] = an all-zero table
+    uint32_t huff_total;        // entries used
     uint8_t tabsel[32][2];      // table_select -> {slot, linbits}
     uint8_t c1_lut[2][16];      // count1: 4-bit peek -> (len<<4)|quad   (table B is the identity on ~peek)
     uint8_t c1a_lut[64];        // count1 table A: 6-bit peek -> (len<<4)|quad
@@ -125,15 +126,18 @@ static void build_huff_lookup(L3Dev& T) {
             }
         }
     }
-    // total must stay below 8192 entries (11-bit offset/4): checked by the caller
+    // slot 0 ("no data in this region") = an all-zero first-level table: length 0, x = y = 0, so K1 needs no special case.
+    // total must stay within 8192 entries (11-bit offset/4): checked by the caller
     T.huff_base[0] = (uint16_t)total;
+    total += 1u << HUF_L1;
+    T.huff_total = total;
 }
 
 static int decode_init_tables(DecodeScratch& ds) {
     static L3Dev T;  // ~80 KB, host staging
     memset(&T, 0, sizeof T);
     build_huff_lookup(T);
-    if (T.huff_base[0] > 8192) return -1;
+    if (T.huff_total > 8192) return -1;
     memcpy(T.tabsel, L3_TABSEL, sizeof T.tabsel);
     // count1 A: 6-bit peek lookup; B: 4-bit
     for (int v = 0; v < 16; v++) {

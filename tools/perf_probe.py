@@ -23,6 +23,8 @@ imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
 print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
 lib = _lib.load()
 eng = m.Engine(device=0, exact=exact)
+if os.environ.get("RG_PIPELINE") == "0":
+    eng.set_option("pipeline", 0)   # one batch at a time, every kernel alone on the device
 arr, keep = m.Engine._inputs(imgs, None)
 cor = C.c_void_p()
 t = time.time()
