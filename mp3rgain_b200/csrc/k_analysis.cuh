@@ -30,8 +30,10 @@ struct RgCoefExact {      // reference order, direct form I
 };
 struct RgCoefFast {       // transposed direct form II of the same cascade
     double a[10], b[11], A[2], B[3];
-    double c2;            // steady-state output offset produced by the two "+1e-10" terms of the reference
+    double k2;            // c2*(1+A1+A2), c2 = steady-state output offset produced by the two "+1e-10" terms of the reference;
+                          // the offset is carried inside the Butterworth states (u0+c2, u1+c2*(1+A1)), so the output needs no add
     double s0[10], u0[2]; // filter states equivalent to the reference's all-zero histories at the start of a track
+    double uz[2];         // Butterworth states of a chain that starts from rest: {c2, c2*(1+A1)}
 };
 
 struct IirState {
@@ -66,7 +68,7 @@ __device__ __forceinline__ double iir_step_exact(IirState& s, const RgCoefExact&
 //     y = b0*x + s1;   s_k' = (b_k*x + s_{k+1}) - a_k*y   (k = 1..10, s_11 = 0)
 // Every state update is an independent 2-FMA chain and only y -> s1' -> y is loop-carried, so a single warp keeps ~10
 // DFMAs in flight, and the state is 12 doubles instead of 24.  The reference's two "+1e-10" terms make its filter affine;
-// an affine filter equals the linear one plus a constant (c2 at the output, once transients have died -- the same
+// an affine filter equals the linear one plus a constant (c2 at the output, carried in the Butterworth states -- the same
 // argument that lets a chain start from zero state one window early) and, at the start of a track, the linear filter
 // started from the non-zero state {s0,u0} that corresponds to the reference's all-zero histories.  Not bit-identical
 // arithmetic: K5 flags every window whose bin decision is within edge_tol of flipping and those tracks are re-run EXACT.
@@ -81,11 +83,11 @@ __device__ __forceinline__ double iir_step_fast(TdfState& st, const RgCoefFast& 
 #pragma unroll
     for (int k = 1; k <= 10; k++) st.s[k - 1] = __fma_rn(-c.a[k - 1], y, t[k - 1]);
     const double v1 = __fma_rn(c.B[1], y, st.u[1]);
-    const double v2 = __dmul_rn(c.B[2], y);
-    const double z = __fma_rn(c.B[0], y, st.u[0]);
+    const double v2 = __fma_rn(c.B[2], y, c.k2);
+    const double z = __fma_rn(c.B[0], y, st.u[0]);   // already includes the affine offset c2
     st.u[0] = __fma_rn(-c.A[0], z, v1);
     st.u[1] = __fma_rn(-c.A[1], z, v2);
-    return __dadd_rn(z, c.c2);
+    return z;
 }
 
 // Per-chain window accounting.
@@ -192,8 +194,8 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
     const bool head = ch.flags & 1u;   // chain starts at the first sample of the track
 #pragma unroll
     for (int i = 0; i < 10; i++) s.s[i] = head ? c.s0[i] : 0.0;
-    s.u[0] = head ? c.u0[0] : 0.0;
-    s.u[1] = head ? c.u0[1] : 0.0;
+    s.u[0] = head ? c.u0[0] : c.uz[0];
+    s.u[1] = head ? c.u0[1] : c.uz[1];
     WinAcc w;
     w.sum = 0.0; w.out = ch.wsum; w.mout = ch.wmax; w.wmax = 0.0f; w.tot = 0; w.win = ch.win;
     float peak = 0.0f;
@@ -208,8 +210,8 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
 }
 
 // the instantiation the engine launches (tools/iir_bench.cu times the alternatives)
-#define K4_FAST_THREADS 128
-#define k_iir_fast k_iir_fast_t<5, K4_FAST_THREADS, 3>
+#define K4_FAST_THREADS 256
+#define k_iir_fast k_iir_fast_t<3, K4_FAST_THREADS, 2>
 
 // ------------------------------------------------------------------------------------------------------------
 // K5: one CTA per track.  Window sums -> bin index -> shared 12000-bin histogram (warp-aggregated atomics)

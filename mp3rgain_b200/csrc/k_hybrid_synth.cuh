@@ -27,7 +27,7 @@
 #define K2_THREADS 256
 #define K2_GC 8            // granule-channels per batch, one per warp
 #define K2_SLOTS 10        // slots of A / S2: (G+1) granules x channels = 5x2 (stereo) or 9x1 (mono)
-#define K2_MAX_G 64        // granules per run, including the two replayed ones
+#define K2_MAX_G 128       // granules per run, including the two replayed ones
 #define ROW 33             // padded row of 32 values
 #define SLOTF (18 * ROW)   // floats per slot
 
@@ -151,6 +151,34 @@ __device__ __forceinline__ void k2_window36(const float (&u)[18], float (&o)[36]
         constexpr float w = L3_WINSGN[BT][i];
         o[i] = __fmul_rn(u[idx36(i)], w);
     });
+}
+
+// P4 of one granule-channel, lane = output column j:
+//   out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]   (p ascending, one fmaf chain)
+// rows t-15..t-1 of slot 0 live in the previous granule's slot (rows 3..17)
+template <bool CLAMP>
+__device__ __forceinline__ void k2_polyphase(const K2Smem& S, const float* __restrict__ cur, const float* __restrict__ prv,
+                                             float* __restrict__ dst, int j) {
+    float wa[8], wb[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][j]; wb[p] = S.wb[p][j]; }
+    const int ia = S.ia[j], ib = S.ib[j];
+    float Av[33], Bv[33];   // rows -15 .. 17 relative to this granule's slot 0
+#pragma unroll
+    for (int r = 0; r < 15; r++) { Av[r] = prv[r * ROW + ia]; Bv[r] = prv[r * ROW + ib]; }
+#pragma unroll
+    for (int t = 0; t < 18; t++) {
+        Av[15 + t] = cur[t * ROW + ia];
+        Bv[15 + t] = cur[t * ROW + ib];
+        float a = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            a = fmaf(Av[15 + t - 2 * p], wa[p], a);
+            a = fmaf(Bv[15 + t - 2 * p - 1], wb[p], a);
+        }
+        if (CLAMP) a = fminf(1.0f, fmaxf(-1.0f, a));
+        dst[32 * t] = a;
+    }
 }
 
 template <int NCH>
@@ -380,32 +408,9 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         // ================= P4: polyphase window -> PCM, lane = output column ==============================================
         if (have && gfirst + gl >= run.g0) {
             const uint32_t g = gfirst + gl;
-            const int j = lane;
-            // out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]  (p ascending, one fmaf chain); rows t-15..t-1 of slot 0
-            // live in the previous granule's slot (rows 3..17)
-            float wa[8], wb[8];
-#pragma unroll
-            for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][j]; wb[p] = S.wb[p][j]; }
-            const int ia = S.ia[j], ib = S.ib[j];
-            const float* cur = S.A[slot];
-            const float* prv = S.A[slot_prev] + 3 * ROW;
-            float Av[33], Bv[33];   // rows -15 .. 17 relative to this granule's slot 0
-#pragma unroll
-            for (int r = 0; r < 15; r++) { Av[r] = prv[r * ROW + ia]; Bv[r] = prv[r * ROW + ib]; }
-            float* dst = pcm + tr.pcm_off + (size_t)my_ch * tr.pcm_plane + (size_t)g * 576 + j;
-#pragma unroll
-            for (int t = 0; t < 18; t++) {
-                Av[15 + t] = cur[t * ROW + ia];
-                Bv[15 + t] = cur[t * ROW + ib];
-                float a = 0.0f;
-#pragma unroll
-                for (int p = 0; p < 8; p++) {
-                    a = fmaf(Av[15 + t - 2 * p], wa[p], a);
-                    a = fmaf(Bv[15 + t - 2 * p - 1], wb[p], a);
-                }
-                if (flags & 0x4u) a = fminf(1.0f, fmaxf(-1.0f, a));
-                dst[32 * t] = a;
-            }
+            float* dst = pcm + tr.pcm_off + (size_t)my_ch * tr.pcm_plane + (size_t)g * 576 + lane;
+            if (flags & 0x4u) k2_polyphase<true>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, lane);
+            else k2_polyphase<false>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, lane);
         }
         __syncthreads();
     }

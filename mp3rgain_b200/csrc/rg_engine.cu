@@ -212,10 +212,14 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         sA += row[23] + row[24];
         for (int i = 0; i < 3; i++) sB += row[25 + i];
         const double c = 1e-10 / sa;
-        f.c2 = (1e-10 + sB * c) / sA;
+        const double c2 = (1e-10 + sB * c) / sA;
         // linear-filter states equivalent to the reference's all-zero histories: y'(-k) = -c, z'(-k) = -c2
         for (int k = 1; k <= 10; k++) { double t = 0; for (int j = k; j <= 10; j++) t += row[j]; f.s0[k - 1] = c * t; }
-        for (int k = 1; k <= 2; k++) { double t = 0; for (int j = k; j <= 2; j++) t += -c * row[25 + j] + f.c2 * row[22 + j]; f.u0[k - 1] = t; }
+        for (int k = 1; k <= 2; k++) { double t = 0; for (int j = k; j <= 2; j++) t += -c * row[25 + j] + c2 * row[22 + j]; f.u0[k - 1] = t; }
+        // the output offset c2 rides inside the Butterworth states: u0 + c2, u1 + c2*(1 + A1); k2 keeps it there
+        f.uz[0] = c2; f.uz[1] = c2 * (1.0 + row[23]);
+        f.u0[0] += f.uz[0]; f.u0[1] += f.uz[1];
+        f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
     int rc = decode_init_tables(e->dec);

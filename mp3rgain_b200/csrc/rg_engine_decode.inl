@@ -9,7 +9,7 @@
 // The host plans batch k+1 (run / chain descriptors need K0's frame counts) while the device works on batch k; two
 // BatchCtx alternate, each with half of the scratch budget.
 
-#define RUN_GRANULES 62   // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
+#define RUN_GRANULES 126  // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
 
 static const uint32_t MPEG1_RATES[3] = {44100, 48000, 32000};
 

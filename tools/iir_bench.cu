@@ -90,17 +90,24 @@ int main(int argc, char** argv) {
         for (int i = 0; i <= 10; i++) cf.b[i] = row[11 + i] * 32768.0;
         cf.A[0] = row[23]; cf.A[1] = row[24];
         for (int i = 0; i < 3; i++) cf.B[i] = row[25 + i];
-        cf.c2 = 2.2e-7;
+        cf.k2 = 2.2e-7;
         for (int i = 0; i < 10; i++) cf.s0[i] = 0;
-        cf.u0[0] = cf.u0[1] = 0;
+        cf.u0[0] = cf.u0[1] = cf.uz[0] = cf.uz[1] = 0;
     }
     const double audio_s = (double)n_tracks * frames / 44100.0;
     printf("%d tracks, %zu chains, %.1f audio-hours\n", n_tracks, chains.size(), audio_s / 3600);
     std::vector<double> ref;
     const uint32_t nc = (uint32_t)chains.size();
 #define RUN(NV, T, B) run<NV, T, B>("nv" #NV " T" #T " minb" #B, d_chains, nc, d_peaks, d_wsum, n_w, ref, audio_s, cf)
+    RUN(5, 128, 3);
     RUN(2, 128, 3);
     RUN(2, 128, 4);
+    RUN(3, 128, 4);
+    RUN(4, 128, 4);
+    RUN(2, 256, 2);
+    RUN(3, 256, 2);
+    RUN(2, 64, 8);
+    RUN(3, 64, 8);
     RUN(2, 128, 5);
     RUN(2, 128, 6);
     RUN(1, 128, 4);
