@@ -109,7 +109,9 @@ const char* rg_status_str(int status);
 /* Tuning knobs (not part of the reference surface). Keys: "iir_block_windows" (50 ms windows per time block of
  * the time-blocked IIR, default 16), "iir_warm_windows" (zero-state warm-up windows before each block, default 1),
  * "edge_tol" (distance of 1000*log10(ms) from an integer below which the time-blocked pass hands the track to the
- * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9).  Returns RG_ERR_INVALID_ARG for an unknown key. */
+ * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9), "pipeline" (default 1:
+ * copy / index / decode / analysis overlap on four streams with two alternating batches; 0 = one batch at a time, every
+ * kernel alone on the device, for profiling).  Returns RG_ERR_INVALID_ARG for an unknown key. */
 int rg_engine_set_option(rg_engine* e, const char* key, double value);
 /* Thread-local detail string for the last failing call (CUDA error text etc.). */
 const char* rg_last_error(void);
@@ -157,6 +159,8 @@ typedef struct {
     uint64_t tracks, frames, exact_reruns;
     float    last_ms_index, last_ms_huffman, last_ms_hybrid, last_ms_synth, last_ms_iir, last_ms_hist;
     float    last_ms_total;     /* CUDA-event time of the last analyse call's device work */
+    uint32_t last_batches;      /* decode/analysis batches (= launches of each of K1, K2, K4, K5) in the last analyse call */
+    uint32_t reserved;
 } rg_stats;
 int rg_engine_stats(rg_engine* e, rg_stats* out);
 

@@ -306,6 +306,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
     CK(cudaSetDevice(e->device));
     e->stats.last_ms_index = e->stats.last_ms_huffman = e->stats.last_ms_hybrid = e->stats.last_ms_synth = 0;
     e->stats.last_ms_iir = e->stats.last_ms_hist = e->stats.last_ms_total = 0;
+    e->stats.last_batches = 0;
     if (first_bad) *first_bad = -1;
     if (!n) return RG_OK;
     CK(cudaEventRecord(e->ev[7], e->stream));
@@ -378,6 +379,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
         if (rc == RG_OK) rc = stage_b_enqueue(e, x, exact_all, hist_out != nullptr, d_album_hist, d_album_peak, !exact_all, true);
         if (rc != RG_OK) return fail(rc);
         x.busy = true;
+        e->stats.last_batches++;
         if (!e->pipeline) { rc = collect(x, false); if (rc != RG_OK) return fail(rc); }
         next = t1;
         k++;
