@@ -71,6 +71,7 @@ def analyze_album_sharded(engine: Engine, images: Sequence, rank: int, world: in
         st = -int(status.item())
         raise ReplayGainError(st, _message(st))
     album_reduce(d_hist, d_peak, group)
+    torch.cuda.synchronize()   # the collective ran on torch's streams; rg_album_finish reads the buffers on the engine's
     alb = _lib.RgAlbumResult()
     rc = lib.rg_album_finish(engine._h, d_hist.data_ptr(), d_peak.data_ptr(), C.byref(alb))
     if rc != 0:
