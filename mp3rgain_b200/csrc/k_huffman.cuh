@@ -23,19 +23,19 @@ struct BitBuf {
     uint32_t lim;        // bytes readable for this frame (later bytes read as zero, like the oracle's reservoir)
     uint32_t wi;         // index of the look-ahead word
     uint32_t nxt;        // look-ahead word (big-endian), not yet in acc
-    uint32_t pos;        // bit position of the next unread bit
     unsigned long long acc;   // unread bits, left-aligned
     int nb;              // valid bits in acc (>= 33 after refill())
     __device__ __forceinline__ uint32_t ld(uint32_t i) const {
-        const uint32_t b = i * 4;
         uint32_t v = __byte_perm(__ldg(w + i), 0, 0x0123);
-        if (b + 4 > lim) v = b >= lim ? 0u : (v & (0xFFFFFFFFu << (8 * (b + 4 - lim))));
+        if (i >= (lim >> 2)) {   // the word reaches past the readable bytes (rare: only at the very end of a frame's data)
+            const uint32_t b = i * 4;
+            v = b >= lim ? 0u : (v & (0xFFFFFFFFu << (8 * (b + 4 - lim))));
+        }
         return v;
     }
     __device__ __forceinline__ void init(const uint8_t* base, uint32_t lim_bytes, uint32_t bitpos) {
         w = reinterpret_cast<const uint32_t*>(base);
         lim = lim_bytes;
-        pos = bitpos;
         wi = bitpos >> 5;
         const uint32_t sh = bitpos & 31;
         acc = ((((unsigned long long)ld(wi)) << 32) | ld(wi + 1)) << sh;
@@ -43,6 +43,8 @@ struct BitBuf {
         wi += 2;
         nxt = ld(wi);
     }
+    // bit position of the next unread bit: words 0..wi-1 have entered acc, nb of their bits are still unread
+    __device__ __forceinline__ uint32_t pos() const { return (wi << 5) - (uint32_t)nb; }
     __device__ __forceinline__ void refill() {
         if (nb <= 32) {
             acc |= (unsigned long long)nxt << (32 - nb);
@@ -52,7 +54,7 @@ struct BitBuf {
         }
     }
     __device__ __forceinline__ uint32_t top() const { return (uint32_t)(acc >> 32); }
-    __device__ __forceinline__ void skip(int n) { acc <<= n; nb -= n; pos += n; }
+    __device__ __forceinline__ void skip(int n) { acc <<= n; nb -= n; }
     __device__ __forceinline__ uint32_t get(int n) {   // n <= 16
         refill();
         const uint32_t v = (top() >> 1) >> (31 - n);
@@ -102,7 +104,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     bool silent = true;
     BitBuf br;
     br.w = reinterpret_cast<const uint32_t*>(md + tr.md_off);
-    br.lim = 0; br.acc = 0; br.nxt = 0; br.wi = 0; br.pos = 0; br.nb = 64;
+    br.lim = 0; br.acc = 0; br.nxt = 0; br.wi = 2; br.nb = 64;
     float* grow = gains + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
     uint8_t* sfl = s_sfl[tid];
 #pragma unroll
@@ -204,10 +206,12 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     }
     if (silent) bv = 0;
 
-    // ---- lockstep pair loop
-    int16_t q2 = 0, q3 = 0;
-    bool have_second = false;
-    int state = silent ? 2 : 0;   // 0 big values, 1 count1, 2 zero tail
+    // ---- lockstep pair loop.  Every iteration each lane emits one pair.  Count1 quads are decoded only on even p (all
+    // lanes of the warp together), a lane keeps up to three decoded pairs queued as 2-bit values; a lane that enters the
+    // count1 region on an odd p decodes its first quad at once.
+    uint32_t cq = 0;              // queued count1 pairs, 4 bits each (x | y<<2, two's complement), next pair in the low nibble
+    int cqn = 0;
+    int state = silent ? 2 : 0;   // 0 big values, 1 count1, 2 no more decoding (queued pairs still drain)
     bool overrun = false;
     uint32_t nz = 0;
     int16_t* my_rows = spectra + ((size_t)tr.gc_base + blk.gc0 + warp * 32) * 576;
@@ -215,17 +219,22 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     const uint8_t* c1 = s_c1[c1tab];
 
     for (int p0 = 0; p0 < 288; p0 += 16) {
-        if (__any_sync(0xffffffffu, state != 2)) {
+        if (__any_sync(0xffffffffu, state != 2 || cqn != 0)) {
 #pragma unroll 1
             for (int pp = 0; pp < 16; pp++) {
                 const int p = p0 + pp;
                 int x = 0, y = 0;
                 if (state == 0 && p >= bv) {
                     // end of the big-values region: an overrun silences the granule-channel (oracle: read_huffman)
-                    if (br.pos > end) { overrun = true; state = 2; }
+                    if (br.pos() > end) { overrun = true; state = 2; }
                     else { state = 1; nz = 2 * bv; }
                 }
-                if (state == 0) {
+                // warp-uniform guards (real branches, not predication): the big-values and the quad decoders are skipped
+                // whenever no lane of the warp needs them in this iteration
+                const bool big = state == 0;
+                const bool quad = state == 1 && (cqn == 0 || (cqn == 1 && !(p & 1)));
+                if (__any_sync(0xffffffffu, big)) {
+                  if (big) {
                     const int line = 2 * p;
                     const uint32_t reg = line < r0 ? reg0 : (line < r1 ? reg1 : reg2);
                     const int linbits = (int)(reg & 0xFFu);
@@ -256,27 +265,38 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                     br.skip(lbx + sx + lby + sy);
                     x = negx ? -x : x;
                     y = negy ? -y : y;
-                } else if (state == 1) {
-                    if (have_second) { x = q2; y = q3; have_second = false; }
-                    else if (br.pos < end && p <= 286) {
-                        br.refill();
-                        const uint32_t e = c1[br.top() >> 26];
-                        br.skip((int)(e >> 4));
-                        // four sign bits at most, present only for the non-zero values, in order v w x y
-                        uint32_t w = br.top();
-                        const int a0 = (e >> 3) & 1, a1 = (e >> 2) & 1, a2 = (e >> 1) & 1, a3 = e & 1;
-                        const int n0 = a0 & (int)(w >> 31); w <<= a0;
-                        const int n1 = a1 & (int)(w >> 31); w <<= a1;
-                        const int n2 = a2 & (int)(w >> 31); w <<= a2;
-                        const int n3 = a3 & (int)(w >> 31);
-                        br.skip(a0 + a1 + a2 + a3);
-                        if (br.pos > end) state = 2;  // quad straddles the end: discarded
-                        else {
-                            x = a0 - 2 * n0; y = a1 - 2 * n1;
-                            q2 = (int16_t)(a2 - 2 * n2); q3 = (int16_t)(a3 - 2 * n3);
-                            have_second = true; nz += 4;
-                        }
-                    } else state = 2;
+                  }
+                }
+                if (__any_sync(0xffffffffu, quad)) {
+                    if (quad) {
+                        // the quad lands at pair p + cqn (oracle: while (pos < end && i <= 572))
+                        if (br.pos() < end && p + cqn <= 286) {
+                            br.refill();
+                            const uint32_t e = c1[br.top() >> 26];
+                            br.skip((int)(e >> 4));
+                            // four sign bits at most, present only for the non-zero values, in order v w x y
+                            uint32_t w = br.top();
+                            const uint32_t a0 = (e >> 3) & 1, a1 = (e >> 2) & 1, a2 = (e >> 1) & 1, a3 = e & 1;
+                            const uint32_t n0 = a0 & (w >> 31); w <<= a0;
+                            const uint32_t n1 = a1 & (w >> 31); w <<= a1;
+                            const uint32_t n2 = a2 & (w >> 31); w <<= a2;
+                            const uint32_t n3 = a3 & (w >> 31);
+                            br.skip((int)(a0 + a1 + a2 + a3));
+                            if (br.pos() > end) state = 2;  // quad straddles the end: discarded
+                            else {
+                                const uint32_t nibs = a0 | (n0 << 1) | (a1 << 2) | (n1 << 3) | (a2 << 4) | (n2 << 5) | (a3 << 6) | (n3 << 7);
+                                cq |= nibs << (4 * cqn);
+                                cqn += 2;
+                                nz += 4;
+                            }
+                        } else state = 2;
+                    }
+                }
+                if (!big && cqn) {
+                    x = ((int)(cq << 30)) >> 30;
+                    y = ((int)(cq << 28)) >> 30;
+                    cq >>= 4;
+                    cqn--;
                 }
                 s_stage[warp][lane][pp] = ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);
             }
@@ -295,7 +315,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         __syncwarp();
     }
     if (state == 0) {  // big_values == 288: the region check never ran inside the loop
-        if (br.pos > end) overrun = true; else nz = 576;
+        if (br.pos() > end) overrun = true; else nz = 576;
     }
     if (active) nz_out[tr.gc_base + gc] = (overrun || silent) ? 0 : (uint16_t)nz;
 }

@@ -288,23 +288,50 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
         for (int sfb = 0; sfb < 21; sfb++) g.sf_l[sfb] = sfv(sfb < 11 ? s1 : s2);
     }
     if (bt == 0) { g.region0_count = rng.below(16); g.region1_count = rng.below(8); }
-    // spectrum: Laplacian magnitudes under a decaying envelope; beyond `knee` only 0/+-1 survive (count1 material)
+    // spectrum: Laplacian magnitudes under a decaying envelope; beyond `knee` only 0/+-1 survive (count1 material) and
+    // nothing above ~16 kHz (an encoder's low-pass at this bitrate).  The overall scale of the magnitudes -- the encoder's
+    // quantiser step -- is then chosen so that the coded granule FILLS its share of the frame's bits, like a real CBR
+    // stream: most of the 576 lines carry data, big_values covers a few hundred lines, the rest is count1 material.
     int knee = 60 + rng.below(260);
+    const int lowpass = (int)(576.0 * 16000.0 / (0.5 * (sr_row == 0 ? 44100 : (sr_row == 1 ? 48000 : 32000))));
+    double base[576];
+    bool neg[576], capped[576];
+    int escape[576];
     for (int i = 0; i < 576; i++) {
-        double f = (bt == 2 && !(g.mixed && i < 36)) ? (double)((i % 192)) * 3.0 : (double)i;  // rough frequency of the line
+        double f = (double)i;  // rough frequency of the line
         if (bt == 2 && !(g.mixed && i < 36)) {
             // bitstream order is [sfb][win][k]; approximate the line's frequency by its sfb start
             int p = i, sfb = 0;
             while (sfb < 12 && p >= 3 * g_short_start[sr_row][sfb + 1]) sfb++;
             f = 3.0 * g_short_start[sr_row][sfb];
         }
-        double env = amp * std::pow(1.0 + f / 6.0, -tilt);
-        double mag = -std::log(1.0 - rng.uni()) * env;
-        int v = (int)mag;
-        if (f > knee) v = std::min(v, 1);
-        if (v > 8206) v = 8206;
-        if (rng.chance(0.0008) && f < 40 && !(g_disable & 64)) v = 16 + rng.below(600);  // occasional linbits escapes
-        g.is[i] = (int16_t)(rng.chance(0.5) ? -v : v);
+        base[i] = f >= lowpass ? 0.0 : -std::log(1.0 - rng.uni()) * std::pow(1.0 + f / 6.0, -tilt);
+        capped[i] = f > knee;
+        escape[i] = (rng.chance(0.0008) && f < 40 && !(g_disable & 64)) ? 16 + rng.below(600) : 0;  // occasional linbits escapes
+        neg[i] = rng.chance(0.5);
+    }
+    auto build = [&](double scale) {
+        for (int i = 0; i < 576; i++) {
+            int v = (int)std::min(8206.0, base[i] * scale);
+            if (capped[i]) v = std::min(v, 1);
+            if (escape[i]) v = escape[i];
+            g.is[i] = (int16_t)(neg[i] ? -v : v);
+        }
+    };
+    g.part2_bits = part2_bits_of(g, scfsi, gr);
+    {
+        const int want = (int)(0.97 * std::min(target_bits, 4095));
+        double lo_s = 0.05, hi_s = 400.0 * std::max(1.0, amp / 20.0);
+        const Rng trial0 = rng;
+        for (int it = 0; it < 14; it++) {
+            const double mid = std::sqrt(lo_s * hi_s);
+            build(mid);
+            partition(g, 576);
+            Rng r2 = trial0;
+            choose_tables_and_count(g, sr_row, r2);
+            if (g.part2_bits + g.part3_bits <= want) lo_s = mid; else hi_s = mid;
+        }
+        build(lo_s);
     }
     int16_t full[576];
     memcpy(full, g.is, sizeof full);
@@ -438,6 +465,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
                 int target = (int)(remain / left * (0.7 + 0.6 * rng.uni()));
                 if (left == 1) target = remain;
                 target = std::max(0, std::min(target, remain));
+                if (ms && ch == 1 && left > 1) target = (int)(target * 0.6);   // the side channel gets the smaller share
                 double a = amp * ((ms && ch == 1) ? 0.35 : 1.0);
                 make_granule(gr[g][ch], rng, sr_row, bts[g], mixed[g], a, tilt, target, scfsi[ch], g, lvl);
                 used += gr[g][ch].part2_bits + gr[g][ch].part3_bits;
