@@ -79,6 +79,8 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     __shared__ uint32_t s_stage[K1_THREADS / 32][32][17];
     __shared__ uint8_t s_sfl[K1_THREADS][24];     // long scalefactors of every thread's granule-channel (scfsi source)
     __shared__ uint8_t s_c1[2][64];               // count1 tables A / B: 6-bit peek -> (len<<4)|quad
+    __shared__ uint16_t s_key[K1_THREADS];        // big_values of the block's granule-channels (sort key)
+    __shared__ uint8_t s_perm[K1_THREADS];        // worker thread -> granule-channel of the block, ordered by big_values
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
         const uint4* src = reinterpret_cast<const uint4*>(T->huff);
@@ -93,9 +95,30 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     const DecTrack tr = tracks[blk.track];
     const uint32_t nch = tr.channels;
     const uint32_t n_gc = tr.n_frames * 2 * nch;
-    const uint32_t gc = blk.gc0 + tid;
-    const bool active = gc < n_gc;
+    // ---- order the block's 128 granule-channels by big_values, so that the lanes of a warp leave the big-values decoder
+    // (and enter the zero tail) at about the same pair: the lockstep loop below pays for the slowest lane of the warp
+    {
+        const uint32_t g = blk.gc0 + tid;
+        uint32_t key = 0x1FF;   // inactive slots sort last
+        if (g < n_gc) {
+            const uint32_t frame = g / (2 * nch), rem = g % (2 * nch);
+            const FrameRec rec = frames[tr.frame_base + frame];
+            const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
+            key = side_field(s, (nch == 1 ? 18 : 20) + 59 * rem + 12, 9);
+        }
+        s_key[tid] = (uint16_t)((key << 7) | tid);   // unique keys: ties keep block order
+    }
     __syncthreads();
+    {
+        const uint32_t mine = s_key[tid];
+        int rank = 0;
+        for (int j = 0; j < K1_THREADS; j++) rank += s_key[j] < mine ? 1 : 0;   // every lane reads the same word: broadcast
+        s_perm[rank] = (uint8_t)tid;
+    }
+    __syncthreads();
+    const int gl = s_perm[tid];                   // my granule-channel within the block
+    const uint32_t gc = blk.gc0 + gl;
+    const bool active = gc < n_gc;
 
     // ---- side info of my granule-channel
     int bv = 0, r0 = 0, r1 = 0, c1tab = 0;
@@ -106,7 +129,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     br.w = reinterpret_cast<const uint32_t*>(md + tr.md_off);
     br.lim = 0; br.acc = 0; br.nxt = 0; br.wi = 2; br.nb = 64;
     float* grow = gains + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
-    uint8_t* sfl = s_sfl[tid];
+    uint8_t* sfl = s_sfl[gl];
 #pragma unroll
     for (int i = 0; i < 6; i++) reinterpret_cast<uint32_t*>(sfl)[i] = 0;
     // part-2 parameters, kept for the gain pass below
@@ -186,12 +209,12 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             }
         }
     }
-    __syncwarp();
+    __syncthreads();
     if (active) {
-        // scfsi: granule 1 reuses granule 0's scalefactors of the same channel (thread lane - nch, same frame, same warp).
+        // scfsi: granule 1 reuses granule 0's scalefactors of the same channel (granule-channel gl - nch: same frame, same block).
         // A short granule 0 has no long scalefactors (zero) except the 8 of a mixed block -- exactly what its row holds.
         if (bt != 2 && scfsi) {
-            const uint8_t* g0 = s_sfl[tid - nch];
+            const uint8_t* g0 = s_sfl[gl - nch];
             for (int sfb = 0; sfb < 21; sfb++) {
                 const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
                 if (scfsi & (8 >> grp)) sfl[sfb] = g0[sfb];
@@ -209,17 +232,120 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     // ---- lockstep pair loop.  Every iteration each lane emits one pair.  Count1 quads are decoded only on even p (all
     // lanes of the warp together), a lane keeps up to three decoded pairs queued as 2-bit values; a lane that enters the
     // count1 region on an odd p decodes its first quad at once.
+    // The loop runs in blocks of 16 pairs (one flush each).  Because the block's granule-channels are sorted by big_values,
+    // most blocks are uniform for the whole warp and run a specialised body with no per-lane state tests:
+    //   blocks below the warp's smallest big_values   -> big-values decoder only
+    //   blocks above the warp's largest big_values    -> quad decoder (even p) + queue drain only
+    //   the few blocks in between                     -> the general body
     uint32_t cq = 0;              // queued count1 pairs, 4 bits each (x | y<<2, two's complement), next pair in the low nibble
     int cqn = 0;
     int state = silent ? 2 : 0;   // 0 big values, 1 count1, 2 no more decoding (queued pairs still drain)
     bool overrun = false;
     uint32_t nz = 0;
-    int16_t* my_rows = spectra + ((size_t)tr.gc_base + blk.gc0 + warp * 32) * 576;
-    const uint32_t warp_gc0 = blk.gc0 + warp * 32;
     const uint8_t* c1 = s_c1[c1tab];
+    // word offset of the spectrum row that lane r of this warp decodes (0xFFFFFFFF: no such granule-channel)
+    __shared__ uint32_t s_rowoff[K1_THREADS];
+    s_rowoff[tid] = active ? (uint32_t)gl * 288u : 0xFFFFFFFFu;
+    uint32_t* blk_words = reinterpret_cast<uint32_t*>(spectra + ((size_t)tr.gc_base + blk.gc0) * 576);
+    const int wmin = __reduce_min_sync(0xffffffffu, state == 0 ? bv : 0);
+    const int wmax = __reduce_max_sync(0xffffffffu, state == 0 ? bv : 0);
+    __syncwarp();
+
+    auto big_pair = [&](int p, int& x, int& y) {
+        const int line = 2 * p;
+        const uint32_t reg = line < r0 ? reg0 : (line < r1 ? reg1 : reg2);
+        const int linbits = (int)(reg & 0xFFu);
+        br.refill();
+        uint32_t w = br.top();
+        uint32_t e = s_huff[(reg >> 8) + (w >> (32 - HUF_L1))];
+        if (e & 0x8000u) {
+            const uint32_t nb2 = (e >> 11) & 15;
+            e = s_huff[((e & 0x7FFu) << 2) + ((w << HUF_L1) >> (32 - nb2))];
+        }
+        br.skip((int)(e >> 8));
+        x = (e >> 4) & 15;
+        y = e & 15;
+        // linbits(x) sign(x) linbits(y) sign(y): at most 28 bits, peeled off one peek
+        br.refill();
+        w = br.top();
+        const int lbx = (x == 15) ? linbits : 0;
+        x += (int)((w >> 1) >> (31 - lbx));
+        w <<= lbx;
+        const int sx = x != 0;
+        const bool negx = sx && (w >> 31);
+        w <<= sx;
+        const int lby = (y == 15) ? linbits : 0;
+        y += (int)((w >> 1) >> (31 - lby));
+        w <<= lby;
+        const int sy = y != 0;
+        const bool negy = sy && (w >> 31);
+        br.skip(lbx + sx + lby + sy);
+        x = negx ? -x : x;
+        y = negy ? -y : y;
+    };
+    auto quad = [&](int p) {
+        // the quad lands at pair p + cqn (oracle: while (pos < end && i <= 572))
+        if (br.pos() < end && p + cqn <= 286) {
+            br.refill();
+            const uint32_t e = c1[br.top() >> 26];
+            br.skip((int)(e >> 4));
+            // four sign bits at most, present only for the non-zero values, in order v w x y
+            uint32_t w = br.top();
+            const uint32_t a0 = (e >> 3) & 1, a1 = (e >> 2) & 1, a2 = (e >> 1) & 1, a3 = e & 1;
+            const uint32_t n0 = a0 & (w >> 31); w <<= a0;
+            const uint32_t n1 = a1 & (w >> 31); w <<= a1;
+            const uint32_t n2 = a2 & (w >> 31); w <<= a2;
+            const uint32_t n3 = a3 & (w >> 31);
+            br.skip((int)(a0 + a1 + a2 + a3));
+            if (br.pos() > end) state = 2;  // quad straddles the end: discarded
+            else {
+                const uint32_t nibs = a0 | (n0 << 1) | (a1 << 2) | (n1 << 3) | (a2 << 4) | (n2 << 5) | (a3 << 6) | (n3 << 7);
+                cq |= nibs << (4 * cqn);
+                cqn += 2;
+                nz += 4;
+            }
+        } else state = 2;
+    };
+    auto pop = [&](int& x, int& y) {
+        if (cqn) {
+            x = ((int)(cq << 30)) >> 30;
+            y = ((int)(cq << 28)) >> 30;
+            cq >>= 4;
+            cqn--;
+        }
+    };
+    auto park = [&](int pp, int x, int y) {
+        s_stage[warp][lane][pp] = ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);
+    };
 
     for (int p0 = 0; p0 < 288; p0 += 16) {
-        if (__any_sync(0xffffffffu, state != 2 || cqn != 0)) {
+        if (p0 + 16 <= wmin) {
+            // every lane is inside its big-values region for the whole block
+#pragma unroll 1
+            for (int pp = 0; pp < 16; pp++) {
+                int x, y;
+                big_pair(p0 + pp, x, y);
+                park(pp, x, y);
+            }
+        } else if (p0 > wmax) {
+            // no lane is in its big-values region any more (and every lane has made its transition)
+            if (__any_sync(0xffffffffu, state != 2 || cqn != 0)) {
+#pragma unroll 1
+                for (int pp = 0; pp < 16; pp += 2) {
+                    if (state == 1 && cqn <= 1) quad(p0 + pp);
+                    int x = 0, y = 0;
+                    pop(x, y);
+                    park(pp, x, y);
+                    x = 0; y = 0;
+                    if (state == 1 && cqn == 0) quad(p0 + pp + 1);   // (only a lane whose previous quad came up short)
+                    pop(x, y);
+                    park(pp + 1, x, y);
+                }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < 16; pp++) s_stage[warp][lane][pp] = 0;
+            }
+        } else {
 #pragma unroll 1
             for (int pp = 0; pp < 16; pp++) {
                 const int p = p0 + pp;
@@ -232,85 +358,24 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 // warp-uniform guards (real branches, not predication): the big-values and the quad decoders are skipped
                 // whenever no lane of the warp needs them in this iteration
                 const bool big = state == 0;
-                const bool quad = state == 1 && (cqn == 0 || (cqn == 1 && !(p & 1)));
+                const bool wantq = state == 1 && (cqn == 0 || (cqn == 1 && !(p & 1)));
                 if (__any_sync(0xffffffffu, big)) {
-                  if (big) {
-                    const int line = 2 * p;
-                    const uint32_t reg = line < r0 ? reg0 : (line < r1 ? reg1 : reg2);
-                    const int linbits = (int)(reg & 0xFFu);
-                    br.refill();
-                    uint32_t w = br.top();
-                    uint32_t e = s_huff[(reg >> 8) + (w >> (32 - HUF_L1))];
-                    if (e & 0x8000u) {
-                        const uint32_t nb2 = (e >> 11) & 15;
-                        e = s_huff[((e & 0x7FFu) << 2) + ((w << HUF_L1) >> (32 - nb2))];
-                    }
-                    br.skip((int)(e >> 8));
-                    x = (e >> 4) & 15;
-                    y = e & 15;
-                    // linbits(x) sign(x) linbits(y) sign(y): at most 28 bits, peeled off one peek
-                    br.refill();
-                    w = br.top();
-                    const int lbx = (x == 15) ? linbits : 0;
-                    x += (int)((w >> 1) >> (31 - lbx));
-                    w <<= lbx;
-                    const int sx = x != 0;
-                    const bool negx = sx && (w >> 31);
-                    w <<= sx;
-                    const int lby = (y == 15) ? linbits : 0;
-                    y += (int)((w >> 1) >> (31 - lby));
-                    w <<= lby;
-                    const int sy = y != 0;
-                    const bool negy = sy && (w >> 31);
-                    br.skip(lbx + sx + lby + sy);
-                    x = negx ? -x : x;
-                    y = negy ? -y : y;
-                  }
+                    if (big) big_pair(p, x, y);
                 }
-                if (__any_sync(0xffffffffu, quad)) {
-                    if (quad) {
-                        // the quad lands at pair p + cqn (oracle: while (pos < end && i <= 572))
-                        if (br.pos() < end && p + cqn <= 286) {
-                            br.refill();
-                            const uint32_t e = c1[br.top() >> 26];
-                            br.skip((int)(e >> 4));
-                            // four sign bits at most, present only for the non-zero values, in order v w x y
-                            uint32_t w = br.top();
-                            const uint32_t a0 = (e >> 3) & 1, a1 = (e >> 2) & 1, a2 = (e >> 1) & 1, a3 = e & 1;
-                            const uint32_t n0 = a0 & (w >> 31); w <<= a0;
-                            const uint32_t n1 = a1 & (w >> 31); w <<= a1;
-                            const uint32_t n2 = a2 & (w >> 31); w <<= a2;
-                            const uint32_t n3 = a3 & (w >> 31);
-                            br.skip((int)(a0 + a1 + a2 + a3));
-                            if (br.pos() > end) state = 2;  // quad straddles the end: discarded
-                            else {
-                                const uint32_t nibs = a0 | (n0 << 1) | (a1 << 2) | (n1 << 3) | (a2 << 4) | (n2 << 5) | (a3 << 6) | (n3 << 7);
-                                cq |= nibs << (4 * cqn);
-                                cqn += 2;
-                                nz += 4;
-                            }
-                        } else state = 2;
-                    }
+                if (__any_sync(0xffffffffu, wantq)) {
+                    if (wantq) quad(p);
                 }
-                if (!big && cqn) {
-                    x = ((int)(cq << 30)) >> 30;
-                    y = ((int)(cq << 28)) >> 30;
-                    cq >>= 4;
-                    cqn--;
-                }
-                s_stage[warp][lane][pp] = ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);
+                if (!big) pop(x, y);
+                park(pp, x, y);
             }
-        } else {
-#pragma unroll
-            for (int pp = 0; pp < 16; pp++) s_stage[warp][lane][pp] = 0;
         }
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const int row = 2 * k + (lane >> 4), col = lane & 15;
             const uint32_t v = s_stage[warp][row][col];
-            if (warp_gc0 + row < n_gc)
-                *reinterpret_cast<uint32_t*>(my_rows + (size_t)row * 576 + 2 * (p0 + col)) = v;
+            const uint32_t ro = s_rowoff[warp * 32 + row];
+            if (ro != 0xFFFFFFFFu) blk_words[ro + p0 + col] = v;
         }
         __syncwarp();
     }
