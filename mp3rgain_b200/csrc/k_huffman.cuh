@@ -19,38 +19,51 @@
 #define K1_GAIN_ROW 64   // floats per granule-channel: [0..21] long sfb, [22..60] short sfb*3+win
 
 struct BitBuf {
-    const uint32_t* w;   // main-data stream as 32-bit words (16-byte aligned base)
+    const uint4* q;      // main-data stream as 16-byte quads (16-byte aligned base)
     uint32_t lim;        // bytes readable for this frame (later bytes read as zero, like the oracle's reservoir)
-    uint32_t wi;         // index of the look-ahead word
-    uint32_t nxt;        // look-ahead word (big-endian), not yet in acc
+    uint32_t wi;         // index of the next word that will enter acc
+    uint32_t c0, c1, c2, c3;   // words wi, wi+1, ... still to enter acc (raw, little-endian as loaded); c0 is next
+    uint4 nx;            // the quad after those: loaded a whole quad ahead, so its latency hides behind ~100 decoded bits
     unsigned long long acc;   // unread bits, left-aligned
     int nb;              // valid bits in acc (>= 33 after refill())
-    __device__ __forceinline__ uint32_t ld(uint32_t i) const {
-        uint32_t v = __byte_perm(__ldg(w + i), 0, 0x0123);
+    // word `i` of the stream, big-endian, with the bytes at or beyond lim zeroed
+    __device__ __forceinline__ uint32_t fix(uint32_t raw, uint32_t i) const {
+        uint32_t v = __byte_perm(raw, 0, 0x0123);
         if (i >= (lim >> 2)) {   // the word reaches past the readable bytes (rare: only at the very end of a frame's data)
             const uint32_t b = i * 4;
             v = b >= lim ? 0u : (v & (0xFFFFFFFFu << (8 * (b + 4 - lim))));
         }
         return v;
     }
+    __device__ __forceinline__ uint32_t take() {   // next word; keeps the quad buffers rolling
+        const uint32_t v = fix(c0, wi);
+        wi++;
+        c0 = c1; c1 = c2; c2 = c3;
+        if ((wi & 3) == 0) {
+            c0 = nx.x; c1 = nx.y; c2 = nx.z; c3 = nx.w;
+            nx = __ldg(q + (wi >> 2) + 1);
+        }
+        return v;
+    }
     __device__ __forceinline__ void init(const uint8_t* base, uint32_t lim_bytes, uint32_t bitpos) {
-        w = reinterpret_cast<const uint32_t*>(base);
+        q = reinterpret_cast<const uint4*>(base);
         lim = lim_bytes;
         wi = bitpos >> 5;
+        const uint4 cur = __ldg(q + (wi >> 2));
+        nx = __ldg(q + (wi >> 2) + 1);
+        c0 = cur.x; c1 = cur.y; c2 = cur.z; c3 = cur.w;
+        for (uint32_t k = 0; k < (wi & 3); k++) { c0 = c1; c1 = c2; c2 = c3; }
         const uint32_t sh = bitpos & 31;
-        acc = ((((unsigned long long)ld(wi)) << 32) | ld(wi + 1)) << sh;
+        const uint32_t hi = take(), lo = take();
+        acc = ((((unsigned long long)hi) << 32) | lo) << sh;
         nb = 64 - (int)sh;
-        wi += 2;
-        nxt = ld(wi);
     }
     // bit position of the next unread bit: words 0..wi-1 have entered acc, nb of their bits are still unread
     __device__ __forceinline__ uint32_t pos() const { return (wi << 5) - (uint32_t)nb; }
     __device__ __forceinline__ void refill() {
         if (nb <= 32) {
-            acc |= (unsigned long long)nxt << (32 - nb);
+            acc |= (unsigned long long)take() << (32 - nb);
             nb += 32;
-            wi++;
-            nxt = ld(wi);
         }
     }
     __device__ __forceinline__ uint32_t top() const { return (uint32_t)(acc >> 32); }
@@ -126,8 +139,9 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     uint32_t end = 0;
     bool silent = true;
     BitBuf br;
-    br.w = reinterpret_cast<const uint32_t*>(md + tr.md_off);
-    br.lim = 0; br.acc = 0; br.nxt = 0; br.wi = 2; br.nb = 64;
+    br.q = reinterpret_cast<const uint4*>(md + tr.md_off);
+    br.lim = 0; br.acc = 0; br.wi = 2; br.nb = 64;
+    br.c0 = br.c1 = br.c2 = br.c3 = 0; br.nx = make_uint4(0, 0, 0, 0);
     float* grow = gains + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
     uint8_t* sfl = s_sfl[gl];
 #pragma unroll
