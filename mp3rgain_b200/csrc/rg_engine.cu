@@ -109,12 +109,14 @@ struct rg_engine {
     // device scratch that lives across batches
     DevBuf d_pcm_in, d_album, d_album_peak, d_misc;
     DevBuf d_tin, d_fbase, d_frames, d_md, d_meta;
+    DevBuf d_tseg, d_segs, d_segout, d_segfin, d_stage;   // speculative segmented frame index (k_frame_index.cuh)
     DevBuf d_corpus;                      // file images of rg_analyze_tracks / rg_analyze_album (kept between calls)
     HostBuf h_meta;
     rg_stats stats = {};
     DecodeScratch dec;
     std::vector<DevBuf*> all_bufs() {
-        std::vector<DevBuf*> v = {&d_pcm_in, &d_album, &d_album_peak, &d_misc, &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_corpus};
+        std::vector<DevBuf*> v = {&d_pcm_in, &d_album, &d_album_peak, &d_misc, &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_corpus,
+                                  &d_tseg, &d_segs, &d_segout, &d_segfin, &d_stage};
         for (auto& c : ctx) for (DevBuf* b : c.bufs()) v.push_back(b);
         return v;
     }

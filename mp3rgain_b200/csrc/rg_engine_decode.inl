@@ -94,9 +94,14 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     ip.group_begin.clear();
     ip.groups_absorbed = 0;
     std::vector<TrackIn> tin(n);
+    std::vector<TrackSeg> tseg(n);
+    std::vector<SegDesc> segs;
     uint64_t fb = 0, mb = 0, bytes = 0;
     for (size_t i = 0; i < n; i++) {
         tin[i].off = c->off[i]; tin[i].len = c->len[i];
+        tseg[i].seg_base = (uint32_t)segs.size();
+        tseg[i].n_seg = (uint32_t)std::max<uint64_t>(1, (c->len[i] + K0_SEG - 1) / K0_SEG);
+        for (uint32_t sg = 0; sg < tseg[i].n_seg; sg++) segs.push_back(SegDesc{(uint32_t)i, sg});
         ip.frame_base[i] = fb; ip.md_base[i] = mb;
         fb += c->len[i] / 96 + 2;                      // smallest MPEG-1 Layer III frame is 96 bytes
         mb += (c->len[i] + 32 + 15) & ~15ull;
@@ -121,11 +126,18 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     CK(e->d_meta.ensure(n * sizeof(TrackMeta)));
     CK(e->h_meta.ensure(n * sizeof(TrackMeta)));
     ip.meta = e->h_meta.as<TrackMeta>();
+    CK(e->d_tseg.ensure(n * sizeof(TrackSeg)));
+    CK(e->d_segs.ensure(segs.size() * sizeof(SegDesc)));
+    CK(e->d_segout.ensure(segs.size() * sizeof(SegOut)));
+    CK(e->d_segfin.ensure(segs.size() * sizeof(SegFin)));
+    CK(e->d_stage.ensure(segs.size() * (size_t)K0_SEG_RECS * sizeof(SegRec)));
+    CK(cudaMemcpyAsync(e->d_tseg.p, tseg.data(), n * sizeof(TrackSeg), cudaMemcpyHostToDevice, e->s_index));
+    CK(cudaMemcpyAsync(e->d_segs.p, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, e->s_index));
     CK(cudaMemcpyAsync(e->d_tin.p, tin.data(), n * sizeof(TrackIn), cudaMemcpyHostToDevice, e->s_index));
     CK(cudaMemcpyAsync(e->d_fbase.p, ip.frame_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->s_index));
     CK(cudaMemcpyAsync(e->d_fbase.as<uint64_t>() + (n + 1), ip.md_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->s_index));
     CK(cudaStreamSynchronize(e->s_index));   // the three sources above are stack / heap temporaries
-    e->stats.h2d_bytes += n * sizeof(TrackIn) + 2 * (n + 1) * sizeof(uint64_t);
+    e->stats.h2d_bytes += n * (sizeof(TrackIn) + sizeof(TrackSeg)) + 2 * (n + 1) * sizeof(uint64_t) + segs.size() * sizeof(SegDesc);
     const size_t ng = ip.group_begin.size() - 1;
     CK(cudaEventRecord(e->ev[1], e->s_index));   // the descriptor tables above are in place
     for (size_t g = 0; g < ng; g++) {
@@ -144,10 +156,22 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
             CK(cudaStreamWaitEvent(si, ev_copied, 0));
         }
         CK(cudaEventRecord(ev_k0a, si));
-        k_frame_index<<<(unsigned)((t1 - t0 + K0_WARPS - 1) / K0_WARPS), 32 * K0_WARPS, 0, si>>>(
-            c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_fbase.as<uint64_t>() + t0, e->d_fbase.as<uint64_t>() + (n + 1) + t0,
-            e->d_frames.as<FrameRec>(), e->d_md.as<uint8_t>(), e->d_meta.as<TrackMeta>() + t0, (uint32_t)(t1 - t0), e->flags);
-        e->stats.kernel_launches++;
+        {
+            const uint32_t seg0 = tseg[t0].seg_base;
+            const uint32_t nsg = (t1 < n ? tseg[t1].seg_base : (uint32_t)segs.size()) - seg0;
+            const unsigned gs = (nsg + K0_WARPS - 1) / K0_WARPS, gt = (unsigned)((t1 - t0 + K0_WARPS - 1) / K0_WARPS);
+            k_index_scan<<<gs, 32 * K0_WARPS, 0, si>>>(c->d_bytes, e->d_tin.as<TrackIn>(), e->d_tseg.as<TrackSeg>(), e->d_segs.as<SegDesc>(),
+                                                       seg0, nsg, e->d_stage.as<SegRec>(), e->d_segout.as<SegOut>(), e->flags);
+            k_index_merge<<<gt, 32 * K0_WARPS, 0, si>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0,
+                                                        e->d_fbase.as<uint64_t>() + (n + 1) + t0, e->d_stage.as<SegRec>(),
+                                                        e->d_segout.as<SegOut>(), e->d_segfin.as<SegFin>(), e->d_md.as<uint8_t>(),
+                                                        e->d_meta.as<TrackMeta>() + t0, (uint32_t)(t1 - t0), e->flags);
+            k_index_finalize<<<gs, 32 * K0_WARPS, 0, si>>>(c->d_bytes, e->d_tin.as<TrackIn>(), e->d_segs.as<SegDesc>(), seg0, nsg,
+                                                           e->d_fbase.as<uint64_t>(), e->d_fbase.as<uint64_t>() + (n + 1),
+                                                           e->d_stage.as<SegRec>(), e->d_segfin.as<SegFin>(), e->d_frames.as<FrameRec>(),
+                                                           e->d_md.as<uint8_t>());
+            e->stats.kernel_launches += 3;
+        }
         CK(cudaGetLastError());
         CK(cudaEventRecord(ev_k0b, si));
         CK(cudaMemcpyAsync(e->h_meta.as<TrackMeta>() + t0, e->d_meta.as<TrackMeta>() + t0, (t1 - t0) * sizeof(TrackMeta),
