@@ -367,9 +367,12 @@ k_md_gather(const uint8_t* __restrict__ corpus, uint8_t* __restrict__ md, const 
         const int nw = (cap - head) >> 2;
         const uint8_t* s4 = src + head;
         uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+        // aligned destination words from two aligned source words each (funnel shift by the source's misalignment)
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(s4) & 3);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s4 - mis);
         for (int w = lane; w < nw; w += 32) {
-            const uint8_t* q = s4 + 4 * w;
-            d4[w] = (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | ((uint32_t)__ldg(q + 3) << 24);
+            const uint32_t lo = __ldg(sw + w), hi = mis ? __ldg(sw + w + 1) : 0u;
+            d4[w] = __funnelshift_r(lo, hi, 8 * mis);
         }
         const int tail0 = head + 4 * nw;
         if (tail0 + lane < cap) dst[tail0 + lane] = __ldg(src + tail0 + lane);
