@@ -107,7 +107,7 @@ int  rg_engine_create(const rg_config* cfg, rg_engine** out);
 void rg_engine_destroy(rg_engine* e);
 const char* rg_status_str(int status);
 /* Tuning knobs (not part of the reference surface). Keys: "iir_block_windows" (50 ms windows per time block of
- * the time-blocked IIR, default 16), "iir_warm_windows" (zero-state warm-up windows before each block, default 1),
+ * the time-blocked IIR; default 0 = chosen per batch so that the equally long chains fill whole waves of the device), "iir_warm_windows" (zero-state warm-up windows before each block, default 1),
  * "edge_tol" (distance of 1000*log10(ms) from an integer below which the time-blocked pass hands the track to the
  * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9), "pipeline" (default 1:
  * copy / index / decode / analysis overlap on four streams with two alternating batches; 0 = one batch at a time, every

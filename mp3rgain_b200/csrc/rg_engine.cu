@@ -100,7 +100,8 @@ struct rg_engine {
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-group events of the pipelined path (grown on demand)
     // options
-    uint32_t block_windows = 16, warm_windows = 1;
+    uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
+    uint32_t k4_capacity = 0;             // chains (threads) of k_iir_fast resident on the device at once
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
     RgCoefFast coef_fast[12];
@@ -224,6 +225,12 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
+    {
+        int per_sm = 0, sms = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iir_fast, K4_FAST_THREADS, 0));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        e->k4_capacity = (uint32_t)(per_sm * sms * K4_FAST_THREADS);
+    }
     int rc = decode_init_tables(e->dec);
     if (rc != RG_OK) { delete e; return rc; }
     *out = e;
@@ -252,7 +259,7 @@ extern "C" void rg_engine_destroy(rg_engine* e) {
 
 extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value) {
     if (!e || !key) return RG_ERR_INVALID_ARG;
-    if (!strcmp(key, "iir_block_windows")) { if (value < 1) return RG_ERR_INVALID_ARG; e->block_windows = (uint32_t)value; return RG_OK; }
+    if (!strcmp(key, "iir_block_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->block_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
@@ -287,8 +294,31 @@ static int fetch_desc(rg_engine* e, cudaStream_t st, void* dst, const void* src_
 }
 static inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
+// Windows per time block of the time-blocked IIR.  All chains of a batch have the same length, so the kernel's time is
+// (number of waves) x (block + warm-up windows): pick the block length that minimises it -- i.e. fill whole waves.
+static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTrack>& tracks) {
+    if (e->block_windows) return e->block_windows;
+    std::vector<std::pair<uint32_t, uint32_t>> nw;   // (windows, channels) per track
+    for (const PcmTrack& t : tracks) {
+        const uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
+        if (t.status == RG_OK && t.frames > 0 && win > 0) nw.push_back({(uint32_t)((t.frames + win - 1) / win), t.nch >= 2 ? 2u : 1u});
+    }
+    const uint64_t cap = e->k4_capacity ? e->k4_capacity : 75776;
+    uint32_t best = 16;
+    uint64_t best_cost = ~0ull;
+    for (uint32_t bw = 6; bw <= 96; bw++) {
+        uint64_t chains = 0;
+        for (auto& p : nw) chains += (uint64_t)((p.first + bw - 1) / bw) * p.second;
+        const uint64_t waves = (chains + cap - 1) / cap;
+        const uint64_t cost = waves * (bw + e->warm_windows);
+        if (cost < best_cost || (cost == best_cost && bw > best)) { best_cost = cost; best = bw; }
+    }
+    return best;
+}
+
 static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, bool exact, double* d_wsum_base, float* d_wmax_base,
                          std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin, size_t& wsum_doubles) {
+    const uint32_t bw = exact ? 0 : choose_block_windows(e, tracks);
     // wsum layout: for each track, channel 0 windows then channel 1 windows
     chains.clear();
     twin.clear();
@@ -319,7 +349,7 @@ static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks
                     ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx; ch.flags = 1;
                     chains.push_back(ch);
                 } else {
-                    const uint32_t bw = e->block_windows, ww = e->warm_windows;
+                    const uint32_t ww = e->warm_windows;
                     for (uint32_t w0 = 0; w0 < n_win; w0 += bw) {
                         uint32_t w1 = std::min(n_win, w0 + bw);
                         uint64_t s0 = (uint64_t)w0 * win;

@@ -80,7 +80,9 @@ struct IndexPlan {                      // K0 bookkeeping of one analyse call
     std::vector<size_t> group_begin;    // tracks [group_begin[g], group_begin[g+1]) form index group g
     std::vector<int> status;            // rg_status per track after host-side checks (valid once its group is absorbed)
     std::vector<uint32_t> sample_rate;
-    size_t groups_absorbed = 0;
+    size_t groups_absorbed = 0, groups_enqueued = 0;
+    std::vector<TrackSeg> tseg;         // per track: its speculative segments
+    size_t n_segs = 0;
     const TrackMeta* meta = nullptr;    // pinned, written by the index stream
 };
 
@@ -92,9 +94,10 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     ip.frame_base.resize(n + 1);
     ip.md_base.resize(n + 1);
     ip.group_begin.clear();
-    ip.groups_absorbed = 0;
+    ip.groups_absorbed = ip.groups_enqueued = 0;
     std::vector<TrackIn> tin(n);
-    std::vector<TrackSeg> tseg(n);
+    std::vector<TrackSeg>& tseg = ip.tseg;
+    tseg.assign(n, TrackSeg{});
     std::vector<SegDesc> segs;
     uint64_t fb = 0, mb = 0, bytes = 0;
     for (size_t i = 0; i < n; i++) {
@@ -112,9 +115,12 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     // the number of tracks); about eight, never smaller than 32 MiB, when the bytes are still arriving from the host, so
     // that indexing starts as soon as the first group has landed
     const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, 32ull << 20) : ~0ull;
+    // (the first two groups are a quarter and a half of that: the pipeline starts as soon as a few files have landed)
     uint64_t acc = 0;
     for (size_t i = 0; i < n; i++) {
-        if (i == 0 || acc >= gbytes) { ip.group_begin.push_back(i); acc = 0; }
+        const size_t k = ip.group_begin.size();   // groups started so far
+        const uint64_t lim = gbytes == ~0ull ? gbytes : (k <= 1 ? gbytes / 4 : (k == 2 ? gbytes / 2 : gbytes));
+        if (i == 0 || acc >= lim) { ip.group_begin.push_back(i); acc = 0; }
         acc += c->len[i];
     }
     ip.group_begin.push_back(n);
@@ -138,9 +144,18 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     CK(cudaMemcpyAsync(e->d_fbase.as<uint64_t>() + (n + 1), ip.md_base.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, e->s_index));
     CK(cudaStreamSynchronize(e->s_index));   // the three sources above are stack / heap temporaries
     e->stats.h2d_bytes += n * (sizeof(TrackIn) + sizeof(TrackSeg)) + 2 * (n + 1) * sizeof(uint64_t) + segs.size() * sizeof(SegDesc);
-    const size_t ng = ip.group_begin.size() - 1;
+    ip.n_segs = segs.size();
     CK(cudaEventRecord(e->ev[1], e->s_index));   // the descriptor tables above are in place
-    for (size_t g = 0; g < ng; g++) {
+    return RG_OK;
+}
+
+// Enqueues the copy (if the group's bytes still live in host memory) and the frame index of group g.  Groups are enqueued a
+// few ahead of the batch loop rather than all at once, so that the host reaches the first decode launch without first paying
+// for every cudaMemcpyAsync call of the corpus.
+static int index_enqueue_group(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t g) {
+    const size_t n = c->len.size();
+    const std::vector<TrackSeg>& tseg = ip.tseg;
+    {
         const size_t t0 = ip.group_begin[g], t1 = ip.group_begin[g + 1];
         cudaStream_t si = (g & 3) == 0 ? e->s_index : e->s_index_x[(g & 3) - 1];
         if (si != e->s_index) CK(cudaStreamWaitEvent(si, e->ev[1], 0));
@@ -158,7 +173,7 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
         CK(cudaEventRecord(ev_k0a, si));
         {
             const uint32_t seg0 = tseg[t0].seg_base;
-            const uint32_t nsg = (t1 < n ? tseg[t1].seg_base : (uint32_t)segs.size()) - seg0;
+            const uint32_t nsg = (t1 < n ? tseg[t1].seg_base : (uint32_t)ip.n_segs) - seg0;
             const unsigned gs = (nsg + K0_WARPS - 1) / K0_WARPS, gt = (unsigned)((t1 - t0 + K0_WARPS - 1) / K0_WARPS);
             k_index_scan<<<gs, 32 * K0_WARPS, 0, si>>>(c->d_bytes, e->d_tin.as<TrackIn>(), e->d_tseg.as<TrackSeg>(), e->d_segs.as<SegDesc>(),
                                                        seg0, nsg, e->d_stage.as<SegRec>(), e->d_segout.as<SegOut>(), e->flags);
@@ -182,6 +197,16 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     return RG_OK;
 }
 
+static int index_enqueue_upto(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t g_end) {
+    const size_t ng = ip.group_begin.size() - 1;
+    while (ip.groups_enqueued < std::min(ng, g_end)) {
+        int rc = index_enqueue_group(e, c, ip, ip.groups_enqueued);
+        if (rc != RG_OK) return rc;
+        ip.groups_enqueued++;
+    }
+    return RG_OK;
+}
+
 // Waits until track `upto - 1` has been indexed and derives the per-track status of every newly finished group.
 // With `opportunistic`, also absorbs later groups that happen to be finished already.
 static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, bool opportunistic) {
@@ -189,6 +214,8 @@ static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, 
     while (ip.groups_absorbed < ng) {
         const size_t g = ip.groups_absorbed;
         const bool needed = ip.group_begin[g] < upto;
+        if (int rc = index_enqueue_upto(e, c, ip, g + (needed ? 4 : 0))) return rc;
+        if (g >= ip.groups_enqueued) break;
         if (!needed) {
             if (!opportunistic || cudaEventQuery(e->pool_event(4 * g + 3)) != cudaSuccess) break;
         }
