@@ -36,7 +36,7 @@ METRIC = "audio-hours/sec analysed"
 def build_corpus(n_tracks, n_frames, seed):
     """n_tracks distinct tracks: seeded random sequences of self-contained frame groups from a seeded pool."""
     import synth_corpus
-    pool = synth_corpus.GroupPool(seed=seed, n_groups=256, group_len=32)
+    pool = synth_corpus.GroupPool(seed=seed, n_groups=256, group_len=32, intensity_prob=0.02)
     return [pool.track(seed * 100003 + i, n_frames) for i in range(n_tracks)]
 
 

@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(K1_THREADS)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
           int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
-          float* __restrict__ gains /* [gc][K1_GAIN_ROW] */) {
+          float* __restrict__ gains /* [gc][K1_GAIN_ROW] */,
+          uint8_t* __restrict__ sfraw /* [gc][K1_GAIN_ROW]: raw scalefactors = is_pos, right channel of intensity-stereo frames only */) {
     __shared__ uint16_t s_huff[8192];
     __shared__ uint32_t s_stage[K1_THREADS / 32][32][17];
     __shared__ uint8_t s_sfl[K1_THREADS][24];     // long scalefactors of every thread's granule-channel (scfsi source)
@@ -143,6 +144,8 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     br.lim = 0; br.acc = 0; br.wi = 2; br.nb = 64;
     br.c0 = br.c1 = br.c2 = br.c3 = 0; br.nx = make_uint4(0, 0, 0, 0);
     float* grow = gains + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
+    uint8_t* srow = sfraw + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
+    bool is_right = false;   // right channel of an intensity-stereo frame: K2 needs its raw scalefactors (is_pos)
     uint8_t* sfl = s_sfl[gl];
 #pragma unroll
     for (int i = 0; i < 6; i++) reinterpret_cast<uint32_t*>(sfl)[i] = 0;
@@ -154,6 +157,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         gr = rem / nch;
         const FrameRec rec = frames[tr.frame_base + frame];
         const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
+        is_right = ch == 1 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 1);
         const int gbase = (nch == 1 ? 18 : 20);
         uint32_t bit = rec.md_start * 8;
         for (uint32_t k = 0; k < rem; k++) bit += side_field(s, gbase + 59 * k, 12);
@@ -211,6 +215,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             for (int q2 = mixed ? 9 : 0; q2 < 36; q2++) {
                 const int v = (int)br.get(q2 < 18 ? slen1 : slen2);
                 const int win = q2 % 3;
+                if (is_right) srow[22 + q2] = (uint8_t)v;
                 grow[22 + q2] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)) - sf_shift * v]);
             }
 #pragma unroll
@@ -236,8 +241,10 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         }
         if (bt != 2 || mixed) {
             const int nl = bt != 2 ? 22 : 8;
-            for (int sfb = 0; sfb < nl; sfb++)
+            for (int sfb = 0; sfb < nl; sfb++) {
                 grow[sfb] = __ldg(&T->gain[base_e - sf_shift * ((int)sfl[sfb] + (preflag ? (int)T->pretab[sfb] : 0))]);
+                if (is_right) srow[sfb] = sfl[sfb];
+            }
         }
         // part 3 starts where part 2 ends by the side info's arithmetic (not where the reads above stopped: scfsi)
     }

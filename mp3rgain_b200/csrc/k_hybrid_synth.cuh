@@ -33,7 +33,7 @@
 
 struct __align__(2) GranInfo {
     uint16_t nz;          // lines decoded by K1 (0 = silent)
-    uint8_t bt, mixed, ms, sb_limit /* subbands with possibly non-zero IMDCT input */;
+    uint8_t bt, mixed, ms /* bit0 MS stereo, bit1 intensity stereo (frame level) */, sb_limit /* subbands with possibly non-zero IMDCT input */;
 };
 
 struct K2Smem {
@@ -43,10 +43,13 @@ struct K2Smem {
     alignas(16) float bandgain[K2_GC][64];    // per band: 2^(exponent/4) ([0..21] long sfb, [22..60] short sfb*3+win), by TMA
     float wa[8][32], wb[8][32];
     GranInfo gi[K2_MAX_G][2];                 // side info of every granule-channel of the run
-    uint32_t p1w[K2_MAX_G][2];                // tsel | ms<<2 | (nz!=0)<<3 | (9*max sb_limit of the granule)<<8
+    uint32_t p1w[K2_MAX_G][2];                // tsel | ms<<2 | (nz!=0)<<3 | intensity<<4 | (9*max sb_limit of the granule)<<8
     uint16_t scat[2][576];                    // bitstream-order line -> reordered line: [0] pure short, [1] mixed
     uint8_t code[3][576];                     // line -> band code: [0] long, [1] pure short, [2] mixed
     uint8_t ia[32], ib[32];
+    uint8_t istab[K2_GC / 2][64];             // intensity stereo: is_pos per band of the right channel's partition, 255 = not intensity coded
+    int istop[K2_GC / 2][4];                  // highest non-zero band of the right channel: [0] long sfb, [1..3] short sfb per window
+    float isr[2][8];                          // is_pos -> left / right factor
     alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
 };
 
@@ -101,9 +104,10 @@ __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corp
     gi.mixed = (gi.bt == 2) ? (uint8_t)(f & 1) : 0;
     const size_t gcb = (size_t)tr.gc_base + (size_t)frame * 2 * nch + gr * nch;
     gi.nz = nz_in[gcb + ch];
-    gi.ms = (nch == 2 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 2)) ? 1 : 0;
-    // subbands whose IMDCT input can be non-zero: the coded lines (of either channel under MS), one more subband for
-    // the alias butterflies; short blocks scatter lines across the whole band, so they keep all 32
+    const bool joint = nch == 2 && ((rec.hdr >> 6) & 3) == 1;
+    gi.ms = (uint8_t)((joint && ((rec.hdr >> 4) & 2) ? 1 : 0) | (joint && ((rec.hdr >> 4) & 1) ? 2 : 0));
+    // subbands whose IMDCT input can be non-zero: the coded lines (of either channel under MS / intensity stereo), one more
+    // subband for the alias butterflies; short blocks scatter lines across the whole band, so they keep all 32
     uint32_t nzm = gi.nz;
     if (gi.ms) nzm = max(nzm, (uint32_t)nz_in[gcb + (ch ^ 1)]);
     gi.sb_limit = nzm == 0 ? 0 : (gi.bt == 2 ? 32 : (uint8_t)min(32u, (nzm + 17) / 18 + 1));
@@ -186,7 +190,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
                                         const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
-                                        float* __restrict__ pcm, uint32_t flags) {
+                                        const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t flags) {
     constexpr int G = K2_GC / NCH;      // granules per batch
     constexpr int NS = G + 1;           // granule slots
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -207,6 +211,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         S.scat[1][i] = T->scatter_mixed[sr][i];
     }
     if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
+    if (tid < 14) S.isr[tid / 7][tid % 7] = T->is_ratio[tid / 7][tid % 7];
     for (int i = tid; i < K2_SLOTS * SLOTF; i += K2_THREADS) { (&S.A[0][0])[i] = 0.0f; (&S.S2[0][0])[i] = 0.0f; }
     if (tid == 0) k2_mbar_init(&S.mbar, 1);
     // side info of every granule-channel of the run, one thread each
@@ -220,7 +225,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         const GranInfo gi = S.gi[gl][ch];
         const int lim = max((int)gi.sb_limit, (int)S.gi[gl][NCH - 1 - ch].sb_limit);
         const uint32_t tsel = gi.bt != 2 ? 0u : (gi.mixed ? 2u : 1u);
-        S.p1w[gl][ch] = tsel | ((uint32_t)gi.ms << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(9 * lim) << 8);
+        S.p1w[gl][ch] = tsel | ((uint32_t)(gi.ms & 1) << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(gi.ms >> 1) << 4) | ((uint32_t)(9 * lim) << 8);
     }
 
     // spectra and band gains of batch b: granule-channels are contiguous in HBM, 1152 + 256 bytes each
@@ -258,6 +263,37 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
             const float* bg1 = S.bandgain[my_gi * NCH + NCH - 1];
             float* x0 = S.A[(gl % NS) * NCH];
             float* x1 = S.A[(gl % NS) * NCH + NCH - 1];
+            const bool ist = NCH == 2 && ((w0 >> 4) & 1);
+            if (NCH == 2 && ist) {
+                // intensity stereo (pair-uniform, rare): bands of the right channel's partition above its last non-zero line
+                // (per window for short blocks) take L*is_l, L*is_r with is_pos = the right channel's raw scalefactor
+                // (K1's sfraw row); is_pos 7 marks a band that is not intensity coded.  ISO 11172-3 2.4.3.4.9.3.
+                int* top = S.istop[my_gi];
+                if (my_ch == 0 && lane < 4) top[lane] = -1;
+                k2_pair_sync(my_gi);
+                for (int pr = lane + 32 * my_ch; pr < 288; pr += 64) {
+                    if (nzf1 && st1[pr] != 0u) {
+                        const int code = S.code[tsel1][2 * pr];
+                        if (code < 22) atomicMax(&top[0], code);
+                        else atomicMax(&top[1 + (code - 22) % 3], (code - 22) / 3);
+                    }
+                }
+                k2_pair_sync(my_gi);
+                const int j = lane + 32 * my_ch;
+                if (j < 61) {
+                    const uint8_t* row = sfraw + ((size_t)tr.gc_base + (size_t)(gfirst + gl) * 2 + 1) * K1_GAIN_ROW;
+                    uint32_t pos = 255;
+                    if (j < 22) {
+                        const bool short_nz = top[1] >= 0 || top[2] >= 0 || top[3] >= 0;
+                        if (tsel1 != 1 && !short_nz && j > top[0]) pos = row[j == 21 ? 20 : j];
+                    } else if (tsel1 != 0) {
+                        const int sfb = (j - 22) / 3, win = (j - 22) % 3;
+                        if (sfb > top[1 + win]) pos = row[22 + (sfb == 12 ? 11 : sfb) * 3 + win];
+                    }
+                    S.istab[my_gi][j] = (uint8_t)(pos < 7 ? pos : 255);
+                }
+                k2_pair_sync(my_gi);
+            }
             for (int pr = lane + 32 * my_ch; pr < lim9; pr += 32 * NCH) {
                 float v[2][2];
 #pragma unroll
@@ -270,7 +306,17 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                     v[ch][0] = q0 < 0 ? -m0 : m0;
                     v[ch][1] = q1 < 0 ? -m1 : m1;
                 }
-                if (NCH == 2 && ms) {
+                uint32_t ipos = 255;
+                if (NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
+                if (NCH == 2 && ipos != 255) {
+                    const float kl = S.isr[0][ipos], kr = S.isr[1][ipos];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const float l = v[0][h];
+                        v[0][h] = __fmul_rn(l, kl);
+                        v[NCH - 1][h] = __fmul_rn(l, kr);
+                    }
+                } else if (NCH == 2 && ms) {
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const float a = v[0][h], c = v[NCH - 1][h];
@@ -420,11 +466,11 @@ __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
                const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
-               float* __restrict__ pcm, uint32_t flags) {
+               const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
-    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, pcm, flags);
-    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, pcm, flags);
+    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, flags);
+    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, flags);
 }

@@ -284,6 +284,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     CK(x.d_spectra.ensure(std::max<uint64_t>(gc_total, 1) * 576 * sizeof(int16_t) + 64));
     CK(x.d_nz.ensure(std::max<uint64_t>(gc_total, 1) * sizeof(uint16_t) + 64));
     CK(x.d_gains.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW * sizeof(float) + 64));
+    CK(x.d_sfraw.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW + 64));
     CK(x.d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
     for (size_t k = 0; k < nb; k++) {
         if (x.pt[k].status != RG_OK) continue;
@@ -312,7 +313,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     if (!hb.empty()) {
         k_huffman<<<(unsigned)hb.size(), K1_THREADS, 0, st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                            x.d_dtracks.as<DecTrack>(), x.d_hblocks.as<HuffBlock>(), e->dec.d_tab,
-                                                           x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(), x.d_gains.as<float>());
+                                                           x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(), x.d_gains.as<float>(), x.d_sfraw.as<uint8_t>());
         e->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
@@ -321,7 +322,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
         k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                                                x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>(), e->dec.d_tab,
                                                                                x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(),
-                                                                               x.d_gains.as<float>(), x.d_pcm.as<float>(), e->flags);
+                                                                               x.d_gains.as<float>(), x.d_sfraw.as<uint8_t>(), x.d_pcm.as<float>(), e->flags);
         e->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
@@ -341,7 +342,7 @@ static void collect_decode_timing(rg_engine* e, BatchCtx& x) {
 
 // Bytes of device scratch one track needs in a batch (spectra + nz + band gains + PCM)
 static uint64_t track_scratch_bytes(const TrackMeta& m) {
-    return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2 + 4 * K1_GAIN_ROW) + 1152ull * 4) + 4096;
+    return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2 + 5 * K1_GAIN_ROW) + 1152ull * 4) + 4096;
 }
 
 static void drain_streams(rg_engine* e) {

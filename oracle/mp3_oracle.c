@@ -325,6 +325,59 @@ static void requantize(const gr_t* q, int sr_row, const int* sf_l, int (*sf_s)[3
     }
 }
 
+/* joint stereo in bitstream order (before the short-block reorder), ISO 11172-3 2.4.3.4.9.3.
+ * MS: (m + s)/sqrt2, (m - s)/sqrt2.  Intensity: scalefactor bands of the RIGHT channel's partition that lie above its last
+ * non-zero line (per window for short blocks) are intensity coded; the right channel's scalefactor there is is_pos, the
+ * last band (long 21 / short 12) borrows the previous band's; is_pos 7 marks a band that is not intensity coded (it gets the
+ * MS treatment if MS is on, like every band below the bound).  L' = L*is_l[is_pos], R' = L*is_r[is_pos], one multiply each. */
+static void ms_band(float xr[2][576], int i0, int n) {
+    for (int i = i0; i < i0 + n; i++) {
+        float m = xr[0][i], sd = xr[1][i];
+        xr[0][i] = (m + sd) * L3_INV_SQRT2;
+        xr[1][i] = (m - sd) * L3_INV_SQRT2;
+    }
+}
+static void joint_stereo(const gr_t* q1, int sr_row, int ms, int intensity, const int* sf_l, int (*sf_s)[3], const int16_t* is1,
+                         float xr[2][576]) {
+    if (!intensity) {
+        if (ms) ms_band(xr, 0, 576);
+        return;
+    }
+    int short_start = 13, long_end = 22;
+    if (q1->block_type == 2) { short_start = q1->mixed ? 3 : 0; long_end = q1->mixed ? 8 : 0; }
+    int end = 576;
+    int nz_short[3] = {0, 0, 0};
+    for (int sfb = 12; sfb >= short_start; sfb--) {
+        int wdt = L3_SFB_SHORT_W[sr_row][sfb];
+        int src = sfb == 12 ? 11 : sfb;
+        for (int w = 2; w >= 0; w--) {
+            end -= wdt;
+            int pos = -1;
+            if (!nz_short[w]) {
+                for (int j = 0; j < wdt; j++) if (is1[end + j] != 0) { nz_short[w] = 1; break; }
+                if (!nz_short[w] && sf_s[src][w] < 7) pos = sf_s[src][w];
+            }
+            if (pos >= 0) {
+                for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * L3_IS_RATIO[0][pos]; xr[1][j] = l * L3_IS_RATIO[1][pos]; }
+            } else if (ms) ms_band(xr, end, wdt);
+        }
+    }
+    int nz = nz_short[0] | nz_short[1] | nz_short[2];
+    for (int sfb = long_end - 1; sfb >= 0; sfb--) {
+        int wdt = L3_SFB_LONG_W[sr_row][sfb];
+        end -= wdt;
+        int pos = -1;
+        if (!nz) {
+            for (int j = 0; j < wdt; j++) if (is1[end + j] != 0) { nz = 1; break; }
+            int src = sfb == 21 ? 20 : sfb;
+            if (!nz && sf_l[src] < 7) pos = sf_l[src];
+        }
+        if (pos >= 0) {
+            for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * L3_IS_RATIO[0][pos]; xr[1][j] = l * L3_IS_RATIO[1][pos]; }
+        } else if (ms) ms_band(xr, end, wdt);
+    }
+}
+
 /* short-block reorder [sfb][win][k] -> [sfb][k][win] */
 static void reorder(const gr_t* q, int sr_row, float* xr) {
     float tmp[576];
@@ -479,13 +532,8 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
                 else nz[ch] = read_huffman(&b, end, q, sr_row, is[ch]);
                 requantize(q, sr_row, d->sf_l[g][ch], d->sf_s[g][ch], is[ch], xr[ch]);
             }
-            if (nch == 2 && h.mode == 1 && (h.mode_ext & 2)) { /* MS stereo */
-                for (int i = 0; i < 576; i++) {
-                    float m = xr[0][i], sd = xr[1][i];
-                    xr[0][i] = (m + sd) * L3_INV_SQRT2;
-                    xr[1][i] = (m - sd) * L3_INV_SQRT2;
-                }
-            }
+            if (nch == 2 && h.mode == 1 && h.mode_ext)
+                joint_stereo(&s.gr[g][1], sr_row, h.mode_ext & 2, h.mode_ext & 1, d->sf_l[g][1], d->sf_s[g][1], is[1], xr);
             for (int ch = 0; ch < nch; ch++) {
                 const gr_t* q = &s.gr[g][ch];
                 if (q->block_type == 2) reorder(q, sr_row, xr[ch]);

@@ -52,7 +52,8 @@ struct HuffEnc {
 HuffEnc g_enc[16];
 int g_long_start[3][23], g_short_start[3][14];
 bool g_init = false;
-unsigned g_disable = 0;  // debug: bit0 short blocks, bit1 mixed, bit2 scfsi, bit3 preflag, bit4 sf_scale, bit5 subblock_gain, bit6 escapes, bit7 random tables, bit8 MS
+double g_is_prob = 0.25;  // share of joint-stereo frames that use intensity stereo (tests: high, for coverage; bench: 2 %, encoders at 128 kbps rarely use it)
+unsigned g_disable = 0;  // debug: bit0 short blocks, bit1 mixed, bit2 scfsi, bit3 preflag, bit4 sf_scale, bit5 subblock_gain, bit6 escapes, bit7 random tables, bit8 MS, bit9 intensity stereo
 
 void init() {
     if (g_init) return;
@@ -270,7 +271,7 @@ double xr_energy_unit(const Granule& g, int sr_row) {
 }
 
 void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double amp, double tilt, int target_bits,
-                  const int* scfsi, int gr, double level_db) {
+                  const int* scfsi, int gr, double level_db, double is_cut = 1e9) {
     g = Granule();
     g.block_type = bt;
     g.window_switching = bt != 0;
@@ -305,9 +306,9 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
             while (sfb < 12 && p >= 3 * g_short_start[sr_row][sfb + 1]) sfb++;
             f = 3.0 * g_short_start[sr_row][sfb];
         }
-        base[i] = f >= lowpass ? 0.0 : -std::log(1.0 - rng.uni()) * std::pow(1.0 + f / 6.0, -tilt);
+        base[i] = (f >= lowpass || f >= is_cut) ? 0.0 : -std::log(1.0 - rng.uni()) * std::pow(1.0 + f / 6.0, -tilt);
         capped[i] = f > knee;
-        escape[i] = (rng.chance(0.0008) && f < 40 && !(g_disable & 64)) ? 16 + rng.below(600) : 0;  // occasional linbits escapes
+        escape[i] = (rng.chance(0.0008) && f < 40 && f < is_cut && !(g_disable & 64)) ? 16 + rng.below(600) : 0;  // occasional linbits escapes
         neg[i] = rng.chance(0.5);
     }
     auto build = [&](double scale) {
@@ -405,6 +406,7 @@ void write_side(BitWriter& w, int nch, int main_data_begin, const int scfsi[2][4
 extern "C" {
 
 void synth_set_disable(unsigned mask) { g_disable = mask; }
+void synth_set_intensity_prob(double p) { g_is_prob = p; }
 
 // One self-contained group of n_frames frames.  br_idx: 1..14 CBR, 0 = VBR (uniform bitrate index per frame).
 // level_db: target loudness of the PCM (dBFS RMS); the group wanders around it.  Returns bytes written (0 if cap too small).
@@ -441,6 +443,9 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         lvl = std::min(level_db + 9.0, std::max(level_db - 14.0, lvl + 1.6 * (rng.uni() - 0.5)));
         bool js = channels == 2 && rng.chance(0.6);
         bool ms = js && rng.chance(0.7) && !(g_disable & 256);
+        // intensity stereo: the right channel is empty above a random bound and its scalefactors there are is_pos values
+        bool ist = js && rng.chance(g_is_prob) && !(g_disable & 512);
+        double is_cut = ist ? 20.0 + 300.0 * rng.uni() : 1e9;
         Granule gr[2][2];
         int scfsi[2][4] = {{0}};
         int bts[2], mixed_g[2];
@@ -467,7 +472,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
                 target = std::max(0, std::min(target, remain));
                 if (ms && ch == 1 && left > 1) target = (int)(target * 0.6);   // the side channel gets the smaller share
                 double a = amp * ((ms && ch == 1) ? 0.35 : 1.0);
-                make_granule(gr[g][ch], rng, sr_row, bts[g], mixed[g], a, tilt, target, scfsi[ch], g, lvl);
+                make_granule(gr[g][ch], rng, sr_row, bts[g], mixed[g], a, tilt, target, scfsi[ch], g, lvl, (ist && ch == 1) ? is_cut : 1e9);
                 used += gr[g][ch].part2_bits + gr[g][ch].part3_bits;
             }
         // header
@@ -475,7 +480,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         hw.put(0x7FF, 11); hw.put(3, 2); hw.put(1, 2); hw.put(1, 1);      // sync, MPEG-1, Layer III, no CRC
         hw.put((uint32_t)bri, 4); hw.put((uint32_t)sr_idx, 2); hw.put((uint32_t)pad, 1); hw.put(0, 1);
         hw.put(channels == 1 ? 3u : (js ? 1u : 0u), 2);
-        hw.put(js ? (ms ? 2u : 0u) : 0u, 2);
+        hw.put(js ? ((ms ? 2u : 0u) | (ist ? 1u : 0u)) : 0u, 2);
         hw.put(0, 1); hw.put(1, 1); hw.put(0, 2);
         write_side(hw, channels, (int)(M - P), scfsi, gr);
         // granule data into the main-data stream at P

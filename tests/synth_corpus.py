@@ -28,6 +28,7 @@ def _load():
         _lib.synth_group.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
         _lib.synth_track.restype = C.c_size_t
         _lib.synth_track.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
+        _lib.synth_set_intensity_prob.argtypes = [C.c_double]
     return _lib
 
 
@@ -40,9 +41,11 @@ def make_group(seed, n_frames=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0
     return buf[:n].copy()
 
 
-def make_track(seed, n_frames=6891, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0):
-    """One unique track (every group freshly generated). br_idx 0 = VBR. Returns a numpy uint8 array."""
+def make_track(seed, n_frames=6891, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0, intensity_prob=0.25):
+    """One unique track (every group freshly generated). br_idx 0 = VBR. Returns a numpy uint8 array.
+    intensity_prob: share of the joint-stereo frames (60 % of stereo frames) that carry intensity stereo."""
     lib = _load()
+    lib.synth_set_intensity_prob(float(intensity_prob))
     cap = n_frames * 1500 + 64
     buf = np.zeros(cap, np.uint8)
     n = lib.synth_track(seed, n_frames, group_len, sr_idx, br_idx, channels, level_db, buf.ctypes.data, cap)
@@ -55,11 +58,16 @@ class GroupPool:
     main_data_begin = 0, so any concatenation is a valid stream).  Lets bench.py build 1,000 distinct 3-minute tracks in
     seconds: every track is still a different bitstream and decodes to different PCM / filter state."""
 
-    def __init__(self, seed=1, n_groups=256, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0):
+    def __init__(self, seed=1, n_groups=256, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0,
+                 intensity_prob=0.25):
         rng = np.random.default_rng(seed)
         self.group_len = group_len
-        self.groups = [make_group(int(seed) * 7919 + g, group_len, sr_idx, br_idx, channels,
-                                  level_db + float(rng.uniform(-8, 4))) for g in range(n_groups)]
+        _load().synth_set_intensity_prob(float(intensity_prob))
+        try:
+            self.groups = [make_group(int(seed) * 7919 + g, group_len, sr_idx, br_idx, channels,
+                                      level_db + float(rng.uniform(-8, 4))) for g in range(n_groups)]
+        finally:
+            _load().synth_set_intensity_prob(0.25)
 
     def track(self, seed, n_frames):
         rng = np.random.default_rng(seed)

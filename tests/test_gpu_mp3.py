@@ -66,6 +66,15 @@ def test_synthetic_streams_pcm_bit_exact(kw, engine_exact, oracle):
     assert info.n_frames == 300
 
 
+@pytest.mark.parametrize("kw", [dict(seed=21), dict(seed=22, sr_idx=1, br_idx=5), dict(seed=23, br_idx=0)])
+def test_intensity_stereo_pcm_bit_exact(kw, engine_exact, oracle):
+    """Streams whose joint-stereo frames all carry intensity stereo (the oracle's handling is pinned against FFmpeg in
+    test_oracle_mp3.py): the device PCM equals the oracle's sample for sample."""
+    img = synth_corpus.make_track(n_frames=300, intensity_prob=1.0, **kw)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 300
+
+
 @pytest.mark.parametrize("kw", SYNTH[:4])
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_synthetic_streams_analysis(kw, mode, engine_exact, engine_fast, oracle):

@@ -72,6 +72,33 @@ def test_synthetic_streams_decode_like_ffmpeg(oracle, kw):
     assert 0.03 < np.sqrt((pcm.astype(np.float64) ** 2).mean()) < 0.3
 
 
+def _count_stereo_modes(img):
+    """(frames, MS frames, intensity-stereo frames) from the headers."""
+    n = ms = ist = 0
+    for f in ffmpeg_ref.split_frames(img):
+        n += 1
+        if (f[3] >> 6) & 3 == 1:
+            ms += (f[3] >> 5) & 1
+            ist += (f[3] >> 4) & 1
+    return n, ms, ist
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", [dict(seed=21), dict(seed=22, sr_idx=1, br_idx=5), dict(seed=23, br_idx=0)])
+def test_intensity_stereo_decodes_like_ffmpeg(oracle, kw):
+    """Every joint-stereo frame carries intensity stereo (with and without MS, long / short / mixed blocks): the oracle's
+    ISO 11172-3 2.4.3.4.9.3 processing agrees with FFmpeg's, and ignoring it would not (the right channel is empty above
+    the intensity bound in the bitstream)."""
+    img = synth_corpus.make_track(n_frames=300, intensity_prob=1.0, **kw)
+    n, ms, ist = _count_stereo_modes(img)
+    assert n == 300 and ist > 100 and 0 < ms < ist
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 300
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+
+
 def test_container_edge_cases(oracle):
     base = synth_corpus.make_track(seed=11, n_frames=50)
     rc0, pcm0, info0 = oracle.decode(base)

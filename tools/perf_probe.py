@@ -18,7 +18,7 @@ n_tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 6891
 exact = len(sys.argv) > 3 and sys.argv[3] == "exact"
 t = time.time()
-pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32)
+pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
 imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
 print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
 lib = _lib.load()
