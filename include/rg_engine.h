@@ -82,7 +82,7 @@ typedef struct {
     uint32_t n_dropped_windows; /* windows whose bin index fell outside [0,12000) (src/replaygain.rs:757) */
     uint32_t n_edge_windows;    /* windows whose 1000*log10 value sat within the edge tolerance of an integer */
     uint32_t exact_rerun;       /* 1 if the time-blocked pass flagged this track and the exact kernel re-ran it */
-    uint32_t reserved;
+    uint32_t index_rewalks;     /* 64 KiB segments of the speculative frame index that the merge had to walk again (diagnostic) */
 } rg_track_result;
 
 /* AlbumGainResult minus the per-track vector (src/replaygain.rs:78-88). */

@@ -46,7 +46,7 @@ class RgTrackResult(C.Structure):
         ("sample_rate", C.c_uint32), ("file_type", C.c_int32), ("status", C.c_int32),
         ("channels", C.c_uint32), ("n_frames", C.c_uint32), ("n_windows", C.c_uint32),
         ("n_dropped_windows", C.c_uint32), ("n_edge_windows", C.c_uint32),
-        ("exact_rerun", C.c_uint32), ("reserved", C.c_uint32),
+        ("exact_rerun", C.c_uint32), ("index_rewalks", C.c_uint32),
     ]
 
 

@@ -242,7 +242,7 @@ k_index_merge(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
     const uint64_t a0 = k0_id3_skip(src, len);
     const TrackSeg ts = tseg[t];
     bool have_ref = false, in_sync = false, stopped = false;
-    uint32_t ref = 0, M = 0, nf = 0, n_total = 0, n_rec_all = 0, skipped = 0;
+    uint32_t ref = 0, M = 0, nf = 0, n_total = 0, n_rec_all = 0, skipped = 0, n_rewalks = 0;
     uint64_t P = a0;
     int status = -5;   // RG_ERR_PROBE until a frame is found
     for (uint32_t s = 0; s < ts.n_seg; s++) {
@@ -261,6 +261,7 @@ k_index_merge(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
                 if ((o.flags & K0F_FOUND) && n_total == 0) redo = true;                                      // it holds the track's first frame
                 if (o.n_rec > 0 && M < 511) redo = true;                                                     // reservoir may still underflow
             }
+            if (redo) n_rewalks++;
             if (redo)
                 o = k0_walk(src, len, s_chunk[warp], s_flen, in_sync ? P : b, e, in_sync, have_ref, ref, n_total == 0, true, M, flags,
                             stage + (size_t)gi * K0_SEG_RECS, lane);
@@ -288,7 +289,7 @@ k_index_merge(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
         if (have_ref && ((ref >> 19) & 3) != 3) {  // LSF: report the real rate index for the host (unsupported anyway)
             m.sr_idx = ((ref >> 10) & 3) | (((ref >> 19) & 3) << 4);
         }
-        m.n_frames = nf; m.md_bytes = M; m.n_dropped = n_rec_all - nf; m.skipped_info = skipped; m.n_total = n_total;
+        m.n_frames = nf; m.md_bytes = M; m.n_dropped = n_rec_all - nf; m.skipped_info = skipped; m.n_total = n_total; m.n_rewalks = n_rewalks;
         meta[t] = m;
     }
 }

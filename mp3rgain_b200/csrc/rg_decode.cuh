@@ -54,7 +54,7 @@ struct L3Dev {
 struct TrackIn { uint64_t off, len; };            // byte range of one file image inside the device corpus buffer
 struct TrackMeta {                                 // K0 output
     int32_t status;
-    uint32_t sr_idx, channels, n_frames, md_bytes, n_dropped, skipped_info, n_total;
+    uint32_t sr_idx, channels, n_frames, md_bytes, n_dropped, skipped_info, n_total, n_rewalks;
 };
 struct FrameRec {                                  // one per PCM-producing frame
     uint32_t file_off;   // frame start, relative to the track's first byte

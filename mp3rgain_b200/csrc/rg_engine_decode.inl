@@ -399,6 +399,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
             if (!x.exact && x.pt[k].status == RG_OK && res[k].n_edge > 0) { flagged.push_back(i); }
             fill_result(&out[i], x.pt[k], res[k], rerun_batch ? 1 : 0, ip.meta[i].n_frames);
             out[i].file_type = c->is_mp4[i] ? 1 : 0;
+            out[i].index_rewalks = ip.meta[i].n_rewalks;
             if (rerun_batch && hist_out) memcpy(hist_out + (size_t)i * RG_HIST_BINS, hist_tmp.data() + k * RG_HIST_BINS, RG_HIST_BINS * sizeof(uint32_t));
             if (!rerun_batch && x.pt[k].status == RG_OK) { e->stats.tracks++; e->stats.frames += ip.meta[i].n_frames; }
         }

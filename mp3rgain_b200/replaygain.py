@@ -55,6 +55,7 @@ class ReplayGainResult:  # src/replaygain.rs:56-75
     n_dropped_windows: int = 0
     n_edge_windows: int = 0
     exact_rerun: int = 0
+    index_rewalks: int = 0
     histogram: Optional[np.ndarray] = None
 
     def gain_steps(self) -> int:
@@ -156,7 +157,7 @@ class Engine:
             loudness_db=r.loudness_db, gain_db=r.gain_db, peak=r.peak, sample_rate=r.sample_rate,
             file_type=AudioFileType(r.file_type), channels=r.channels, n_frames=r.n_frames, n_windows=r.n_windows,
             n_dropped_windows=r.n_dropped_windows, n_edge_windows=r.n_edge_windows, exact_rerun=r.exact_rerun,
-            histogram=hist)
+            index_rewalks=r.index_rewalks, histogram=hist)
 
     # ---- batch API --------------------------------------------------------------------------------
     def analyze_images(self, images: Sequence, track_index: Optional[int] = None, want_hist: bool = False,

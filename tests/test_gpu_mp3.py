@@ -82,6 +82,61 @@ def test_synthetic_streams_analysis(kw, mode, engine_exact, engine_fast, oracle)
     _check_analysis(engine_exact if mode == "exact" else engine_fast, oracle, img)
 
 
+def _frame_starts(img):
+    """Byte offsets of the frames of a clean synthetic stream (header walk)."""
+    br = synth_corpus.BITRATES
+    pos, out, b = 0, [], bytes(img)
+    while pos + 4 <= len(b):
+        bi, si, pad = b[pos + 2] >> 4, (b[pos + 2] >> 2) & 3, (b[pos + 2] >> 1) & 1
+        out.append(pos)
+        pos += 144 * br[bi] * 1000 // synth_corpus.RATES[si] + pad
+    return out
+
+
+def test_segmented_frame_index_equals_serial_walk(engine_exact, oracle):
+    """K0 walks 64 KiB segments speculatively and stitches them (k_frame_index.cuh).  These streams span many segments and
+    put the hard cases AT the segment boundaries: a tag larger than a segment, junk across a boundary, and -- the case the
+    stitching exists for -- bytes inside a frame's payload just after a boundary that look like two consecutive valid
+    headers, so that the segment's own scan locks onto a false sync and must be re-walked from the true position."""
+    SEG = 64 * 1024
+    base = synth_corpus.make_track(seed=31, n_frames=1500)           # ~ 627 kB = 10 segments
+    assert len(base) > 9 * SEG
+    starts = _frame_starts(base)
+    hdr = bytes(base[:4])
+    flen = starts[1] - starts[0]
+    # (a) a 150 kB ID3v2 tag in front: the audio starts in the third segment
+    tagged = np.frombuffer(synth_corpus.id3v2_tag(150_000) + bytes(base), np.uint8)
+    # (b) junk that straddles a segment boundary (sync lost before the boundary, regained after it)
+    cut = max(p for p in starts if p < 3 * SEG)
+    nxt = min(p for p in starts if p >= 3 * SEG + 700)
+    junk = np.concatenate([base[:cut], np.full(1234, 0x00, np.uint8), base[nxt:]])
+    # (c) false syncs: right after the boundaries of segments 2..8, inside whatever frame's payload lies there, plant a
+    # valid header followed, one (fake) frame length later, by another one
+    fake = base.copy()
+    planted = 0
+    for k in range(2, 9):
+        b0 = k * SEG
+        f0 = max(p for p in starts if p <= b0)              # the frame that contains the boundary
+        p1 = b0 + 40                                         # well inside its payload? (keep header + side info intact)
+        if p1 < f0 + 40 or p1 + flen + 4 > len(fake):
+            continue
+        fake[p1:p1 + 4] = np.frombuffer(hdr, np.uint8)
+        fake[p1 + flen:p1 + flen + 4] = np.frombuffer(hdr, np.uint8)   # may land in the next frame: also payload or header-safe
+        planted += 1
+    assert planted >= 5
+    rewalks = {}
+    for name, img in (("base", base), ("tagged", tagged), ("junk", junk), ("fake", fake)):
+        rc, ores, ohist, info = oracle.analyze_mp3(img)
+        assert rc == 0
+        res, sts = engine_exact.analyze_images([img], want_hist=True)
+        assert sts[0] == 0
+        assert res[0].n_frames == info.n_frames, (name, res[0].n_frames, info.n_frames)
+        assert (res[0].histogram == ohist).all() and res[0].peak == ores.peak, name
+        rewalks[name] = res[0].index_rewalks
+    # the clean stream stitches without a single re-walk; every planted false sync costs (at least) one
+    assert rewalks["base"] == 0 and rewalks["fake"] >= planted, rewalks
+
+
 def test_container_edge_cases(engine_exact, oracle):
     base = synth_corpus.make_track(seed=11, n_frames=50)
     variants = [
