@@ -111,7 +111,8 @@ const char* rg_status_str(int status);
  * "edge_tol" (distance of 1000*log10(ms) from an integer below which the time-blocked pass hands the track to the
  * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9), "pipeline" (default 1:
  * copy / index / decode / analysis overlap on four streams with two alternating batches; 0 = one batch at a time, every
- * kernel alone on the device, for profiling).  Returns RG_ERR_INVALID_ARG for an unknown key. */
+ * kernel alone on the device, for profiling), "group_bytes_min" (smallest copy / index group of the end-to-end path, default
+ * 32 MiB).  Returns RG_ERR_INVALID_ARG for an unknown key. */
 int rg_engine_set_option(rg_engine* e, const char* key, double value);
 /* Thread-local detail string for the last failing call (CUDA error text etc.). */
 const char* rg_last_error(void);

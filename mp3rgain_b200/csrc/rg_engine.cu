@@ -103,6 +103,7 @@ struct rg_engine {
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
     uint32_t k4_capacity = 0;             // chains (threads) of k_iir_fast resident on the device at once
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
+    uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
     RgCoefFast coef_fast[12];
     double edge_tol = 1e-9;
@@ -263,6 +264,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
+    if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
     if (!strcmp(key, "exact_iir")) { if (value != 0) e->flags |= RG_FLAG_EXACT_IIR; else e->flags &= ~RG_FLAG_EXACT_IIR; return RG_OK; }
     return RG_ERR_INVALID_ARG;
 }

@@ -114,7 +114,7 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     // index groups: one when the corpus is already resident (K0 is a serial walk per track, so its time does not depend on
     // the number of tracks); about eight, never smaller than 32 MiB, when the bytes are still arriving from the host, so
     // that indexing starts as soon as the first group has landed
-    const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, 32ull << 20) : ~0ull;
+    const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, e->group_bytes_min) : ~0ull;
     // (the first two groups are a quarter and a half of that: the pipeline starts as soon as a few files have landed)
     uint64_t acc = 0;
     for (size_t i = 0; i < n; i++) {

@@ -237,3 +237,31 @@ def test_batch_of_many_tracks_and_small_scratch(oracle):
     for i in (0, 7, 19, 39):
         rc, ores, ohist, info = oracle.analyze_mp3(imgs[i])
         assert (res[i].histogram == ohist).all() and res[i].loudness_db == ores.loudness_db and res[i].peak == ores.peak
+
+
+def test_mixed_corpus_through_the_pipeline(oracle):
+    """BASELINE configs[3] in miniature: VBR 32-320 kbps, 44.1 / 48 / 32 kHz, mono and stereo, different lengths, plus
+    files that fail (garbage, MPEG-2, empty) in the middle of the list -- all in ONE rg_analyze_tracks call that is forced
+    through many copy/index groups and many scratch batches.  Every per-file result equals the oracle's and a failing file
+    does not disturb its neighbours (track mode keeps going, src/main.rs:1988-1999)."""
+    import mp3rgain_b200 as m
+    imgs = []
+    for i in range(36):
+        imgs.append(synth_corpus.make_track(seed=300 + i, n_frames=90 + 41 * (i % 7), sr_idx=i % 3, br_idx=(0 if i % 4 == 0 else 3 + i % 11),
+                                            channels=1 + (i % 5 != 0)))
+    lsf = np.frombuffer((bytes([0xFF, 0xF3, 0x80, 0x00]) + bytes(72 * 64000 // 22050 - 4)) * 4, np.uint8)
+    imgs[5] = np.zeros(4000, np.uint8)            # not an MP3: "Failed to probe format"
+    imgs[17] = lsf                                 # MPEG-2 Layer III: recognised, unsupported
+    imgs[29] = np.zeros(0, np.uint8)              # empty file
+    for exact in (False, True):
+        with m.Engine(device=0, exact=exact, scratch_bytes=24 << 20) as eng:
+            eng.set_option("group_bytes_min", 100_000)
+            res, sts = eng.analyze_images(imgs, want_hist=True)
+            assert eng.stats().last_batches >= 4
+        for i, im in enumerate(imgs):
+            rc, ores, ohist, info = oracle.analyze_mp3(im)
+            assert sts[i] == rc, (i, sts[i], rc)
+            if rc == 0:
+                assert (res[i].histogram == ohist).all(), i
+                assert res[i].loudness_db == ores.loudness_db and res[i].peak == ores.peak and res[i].n_frames == info.n_frames, i
+                assert res[i].sample_rate == info.sample_rate and res[i].channels == info.channels, i
