@@ -147,6 +147,62 @@ __device__ __forceinline__ void k2_pair_sync(int pair) {   // immediate ids, so 
     }
 }
 
+// 3-point DFT of complex numbers (W3 = e^{-2 pi i/3}): X0 = x0 + s, X1 = m - i q, X2 = m + i q with s = x1 + x2,
+// m = x0 - s/2 (one fmaf per component), q = (sqrt3/2)(x1 - x2).  Operation for operation the oracle's dft3().
+__device__ __forceinline__ void k2_dft3(float x0r, float x0i, float x1r, float x1i, float x2r, float x2i,
+                                        float& y0r, float& y0i, float& y1r, float& y1i, float& y2r, float& y2i) {
+    const float sr = __fadd_rn(x1r, x2r), si = __fadd_rn(x1i, x2i), dr = __fsub_rn(x1r, x2r), di = __fsub_rn(x1i, x2i);
+    y0r = __fadd_rn(x0r, sr); y0i = __fadd_rn(x0i, si);
+    const float mr = fmaf(-0.5f, sr, x0r), mi = fmaf(-0.5f, si, x0i);
+    const float qr = __fmul_rn(L3_SQRT3_2, dr), qi = __fmul_rn(L3_SQRT3_2, di);
+    y1r = __fadd_rn(mr, qi); y1i = __fsub_rn(mi, qr);
+    y2r = __fsub_rn(mr, qi); y2i = __fadd_rn(mi, qr);
+}
+
+// 18-point DCT-IV u[m] = sum_k X[k] cos(pi/72 (2m+1)(2k+1)) through a 9-point complex FFT (3 x 3 Cooley-Tukey), 172 FP
+// instructions instead of the 324 FFMAs of the matrix form; all twiddles are instruction immediates:
+//   v[n] = (X[2n] + i X[17-2n]) e^{-i pi (4n+1)/72},  V = FFT9(v),  y[k] = V[k] e^{-i pi k/18},  u[2k] = Re y[k], u[17-2k] = -Im y[k]
+// A complex product (a + i b)(c + i d) is evaluated as (fmaf(-b, d, a*c), fmaf(a, d, b*c)) -- the oracle's dct4_18().
+__device__ __forceinline__ void k2_dct4_18(const float (&X)[18], float (&u)[18]) {
+    float vr[9], vi[9];
+    static_for<0, 9>([&](auto nc) {
+        constexpr int n = decltype(nc)::value;
+        constexpr float c = L3_D4_PRE[0][n], s = L3_D4_PRE[1][n];
+        const float a = X[2 * n], b = X[17 - 2 * n];
+        vr[n] = fmaf(b, s, __fmul_rn(a, c));
+        vi[n] = fmaf(-a, s, __fmul_rn(b, c));
+    });
+    float tr[3][3], ti[3][3];   // [b][c]
+    static_for<0, 3>([&](auto bc) {
+        constexpr int b = decltype(bc)::value;
+        k2_dft3(vr[b], vi[b], vr[3 + b], vi[3 + b], vr[6 + b], vi[6 + b], tr[b][0], ti[b][0], tr[b][1], ti[b][1], tr[b][2], ti[b][2]);
+    });
+    static_for<0, 4>([&](auto ic) {
+        constexpr int b = 1 + decltype(ic)::value / 2, c = 1 + decltype(ic)::value % 2;
+        constexpr int e = b * c == 1 ? 0 : (b * c == 2 ? 1 : 2);   // W9^{bc}: exponents 1, 2, 4
+        constexpr float wr = L3_D4_W9[0][e], wi = L3_D4_W9[1][e];
+        const float zr = tr[b][c], zi = ti[b][c];
+        tr[b][c] = fmaf(-zi, wi, __fmul_rn(zr, wr));
+        ti[b][c] = fmaf(zr, wi, __fmul_rn(zi, wr));
+    });
+    static_for<0, 3>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        float yr[3], yi[3];
+        k2_dft3(tr[0][c], ti[0][c], tr[1][c], ti[1][c], tr[2][c], ti[2][c], yr[0], yi[0], yr[1], yi[1], yr[2], yi[2]);
+        static_for<0, 3>([&](auto dc) {
+            constexpr int d = decltype(dc)::value, k = c + 3 * d;
+            float re = yr[d], im = yi[d];
+            if constexpr (k != 0) {
+                constexpr float pc = L3_D4_POST[0][k], ps = L3_D4_POST[1][k];
+                re = fmaf(yi[d], ps, __fmul_rn(yr[d], pc));
+                im = fmaf(-yr[d], ps, __fmul_rn(yi[d], pc));
+            }
+            u[2 * k] = re;
+            u[17 - 2 * k] = -im;
+        });
+    });
+}
+
 // long-block window: o[i] = u[idx36(i)] * win[BT][i]
 template <int BT>
 __device__ __forceinline__ void k2_window36(const float (&u)[18], float (&o)[36]) {
@@ -380,16 +436,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 float o[36];
                 if (!is_short) {
                     float u[18];
-                    static_for<0, 18>([&](auto mc) {
-                        constexpr int m = decltype(mc)::value;
-                        float a = 0.0f;
-                        static_for<0, 18>([&](auto kc) {
-                            constexpr int k = decltype(kc)::value;
-                            constexpr float c = L3_DCT4_18[m][k];
-                            a = fmaf(X[k], c, a);
-                        });
-                        u[m] = a;
-                    });
+                    k2_dct4_18(X, u);
                     const int bt = (gi.bt == 2) ? 0 : gi.bt;  // long subbands of a mixed block use the normal window
                     if (bt == 0) k2_window36<0>(u, o);
                     else if (bt == 1) k2_window36<1>(u, o);

@@ -400,15 +400,61 @@ static void alias_reduce(const gr_t* q, float* xr) {
 }
 
 /* IMDCT + window + overlap-add + frequency inversion for one subband; out[t] = subband sample at time slot t */
+/* 3-point DFT of complex numbers (W3 = e^{-2 pi i/3}): X0 = x0 + s, X1 = m - i q, X2 = m + i q with s = x1 + x2,
+ * m = x0 - s/2 (one fmaf per component), q = (sqrt3/2)(x1 - x2).  Every operation rounds separately. */
+static void dft3(const float* xr, const float* xi, float* yr, float* yi) {
+    float sr = xr[1] + xr[2], si = xi[1] + xi[2], dr = xr[1] - xr[2], di = xi[1] - xi[2];
+    yr[0] = xr[0] + sr; yi[0] = xi[0] + si;
+    float mr = fmaf(-0.5f, sr, xr[0]), mi = fmaf(-0.5f, si, xi[0]);
+    float qr = L3_SQRT3_2 * dr, qi = L3_SQRT3_2 * di;
+    yr[1] = mr + qi; yi[1] = mi - qr;
+    yr[2] = mr - qi; yi[2] = mi + qr;
+}
+
+/* 18-point DCT-IV u[m] = sum_k X[k] cos(pi/72 (2m+1)(2k+1)) through a 9-point complex FFT (3 x 3 Cooley-Tukey):
+ *   v[n] = (X[2n] + i X[17-2n]) e^{-i pi (4n+1)/72},  V = FFT9(v),  y[k] = V[k] e^{-i pi k/18},  u[2k] = Re y[k], u[17-2k] = -Im y[k].
+ * A complex product (a + i b)(c + i d) is evaluated as (fmaf(-b, d, a*c), fmaf(a, d, b*c)). */
+static void dct4_18(const float* X, float* u) {
+    float vr[9], vi[9];
+    for (int n = 0; n < 9; n++) {
+        float a = X[2 * n], b = X[17 - 2 * n], c = L3_D4_PRE[0][n], s = L3_D4_PRE[1][n];
+        vr[n] = fmaf(b, s, a * c);      /* (a + i b)(c - i s) */
+        vi[n] = fmaf(-a, s, b * c);
+    }
+    float tr[3][3], ti[3][3];           /* [b][c]: 3-point DFTs over a of v[3a + b], then times W9^{bc} */
+    for (int b = 0; b < 3; b++) {
+        float xr[3] = {vr[b], vr[3 + b], vr[6 + b]}, xi[3] = {vi[b], vi[3 + b], vi[6 + b]};
+        dft3(xr, xi, tr[b], ti[b]);
+    }
+    static const int tw[3][3] = {{-1, -1, -1}, {-1, 0, 1}, {-1, 1, 2}};   /* index into L3_D4_W9 (exponents 1, 2, 4), -1 = 1 */
+    for (int b = 1; b < 3; b++)
+        for (int c = 1; c < 3; c++) {
+            float wr = L3_D4_W9[0][tw[b][c]], wi = L3_D4_W9[1][tw[b][c]], zr = tr[b][c], zi = ti[b][c];
+            tr[b][c] = fmaf(-zi, wi, zr * wr);
+            ti[b][c] = fmaf(zr, wi, zi * wr);
+        }
+    for (int c = 0; c < 3; c++) {
+        float xr[3] = {tr[0][c], tr[1][c], tr[2][c]}, xi[3] = {ti[0][c], ti[1][c], ti[2][c]}, yr[3], yi[3];
+        dft3(xr, xi, yr, yi);
+        for (int d = 0; d < 3; d++) {
+            int k = c + 3 * d;
+            float re = yr[d], im = yi[d];
+            if (k) {                     /* y = V (pc - i ps) */
+                float pc = L3_D4_POST[0][k], ps = L3_D4_POST[1][k];
+                re = fmaf(yi[d], ps, yr[d] * pc);
+                im = fmaf(-yr[d], ps, yi[d] * pc);
+            }
+            u[2 * k] = re;
+            u[17 - 2 * k] = -im;
+        }
+    }
+}
+
 static void hybrid_sb(const float* X, int bt, float* prev, int sb, float* out) {
     float raw[36];
     if (bt != 2) {
         float u[18];
-        for (int m = 0; m < 18; m++) {
-            float a = 0.0f;
-            for (int k = 0; k < 18; k++) a = fmaf(X[k], L3_DCT4_18[m][k], a);
-            u[m] = a;
-        }
+        dct4_18(X, u);
         for (int i = 0; i < 36; i++) raw[i] = u[L3_IMDCT36_IDX[i]] * L3_WINSGN[bt][i];
     } else {
         for (int i = 0; i < 36; i++) raw[i] = 0.0f;

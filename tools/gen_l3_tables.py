@@ -96,6 +96,14 @@ sgn = np.where(i36 < 9, 1.0, -1.0)
 uidx = np.where(i36 < 9, i36 + 9, np.where(i36 < 27, 26 - i36, i36 - 27)).astype(int)
 winsgn = f32(win * sgn[None, :])
 winsgn[2] = f32(win[2])                                                   # short window keeps its own sign
+# Fast 18-point DCT-IV through a 9-point complex FFT (3 x 3):
+#   v[n] = (X[2n] + i X[17-2n]) e^{-i pi (4n+1)/72};  V = FFT9(v);  y[k] = V[k] e^{-i pi k/18};  u[2k] = Re y[k], u[17-2k] = -Im y[k]
+n9 = np.arange(9)
+d4_pre = f32(np.stack([np.cos(np.pi * (4 * n9 + 1) / 72.0), np.sin(np.pi * (4 * n9 + 1) / 72.0)]))
+d4_post = f32(np.stack([np.cos(np.pi * n9 / 18.0), np.sin(np.pi * n9 / 18.0)]))
+e9 = np.array([1.0, 2.0, 4.0])
+d4_w9 = f32(np.stack([np.cos(2 * np.pi * e9 / 9.0), -np.sin(2 * np.pi * e9 / 9.0)]))   # W9^e = (re, im), e = 1, 2, 4
+sqrt3_2 = np.float32(np.sqrt(3.0) / 2.0)
 # Lee DCT-II secants: level N in {32,16,8,4,2}: 1/(2cos(pi(2n+1)/(2N))), n < N/2, concatenated
 sec = []
 for N in (32, 16, 8, 4, 2):
@@ -184,6 +192,11 @@ def emit(path, guard, note):
     o.append("/* u[m] = sum_k X[k]*L3_DCT4_18[m][k]  (18-point DCT-IV; IMDCT-36 output i = +-u[L3_IMDCT36_IDX[i]]) */")
     o.append(carr_f32("L3_DCT4_18", dct4_18))
     o.append(carr_int("L3_IMDCT36_IDX", "uint8_t", uidx))
+    o.append("/* the same u[] through a 9-point complex FFT: pre-twiddle (cos, sin)(pi(4n+1)/72), W9^{1,2,4} as (re, im), post-twiddle (cos, sin)(pi k/18) */")
+    o.append(carr_f32("L3_D4_PRE", d4_pre))
+    o.append(carr_f32("L3_D4_W9", d4_w9))
+    o.append(carr_f32("L3_D4_POST", d4_post))
+    o.append(f"#define L3_SQRT3_2 {float(sqrt3_2).hex()}f")
     o.append("/* block-type windows with the IMDCT-36 sign folded in (row 2: 12-tap short window, plain) */")
     o.append(carr_f32("L3_WINSGN", winsgn))
     o.append(carr_f32("L3_IMDCT12", imdct12))
