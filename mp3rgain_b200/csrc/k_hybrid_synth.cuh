@@ -216,14 +216,17 @@ __device__ __forceinline__ void k2_window36(const float (&u)[18], float (&o)[36]
 // P4 of one granule-channel, lane = output column j:
 //   out[t][j] = sum_p A[t-2p]*wa[p] + B[t-2p-1]*wb[p]   (p ascending, one fmaf chain)
 // rows t-15..t-1 of slot 0 live in the previous granule's slot (rows 3..17)
-template <bool CLAMP>
+// PEAK: no PCM is stored; the granule-channel's max |sample| is folded into *peak_bits (float bits, atomicMax) instead --
+// the peak-only path of find_peak_amplitude (src/replaygain.rs:1140-1249).
+template <bool CLAMP, bool PEAK>
 __device__ __forceinline__ void k2_polyphase(const K2Smem& S, const float* __restrict__ cur, const float* __restrict__ prv,
-                                             float* __restrict__ dst, int j) {
+                                             float* __restrict__ dst, uint32_t* __restrict__ peak_bits, int j) {
     float wa[8], wb[8];
 #pragma unroll
     for (int p = 0; p < 8; p++) { wa[p] = S.wa[p][j]; wb[p] = S.wb[p][j]; }
     const int ia = S.ia[j], ib = S.ib[j];
     float Av[33], Bv[33];   // rows -15 .. 17 relative to this granule's slot 0
+    float mx = 0.0f;
 #pragma unroll
     for (int r = 0; r < 15; r++) { Av[r] = prv[r * ROW + ia]; Bv[r] = prv[r * ROW + ib]; }
 #pragma unroll
@@ -237,7 +240,12 @@ __device__ __forceinline__ void k2_polyphase(const K2Smem& S, const float* __res
             a = fmaf(Bv[15 + t - 2 * p - 1], wb[p], a);
         }
         if (CLAMP) a = fminf(1.0f, fmaxf(-1.0f, a));
-        dst[32 * t] = a;
+        if (PEAK) mx = fmaxf(mx, fabsf(a));
+        else dst[32 * t] = a;
+    }
+    if (PEAK) {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));   // non-negative floats order like their bit patterns
+        if (j == 0) atomicMax(peak_bits, m);
     }
 }
 
@@ -246,7 +254,8 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
                                         const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
-                                        const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t flags) {
+                                        const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits,
+                                        uint32_t flags) {
     constexpr int G = K2_GC / NCH;      // granules per batch
     constexpr int NS = G + 1;           // granule slots
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -501,9 +510,14 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         // ================= P4: polyphase window -> PCM, lane = output column ==============================================
         if (have && gfirst + gl >= run.g0) {
             const uint32_t g = gfirst + gl;
-            float* dst = pcm + tr.pcm_off + (size_t)my_ch * tr.pcm_plane + (size_t)g * 576 + lane;
-            if (flags & 0x4u) k2_polyphase<true>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, lane);
-            else k2_polyphase<false>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, lane);
+            if (peak_bits) {   // peak-only path: nothing is stored
+                if (flags & 0x4u) k2_polyphase<true, true>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, nullptr, peak_bits + run.track, lane);
+                else k2_polyphase<false, true>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, nullptr, peak_bits + run.track, lane);
+            } else {
+                float* dst = pcm + tr.pcm_off + (size_t)my_ch * tr.pcm_plane + (size_t)g * 576 + lane;
+                if (flags & 0x4u) k2_polyphase<true, false>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, nullptr, lane);
+                else k2_polyphase<false, false>(S, S.A[slot], S.A[slot_prev] + 3 * ROW, dst, nullptr, lane);
+            }
         }
         __syncthreads();
     }
@@ -513,11 +527,12 @@ __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
                const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
-               const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t flags) {
+               const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits /* [track] or null */,
+               uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
-    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, flags);
-    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, flags);
+    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
+    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
 }

@@ -75,7 +75,7 @@ struct BatchCtx {
     // stage A scratch
     DevBuf d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_gains, d_sfraw, d_pcm;
     // stage B scratch
-    DevBuf d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_perm;
+    DevBuf d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_perm, d_tpeak;
     HostBuf h_desc_a, h_desc, h_tout;      // pinned: descriptor staging (decode / analysis), results
     cudaEvent_t ev_a[4] = {};              // decode stream: gather start, K1 end = K2 start, K2 end, gather end = K1 start
     cudaEvent_t ev_b[4] = {};              // analysis stream: K4 start, K4 end = K5 start, K5 end, results on the host
@@ -86,7 +86,7 @@ struct BatchCtx {
     size_t n_chains = 0;
     uint32_t* hist_host = nullptr;         // where this batch's per-track histograms go (n x 12000), or null
     std::vector<DevBuf*> bufs() {
-        return {&d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_gains, &d_sfraw, &d_pcm, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_perm};
+        return {&d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_gains, &d_sfraw, &d_pcm, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_perm, &d_tpeak};
     }
 };
 

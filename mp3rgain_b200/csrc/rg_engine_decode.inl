@@ -244,7 +244,7 @@ static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, 
 }
 
 // Enqueues K1 + K2 for the tracks `x.ids` of the corpus on the decode stream; fills x.pt with the PCM views.
-static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, BatchCtx& x) {
+static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, BatchCtx& x, bool peak_only = false) {
     const size_t nb = x.ids.size();
     x.pt.assign(nb, PcmTrack{});
     x.decoded = false;
@@ -285,9 +285,15 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     CK(x.d_nz.ensure(std::max<uint64_t>(gc_total, 1) * sizeof(uint16_t) + 64));
     CK(x.d_gains.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW * sizeof(float) + 64));
     CK(x.d_sfraw.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW + 64));
-    CK(x.d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
+    if (!peak_only) CK(x.d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
+    if (peak_only) {
+        CK(x.d_tpeak.ensure(std::max<size_t>(nb, 1) * sizeof(uint32_t)));
+        CK(x.h_tout.ensure(std::max<size_t>(nb, 1) * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(x.d_tpeak.p, 0, std::max<size_t>(nb, 1) * sizeof(uint32_t), e->s_dec));
+    }
     for (size_t k = 0; k < nb; k++) {
         if (x.pt[k].status != RG_OK) continue;
+        if (peak_only) continue;
         x.pt[k].d_ch[0] = x.d_pcm.as<float>() + dt[k].pcm_off;
         x.pt[k].d_ch[1] = x.pt[k].nch >= 2 ? x.pt[k].d_ch[0] + dt[k].pcm_plane : nullptr;
     }
@@ -322,11 +328,17 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
         k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                                                x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>(), e->dec.d_tab,
                                                                                x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(),
-                                                                               x.d_gains.as<float>(), x.d_sfraw.as<uint8_t>(), x.d_pcm.as<float>(), e->flags);
+                                                                               x.d_gains.as<float>(), x.d_sfraw.as<uint8_t>(), peak_only ? nullptr : x.d_pcm.as<float>(),
+                                                                               peak_only ? x.d_tpeak.as<uint32_t>() : nullptr, e->flags);
         e->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(x.ev_a[2], st));
+    if (peak_only) {
+        CK(cudaMemcpyAsync(x.h_tout.p, x.d_tpeak.p, std::max<size_t>(nb, 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        e->stats.d2h_bytes += nb * sizeof(uint32_t);
+        CK(cudaEventRecord(x.ev_b[3], st));
+    }
     x.decoded = true;
     return RG_OK;
 }
@@ -552,18 +564,71 @@ extern "C" int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_t
     return RG_OK;
 }
 
+// Bytes of device scratch one track needs in a peak-only batch (no PCM is stored)
+static uint64_t track_scratch_bytes_peak(const TrackMeta& m) {
+    return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2 + 5 * K1_GAIN_ROW)) + 4096;
+}
+
 extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_result* out) {
-    // find_peak_amplitude (src/replaygain.rs:1140-1249): max |sample| over all channels of the decoded stream.  The
-    // analysis pass already tracks exactly that, so this is the same device pipeline with the loudness fields dropped.
+    // find_peak_amplitude (src/replaygain.rs:1140-1249): max |sample| over all channels of the decoded stream.  The same
+    // copy / index / decode pipeline as the analysis, but K2 folds |sample| into one word per track instead of storing PCM,
+    // and there is no filter / histogram stage.
     if (!e || (n && (!in || !out))) return RG_ERR_INVALID_ARG;
-    std::vector<rg_track_result> res(n);
-    int rc = rg_analyze_tracks(e, in, n, res.data(), nullptr);
+    rg_corpus c;
+    int rc = host_corpus(e, in, n, c);
     if (rc != RG_OK) return rc;
-    for (size_t i = 0; i < n; i++) {
-        out[i].status = res[i].status;
-        out[i].sample_rate = res[i].sample_rate;
-        out[i].peak = res[i].status == RG_OK ? res[i].peak : 0.0;
-        out[i].peak_pcm = out[i].peak * 32768.0;
+    e->stats.last_ms_index = e->stats.last_ms_huffman = e->stats.last_ms_hybrid = e->stats.last_ms_iir = e->stats.last_ms_hist = 0;
+    e->stats.last_batches = 0;
+    if (!n) return RG_OK;
+    IndexPlan ip;
+    rc = index_enqueue(e, &c, ip);
+    if (rc != RG_OK) { drain_streams(e); return rc; }
+    const uint64_t budget = e->pipeline ? e->scratch_bytes / 2 : e->scratch_bytes;
+    auto collect = [&](BatchCtx& x) -> int {
+        if (!x.busy) return RG_OK;
+        CK(cudaEventSynchronize(x.ev_b[3]));
+        collect_decode_timing(e, x);
+        const uint32_t* bits = x.h_tout.as<uint32_t>();
+        for (size_t k = 0; k < x.ids.size(); k++) {
+            const uint32_t i = x.ids[k];
+            float pk;
+            memcpy(&pk, &bits[k], sizeof pk);
+            out[i].status = x.pt[k].status;
+            out[i].sample_rate = x.pt[k].sample_rate;
+            out[i].peak = x.pt[k].status == RG_OK ? (double)pk : 0.0;
+            out[i].peak_pcm = out[i].peak * 32768.0;
+        }
+        x.busy = false;
+        return RG_OK;
+    };
+    size_t next = 0, k = 0;
+    while (next < n) {
+        rc = index_absorb(e, &c, ip, next + 1, true);
+        if (rc != RG_OK) { drain_streams(e); return rc; }
+        const size_t indexed_end = ip.group_begin[ip.groups_absorbed];
+        size_t t1 = next;
+        uint64_t bytes = 0;
+        while (t1 < indexed_end) {
+            const uint64_t b = ip.status[t1] == RG_OK ? track_scratch_bytes_peak(ip.meta[t1]) : 0;
+            if (t1 > next && bytes + b > budget) break;
+            bytes += b;
+            t1++;
+        }
+        BatchCtx& x = e->ctx[e->pipeline ? (k & 1) : 0];
+        rc = collect(x);
+        if (rc != RG_OK) { drain_streams(e); return rc; }
+        x.ids.resize(t1 - next);
+        for (size_t i = next; i < t1; i++) x.ids[i - next] = (uint32_t)i;
+        rc = decode_enqueue(e, &c, ip, x, true);
+        if (rc != RG_OK) { drain_streams(e); return rc; }
+        x.busy = true;
+        e->stats.last_batches++;
+        next = t1;
+        k++;
+    }
+    for (size_t j = 0; j < 2; j++) {
+        rc = collect(e->ctx[(k + j) & 1]);
+        if (rc != RG_OK) { drain_streams(e); return rc; }
     }
     return RG_OK;
 }

@@ -265,3 +265,22 @@ def test_mixed_corpus_through_the_pipeline(oracle):
                 assert (res[i].histogram == ohist).all(), i
                 assert res[i].loudness_db == ores.loudness_db and res[i].peak == ores.peak and res[i].n_frames == info.n_frames, i
                 assert res[i].sample_rate == info.sample_rate and res[i].channels == info.channels, i
+
+
+def test_peak_only_path_equals_the_analysis_peak(oracle):
+    """rg_find_peak runs the decode kernels with K2 in peak mode (no PCM stored, no filter / histogram stage): per file the
+    peak equals the oracle's max |sample| (and so the analysis path's), failing files report their status, and the call
+    goes through several batches."""
+    import mp3rgain_b200 as m
+    imgs = [synth_corpus.make_track(seed=400 + i, n_frames=120 + 30 * (i % 4), sr_idx=i % 3, channels=1 + (i % 3 != 0)) for i in range(14)]
+    imgs[6] = np.zeros(3000, np.uint8)
+    with m.Engine(device=0, scratch_bytes=6 << 20) as eng:
+        eng.set_option("group_bytes_min", 150_000)
+        peaks = eng.find_peak_images(imgs)
+        assert eng.stats().last_batches >= 3
+    for i, im in enumerate(imgs):
+        rc, ores, ohist, info = oracle.analyze_mp3(im)
+        pk, st = peaks[i]
+        assert st == rc, (i, st, rc)
+        if rc == 0:
+            assert pk.peak == ores.peak and pk.peak_pcm == ores.peak * 32768.0 and pk.sample_rate == info.sample_rate, i

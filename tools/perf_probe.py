@@ -67,3 +67,13 @@ if len(sys.argv) > 4 and sys.argv[4] == "e2e":
         st = eng.stats()
         print("e2e rc", rc, "wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f" % (
             dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt), flush=True)
+
+if len(sys.argv) > 4 and sys.argv[4] == "peak":
+    pk = (_lib.RgPeakResult * n_tracks)()
+    for it in range(3):
+        t = time.time()
+        rc = lib.rg_find_peak(eng._h, arr, n_tracks, pk)
+        dt = time.time() - t
+        st = eng.stats()
+        print("peak-only rc", rc, "wall %.3fs (pageable host buffers) | index %.1f huff %.1f hybrid %.1f | audio-h/s %.1f | peak[0] %.6f" % (
+            dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, audio_s / 3600.0 / dt, pk[0].peak), flush=True)
