@@ -15,7 +15,7 @@
 // reach HBM as full sectors although every lane owns a different 1152-byte row.
 #pragma once
 
-#define K1_THREADS 128
+#define K1_THREADS 256
 #define K1_GAIN_ROW 64   // floats per granule-channel: [0..21] long sfb, [22..60] short sfb*3+win
 
 struct BitBuf {
@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t side_field(const uint8_t* __restrict__ s, in
     return (w >> (24 - n - (bit & 7))) & ((1u << n) - 1);
 }
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 4)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
           int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
@@ -93,7 +93,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     __shared__ uint32_t s_stage[K1_THREADS / 32][32][17];
     __shared__ uint8_t s_sfl[K1_THREADS][24];     // long scalefactors of every thread's granule-channel (scfsi source)
     __shared__ uint8_t s_c1[2][64];               // count1 tables A / B: 6-bit peek -> (len<<4)|quad
-    __shared__ uint16_t s_key[K1_THREADS];        // big_values of the block's granule-channels (sort key)
+    __shared__ uint32_t s_key[K1_THREADS];        // big_values of the block's granule-channels (sort key)
     __shared__ uint8_t s_perm[K1_THREADS];        // worker thread -> granule-channel of the block, ordered by big_values
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -109,7 +109,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     const DecTrack tr = tracks[blk.track];
     const uint32_t nch = tr.channels;
     const uint32_t n_gc = tr.n_frames * 2 * nch;
-    // ---- order the block's 128 granule-channels by big_values, so that the lanes of a warp leave the big-values decoder
+    // ---- order the block's granule-channels by big_values, so that the lanes of a warp leave the big-values decoder
     // (and enter the zero tail) at about the same pair: the lockstep loop below pays for the slowest lane of the warp
     {
         const uint32_t g = blk.gc0 + tid;
@@ -120,7 +120,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
             key = side_field(s, (nch == 1 ? 18 : 20) + 59 * rem + 12, 9);
         }
-        s_key[tid] = (uint16_t)((key << 7) | tid);   // unique keys: ties keep block order
+        s_key[tid] = (key << 8) | (uint32_t)tid;   // unique keys: ties keep block order
     }
     __syncthreads();
     {
