@@ -272,6 +272,25 @@ def main():
                         "profiles/), k_iir FP64-pipe bound (74 %); the compressed stream is ~0.5 % of HBM peak by construction "
                         "(DESIGN.md 6). staged_dram_gbs_whole_step = ncu DRAM bytes of all kernels (spectra, PCM round trips) / step time"}
 
+    # ---- the roofline that actually binds the second-largest kernel: k_iir is FP64-pipe bound.  28 FP64 instructions per
+    # channel-sample (21 Yule + 5 Butterworth + square-accumulate + the b10 product) over every sample the
+    # time-blocked chains touch (block + one warm-up window), against the DFMA rate tools/fp64_pipe.cu measured on this
+    # GPU type (profiles/fp64_peak.json), else 64 DFMA/clk/SM at the SM clock sampled during the run.
+    bw = max(1, int(st1.last_block_windows)) if not args.exact else 0
+    warm = (bw + 1.0) / bw if bw else 1.0
+    fp64_ops = n * args.frames * 1152.0 * 2 * warm * 28.0
+    iir_s = float(np.mean(iir_ms)) / 1000.0
+    fp64_peak = None
+    try:
+        fp64_peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json"))).get("dfma_per_s")
+    except Exception:  # noqa: BLE001
+        pass
+    if not fp64_peak:
+        fp64_peak = 64.0 * 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+    roofline["fp64"] = {"kernel": "k_iir_fast", "bound": "fp64 pipe", "achieved": fp64_ops / iir_s / 1e12, "peak": fp64_peak / 1e12,
+                        "unit": "T FP64 instr/s (DFMA = 1)", "frac": fp64_ops / iir_s / fp64_peak, "ops_per_channel_sample": 28,
+                        "block_windows": bw}
+
     line = {"metric": METRIC, "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_ms, "device_ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,

@@ -161,7 +161,7 @@ typedef struct {
     float    last_ms_index, last_ms_huffman, last_ms_hybrid, last_ms_synth, last_ms_iir, last_ms_hist;
     float    last_ms_total;     /* CUDA-event time of the last analyse call's device work */
     uint32_t last_batches;      /* decode/analysis batches (= launches of each of K1, K2, K4, K5) in the last analyse call */
-    uint32_t reserved;
+    uint32_t last_block_windows;/* windows per time block the time-blocked IIR used in the last batch (0 = exact mode) */
 } rg_stats;
 int rg_engine_stats(rg_engine* e, rg_stats* out);
 

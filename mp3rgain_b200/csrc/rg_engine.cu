@@ -318,9 +318,10 @@ static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTr
     return best;
 }
 
-static void build_chains(const rg_engine* e, const std::vector<PcmTrack>& tracks, bool exact, double* d_wsum_base, float* d_wmax_base,
+static void build_chains(rg_engine* e, const std::vector<PcmTrack>& tracks, bool exact, double* d_wsum_base, float* d_wmax_base,
                          std::vector<RgChain>& chains, std::vector<RgTrackWin>& twin, size_t& wsum_doubles) {
     const uint32_t bw = exact ? 0 : choose_block_windows(e, tracks);
+    e->stats.last_block_windows = bw;
     // wsum layout: for each track, channel 0 windows then channel 1 windows
     chains.clear();
     twin.clear();
