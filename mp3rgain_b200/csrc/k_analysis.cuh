@@ -142,12 +142,33 @@ __device__ __forceinline__ void iir_run(State& s, const Coef& c, WinAcc& w, floa
 #pragma unroll
                 for (int k = 0; k < NV; k++) buf[k] = __ldg(p4 + k);
             }
+            if (ACCUM && w.tot + 4 * NV < w.win) {
+                // the window cannot end inside this group: no per-sample bookkeeping, so the FP64 work of consecutive samples
+                // overlaps freely
+                float m = w.wmax;
 #pragma unroll
-            for (int k = 0; k < NV; k++) {
-                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].x);
-                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].y);
-                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].z);
-                iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].w);
+                for (int k = 0; k < NV; k++) {
+                    const float xs[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        double z;
+                        if constexpr (FAST) z = iir_step_fast(s, c, xs[q]);
+                        else z = iir_step_exact(s, c, xs[q]);
+                        m = fmaxf(m, fabsf(xs[q]));
+                        if (FAST) w.sum = __fma_rn(z, z, w.sum);
+                        else w.sum = __dadd_rn(w.sum, __dmul_rn(z, z));
+                    }
+                }
+                w.wmax = m;
+                w.tot += 4 * NV;
+            } else {
+#pragma unroll
+                for (int k = 0; k < NV; k++) {
+                    iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].x);
+                    iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].y);
+                    iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].z);
+                    iir_sample<FAST, ACCUM>(s, c, w, peak, cur[k].w);
+                }
             }
         }
     }
