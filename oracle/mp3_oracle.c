@@ -30,7 +30,7 @@
 #define HUFF_L1_BITS 9
 typedef struct { uint16_t* tab; int size; } hufftab_t; /* entry: leaf = (len<<8)|sym ; link = 0x8000 | (bits<<10)... see build */
 static hufftab_t g_huff[16];
-static int g_long_start[3][23], g_short_start[3][14];
+static int g_long_start[9][23], g_short_start[9][14];
 static int g_init_done = 0;
 
 /* two-level table: first level indexed by HUFF_L1_BITS bits.  leaf: bit15=0, bits 8..12 = code length, bits 0..7 = sym.
@@ -80,7 +80,7 @@ static void build_huff(int slot) {
 static void init_once(void) {
     if (g_init_done) return;
     for (int s = 1; s <= L3_NUM_HUFF; s++) build_huff(s);
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 9; r++) {
         int a = 0;
         for (int i = 0; i < 22; i++) { g_long_start[r][i] = a; a += L3_SFB_LONG_W[r][i]; }
         g_long_start[r][22] = a;
@@ -160,19 +160,28 @@ typedef struct {
 } gr_t;
 typedef struct { int main_data_begin; int scfsi[2][4]; gr_t gr[2][2]; int valid; } side_t;
 
-static void parse_side(const uint8_t* p, int nch, side_t* s) {
+/* MPEG-1 (ISO 11172-3 2.4.1.7): 9-bit main_data_begin, scfsi, two granules, 4-bit scalefac_compress, preflag bit.
+ * MPEG-2 / 2.5 "LSF" (ISO 13818-3 2.4.1.7): 8-bit main_data_begin, no scfsi, ONE granule, 9-bit scalefac_compress, no preflag bit
+ * (preflag follows from scalefac_compress). */
+static void parse_side(const uint8_t* p, int nch, int lsf, side_t* s) {
     bits_t b = {p, 32, 0};
     s->valid = 1;
-    s->main_data_begin = getbits(&b, 9);
-    getbits(&b, nch == 1 ? 5 : 3);
-    for (int ch = 0; ch < nch; ch++) for (int i = 0; i < 4; i++) s->scfsi[ch][i] = getbits(&b, 1);
-    for (int g = 0; g < 2; g++)
+    memset(s->scfsi, 0, sizeof s->scfsi);
+    if (lsf) {
+        s->main_data_begin = getbits(&b, 8);
+        getbits(&b, nch == 1 ? 1 : 2);
+    } else {
+        s->main_data_begin = getbits(&b, 9);
+        getbits(&b, nch == 1 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) for (int i = 0; i < 4; i++) s->scfsi[ch][i] = getbits(&b, 1);
+    }
+    for (int g = 0; g < (lsf ? 1 : 2); g++)
         for (int ch = 0; ch < nch; ch++) {
             gr_t* q = &s->gr[g][ch];
             q->part2_3_length = getbits(&b, 12);
             q->big_values = getbits(&b, 9);
             q->global_gain = getbits(&b, 8);
-            q->scalefac_compress = getbits(&b, 4);
+            q->scalefac_compress = getbits(&b, lsf ? 9 : 4);
             q->window_switching = getbits(&b, 1);
             if (q->window_switching) {
                 q->block_type = getbits(&b, 2);
@@ -192,7 +201,7 @@ static void parse_side(const uint8_t* p, int nch, side_t* s) {
                 q->mixed = 0;
                 q->subblock_gain[0] = q->subblock_gain[1] = q->subblock_gain[2] = 0;
             }
-            q->preflag = getbits(&b, 1);
+            q->preflag = lsf ? (q->scalefac_compress >= 500) : (int)getbits(&b, 1);
             q->scalefac_scale = getbits(&b, 1);
             q->count1table = getbits(&b, 1);
             if (q->big_values > 288) s->valid = 0;
@@ -236,12 +245,37 @@ static void read_scalefactors(bits_t* b, const side_t* s, int g, int ch, dec_t* 
     }
 }
 
+/* part 2, MPEG-2 / 2.5 (ISO 13818-3 2.4.3.2): scalefac_compress -> four field widths and, through L3_LSF_NSF, how many
+ * scalefactors use each; the values come in band order (long: sfb 0..20; short: sfb 0..11 x 3 windows; mixed: 6 long
+ * bands, then short sfb 3..11 x 3 windows).  (Intensity-stereo right channels use other tables: such streams are rejected.) */
+static void read_scalefactors_lsf(bits_t* b, const gr_t* q, int* sl, int (*ss)[3]) {
+    memset(sl, 0, 22 * sizeof(int));
+    memset(ss, 0, 13 * 3 * sizeof(int));
+    int sfc = q->scalefac_compress, slen[4], tbl;
+    if (sfc < 400) { slen[0] = (sfc >> 4) / 5; slen[1] = (sfc >> 4) % 5; slen[2] = (sfc % 16) >> 2; slen[3] = sfc % 4; tbl = 0; }
+    else if (sfc < 500) { sfc -= 400; slen[0] = (sfc >> 2) / 5; slen[1] = (sfc >> 2) % 5; slen[2] = sfc % 4; slen[3] = 0; tbl = 1; }
+    else { sfc -= 500; slen[0] = sfc / 3; slen[1] = sfc % 3; slen[2] = slen[3] = 0; tbl = 2; }
+    int cls = q->block_type != 2 ? 0 : (q->mixed ? 2 : 1);
+    int v[40], n = 0;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < L3_LSF_NSF[tbl][cls][i]; j++) v[n++] = getbits(b, slen[i]);
+    int k = 0;
+    if (cls == 0) { for (int sfb = 0; sfb < 21 && k < n; sfb++) sl[sfb] = v[k++]; }
+    else {
+        int s0 = 0;
+        if (cls == 2) { for (int sfb = 0; sfb < 6; sfb++) sl[sfb] = v[k++]; s0 = 3; }
+        for (int sfb = s0; sfb < 12; sfb++) for (int w = 0; w < 3; w++) if (k < n) ss[sfb][w] = v[k++];
+    }
+}
+
 /* part 3: Huffman.  Returns the number of lines decoded (start of the all-zero tail). */
 static int read_huffman(bits_t* b, size_t end, const gr_t* q, int sr_row, int16_t* is) {
     memset(is, 0, 576 * sizeof(int16_t));
     int bv2 = q->big_values * 2;
     int r0, r1;
-    if (q->window_switching) { r0 = 36; r1 = 576; }
+    /* window switching: region 0 = region0_count 7 (8 for pure short) bands, i.e. the first 8 long bands or the first 3 short
+     * bands x 3 windows -- 36 lines at every MPEG-1 rate, 54 / 36 at the MPEG-2 rates, 108 / 72 at 8 kHz */
+    if (q->window_switching) { r0 = q->block_type == 2 ? 3 * g_short_start[sr_row][3] : g_long_start[sr_row][8]; r1 = 576; }
     else {
         r0 = g_long_start[sr_row][q->region0_count + 1];
         int k = q->region0_count + q->region1_count + 2;
@@ -298,7 +332,8 @@ static void requantize(const gr_t* q, int sr_row, const int* sf_l, int (*sf_s)[3
     int mult = q->scalefac_scale ? 4 : 2;
     int i = 0;
     if (q->block_type != 2 || q->mixed) {
-        int nl = q->block_type == 2 ? 8 : 22;
+        int nl = 22;
+        if (q->block_type == 2) for (nl = 0; g_long_start[sr_row][nl] < 36; nl++) {}   /* mixed: the long bands below line 36 (8 in MPEG-1, 6 in LSF) */
         for (int sfb = 0; sfb < nl; sfb++) {
             int e = q->global_gain - 210 - mult * (sf_l[sfb] + (q->preflag ? L3_PRETAB[sfb] : 0));
             float g = L3_GAIN[e - L3_GAIN_MIN];
@@ -546,7 +581,6 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         if (!have_ref) {
             ref = h; have_ref = 1;
             info->sample_rate = h.sr; info->channels = h.channels;
-            if (h.ver != 3) { status = MP3O_ERR_UNSUPPORTED_FORMAT; break; }
             status = 0;
         }
         const uint8_t* fp = data + pos;
@@ -557,8 +591,10 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         }
         int nch = h.channels;
         size_t so = 4 + (h.crc ? 2 : 0);
+        const int lsf = h.ver != 3, ngr = lsf ? 1 : 2;
         side_t s;
-        parse_side(fp + so, nch, &s);
+        parse_side(fp + so, nch, lsf, &s);
+        if (lsf && h.mode == 1 && (h.mode_ext & 1)) s.valid = 0;   /* MPEG-2 intensity stereo: not decoded, the frame is dropped */
         size_t mdo = so + h.side_len;
         size_t md_start_ok = s.main_data_begin <= (int)md_len;
         size_t start = md_len - (md_start_ok ? s.main_data_begin : 0);
@@ -566,14 +602,16 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         if (!s.valid || !md_start_ok) { info->n_dropped_frames++; continue; }
         memset(md + md_len, 0, 32);
 
-        int sr_row = h.sr_idx; /* rows 0..2 of the band tables are 44100, 48000, 32000 = sr_idx order */
+        /* rows of the band tables: 44100, 48000, 32000 | 22050, 24000, 16000 | 11025, 12000, 8000 */
+        int sr_row = (h.ver == 3 ? 0 : (h.ver == 2 ? 3 : 6)) + h.sr_idx;
         bits_t b = {md, md_len + 32, start * 8};
-        for (int g = 0; g < 2; g++) {
+        for (int g = 0; g < ngr; g++) {
             int nz[2] = {0, 0};
             for (int ch = 0; ch < nch; ch++) {
                 const gr_t* q = &s.gr[g][ch];
                 size_t end = b.pos + q->part2_3_length;
-                read_scalefactors(&b, &s, g, ch, d);
+                if (lsf) read_scalefactors_lsf(&b, q, d->sf_l[g][ch], d->sf_s[g][ch]);
+                else read_scalefactors(&b, &s, g, ch, d);
                 if (b.pos > end) { memset(is[ch], 0, sizeof is[ch]); b.pos = end; nz[ch] = 0; }
                 else nz[ch] = read_huffman(&b, end, q, sr_row, is[ch]);
                 requantize(q, sr_row, d->sf_l[g][ch], d->sf_s[g][ch], is[ch], xr[ch]);
@@ -597,10 +635,10 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         }
         if (flags & MP3O_FLAG_CLAMP_PCM)
             for (int ch = 0; ch < nch; ch++)
-                for (int i = 0; i < 1152; i++) pcm[ch][i] = pcm[ch][i] > 1.0f ? 1.0f : (pcm[ch][i] < -1.0f ? -1.0f : pcm[ch][i]);
-        sink(ctx, pcm[0], nch == 2 ? pcm[1] : NULL, 1152);
+                for (int i = 0; i < 576 * ngr; i++) pcm[ch][i] = pcm[ch][i] > 1.0f ? 1.0f : (pcm[ch][i] < -1.0f ? -1.0f : pcm[ch][i]);
+        sink(ctx, pcm[0], nch == 2 ? pcm[1] : NULL, 576 * ngr);
         info->n_frames++;
-        info->n_samples += 1152;
+        info->n_samples += 576 * ngr;
     }
     free(md);
     free(d);

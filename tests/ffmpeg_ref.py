@@ -105,19 +105,24 @@ def split_frames(img):
     frames = []
     first = True
     while pos + 4 <= len(d):
-        if d[pos] != 0xFF or (d[pos + 1] & 0xE0) != 0xE0 or ((d[pos + 1] >> 1) & 3) != 1 or ((d[pos + 1] >> 3) & 3) != 3:
+        ver = (d[pos + 1] >> 3) & 3   # 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5
+        if d[pos] != 0xFF or (d[pos + 1] & 0xE0) != 0xE0 or ((d[pos + 1] >> 1) & 3) != 1 or ver == 1:
             pos += 1
             continue
         bi, si = d[pos + 2] >> 4, (d[pos + 2] >> 2) & 3
         if bi in (0, 15) or si == 3:
             pos += 1
             continue
-        flen = 144 * br1[bi] * 1000 // sr1[si] + ((d[pos + 2] >> 1) & 1)
+        if ver == 3:
+            flen = 144 * br1[bi] * 1000 // sr1[si] + ((d[pos + 2] >> 1) & 1)
+        else:
+            br2 = [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160]
+            flen = 72 * br2[bi] * 1000 // (sr1[si] >> (1 if ver == 2 else 2)) + ((d[pos + 2] >> 1) & 1)
         if pos + flen > len(d):
             break
         fb = d[pos:pos + flen]
         mono = (d[pos + 3] >> 6) == 3
-        o = 4 + (0 if d[pos + 1] & 1 else 2) + (17 if mono else 32)
+        o = 4 + (0 if d[pos + 1] & 1 else 2) + ((17 if mono else 32) if ver == 3 else (9 if mono else 17))
         if first and fb[o:o + 4] in (b"Xing", b"Info"):
             first = False
             pos += flen

@@ -50,9 +50,10 @@ struct HuffEnc {
     int side;
 };
 HuffEnc g_enc[16];
-int g_long_start[3][23], g_short_start[3][14];
+int g_long_start[9][23], g_short_start[9][14];
 bool g_init = false;
 double g_is_prob = 0.25;  // share of joint-stereo frames that use intensity stereo (tests: high, for coverage; bench: 2 %, encoders at 128 kbps rarely use it)
+int g_version = 3;        // MPEG version field of the streams: 3 = MPEG-1, 2 = MPEG-2 (LSF), 0 = MPEG-2.5 (LSF)
 unsigned g_disable = 0;  // debug: bit0 short blocks, bit1 mixed, bit2 scfsi, bit3 preflag, bit4 sf_scale, bit5 subblock_gain, bit6 escapes, bit7 random tables, bit8 MS, bit9 intensity stereo
 
 void init() {
@@ -68,7 +69,7 @@ void init() {
             c += 1u << (32 - l);
         }
     }
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 9; r++) {
         int a = 0;
         for (int i = 0; i < 22; i++) { g_long_start[r][i] = a; a += L3_SFB_LONG_W[r][i]; }
         g_long_start[r][22] = a;
@@ -81,6 +82,8 @@ void init() {
 
 const int BR_V1_L3[15] = {0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320};
 const int SR_V1[3] = {44100, 48000, 32000};
+const int BR_V2_L3[15] = {0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160};
+const int SR_ROW_HZ[9] = {44100, 48000, 32000, 22050, 24000, 16000, 11025, 12000, 8000};
 
 struct Granule {
     int block_type = 0, mixed = 0, window_switching = 0;
@@ -90,6 +93,7 @@ struct Granule {
     int sf_l[22] = {0}, sf_s[13][3] = {{0}};
     int16_t is[576] = {0};
     int part2_bits = 0, part3_bits = 0;
+    int lsf_slen[4] = {0, 0, 0, 0}, lsf_tbl = 0;   // MPEG-2: field widths and the L3_LSF_NSF table chosen by scalefac_compress
 };
 
 int max_of_table(int sel) {  // largest codable value with table_select `sel`
@@ -125,7 +129,7 @@ void put_pair(BitWriter& w, int sel, int x, int y) {
 }
 
 void region_bounds(const Granule& g, int sr_row, int& r0, int& r1) {
-    if (g.window_switching) { r0 = 36; r1 = 576; return; }
+    if (g.window_switching) { r0 = g.block_type == 2 ? 3 * g_short_start[sr_row][3] : g_long_start[sr_row][8]; r1 = 576; return; }
     r0 = g_long_start[sr_row][g.region0_count + 1];
     int k = g.region0_count + g.region1_count + 2;
     r1 = g_long_start[sr_row][k > 22 ? 22 : k];
@@ -178,7 +182,24 @@ void choose_tables_and_count(Granule& g, int sr_row, Rng& rng) {
     g.part3_bits = bits;
 }
 
+// MPEG-2 scalefactors in bitstream order (long: sfb 0..20; short: sfb 0..11 x 3; mixed: 6 long bands, short sfb 3..11 x 3)
+int lsf_values(const Granule& g, int* v) {
+    int n = 0;
+    if (g.block_type != 2) { for (int sfb = 0; sfb < 21; sfb++) v[n++] = g.sf_l[sfb]; }
+    else {
+        int s0 = 0;
+        if (g.mixed) { for (int sfb = 0; sfb < 6; sfb++) v[n++] = g.sf_l[sfb]; s0 = 3; }
+        for (int sfb = s0; sfb < 12; sfb++) for (int k = 0; k < 3; k++) v[n++] = g.sf_s[sfb][k];
+    }
+    return n;
+}
+
 int part2_bits_of(const Granule& g, const int* scfsi, int gr) {
+    if (g_version != 3) {
+        int cls = g.block_type != 2 ? 0 : (g.mixed ? 2 : 1), bits = 0;
+        for (int i = 0; i < 4; i++) bits += L3_LSF_NSF[g.lsf_tbl][cls][i] * g.lsf_slen[i];
+        return bits;
+    }
     int s1 = L3_SLEN[0][g.scalefac_compress], s2 = L3_SLEN[1][g.scalefac_compress];
     if (g.block_type == 2) {
         if (g.mixed) return 8 * s1 + 9 * s1 + 18 * s2;
@@ -192,8 +213,13 @@ int part2_bits_of(const Granule& g, const int* scfsi, int gr) {
 }
 
 void write_granule_data(BitWriter& w, const Granule& g, const int* scfsi, int gr, int sr_row) {
-    int s1 = L3_SLEN[0][g.scalefac_compress], s2 = L3_SLEN[1][g.scalefac_compress];
-    if (g.block_type == 2) {
+    int s1 = L3_SLEN[0][g.scalefac_compress & 15], s2 = L3_SLEN[1][g.scalefac_compress & 15];
+    if (g_version != 3) {
+        int v[40], cls = g.block_type != 2 ? 0 : (g.mixed ? 2 : 1), k = 0;
+        lsf_values(g, v);
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < L3_LSF_NSF[g.lsf_tbl][cls][i]; j++) w.put((uint32_t)v[k++], g.lsf_slen[i]);
+    } else if (g.block_type == 2) {
         int s0 = 0;
         if (g.mixed) { for (int sfb = 0; sfb < 8; sfb++) w.put(g.sf_l[sfb], s1); s0 = 3; }
         for (int sfb = s0; sfb < 6; sfb++) for (int k = 0; k < 3; k++) w.put(g.sf_s[sfb][k], s1);
@@ -249,7 +275,8 @@ double xr_energy_unit(const Granule& g, int sr_row) {
     int mult = g.scalefac_scale ? 4 : 2;
     int i = 0;
     if (g.block_type != 2 || g.mixed) {
-        int nl = g.block_type == 2 ? 8 : 22;
+        int nl = 22;
+        if (g.block_type == 2) for (nl = 0; g_long_start[sr_row][nl] < 36; nl++) {}
         for (int sfb = 0; sfb < nl; sfb++) {
             double sc = std::exp2(-0.25 * mult * (g.sf_l[sfb] + (g.preflag ? L3_PRETAB[sfb] : 0)));
             for (int k = 0; k < L3_SFB_LONG_W[sr_row][sfb]; k++, i++) {
@@ -281,7 +308,27 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
     g.scalefac_compress = rng.below(16);
     int s1 = L3_SLEN[0][g.scalefac_compress], s2 = L3_SLEN[1][g.scalefac_compress];
     auto sfv = [&](int bits) { if (!bits) return 0; int m = (1 << bits) - 1; int v = (int)(-std::log(1.0 - rng.uni()) * 1.2); return std::min(v, m); };
-    if (bt == 2) {
+    if (g_version != 3) {
+        // MPEG-2: pick one of the three scalefac_compress ranges, then field widths, then values band by band
+        int pick = rng.below(10);
+        int* sl = g.lsf_slen;
+        if (pick < 7) { sl[0] = rng.below(5); sl[1] = rng.below(5); sl[2] = rng.below(4); sl[3] = rng.below(4);
+                        g.scalefac_compress = ((sl[0] * 5 + sl[1]) << 4) | (sl[2] << 2) | sl[3]; g.lsf_tbl = 0; g.preflag = 0; }
+        else if (pick < 9) { sl[0] = rng.below(5); sl[1] = rng.below(5); sl[2] = rng.below(4); sl[3] = 0;
+                             g.scalefac_compress = 400 + (((sl[0] * 5 + sl[1]) << 2) | sl[2]); g.lsf_tbl = 1; g.preflag = 0; }
+        else { sl[0] = rng.below(4); sl[1] = rng.below(3); sl[2] = sl[3] = 0;
+               g.scalefac_compress = 500 + sl[0] * 3 + sl[1]; g.lsf_tbl = 2; g.preflag = 1; }
+        int cls = bt != 2 ? 0 : (g.mixed ? 2 : 1), v[40], k = 0;
+        for (int i = 0; i < 4; i++) for (int j = 0; j < L3_LSF_NSF[g.lsf_tbl][cls][i]; j++) v[k++] = sfv(sl[i]);
+        k = 0;
+        if (cls == 0) { for (int sfb = 0; sfb < 21; sfb++) g.sf_l[sfb] = v[k++]; }
+        else {
+            int s0 = 0;
+            if (cls == 2) { for (int sfb = 0; sfb < 6; sfb++) g.sf_l[sfb] = v[k++]; s0 = 3; }
+            for (int sfb = s0; sfb < 12; sfb++) for (int w3 = 0; w3 < 3; w3++) g.sf_s[sfb][w3] = v[k++];
+        }
+        for (int w3 = 0; w3 < 3; w3++) g.subblock_gain[w3] = (bt == 2 && rng.chance(0.3) && !(g_disable & 32)) ? rng.below(4) : 0;
+    } else if (bt == 2) {
         if (g.mixed) for (int sfb = 0; sfb < 8; sfb++) g.sf_l[sfb] = sfv(s1);
         for (int sfb = g.mixed ? 3 : 0; sfb < 12; sfb++) for (int k = 0; k < 3; k++) g.sf_s[sfb][k] = sfv(sfb < 6 ? s1 : s2);
         for (int k = 0; k < 3; k++) g.subblock_gain[k] = (rng.chance(0.3) && !(g_disable & 32)) ? rng.below(4) : 0;
@@ -294,7 +341,7 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
     // quantiser step -- is then chosen so that the coded granule FILLS its share of the frame's bits, like a real CBR
     // stream: most of the 576 lines carry data, big_values covers a few hundred lines, the rest is count1 material.
     int knee = 60 + rng.below(260);
-    const int lowpass = (int)(576.0 * 16000.0 / (0.5 * (sr_row == 0 ? 44100 : (sr_row == 1 ? 48000 : 32000))));
+    const int lowpass = (int)std::min(576.0, 576.0 * 16000.0 / (0.5 * SR_ROW_HZ[sr_row]));
     double base[576];
     bool neg[576], capped[576];
     int escape[576];
@@ -341,6 +388,8 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
     g.part2_bits = part2_bits_of(g, scfsi, gr);
     if (g.part2_bits > std::min(target_bits, 4095)) {  // no room even for scalefactors: slen 0/0
         g.scalefac_compress = 0;
+        g.lsf_slen[0] = g.lsf_slen[1] = g.lsf_slen[2] = g.lsf_slen[3] = 0; g.lsf_tbl = 0;
+        if (g_version != 3) g.preflag = 0;
         memset(g.sf_l, 0, sizeof g.sf_l);
         memset(g.sf_s, 0, sizeof g.sf_s);
         g.part2_bits = 0;
@@ -373,16 +422,22 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
 }
 
 void write_side(BitWriter& w, int nch, int main_data_begin, const int scfsi[2][4], const Granule gr[2][2]) {
-    w.put((uint32_t)main_data_begin, 9);
-    w.put(0, nch == 1 ? 5 : 3);
-    for (int ch = 0; ch < nch; ch++) for (int i = 0; i < 4; i++) w.put(scfsi[ch][i], 1);
-    for (int g = 0; g < 2; g++)
+    const bool lsf = g_version != 3;
+    if (lsf) {
+        w.put((uint32_t)main_data_begin, 8);
+        w.put(0, nch == 1 ? 1 : 2);
+    } else {
+        w.put((uint32_t)main_data_begin, 9);
+        w.put(0, nch == 1 ? 5 : 3);
+        for (int ch = 0; ch < nch; ch++) for (int i = 0; i < 4; i++) w.put(scfsi[ch][i], 1);
+    }
+    for (int g = 0; g < (lsf ? 1 : 2); g++)
         for (int ch = 0; ch < nch; ch++) {
             const Granule& q = gr[g][ch];
             w.put((uint32_t)(q.part2_bits + q.part3_bits), 12);
             w.put((uint32_t)q.big_values, 9);
             w.put((uint32_t)q.global_gain, 8);
-            w.put((uint32_t)q.scalefac_compress, 4);
+            w.put((uint32_t)q.scalefac_compress, lsf ? 9 : 4);
             w.put((uint32_t)q.window_switching, 1);
             if (q.window_switching) {
                 w.put((uint32_t)q.block_type, 2);
@@ -395,7 +450,7 @@ void write_side(BitWriter& w, int nch, int main_data_begin, const int scfsi[2][4
                 w.put((uint32_t)q.region0_count, 4);
                 w.put((uint32_t)q.region1_count, 3);
             }
-            w.put((uint32_t)q.preflag, 1);
+            if (!lsf) w.put((uint32_t)q.preflag, 1);
             w.put((uint32_t)q.scalefac_scale, 1);
             w.put((uint32_t)q.count1table, 1);
         }
@@ -407,14 +462,18 @@ extern "C" {
 
 void synth_set_disable(unsigned mask) { g_disable = mask; }
 void synth_set_intensity_prob(double p) { g_is_prob = p; }
+void synth_set_version(int v) { g_version = v; }   // 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5
 
 // One self-contained group of n_frames frames.  br_idx: 1..14 CBR, 0 = VBR (uniform bitrate index per frame).
 // level_db: target loudness of the PCM (dBFS RMS); the group wanders around it.  Returns bytes written (0 if cap too small).
 size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int channels, double level_db, uint8_t* out, size_t cap) {
     init();
     Rng rng(seed);
-    const int sr_row = sr_idx, sr = SR_V1[sr_idx];
-    const int side_len = channels == 1 ? 17 : 32;
+    const bool lsf = g_version != 3;
+    const int sr_row = (g_version == 3 ? 0 : (g_version == 2 ? 3 : 6)) + sr_idx, sr = SR_ROW_HZ[sr_row];
+    const int side_len = lsf ? (channels == 1 ? 9 : 17) : (channels == 1 ? 17 : 32);
+    const int ngr = lsf ? 1 : 2;
+    const size_t mdb_max = lsf ? 255 : 511;
     std::vector<uint8_t> frames;        // finished frame bytes (header + side + payload area)
     std::vector<size_t> frame_off, payload_off, payload_len;
     std::vector<uint8_t> md;            // main-data stream (concatenated payload areas) written by position
@@ -427,14 +486,14 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
     double lvl = level_db + 6.0 * (rng.uni() - 0.5);
     for (int f = 0; f < n_frames; f++) {
         int bri = br_idx ? br_idx : 1 + rng.below(14);
-        double exact = 144.0 * BR_V1_L3[bri] * 1000.0 / sr;
+        double exact = (lsf ? 72.0 * BR_V2_L3[bri] : 144.0 * BR_V1_L3[bri]) * 1000.0 / sr;
         int base = (int)exact;
         pad_acc += exact - base;
         int pad = 0;
         if (pad_acc >= 1.0) { pad = 1; pad_acc -= 1.0; }
         int flen = base + pad;
         int cap_f = flen - 4 - side_len;
-        size_t P = std::max<size_t>(E, M > 511 ? M - 511 : 0);
+        size_t P = std::max<size_t>(E, M > mdb_max ? M - mdb_max : 0);
         if (f == 0) P = M;
         int budget = (int)((M + cap_f - P) * 8);
         // slow random walks of spectral shape and level so that 50 ms windows spread over many histogram bins
@@ -444,13 +503,14 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         bool js = channels == 2 && rng.chance(0.6);
         bool ms = js && rng.chance(0.7) && !(g_disable & 256);
         // intensity stereo: the right channel is empty above a random bound and its scalefactors there are is_pos values
-        bool ist = js && rng.chance(g_is_prob) && !(g_disable & 512);
+        bool ist = js && !lsf && rng.chance(g_is_prob) && !(g_disable & 512);   // (MPEG-2 intensity stereo is not generated)
         double is_cut = ist ? 20.0 + 300.0 * rng.uni() : 1e9;
         Granule gr[2][2];
         int scfsi[2][4] = {{0}};
         int bts[2], mixed_g[2];
-        for (int g = 0; g < 2; g++) {
-            if (bt_state == 0) { bt_state = (rng.chance(0.03) && !(g_disable & 1)) ? 1 : 0; if (bt_state) run_mixed = rng.chance(0.25) && !(g_disable & 2); }
+        bts[1] = 0; mixed_g[1] = 0;
+        for (int g = 0; g < ngr; g++) {   // the window sequence 0 -> 1 -> 2.. -> 3 -> 0 advances once per coded granule
+            if (bt_state == 0) { bt_state = (rng.chance(0.03) && !(g_disable & 1)) ? 1 : 0; if (bt_state) run_mixed = rng.chance(0.25) && !(g_disable & 2) && sr_row != 8; }   // (8 kHz mixed blocks: decoders disagree on the long/short split, none generated)
             else if (bt_state == 1) bt_state = 2;
             else if (bt_state == 2) bt_state = rng.chance(0.5) ? 2 : 3;
             else bt_state = 0;
@@ -461,11 +521,11 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         // run; flipping it mid-run is legal syntax but decoders disagree on the resulting overlap, FFmpeg included)
         int mixed[2] = {mixed_g[0], mixed_g[1]};
         int used = 0;
-        for (int g = 0; g < 2; g++)
+        for (int g = 0; g < ngr; g++)
             for (int ch = 0; ch < channels; ch++) {
                 if (g == 1 && bts[0] != 2 && bts[1] != 2)
                     for (int i = 0; i < 4; i++) scfsi[ch][i] = rng.chance(0.3) && !(g_disable & 4);
-                int left = (2 - g) * channels - ch;
+                int left = (ngr - g) * channels - ch;
                 int remain = budget - used;
                 int target = (int)(remain / left * (0.7 + 0.6 * rng.uni()));
                 if (left == 1) target = remain;
@@ -477,7 +537,8 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
             }
         // header
         BitWriter hw;
-        hw.put(0x7FF, 11); hw.put(3, 2); hw.put(1, 2); hw.put(1, 1);      // sync, MPEG-1, Layer III, no CRC
+        hw.put(0x7FF, 11); hw.put((uint32_t)g_version, 2);                          // sync, MPEG-1 (11) / MPEG-2 (10) / MPEG-2.5 (00)
+        hw.put(1, 2); hw.put(1, 1);                                                 // Layer III, no CRC
         hw.put((uint32_t)bri, 4); hw.put((uint32_t)sr_idx, 2); hw.put((uint32_t)pad, 1); hw.put(0, 1);
         hw.put(channels == 1 ? 3u : (js ? 1u : 0u), 2);
         hw.put(js ? ((ms ? 2u : 0u) | (ist ? 1u : 0u)) : 0u, 2);
@@ -485,7 +546,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         write_side(hw, channels, (int)(M - P), scfsi, gr);
         // granule data into the main-data stream at P
         BitWriter dw;
-        for (int g = 0; g < 2; g++) for (int ch = 0; ch < channels; ch++) write_granule_data(dw, gr[g][ch], scfsi[ch], g, sr_row);
+        for (int g = 0; g < ngr; g++) for (int ch = 0; ch < channels; ch++) write_granule_data(dw, gr[g][ch], scfsi[ch], g, sr_row);
         size_t need = P + dw.buf.size();
         if (md.size() < M + cap_f) md.resize(M + cap_f, 0);
         if (need > md.size()) return 0;  // cannot happen: budget enforced

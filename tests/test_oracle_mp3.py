@@ -132,10 +132,35 @@ def test_container_edge_cases(oracle):
     assert rc == -5
 
 
-def test_lsf_stream_is_reported_unsupported(oracle):
-    # MPEG-2 Layer III header (22.05 kHz, 64 kbps): recognised, not decoded (row f4 of SURVEY.md 8, "next")
-    hdr = bytes([0xFF, 0xF3, 0x80, 0x00])
-    flen = 72 * 64000 // 22050
-    img = np.frombuffer((hdr + bytes(flen - 4)) * 4, np.uint8)
-    rc, _, info = oracle.decode(img)
-    assert rc == -10 and info.sample_rate == 22050
+LSF = [dict(version=2, seed=41), dict(version=2, seed=42, channels=1, sr_idx=1, br_idx=0), dict(version=2, seed=43, sr_idx=2, br_idx=4),
+       dict(version=0, seed=44), dict(version=0, seed=45, sr_idx=1, br_idx=0), dict(version=0, seed=46, sr_idx=2, br_idx=2, channels=1)]
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", LSF)
+def test_mpeg2_streams_decode_like_ffmpeg(oracle, kw):
+    """MPEG-2 and MPEG-2.5 Layer III (22.05 / 24 / 16 and 11.025 / 12 / 8 kHz, 576-sample frames, one granule, 9-bit
+    scalefac_compress with the ISO 13818-3 partition tables, all three scalefac_compress ranges, long / start / short / stop /
+    mixed blocks, MS stereo): the oracle agrees with FFmpeg to float rounding."""
+    img = synth_corpus.make_track(n_frames=400, **kw)
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 400 and info.n_dropped_frames == 0
+    assert info.sample_rate == synth_corpus.RATES_BY_VERSION[kw["version"]][kw.get("sr_idx", 0)]
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape == (kw.get("channels", 2), 400 * 576)
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+    assert 0.03 < np.sqrt((pcm.astype(np.float64) ** 2).mean()) < 0.3
+
+
+def test_mpeg2_intensity_stereo_frames_are_dropped(oracle):
+    """MPEG-2 intensity stereo (its own scalefactor partition and ratio tables) is not decoded: such frames are dropped like
+    frames with invalid side info, the rest of the stream decodes."""
+    img = synth_corpus.make_track(n_frames=60, version=2, seed=47).copy()
+    starts, pos, b = [], 0, bytes(img)
+    while pos + 4 <= len(b):
+        starts.append(pos)
+        pos += 72 * [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160][b[pos + 2] >> 4] * 1000 // 22050 + ((b[pos + 2] >> 1) & 1)
+    for p0 in starts[10:14]:
+        img[p0 + 3] = (img[p0 + 3] & 0x0F) | 0x50          # joint stereo, mode_extension = intensity only
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 56 and info.n_dropped_frames == 4
