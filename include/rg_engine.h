@@ -40,7 +40,7 @@ typedef enum {
     RG_ERR_TRACK_INDEX = -7,        /* "Track index {i} out of range (file has 1 audio track(s))" */
     RG_ERR_UNKNOWN_SAMPLE_RATE = -8,/* "Unknown sample rate" */
     RG_ERR_UNSUPPORTED_RATE = -9,   /* "Unsupported sample rate: {sr} Hz. Supported rates: ..." */
-    RG_ERR_UNSUPPORTED_FORMAT = -10,/* MP4/AAC container or a layer/version this engine does not decode */
+    RG_ERR_UNSUPPORTED_FORMAT = -10,/* MP4/AAC container (the engine decodes MPEG-1 / 2 / 2.5 Layer III) */
     RG_ERR_NO_MEMORY = -11
 } rg_status;
 

@@ -37,6 +37,12 @@ __device__ __forceinline__ int k0_frame_len(uint32_t h) {
     return 72 * kbps * 1000 / (sr1 >> (ver == 2 ? 1 : 2)) + pad;
 }
 
+// bytes of side info: MPEG-1 17 / 32, MPEG-2 and 2.5 (LSF) 9 / 17 (mono / not)
+__device__ __forceinline__ int k0_side_len(uint32_t h) {
+    const bool mono = ((h >> 6) & 3) == 3;
+    return (((h >> 19) & 3) == 3) ? (mono ? 17 : 32) : (mono ? 9 : 17);
+}
+
 // valid Layer III header of any MPEG version (so LSF streams are recognised and reported, like the oracle's parse_hdr)
 __device__ __forceinline__ bool k0_hdr_valid(uint32_t h) {
     if ((h & 0xFFE00000u) != 0xFFE00000u) return false;
@@ -132,12 +138,10 @@ __device__ SegOut k0_walk(const uint8_t* __restrict__ src, uint64_t len, uint8_t
         if (!ok) { in_sync = false; pos++; continue; }
         in_sync = true;
         if (!(o.flags & K0F_FOUND)) { o.flags |= K0F_FOUND; o.first_pos = (uint32_t)pos; if (!have_ref) o.ref = h; }
-        if (!have_ref) {
-            ref = h; have_ref = true;
-            if (((h >> 19) & 3) != 3) { o.flags |= K0F_STOP | K0F_LSF; break; }  // MPEG-2/2.5: recognised, not decoded by this engine
-        }
+        if (!have_ref) { ref = h; have_ref = true; }
         const int mono = ((h >> 6) & 3) == 3;
-        const int side_len = mono ? 17 : 32;
+        const bool lsf = ((h >> 19) & 3) != 3;
+        const int side_len = k0_side_len(h);
         const int so = 4 + ((h & 0x10000u) ? 0 : 2);
         const uint32_t fpos = (uint32_t)pos;
         pos += flen;
@@ -153,20 +157,23 @@ __device__ SegOut k0_walk(const uint8_t* __restrict__ src, uint64_t len, uint8_t
             }
         }
         // side info: main_data_begin + validity (big_values <= 288, block_type != 0 when window switching); lane = granule-channel
+        // MPEG-1: 9-bit main_data_begin, 59 bits per granule-channel from bit 18 / 20, two granules; MPEG-2 / 2.5: 8-bit
+        // main_data_begin, 63 bits per granule-channel from bit 9 / 10, one granule (9-bit scalefac_compress, no preflag bit)
         const uint8_t* s = p + so;
-        const int mdb = ((int)s[0] << 1) | (s[1] >> 7);
+        const int mdb = lsf ? (int)s[0] : (((int)s[0] << 1) | (s[1] >> 7));
         bool bad = false;
-        if (lane < (mono ? 2 : 4)) {
-            const int b0 = (mono ? 18 : 20) + 59 * lane;
+        if (lane < (mono ? 1 : 2) * (lsf ? 1 : 2)) {
+            const int b0 = lsf ? (mono ? 9 : 10) + 63 * lane : (mono ? 18 : 20) + 59 * lane;
             const int bb = b0 + 12;  // big_values: 9 bits
             const uint32_t w = ((uint32_t)s[bb >> 3] << 16) | ((uint32_t)s[(bb >> 3) + 1] << 8) | s[(bb >> 3) + 2];
             const int bv = (w >> (24 - 9 - (bb & 7))) & 0x1FF;
-            const int wb = b0 + 33;  // window_switching, block_type(2)
+            const int wb = b0 + (lsf ? 38 : 33);  // window_switching, block_type(2)
             const uint32_t w2 = ((uint32_t)s[wb >> 3] << 8) | s[(wb >> 3) + 1];
             const int ws_bt = (w2 >> (16 - 3 - (wb & 7))) & 7;
             bad = bv > 288 || ((ws_bt & 4) && !(ws_bt & 3));
         }
-        const bool valid = !__any_sync(0xffffffffu, bad);
+        // (MPEG-2 intensity stereo has its own scalefactor partition and ratio tables: not decoded, the frame is dropped)
+        const bool valid = !__any_sync(0xffffffffu, bad) && !(lsf && ((h >> 6) & 3) == 1 && ((h >> 4) & 1));
         const int mdo_off = so + side_len;
         const int cap = flen > mdo_off ? flen - mdo_off : 0;
         const bool start_ok = !m_known || (uint32_t)mdb <= M0 + M;
@@ -284,11 +291,8 @@ k_index_merge(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__ ti
     if (lane == 0) {
         TrackMeta m;
         m.status = status;
-        m.sr_idx = have_ref ? ((ref >> 10) & 3) : 0;
+        m.sr_idx = have_ref ? (((ref >> 10) & 3) | (((ref >> 19) & 3) << 4)) : 0;   // sample-rate index | MPEG version << 4
         m.channels = have_ref ? ((((ref >> 6) & 3) == 3) ? 1 : 2) : 0;
-        if (have_ref && ((ref >> 19) & 3) != 3) {  // LSF: report the real rate index for the host (unsupported anyway)
-            m.sr_idx = ((ref >> 10) & 3) | (((ref >> 19) & 3) << 4);
-        }
         m.n_frames = nf; m.md_bytes = M; m.n_dropped = n_rec_all - nf; m.skipped_info = skipped; m.n_total = n_total; m.n_rewalks = n_rewalks;
         meta[t] = m;
     }
@@ -333,7 +337,7 @@ k_index_finalize(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__
             dropped &= dropped - 1;
             const uint32_t fpos = __shfl_sync(0xffffffffu, rec.fpos, l), hdr = __shfl_sync(0xffffffffu, rec.hdr, l);
             const uint32_t c = __shfl_sync(0xffffffffu, cap, l), mb = __shfl_sync(0xffffffffu, m_before, l);
-            const int off = 4 + ((hdr & 0x10000u) ? 0 : 2) + ((((hdr >> 6) & 3) == 3) ? 17 : 32);
+            const int off = 4 + ((hdr & 0x10000u) ? 0 : 2) + k0_side_len(hdr);
             const uint8_t* sp = corpus + tin[sd.track].off + fpos + off;
             uint8_t* dp = md + md_base[sd.track] + mb;
             for (uint32_t bb = lane; bb < c; bb += 32) dp[bb] = sp[bb];
@@ -352,11 +356,11 @@ k_md_gather(const uint8_t* __restrict__ corpus, uint8_t* __restrict__ md, const 
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t f0 = run.g0 >> 1, f1 = (run.g0 + run.ng + 1) >> 1;
+    const uint32_t f0 = run.g0 / tr.gpf, f1 = (run.g0 + run.ng + tr.gpf - 1) / tr.gpf;
     for (uint32_t f = f0 + warp; f < f1; f += K0B_THREADS / 32) {
         const FrameRec rec = frames[tr.frame_base + f];
         const uint32_t h = rec.hdr;
-        const int off = 4 + ((h & 0x10000u) ? 0 : 2) + ((((h >> 6) & 3) == 3) ? 17 : 32);
+        const int off = 4 + ((h & 0x10000u) ? 0 : 2) + k0_side_len(h);
         const int flen = k0_frame_len(h);
         const int cap = flen > off ? flen - off : 0;
         const uint8_t* src = corpus + tr.corpus_off + rec.file_off + off;

@@ -107,18 +107,19 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     }
     const HuffBlock blk = blocks[blockIdx.x];
     const DecTrack tr = tracks[blk.track];
-    const uint32_t nch = tr.channels;
-    const uint32_t n_gc = tr.n_frames * 2 * nch;
+    const uint32_t nch = tr.channels, gpf = tr.gpf;
+    const bool lsf = gpf == 1;   // MPEG-2 / 2.5: one granule per frame, 63-bit side info per granule-channel (ISO 13818-3 2.4.1.7)
+    const uint32_t n_gc = tr.n_frames * gpf * nch;
     // ---- order the block's granule-channels by big_values, so that the lanes of a warp leave the big-values decoder
     // (and enter the zero tail) at about the same pair: the lockstep loop below pays for the slowest lane of the warp
     {
         const uint32_t g = blk.gc0 + tid;
         uint32_t key = 0x1FF;   // inactive slots sort last
         if (g < n_gc) {
-            const uint32_t frame = g / (2 * nch), rem = g % (2 * nch);
+            const uint32_t frame = g / (gpf * nch), rem = g % (gpf * nch);
             const FrameRec rec = frames[tr.frame_base + frame];
             const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-            key = side_field(s, (nch == 1 ? 18 : 20) + 59 * rem + 12, 9);
+            key = side_field(s, (lsf ? (nch == 1 ? 9 : 10) + 63 * rem : (nch == 1 ? 18 : 20) + 59 * rem) + 12, 9);
         }
         s_key[tid] = (key << 8) | (uint32_t)tid;   // unique keys: ties keep block order
     }
@@ -153,56 +154,70 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     int bt = 0, mixed = 0, slen1 = 0, slen2 = 0, scfsi = 0, base_e = 0, sf_shift = 2, preflag = 0, sbg0 = 0, sbg1 = 0, sbg2 = 0;
     uint32_t gr = 0;
     if (active) {
-        const uint32_t frame = gc / (2 * nch), rem = gc % (2 * nch), ch = rem % nch;
+        const uint32_t frame = gc / (gpf * nch), rem = gc % (gpf * nch), ch = rem % nch;
         gr = rem / nch;
         const FrameRec rec = frames[tr.frame_base + frame];
         const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-        is_right = ch == 1 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 1);
-        const int gbase = (nch == 1 ? 18 : 20);
+        is_right = !lsf && ch == 1 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 1);
+        // field offsets inside one granule-channel: MPEG-1 has a 4-bit scalefac_compress and a preflag bit (59 bits in all),
+        // MPEG-2 a 9-bit scalefac_compress and no preflag bit (63 bits)
+        const int gbase = lsf ? (nch == 1 ? 9 : 10) : (nch == 1 ? 18 : 20), gstride = lsf ? 63 : 59, x5 = lsf ? 5 : 0;
         uint32_t bit = rec.md_start * 8;
-        for (uint32_t k = 0; k < rem; k++) bit += side_field(s, gbase + 59 * k, 12);
-        const int b0 = gbase + 59 * rem;
+        for (uint32_t k = 0; k < rem; k++) bit += side_field(s, gbase + gstride * k, 12);
+        const int b0 = gbase + gstride * rem;
         const uint32_t p23 = side_field(s, b0, 12);
         bv = side_field(s, b0 + 12, 9);
         base_e = (int)side_field(s, b0 + 21, 8) - 210 - L3_GAIN_MIN;
-        const int sfc = side_field(s, b0 + 29, 4);
-        const int ws = side_field(s, b0 + 33, 1);
+        const int sfc = side_field(s, b0 + 29, lsf ? 9 : 4);
+        const int ws = side_field(s, b0 + 33 + x5, 1);
         int sel0, sel1, sel2 = 0;
         if (ws) {
-            bt = side_field(s, b0 + 34, 2);
-            mixed = side_field(s, b0 + 36, 1);
-            sel0 = side_field(s, b0 + 37, 5);
-            sel1 = side_field(s, b0 + 42, 5);
-            sbg0 = side_field(s, b0 + 47, 3); sbg1 = side_field(s, b0 + 50, 3); sbg2 = side_field(s, b0 + 53, 3);
-            r0 = 36; r1 = 576;
+            bt = side_field(s, b0 + 34 + x5, 2);
+            mixed = side_field(s, b0 + 36 + x5, 1);
+            sel0 = side_field(s, b0 + 37 + x5, 5);
+            sel1 = side_field(s, b0 + 42 + x5, 5);
+            sbg0 = side_field(s, b0 + 47 + x5, 3); sbg1 = side_field(s, b0 + 50 + x5, 3); sbg2 = side_field(s, b0 + 53 + x5, 3);
+            // region 0 = the first 8 long bands, or the first 3 short bands x 3 windows: 36 lines at every MPEG-1 rate,
+            // 54 / 36 at the MPEG-2 rates, 108 / 72 at 8 kHz
+            r0 = bt == 2 ? 3 * T->short_start[tr.sr_idx][3] : T->long_start[tr.sr_idx][8];
+            r1 = 576;
         } else {
-            sel0 = side_field(s, b0 + 34, 5);
-            sel1 = side_field(s, b0 + 39, 5);
-            sel2 = side_field(s, b0 + 44, 5);
-            const int rc0 = side_field(s, b0 + 49, 4), rc1 = side_field(s, b0 + 53, 3);
+            sel0 = side_field(s, b0 + 34 + x5, 5);
+            sel1 = side_field(s, b0 + 39 + x5, 5);
+            sel2 = side_field(s, b0 + 44 + x5, 5);
+            const int rc0 = side_field(s, b0 + 49 + x5, 4), rc1 = side_field(s, b0 + 53 + x5, 3);
             r0 = T->long_start[tr.sr_idx][rc0 + 1];
             const int k = rc0 + rc1 + 2;
             r1 = T->long_start[tr.sr_idx][k > 22 ? 22 : k];
         }
         if (bt != 2) mixed = 0;
-        preflag = side_field(s, b0 + 56, 1);
-        sf_shift = side_field(s, b0 + 57, 1) ? 4 : 2;
-        c1tab = side_field(s, b0 + 58, 1);
+        preflag = lsf ? (sfc >= 500) : (int)side_field(s, b0 + 56, 1);
+        sf_shift = side_field(s, b0 + (lsf ? 61 : 57), 1) ? 4 : 2;
+        c1tab = side_field(s, b0 + (lsf ? 62 : 58), 1);
         // slot 0 ("no data") reads the all-zero first-level table at huff_base[0]: length 0, x = y = 0
         reg0 = ((uint32_t)T->huff_base[T->tabsel[sel0][0]] << 8) | T->tabsel[sel0][1];
         reg1 = ((uint32_t)T->huff_base[T->tabsel[sel1][0]] << 8) | T->tabsel[sel1][1];
         reg2 = ((uint32_t)T->huff_base[T->tabsel[sel2][0]] << 8) | T->tabsel[sel2][1];
         // part-2 length
-        slen1 = T->slen[0][sfc]; slen2 = T->slen[1][sfc];
-        int part2;
-        if (bt == 2) part2 = (mixed ? 17 : 18) * slen1 + 18 * slen2;
-        else {
-            scfsi = (gr == 1) ? (int)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;  // band group 0 first
-            part2 = 0;
-            part2 += (scfsi & 8) ? 0 : 6 * slen1;
-            part2 += (scfsi & 4) ? 0 : 5 * slen1;
-            part2 += (scfsi & 2) ? 0 : 5 * slen2;
-            part2 += (scfsi & 1) ? 0 : 5 * slen2;
+        int part2 = 0;
+        int ls[4] = {0, 0, 0, 0}, ltbl = 0;   // MPEG-2: field widths and partition table from scalefac_compress
+        const int cls = bt != 2 ? 0 : (mixed ? 2 : 1);
+        if (lsf) {
+            int c = sfc;
+            if (c < 400) { ls[0] = (c >> 4) / 5; ls[1] = (c >> 4) % 5; ls[2] = (c % 16) >> 2; ls[3] = c % 4; ltbl = 0; }
+            else if (c < 500) { c -= 400; ls[0] = (c >> 2) / 5; ls[1] = (c >> 2) % 5; ls[2] = c % 4; ltbl = 1; }
+            else { c -= 500; ls[0] = c / 3; ls[1] = c % 3; ltbl = 2; }
+            for (int i = 0; i < 4; i++) part2 += T->lsf_nsf[ltbl][cls][i] * ls[i];
+        } else {
+            slen1 = T->slen[0][sfc]; slen2 = T->slen[1][sfc];
+            if (bt == 2) part2 = (mixed ? 17 : 18) * slen1 + 18 * slen2;
+            else {
+                scfsi = (gr == 1) ? (int)side_field(s, (nch == 1 ? 14 : 12) + 4 * ch, 4) : 0;  // band group 0 first
+                part2 += (scfsi & 8) ? 0 : 6 * slen1;
+                part2 += (scfsi & 4) ? 0 : 5 * slen1;
+                part2 += (scfsi & 2) ? 0 : 5 * slen2;
+                part2 += (scfsi & 1) ? 0 : 5 * slen2;
+            }
         }
         end = bit + p23;
         silent = (uint32_t)part2 > p23;
@@ -210,7 +225,26 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
 
         // ---- part 2 (ISO 11172-3 2.4.2.7): my own scalefactors.  Long ones go to shared memory (granule 1 may need them),
         // short ones straight into their band gain.
-        if (bt == 2) {
+        if (lsf) {
+            // ISO 13818-3 2.4.3.2: the values come in band order, lsf_nsf[..][i] of them ls[i] bits wide: long sfb 0..20, or
+            // (mixed: 6 long bands, then) short sfb x 3 windows
+            int k = 0, fld = 0, left = T->lsf_nsf[ltbl][cls][0];
+            const int n_long = cls == 0 ? 21 : (cls == 2 ? 6 : 0);
+            const int n_all = n_long + (cls == 0 ? 0 : (cls == 2 ? 27 : 36));
+            for (; k < n_all; k++) {
+                while (left == 0 && fld < 3) left = T->lsf_nsf[ltbl][cls][++fld];
+                const int v = left ? (int)br.get(ls[fld]) : 0;
+                if (left) left--;
+                if (k < n_long) sfl[k] = (uint8_t)v;
+                else {
+                    const int q2 = k - n_long + (cls == 2 ? 9 : 0), win = q2 % 3;
+                    grow[22 + q2] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)) - sf_shift * v]);
+                }
+            }
+            if (cls)
+#pragma unroll
+                for (int win = 0; win < 3; win++) grow[22 + 36 + win] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2))]);
+        } else if (bt == 2) {
             if (mixed) for (int sfb = 0; sfb < 8; sfb++) sfl[sfb] = (uint8_t)br.get(slen1);
             for (int q2 = mixed ? 9 : 0; q2 < 36; q2++) {
                 const int v = (int)br.get(q2 < 18 ? slen1 : slen2);

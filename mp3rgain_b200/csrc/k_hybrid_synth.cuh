@@ -94,15 +94,16 @@ __device__ __forceinline__ constexpr int idx36(int i) { return i < 9 ? i + 9 : (
 // the side-info fields K2 still needs of granule g (0 = first granule of the track), channel ch
 __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corpus, const DecTrack& tr, const FrameRec* __restrict__ frames,
                                                 const uint16_t* __restrict__ nz_in, uint32_t g, uint32_t ch, int nch) {
-    const uint32_t frame = g >> 1, gr = g & 1;
+    const uint32_t gpf = tr.gpf, frame = g / gpf, gr = g % gpf;
     const FrameRec rec = frames[tr.frame_base + frame];
     const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-    const int b0 = (nch == 1 ? 18 : 20) + 59 * (gr * nch + ch);
+    // MPEG-1: 59 bits per granule-channel from bit 18 / 20, window switching at +33; MPEG-2 / 2.5: 63 bits from bit 9 / 10, at +38
+    const int b0 = gpf == 1 ? (nch == 1 ? 9 : 10) + 63 * (int)ch + 5 : (nch == 1 ? 18 : 20) + 59 * (int)(gr * nch + ch);
     GranInfo gi;
     const uint32_t f = side_field(s, b0 + 33, 4);   // window_switching(1) block_type(2) mixed(1)
     gi.bt = (f & 8) ? (uint8_t)((f >> 1) & 3) : 0;
     gi.mixed = (gi.bt == 2) ? (uint8_t)(f & 1) : 0;
-    const size_t gcb = (size_t)tr.gc_base + (size_t)frame * 2 * nch + gr * nch;
+    const size_t gcb = (size_t)tr.gc_base + (size_t)g * nch;
     gi.nz = nz_in[gcb + ch];
     const bool joint = nch == 2 && ((rec.hdr >> 6) & 3) == 1;
     gi.ms = (uint8_t)((joint && ((rec.hdr >> 4) & 2) ? 1 : 0) | (joint && ((rec.hdr >> 4) & 1) ? 2 : 0));

@@ -28,16 +28,17 @@ struct L3Dev {
     uint8_t tabsel[32][2];      // table_select -> {slot, linbits}
     uint8_t c1_lut[2][16];      // count1: 4-bit peek -> (len<<4)|quad   (table B is the identity on ~peek)
     uint8_t c1a_lut[64];        // count1 table A: 6-bit peek -> (len<<4)|quad
-    uint16_t long_start[3][24];
-    uint16_t short_start[3][16];
+    uint16_t long_start[9][24];   // rows: 44100, 48000, 32000 | 22050, 24000, 16000 | 11025, 12000, 8000
+    uint16_t short_start[9][16];
+    uint8_t lsf_nsf[6][3][4];      // MPEG-2 scalefactor partition: [scalefac_compress range][long/short/mixed][field] -> count
     uint8_t slen[2][16];
     uint8_t pretab[24];
     // per sample-rate row line maps for requantisation / reorder
-    uint8_t line_sfb_long[3][576];        // line -> long sfb
-    uint8_t line_sfb_short[3][576];       // bitstream-order line (pure short) -> sfb*3+win
-    uint8_t line_sfb_mixed[3][576];       // mixed: lines <36 -> long sfb (0..7), else 32 + sfb*3+win
-    uint16_t scatter_short[3][576];       // bitstream-order line -> line after the short-block reorder (pure short)
-    uint16_t scatter_mixed[3][576];       // same for mixed blocks (first 36 lines stay)
+    uint8_t line_sfb_long[9][576];        // line -> long sfb
+    uint8_t line_sfb_short[9][576];       // bitstream-order line (pure short) -> sfb*3+win
+    uint8_t line_sfb_mixed[9][576];       // mixed: lines <36 -> long sfb (0..7), else 32 + sfb*3+win
+    uint16_t scatter_short[9][576];       // bitstream-order line -> line after the short-block reorder (pure short)
+    uint16_t scatter_mixed[9][576];       // same for mixed blocks (first 36 lines stay)
     float pow43[L3_POW43_N];
     float gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
     float alias_cs[8], alias_ca[8];
@@ -75,7 +76,9 @@ struct DecTrack {   // per-track addressing shared by K1/K2 (device array)
     uint64_t gc_base;        // first granule-channel slot (int16 spectra + nz) of this track within the batch
     uint64_t pcm_off;        // first PCM float of plane 0 (plane 1 follows at +pcm_plane)
     uint64_t pcm_plane;      // floats per plane
-    uint32_t n_frames, channels, sr_idx, md_bytes;
+    uint32_t n_frames, channels, sr_idx /* row of the band tables, 0..8 */, md_bytes;
+    uint32_t gpf;            // granules per frame: 2 (MPEG-1) or 1 (MPEG-2 / 2.5)
+    uint32_t pad;
 };
 
 #include "k_frame_index.cuh"
@@ -146,7 +149,8 @@ static int decode_init_tables(DecodeScratch& ds) {
         for (int k = 0; k < (1 << (6 - len)); k++) T.c1a_lut[(bits << (6 - len)) + k] = (uint8_t)((len << 4) | v);
         T.c1_lut[1][L3_C1_BITS[1][v]] = (uint8_t)((4 << 4) | v);
     }
-    for (int r = 0; r < 3; r++) {
+    memcpy(T.lsf_nsf, L3_LSF_NSF, sizeof T.lsf_nsf);
+    for (int r = 0; r < 9; r++) {
         int a = 0;
         for (int i = 0; i < 22; i++) { T.long_start[r][i] = (uint16_t)a; for (int k = 0; k < L3_SFB_LONG_W[r][i]; k++) T.line_sfb_long[r][a + k] = (uint8_t)i; a += L3_SFB_LONG_W[r][i]; }
         T.long_start[r][22] = (uint16_t)a; T.long_start[r][23] = (uint16_t)a;

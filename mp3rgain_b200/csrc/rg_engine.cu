@@ -168,7 +168,7 @@ extern "C" const char* rg_status_str(int status) {
         case RG_ERR_UNSUPPORTED_RATE:
             return "Unsupported sample rate. Supported rates: 96000, 88200, 64000, 48000, 44100, 32000, 24000, "
                    "22050, 16000, 12000, 11025, 8000";
-        case RG_ERR_UNSUPPORTED_FORMAT: return "Unsupported format (not an MPEG-1 Layer III stream)";
+        case RG_ERR_UNSUPPORTED_FORMAT: return "Unsupported format (MP4/AAC container: this engine decodes MPEG-1/2/2.5 Layer III)";
         case RG_ERR_NO_MEMORY: return "out of memory";
         default: return "unknown status";
     }

@@ -12,6 +12,11 @@
 #define RUN_GRANULES 126  // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
 
 static const uint32_t MPEG1_RATES[3] = {44100, 48000, 32000};
+// TrackMeta.sr_idx = sample-rate index | MPEG version << 4 (3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5)
+static inline uint32_t meta_version(const TrackMeta& m) { return (m.sr_idx >> 4) & 3; }
+static inline uint32_t meta_gpf(const TrackMeta& m) { return meta_version(m) == 3 ? 2u : 1u; }           // granules per frame
+static inline uint32_t meta_sr_row(const TrackMeta& m) { return (meta_version(m) == 3 ? 0u : (meta_version(m) == 2 ? 3u : 6u)) + (m.sr_idx & 3); }
+static inline uint32_t meta_rate(const TrackMeta& m) { return MPEG1_RATES[m.sr_idx & 3] >> (meta_version(m) == 3 ? 0 : (meta_version(m) == 2 ? 1 : 2)); }
 
 // mp4meta::is_mp4_file (src/mp4meta.rs:872-889): ftyp box with a known brand => AudioFileType::Aac
 static bool sniff_mp4(const uint8_t* d, uint64_t len) {
@@ -227,14 +232,11 @@ static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, 
             int st = m.status;
             if (c->is_mp4[i]) st = RG_ERR_UNSUPPORTED_FORMAT;          // AAC/M4A: out of scope for this engine
             else if (st == RG_OK) {
-                ip.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3];
+                ip.sample_rate[i] = meta_rate(m);
                 // MP3 carries exactly one audio track (src/replaygain.rs:838-851)
                 if (c->track_index[i] > 0) st = RG_ERR_TRACK_INDEX;
                 else if (c->track_index[i] < -1) st = RG_ERR_INVALID_ARG;
                 else if (rate_index(ip.sample_rate[i]) < 0) st = RG_ERR_UNSUPPORTED_RATE;
-            } else if (st == RG_ERR_UNSUPPORTED_FORMAT) {
-                const uint32_t ver = (m.sr_idx >> 4) & 3;
-                ip.sample_rate[i] = MPEG1_RATES[m.sr_idx & 3] >> (ver == 2 ? 1 : 2);
             }
             ip.status[i] = st;
         }
@@ -267,13 +269,14 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
         t.md_off = ip.md_base[i];
         t.frame_base = ip.frame_base[i];
         t.gc_base = gc_total;
-        t.n_frames = m.n_frames; t.channels = m.channels; t.sr_idx = m.sr_idx & 3; t.md_bytes = m.md_bytes;
-        const uint64_t plane = (uint64_t)m.n_frames * 1152;
+        const uint32_t gpf = meta_gpf(m), n_gran = m.n_frames * gpf;
+        t.n_frames = m.n_frames; t.channels = m.channels; t.sr_idx = meta_sr_row(m); t.md_bytes = m.md_bytes; t.gpf = gpf;
+        const uint64_t plane = (uint64_t)n_gran * 576;
         t.pcm_off = pcm_total; t.pcm_plane = plane;
-        const uint32_t n_gc = m.n_frames * 2 * m.channels;
+        const uint32_t n_gc = n_gran * m.channels;
         for (uint32_t g0 = 0; g0 < n_gc; g0 += K1_THREADS) hb.push_back(HuffBlock{(uint32_t)k, g0});
-        for (uint32_t g0 = 0; g0 < m.n_frames * 2; g0 += RUN_GRANULES)
-            runs.push_back(RunDesc{(uint32_t)k, g0, std::min<uint32_t>(RUN_GRANULES, m.n_frames * 2 - g0), 0});
+        for (uint32_t g0 = 0; g0 < n_gran; g0 += RUN_GRANULES)
+            runs.push_back(RunDesc{(uint32_t)k, g0, std::min<uint32_t>(RUN_GRANULES, n_gran - g0), 0});
         gc_total += n_gc;
         pcm_total += plane * m.channels;
         p.frames = plane;
@@ -354,7 +357,7 @@ static void collect_decode_timing(rg_engine* e, BatchCtx& x) {
 
 // Bytes of device scratch one track needs in a batch (spectra + nz + band gains + PCM)
 static uint64_t track_scratch_bytes(const TrackMeta& m) {
-    return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2 + 5 * K1_GAIN_ROW) + 1152ull * 4) + 4096;
+    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * ((576 * 2 + 2 + 5 * K1_GAIN_ROW) + 576ull * 4) + 4096;
 }
 
 static void drain_streams(rg_engine* e) {
@@ -566,7 +569,7 @@ extern "C" int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_t
 
 // Bytes of device scratch one track needs in a peak-only batch (no PCM is stored)
 static uint64_t track_scratch_bytes_peak(const TrackMeta& m) {
-    return (uint64_t)m.n_frames * m.channels * (2ull * (576 * 2 + 2 + 5 * K1_GAIN_ROW)) + 4096;
+    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * (576 * 2 + 2 + 5 * K1_GAIN_ROW) + 4096;
 }
 
 extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_result* out) {

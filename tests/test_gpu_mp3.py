@@ -75,6 +75,23 @@ def test_intensity_stereo_pcm_bit_exact(kw, engine_exact, oracle):
     assert info.n_frames == 300
 
 
+LSF = [dict(version=2, seed=41), dict(version=2, seed=42, channels=1, sr_idx=1, br_idx=0), dict(version=2, seed=43, sr_idx=2, br_idx=4),
+       dict(version=0, seed=44), dict(version=0, seed=45, sr_idx=1, br_idx=0), dict(version=0, seed=46, sr_idx=2, br_idx=2, channels=1)]
+
+
+@pytest.mark.parametrize("kw", LSF)
+def test_mpeg2_streams_pcm_bit_exact_and_analysis(kw, engine_exact, engine_fast, oracle):
+    """MPEG-2 / 2.5 Layer III at all six low sample rates (the oracle's handling is pinned against FFmpeg in
+    test_oracle_mp3.py): device PCM equals the oracle's sample for sample, and the analysis (50 ms windows of 1102 / 1200 /
+    800 / 551 / 600 / 400 samples, the low-rate filter coefficients of src/replaygain.rs:320-525) gives identical histograms
+    in exact and time-blocked mode."""
+    img = synth_corpus.make_track(n_frames=500, **kw)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 500 and info.sample_rate == synth_corpus.RATES_BY_VERSION[kw["version"]][kw.get("sr_idx", 0)]
+    _check_analysis(engine_exact, oracle, img)
+    _check_analysis(engine_fast, oracle, img)
+
+
 @pytest.mark.parametrize("kw", SYNTH[:4])
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_synthetic_streams_analysis(kw, mode, engine_exact, engine_fast, oracle):
@@ -179,10 +196,9 @@ def test_errors_match_reference_messages(engine_exact):
     with pytest.raises(m.ReplayGainError) as ei:
         engine_exact.analyze_images([_img("test_mono")], track_index=3, raise_on_error=True)
     assert "Track index 3 out of range (file has 1 audio track(s))" in str(ei.value)
-    hdr = bytes([0xFF, 0xF3, 0x80, 0x00])
-    lsf = np.frombuffer((hdr + bytes(72 * 64000 // 22050 - 4)) * 4, np.uint8)
-    res, sts = engine_exact.analyze_images([lsf])
-    assert sts == [-10] and res[0].sample_rate == 22050
+    mp4 = np.frombuffer(bytes([0, 0, 0, 24]) + b"ftypM4A " + bytes(3000), np.uint8)
+    res, sts = engine_exact.analyze_images([mp4])
+    assert sts == [-10] and res[0].file_type == m.AudioFileType.Aac   # AAC/M4A containers are recognised, not decoded
 
 
 def test_module_level_api_on_files(oracle, tmp_path):
@@ -251,7 +267,7 @@ def test_mixed_corpus_through_the_pipeline(oracle):
                                             channels=1 + (i % 5 != 0)))
     lsf = np.frombuffer((bytes([0xFF, 0xF3, 0x80, 0x00]) + bytes(72 * 64000 // 22050 - 4)) * 4, np.uint8)
     imgs[5] = np.zeros(4000, np.uint8)            # not an MP3: "Failed to probe format"
-    imgs[17] = lsf                                 # MPEG-2 Layer III: recognised, unsupported
+    imgs[17] = lsf                                 # MPEG-2 Layer III, four empty frames: decodes to digital silence
     imgs[29] = np.zeros(0, np.uint8)              # empty file
     for exact in (False, True):
         with m.Engine(device=0, exact=exact, scratch_bytes=24 << 20) as eng:
