@@ -162,6 +162,7 @@ typedef struct {
     float    last_ms_total;     /* CUDA-event time of the last analyse call's device work */
     uint32_t last_batches;      /* decode/analysis batches (= launches of each of K1, K2, K4, K5) in the last analyse call */
     uint32_t last_block_windows;/* windows per time block the time-blocked IIR used in the last batch (0 = exact mode) */
+    uint64_t last_iir_samples;  /* channel-samples the time-blocked IIR ran in the last analyse call, warm-up included */
 } rg_stats;
 int rg_engine_stats(rg_engine* e, rg_stats* out);
 

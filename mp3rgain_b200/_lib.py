@@ -64,7 +64,7 @@ class RgStats(C.Structure):
         ("tracks", C.c_uint64), ("frames", C.c_uint64), ("exact_reruns", C.c_uint64),
         ("last_ms_index", C.c_float), ("last_ms_huffman", C.c_float), ("last_ms_hybrid", C.c_float),
         ("last_ms_synth", C.c_float), ("last_ms_iir", C.c_float), ("last_ms_hist", C.c_float),
-        ("last_ms_total", C.c_float), ("last_batches", C.c_uint32), ("last_block_windows", C.c_uint32),
+        ("last_ms_total", C.c_float), ("last_batches", C.c_uint32), ("last_block_windows", C.c_uint32), ("last_iir_samples", C.c_uint64),
     ]
 
 

@@ -101,7 +101,7 @@ struct rg_engine {
     std::vector<cudaEvent_t> ev_pool;     // per-group events of the pipelined path (grown on demand)
     // options
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
-    uint32_t k4_capacity = 0;             // chains (threads) of k_iir_fast resident on the device at once
+    uint32_t k4_round = 0;                // chains in one round of k_iir_fast CTAs: one CTA per SM
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
@@ -227,10 +227,9 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     }
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
     {
-        int per_sm = 0, sms = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_iir_fast, K4_FAST_THREADS, 0));
+        int sms = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        e->k4_capacity = (uint32_t)(per_sm * sms * K4_FAST_THREADS);
+        e->k4_round = (uint32_t)(sms * K4_FAST_THREADS);
     }
     int rc = decode_init_tables(e->dec);
     if (rc != RG_OK) { delete e; return rc; }
@@ -296,8 +295,7 @@ static int fetch_desc(rg_engine* e, cudaStream_t st, void* dst, const void* src_
 }
 static inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
-// Windows per time block of the time-blocked IIR.  All chains of a batch have the same length, so the kernel's time is
-// (number of waves) x (block + warm-up windows): pick the block length that minimises it -- i.e. fill whole waves.
+// Windows per time block of the time-blocked IIR.
 static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTrack>& tracks) {
     if (e->block_windows) return e->block_windows;
     std::vector<std::pair<uint32_t, uint32_t>> nw;   // (windows, channels) per track
@@ -305,15 +303,20 @@ static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTr
         const uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
         if (t.status == RG_OK && t.frames > 0 && win > 0) nw.push_back({(uint32_t)((t.frames + win - 1) / win), t.nch >= 2 ? 2u : 1u});
     }
-    const uint64_t cap = e->k4_capacity ? e->k4_capacity : 75776;
+    // Cost model (measured, tools/iir_bench.cu with the block length as a parameter): one CTA of chains already saturates an
+    // SM's FP64 pipe, all chains are equally long, and CTAs are handed to SMs greedily -- so the kernel takes
+    // ceil(CTAs / SMs) rounds of (block + warm-up) windows each.  Pick the block length that minimises rounds x length
+    // (ties: the longer block, less warm-up work).
+    const uint64_t unit = e->k4_round ? e->k4_round : 148 * K4_FAST_THREADS;
     uint32_t best = 16;
     uint64_t best_cost = ~0ull;
-    for (uint32_t bw = 6; bw <= 96; bw++) {
+    for (uint32_t bw = 8; bw <= 96; bw++) {
         uint64_t chains = 0;
         for (auto& p : nw) chains += (uint64_t)((p.first + bw - 1) / bw) * p.second;
-        const uint64_t waves = (chains + cap - 1) / cap;
-        const uint64_t cost = waves * (bw + e->warm_windows);
-        if (cost < best_cost || (cost == best_cost && bw > best)) { best_cost = cost; best = bw; }
+        const uint64_t ctas = (chains + K4_FAST_THREADS - 1) / K4_FAST_THREADS;
+        const uint64_t rounds = (ctas * K4_FAST_THREADS + unit - 1) / unit;
+        const uint64_t cost = rounds * (bw + e->warm_windows);
+        if (cost <= best_cost) { best_cost = cost; best = bw; }
     }
     return best;
 }
@@ -398,6 +401,7 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
     build_chains(e, c.pt, exact, c.d_wsum.as<double>(), c.d_wmax.as<float>(), chains, twin, wd);
     for (auto& tw : twin) tw.flags = (d_album_hist != nullptr) ? 1u : 0u;
     c.n_chains = chains.size();
+    if (!exact) for (const RgChain& ch : chains) e->stats.last_iir_samples += (uint64_t)ch.n_warm + ch.n_main;
 
     // group chains by sample rate so each launch reads one coefficient row through uniform constant operands
     bool mixed = false;

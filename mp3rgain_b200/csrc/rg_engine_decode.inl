@@ -374,6 +374,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
     e->stats.last_ms_index = e->stats.last_ms_huffman = e->stats.last_ms_hybrid = e->stats.last_ms_synth = 0;
     e->stats.last_ms_iir = e->stats.last_ms_hist = e->stats.last_ms_total = 0;
     e->stats.last_batches = 0;
+    e->stats.last_iir_samples = 0;
     if (first_bad) *first_bad = -1;
     if (!n) return RG_OK;
     CK(cudaEventRecord(e->ev[7], e->stream));

@@ -53,7 +53,7 @@ static double run(const char* name, const RgChain* d_chains, uint32_t n_chains, 
 
 int main(int argc, char** argv) {
     const int n_tracks = argc > 1 ? atoi(argv[1]) : 200;
-    const uint32_t win = 2205, bw = 16;
+    const uint32_t win = 2205, bw = argc > 2 ? (uint32_t)atoi(argv[2]) : 16;
     const size_t frames = 6891ull * 1152;
     const uint32_t n_win = (uint32_t)((frames + win - 1) / win);
     const size_t plane = frames;
@@ -99,6 +99,7 @@ int main(int argc, char** argv) {
     std::vector<double> ref;
     const uint32_t nc = (uint32_t)chains.size();
 #define RUN(NV, T, B) run<NV, T, B>("nv" #NV " T" #T " minb" #B, d_chains, nc, d_peaks, d_wsum, n_w, ref, audio_s, cf)
+    if (argc > 2) { printf("block_windows %u\n", bw); RUN(3, 256, 2); return 0; }
     RUN(5, 128, 3);
     RUN(2, 128, 3);
     RUN(2, 128, 4);
