@@ -251,7 +251,7 @@ __device__ __forceinline__ void k2_polyphase(const K2Smem& S, const float* __res
 }
 
 template <int NCH>
-__device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md,
+__device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus,
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
                                         const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
@@ -525,7 +525,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 }
 
 __global__ void __launch_bounds__(K2_THREADS, 3)
-k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
+k_hybrid_synth(const uint8_t* __restrict__ corpus, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
                const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
                const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits /* [track] or null */,
@@ -534,6 +534,6 @@ k_hybrid_synth(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ m
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
-    if (tr.channels == 1) k2_body<1>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
-    else k2_body<2>(S, corpus, md, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
+    if (tr.channels == 1) k2_body<1>(S, corpus, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
+    else k2_body<2>(S, corpus, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
 }

@@ -26,7 +26,6 @@ struct L3Dev {
     uint16_t huff_base[16];     // first-level base of book slot s (1..15); [0] = an all-zero table
     uint32_t huff_total;        // entries used
     uint8_t tabsel[32][2];      // table_select -> {slot, linbits}
-    uint8_t c1_lut[2][16];      // count1: 4-bit peek -> (len<<4)|quad   (table B is the identity on ~peek)
     uint8_t c1a_lut[64];        // count1 table A: 6-bit peek -> (len<<4)|quad
     uint16_t long_start[9][24];   // rows: 44100, 48000, 32000 | 22050, 24000, 16000 | 11025, 12000, 8000
     uint16_t short_start[9][16];
@@ -41,11 +40,6 @@ struct L3Dev {
     uint16_t scatter_mixed[9][576];       // same for mixed blocks (first 36 lines stay)
     float pow43[L3_POW43_N];
     float gain[L3_GAIN_MAX - L3_GAIN_MIN + 1];
-    float alias_cs[8], alias_ca[8];
-    float dct4_18[18][18];
-    uint8_t imdct36_idx[36];
-    float winsgn[4][36];
-    float imdct12[12][6];
     float synth_wa[8][32], synth_wb[8][32];
     uint8_t synth_ia[32], synth_ib[32];
     float is_ratio[2][8];       // intensity stereo: is_pos -> left / right factor
@@ -147,7 +141,6 @@ static int decode_init_tables(DecodeScratch& ds) {
     for (int v = 0; v < 16; v++) {
         int len = L3_C1_LENS[0][v], bits = L3_C1_BITS[0][v];
         for (int k = 0; k < (1 << (6 - len)); k++) T.c1a_lut[(bits << (6 - len)) + k] = (uint8_t)((len << 4) | v);
-        T.c1_lut[1][L3_C1_BITS[1][v]] = (uint8_t)((4 << 4) | v);
     }
     memcpy(T.lsf_nsf, L3_LSF_NSF, sizeof T.lsf_nsf);
     for (int r = 0; r < 9; r++) {
@@ -177,12 +170,6 @@ static int decode_init_tables(DecodeScratch& ds) {
     memcpy(T.pretab, L3_PRETAB, 22);
     memcpy(T.pow43, L3_POW43, sizeof T.pow43);
     memcpy(T.gain, L3_GAIN, sizeof T.gain);
-    memcpy(T.alias_cs, L3_ALIAS_CS, sizeof T.alias_cs);
-    memcpy(T.alias_ca, L3_ALIAS_CA, sizeof T.alias_ca);
-    memcpy(T.dct4_18, L3_DCT4_18, sizeof T.dct4_18);
-    memcpy(T.imdct36_idx, L3_IMDCT36_IDX, sizeof T.imdct36_idx);
-    memcpy(T.winsgn, L3_WINSGN, sizeof T.winsgn);
-    memcpy(T.imdct12, L3_IMDCT12, sizeof T.imdct12);
     memcpy(T.synth_wa, L3_SYNTH_WA, sizeof T.synth_wa);
     memcpy(T.synth_wb, L3_SYNTH_WB, sizeof T.synth_wb);
     memcpy(T.synth_ia, L3_SYNTH_IA, sizeof T.synth_ia);

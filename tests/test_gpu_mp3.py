@@ -187,6 +187,36 @@ def test_keep_info_frame_flag(oracle):
     assert info.n_frames == 41 and gpcm.shape == opcm.shape and (gpcm == opcm).all()
 
 
+def test_clamp_pcm_flag(oracle):
+    """RG_FLAG_CLAMP_PCM (the symphonia-behaviour switch of DESIGN.md 4): a loud stream whose samples exceed +-1.0 is clamped
+    identically by the oracle and by K2, in the PCM and therefore in peak and histogram."""
+    import mp3rgain_b200 as m
+    img = synth_corpus.make_track(seed=77, n_frames=200, level_db=-1.0)
+    rc, opcm, info = oracle.decode(img)
+    assert np.abs(opcm).max() > 1.0                       # the unclamped decode really overshoots
+    rc, cpcm, info = oracle.decode(img, flags=0x4)
+    assert np.abs(cpcm).max() == 1.0
+    with m.Engine(device=0, exact=True, flags=0x4) as eng:
+        gpcm, sr = eng.decode_pcm(img)
+        res, sts = eng.analyze_images([img], want_hist=True)
+    assert gpcm.shape == cpcm.shape and (gpcm == cpcm).all()
+    rc, ores, ohist, info = oracle.analyze_mp3(img, flags=0x4)
+    assert sts == [0] and (res[0].histogram == ohist).all() and res[0].peak == ores.peak == 1.0
+
+
+def test_pipeline_off_gives_identical_results(oracle):
+    """The "pipeline" option only changes scheduling (one batch at a time, every kernel alone): results are identical."""
+    import mp3rgain_b200 as m
+    imgs = [synth_corpus.make_track(seed=500 + i, n_frames=150 + 20 * i, channels=1 + i % 2) for i in range(6)]
+    outs = []
+    for pipe in (1, 0):
+        with m.Engine(device=0, scratch_bytes=16 << 20) as eng:
+            eng.set_option("pipeline", pipe)
+            res, sts = eng.analyze_images(imgs, want_hist=True)
+            outs.append([(r.loudness_db, r.peak, r.n_frames, r.histogram.tobytes()) for r in res])
+    assert outs[0] == outs[1]
+
+
 def test_errors_match_reference_messages(engine_exact):
     import mp3rgain_b200 as m
     res, sts = engine_exact.analyze_images([np.zeros(5000, np.uint8), np.zeros(0, np.uint8), _img("test_mono")])
