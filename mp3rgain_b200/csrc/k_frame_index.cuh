@@ -172,8 +172,7 @@ __device__ SegOut k0_walk(const uint8_t* __restrict__ src, uint64_t len, uint8_t
             const int ws_bt = (w2 >> (16 - 3 - (wb & 7))) & 7;
             bad = bv > 288 || ((ws_bt & 4) && !(ws_bt & 3));
         }
-        // (MPEG-2 intensity stereo has its own scalefactor partition and ratio tables: not decoded, the frame is dropped)
-        const bool valid = !__any_sync(0xffffffffu, bad) && !(lsf && ((h >> 6) & 3) == 1 && ((h >> 4) & 1));
+        const bool valid = !__any_sync(0xffffffffu, bad);
         const int mdo_off = so + side_len;
         const int cap = flen > mdo_off ? flen - mdo_off : 0;
         const bool start_ok = !m_known || (uint32_t)mdb <= M0 + M;

@@ -158,7 +158,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         gr = rem / nch;
         const FrameRec rec = frames[tr.frame_base + frame];
         const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
-        is_right = !lsf && ch == 1 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 1);
+        is_right = ch == 1 && ((rec.hdr >> 6) & 3) == 1 && ((rec.hdr >> 4) & 1);
         // field offsets inside one granule-channel: MPEG-1 has a 4-bit scalefac_compress and a preflag bit (59 bits in all),
         // MPEG-2 a 9-bit scalefac_compress and no preflag bit (63 bits)
         const int gbase = lsf ? (nch == 1 ? 9 : 10) : (nch == 1 ? 18 : 20), gstride = lsf ? 63 : 59, x5 = lsf ? 5 : 0;
@@ -191,7 +191,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             r1 = T->long_start[tr.sr_idx][k > 22 ? 22 : k];
         }
         if (bt != 2) mixed = 0;
-        preflag = lsf ? (sfc >= 500) : (int)side_field(s, b0 + 56, 1);
+        preflag = lsf ? (sfc >= 500 && !is_right) : (int)side_field(s, b0 + 56, 1);
         sf_shift = side_field(s, b0 + (lsf ? 61 : 57), 1) ? 4 : 2;
         c1tab = side_field(s, b0 + (lsf ? 62 : 58), 1);
         // slot 0 ("no data") reads the all-zero first-level table at huff_base[0]: length 0, x = y = 0
@@ -204,7 +204,12 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         const int cls = bt != 2 ? 0 : (mixed ? 2 : 1);
         if (lsf) {
             int c = sfc;
-            if (c < 400) { ls[0] = (c >> 4) / 5; ls[1] = (c >> 4) % 5; ls[2] = (c % 16) >> 2; ls[3] = c % 4; ltbl = 0; }
+            if (is_right) {   // the scalefactors of an intensity-stereo right channel are is_pos values: other partition tables
+                c >>= 1;
+                if (c < 180) { ls[0] = c / 36; ls[1] = (c % 36) / 6; ls[2] = (c % 36) % 6; ltbl = 3; }
+                else if (c < 244) { c -= 180; ls[0] = (c % 64) >> 4; ls[1] = (c % 16) >> 2; ls[2] = c % 4; ltbl = 4; }
+                else { c -= 244; ls[0] = c / 3; ls[1] = c % 3; ltbl = 5; }
+            } else if (c < 400) { ls[0] = (c >> 4) / 5; ls[1] = (c >> 4) % 5; ls[2] = (c % 16) >> 2; ls[3] = c % 4; ltbl = 0; }
             else if (c < 500) { c -= 400; ls[0] = (c >> 2) / 5; ls[1] = (c >> 2) % 5; ls[2] = c % 4; ltbl = 1; }
             else { c -= 500; ls[0] = c / 3; ls[1] = c % 3; ltbl = 2; }
             for (int i = 0; i < 4; i++) part2 += T->lsf_nsf[ltbl][cls][i] * ls[i];
@@ -219,6 +224,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 part2 += (scfsi & 1) ? 0 : 5 * slen2;
             }
         }
+        if (is_right) srow[63] = (uint8_t)(lsf ? (sfc & 1) : 0);   // MPEG-2: intensity_scale
         end = bit + p23;
         silent = (uint32_t)part2 > p23;
         br.init(md + tr.md_off, rec.md_end, bit);
@@ -235,9 +241,12 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 while (left == 0 && fld < 3) left = T->lsf_nsf[ltbl][cls][++fld];
                 const int v = left ? (int)br.get(ls[fld]) : 0;
                 if (left) left--;
-                if (k < n_long) sfl[k] = (uint8_t)v;
+                // intensity position for K2: 255 = the illegal (all-ones) position of a non-empty field -> band not intensity coded
+                const uint8_t ipos = (ls[fld] > 0 && v == (1 << ls[fld]) - 1) ? 255 : (uint8_t)v;
+                if (k < n_long) { sfl[k] = (uint8_t)v; if (is_right) srow[k] = ipos; }
                 else {
                     const int q2 = k - n_long + (cls == 2 ? 9 : 0), win = q2 % 3;
+                    if (is_right) srow[22 + q2] = ipos;
                     grow[22 + q2] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)) - sf_shift * v]);
                 }
             }
@@ -249,7 +258,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             for (int q2 = mixed ? 9 : 0; q2 < 36; q2++) {
                 const int v = (int)br.get(q2 < 18 ? slen1 : slen2);
                 const int win = q2 % 3;
-                if (is_right) srow[22 + q2] = (uint8_t)v;
+                if (is_right) srow[22 + q2] = (uint8_t)(v < 7 ? v : 255);
                 grow[22 + q2] = __ldg(&T->gain[base_e - 8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)) - sf_shift * v]);
             }
 #pragma unroll
@@ -277,7 +286,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const int nl = bt != 2 ? 22 : 8;
             for (int sfb = 0; sfb < nl; sfb++) {
                 grow[sfb] = __ldg(&T->gain[base_e - sf_shift * ((int)sfl[sfb] + (preflag ? (int)T->pretab[sfb] : 0))]);
-                if (is_right) srow[sfb] = sfl[sfb];
+                if (is_right && !lsf) srow[sfb] = sfl[sfb] < 7 ? sfl[sfb] : 255;   // MPEG-1: is_pos 7 (and above) = not intensity coded
             }
         }
         // part 3 starts where part 2 ends by the side info's arithmetic (not where the reads above stopped: scfsi)

@@ -49,7 +49,9 @@ struct K2Smem {
     uint8_t ia[32], ib[32];
     uint8_t istab[K2_GC / 2][64];             // intensity stereo: is_pos per band of the right channel's partition, 255 = not intensity coded
     int istop[K2_GC / 2][4];                  // highest non-zero band of the right channel: [0] long sfb, [1..3] short sfb per window
-    float isr[2][8];                          // is_pos -> left / right factor
+    float isr[2][8];                          // MPEG-1: is_pos -> left / right factor
+    float isl[2][2][32];                      // MPEG-2: [intensity_scale][left / right][is_pos]
+    uint8_t iscale[K2_GC / 2];                // MPEG-2: intensity_scale of the granule's right channel
     alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
 };
 
@@ -278,6 +280,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
     }
     if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
     if (tid < 14) S.isr[tid / 7][tid % 7] = T->is_ratio[tid / 7][tid % 7];
+    if (tid < 128) (&S.isl[0][0][0])[tid] = (&T->is_lsf[0][0][0])[tid];
     for (int i = tid; i < K2_SLOTS * SLOTF; i += K2_THREADS) { (&S.A[0][0])[i] = 0.0f; (&S.S2[0][0])[i] = 0.0f; }
     if (tid == 0) k2_mbar_init(&S.mbar, 1);
     // side info of every granule-channel of the run, one thread each
@@ -348,7 +351,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 const int j = lane + 32 * my_ch;
                 if (j < 61) {
                     const uint8_t* row = sfraw + ((size_t)tr.gc_base + (size_t)(gfirst + gl) * 2 + 1) * K1_GAIN_ROW;
-                    uint32_t pos = 255;
+                    uint32_t pos = 255;   // K1 wrote 255 for "not intensity coded" (MPEG-1: is_pos >= 7, MPEG-2: the all-ones position)
                     if (j < 22) {
                         const bool short_nz = top[1] >= 0 || top[2] >= 0 || top[3] >= 0;
                         if (tsel1 != 1 && !short_nz && j > top[0]) pos = row[j == 21 ? 20 : j];
@@ -356,7 +359,8 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                         const int sfb = (j - 22) / 3, win = (j - 22) % 3;
                         if (sfb > top[1 + win]) pos = row[22 + (sfb == 12 ? 11 : sfb) * 3 + win];
                     }
-                    S.istab[my_gi][j] = (uint8_t)(pos < 7 ? pos : 255);
+                    S.istab[my_gi][j] = (uint8_t)pos;
+                    if (j == 0) S.iscale[my_gi] = row[63];
                 }
                 k2_pair_sync(my_gi);
             }
@@ -375,7 +379,8 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 uint32_t ipos = 255;
                 if (NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
                 if (NCH == 2 && ipos != 255) {
-                    const float kl = S.isr[0][ipos], kr = S.isr[1][ipos];
+                    const float kl = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][0][ipos & 31] : S.isr[0][ipos & 7];
+                    const float kr = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][1][ipos & 31] : S.isr[1][ipos & 7];
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const float l = v[0][h];

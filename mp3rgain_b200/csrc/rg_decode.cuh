@@ -43,6 +43,7 @@ struct L3Dev {
     float synth_wa[8][32], synth_wb[8][32];
     uint8_t synth_ia[32], synth_ib[32];
     float is_ratio[2][8];       // intensity stereo: is_pos -> left / right factor
+    float is_lsf[2][2][32];     // MPEG-2 intensity stereo: [intensity_scale][left / right][is_pos]
 };
 
 
@@ -175,6 +176,7 @@ static int decode_init_tables(DecodeScratch& ds) {
     memcpy(T.synth_ia, L3_SYNTH_IA, sizeof T.synth_ia);
     memcpy(T.synth_ib, L3_SYNTH_IB, sizeof T.synth_ib);
     for (int r = 0; r < 2; r++) for (int k = 0; k < 7; k++) T.is_ratio[r][k] = L3_IS_RATIO[r][k];
+    memcpy(T.is_lsf, L3_IS_LSF, sizeof T.is_lsf);
     if (cudaMalloc(&ds.d_tab, sizeof(L3Dev)) != cudaSuccess) return -3;
     if (cudaMemcpy(ds.d_tab, &T, sizeof(L3Dev), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
     return 0;

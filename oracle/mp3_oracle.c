@@ -215,6 +215,7 @@ typedef struct {
     int head[2];
     int sf_l[2][2][22];       /* [gr][ch] long scalefactors */
     int sf_s[2][2][13][3];    /* [gr][ch] short scalefactors */
+    int ill_l[22], ill_s[13][3]; /* MPEG-2 intensity stereo, right channel of the current frame: band carries the "illegal" is_pos */
 } dec_t;
 
 /* part 2: scalefactors (ISO 11172-3 2.4.2.7) */
@@ -248,23 +249,38 @@ static void read_scalefactors(bits_t* b, const side_t* s, int g, int ch, dec_t* 
 /* part 2, MPEG-2 / 2.5 (ISO 13818-3 2.4.3.2): scalefac_compress -> four field widths and, through L3_LSF_NSF, how many
  * scalefactors use each; the values come in band order (long: sfb 0..20; short: sfb 0..11 x 3 windows; mixed: 6 long
  * bands, then short sfb 3..11 x 3 windows).  (Intensity-stereo right channels use other tables: such streams are rejected.) */
-static void read_scalefactors_lsf(bits_t* b, const gr_t* q, int* sl, int (*ss)[3]) {
+static void read_scalefactors_lsf(bits_t* b, const gr_t* q, int is_right, int* sl, int (*ss)[3], int* ill_l, int (*ill_s)[3]) {
     memset(sl, 0, 22 * sizeof(int));
     memset(ss, 0, 13 * 3 * sizeof(int));
-    int sfc = q->scalefac_compress, slen[4], tbl;
-    if (sfc < 400) { slen[0] = (sfc >> 4) / 5; slen[1] = (sfc >> 4) % 5; slen[2] = (sfc % 16) >> 2; slen[3] = sfc % 4; tbl = 0; }
-    else if (sfc < 500) { sfc -= 400; slen[0] = (sfc >> 2) / 5; slen[1] = (sfc >> 2) % 5; slen[2] = sfc % 4; slen[3] = 0; tbl = 1; }
-    else { sfc -= 500; slen[0] = sfc / 3; slen[1] = sfc % 3; slen[2] = slen[3] = 0; tbl = 2; }
+    memset(ill_l, 0, 22 * sizeof(int));
+    memset(ill_s, 0, 13 * 3 * sizeof(int));
+    int sfc = q->scalefac_compress, slen[4] = {0, 0, 0, 0}, tbl;
+    if (!is_right) {
+        if (sfc < 400) { slen[0] = (sfc >> 4) / 5; slen[1] = (sfc >> 4) % 5; slen[2] = (sfc % 16) >> 2; slen[3] = sfc % 4; tbl = 0; }
+        else if (sfc < 500) { sfc -= 400; slen[0] = (sfc >> 2) / 5; slen[1] = (sfc >> 2) % 5; slen[2] = sfc % 4; tbl = 1; }
+        else { sfc -= 500; slen[0] = sfc / 3; slen[1] = sfc % 3; tbl = 2; }
+    } else {   /* right channel of an intensity-stereo frame: the scalefactors are is_pos values, other partition tables */
+        int isc = sfc >> 1;
+        if (isc < 180) { slen[0] = isc / 36; slen[1] = (isc % 36) / 6; slen[2] = (isc % 36) % 6; tbl = 3; }
+        else if (isc < 244) { isc -= 180; slen[0] = (isc % 64) >> 4; slen[1] = (isc % 16) >> 2; slen[2] = isc % 4; tbl = 4; }
+        else { isc -= 244; slen[0] = isc / 3; slen[1] = isc % 3; tbl = 5; }
+    }
     int cls = q->block_type != 2 ? 0 : (q->mixed ? 2 : 1);
-    int v[40], n = 0;
+    int v[40], il[40], n = 0;
     for (int i = 0; i < 4; i++)
-        for (int j = 0; j < L3_LSF_NSF[tbl][cls][i]; j++) v[n++] = getbits(b, slen[i]);
+        for (int j = 0; j < L3_LSF_NSF[tbl][cls][i]; j++) {
+            v[n] = getbits(b, slen[i]);
+            /* the illegal intensity position (all ones): this band is not intensity coded.  A 0-bit field reads as position 0,
+             * which FFmpeg and minimp3 take as a valid position (libmad as the illegal one); this restatement follows the former. */
+            il[n] = is_right && slen[i] > 0 && v[n] == (1 << slen[i]) - 1;
+            n++;
+        }
     int k = 0;
-    if (cls == 0) { for (int sfb = 0; sfb < 21 && k < n; sfb++) sl[sfb] = v[k++]; }
+    if (cls == 0) { for (int sfb = 0; sfb < 21 && k < n; sfb++) { sl[sfb] = v[k]; ill_l[sfb] = il[k]; k++; } }
     else {
         int s0 = 0;
-        if (cls == 2) { for (int sfb = 0; sfb < 6; sfb++) sl[sfb] = v[k++]; s0 = 3; }
-        for (int sfb = s0; sfb < 12; sfb++) for (int w = 0; w < 3; w++) if (k < n) ss[sfb][w] = v[k++];
+        if (cls == 2) { for (int sfb = 0; sfb < 6; sfb++) { sl[sfb] = v[k]; ill_l[sfb] = il[k]; k++; } s0 = 3; }
+        for (int sfb = s0; sfb < 12; sfb++) for (int w = 0; w < 3; w++) if (k < n) { ss[sfb][w] = v[k]; ill_s[sfb][w] = il[k]; k++; }
     }
 }
 
@@ -372,14 +388,18 @@ static void ms_band(float xr[2][576], int i0, int n) {
         xr[1][i] = (m - sd) * L3_INV_SQRT2;
     }
 }
+/* MPEG-2 (ISO 13818-3 2.4.3.2): same band rule; the factors come from L3_IS_LSF[intensity_scale = scalefac_compress & 1] and a
+ * band is excluded when it carries the illegal position (1 << slen) - 1 of its scalefactor field instead of is_pos 7. */
 static void joint_stereo(const gr_t* q1, int sr_row, int ms, int intensity, const int* sf_l, int (*sf_s)[3], const int16_t* is1,
-                         float xr[2][576]) {
+                         float xr[2][576], int lsf, const int* ill_l, int (*ill_s)[3]) {
     if (!intensity) {
         if (ms) ms_band(xr, 0, 576);
         return;
     }
+    const float* kl = lsf ? L3_IS_LSF[q1->scalefac_compress & 1][0] : L3_IS_RATIO[0];
+    const float* kr = lsf ? L3_IS_LSF[q1->scalefac_compress & 1][1] : L3_IS_RATIO[1];
     int short_start = 13, long_end = 22;
-    if (q1->block_type == 2) { short_start = q1->mixed ? 3 : 0; long_end = q1->mixed ? 8 : 0; }
+    if (q1->block_type == 2) { short_start = q1->mixed ? 3 : 0; long_end = q1->mixed ? (lsf ? 6 : 8) : 0; }
     int end = 576;
     int nz_short[3] = {0, 0, 0};
     for (int sfb = 12; sfb >= short_start; sfb--) {
@@ -390,10 +410,10 @@ static void joint_stereo(const gr_t* q1, int sr_row, int ms, int intensity, cons
             int pos = -1;
             if (!nz_short[w]) {
                 for (int j = 0; j < wdt; j++) if (is1[end + j] != 0) { nz_short[w] = 1; break; }
-                if (!nz_short[w] && sf_s[src][w] < 7) pos = sf_s[src][w];
+                if (!nz_short[w] && (lsf ? !ill_s[src][w] : sf_s[src][w] < 7)) pos = sf_s[src][w];
             }
             if (pos >= 0) {
-                for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * L3_IS_RATIO[0][pos]; xr[1][j] = l * L3_IS_RATIO[1][pos]; }
+                for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * kl[pos]; xr[1][j] = l * kr[pos]; }
             } else if (ms) ms_band(xr, end, wdt);
         }
     }
@@ -405,10 +425,10 @@ static void joint_stereo(const gr_t* q1, int sr_row, int ms, int intensity, cons
         if (!nz) {
             for (int j = 0; j < wdt; j++) if (is1[end + j] != 0) { nz = 1; break; }
             int src = sfb == 21 ? 20 : sfb;
-            if (!nz && sf_l[src] < 7) pos = sf_l[src];
+            if (!nz && (lsf ? !ill_l[src] : sf_l[src] < 7)) pos = sf_l[src];
         }
         if (pos >= 0) {
-            for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * L3_IS_RATIO[0][pos]; xr[1][j] = l * L3_IS_RATIO[1][pos]; }
+            for (int j = end; j < end + wdt; j++) { float l = xr[0][j]; xr[0][j] = l * kl[pos]; xr[1][j] = l * kr[pos]; }
         } else if (ms) ms_band(xr, end, wdt);
     }
 }
@@ -594,7 +614,6 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         const int lsf = h.ver != 3, ngr = lsf ? 1 : 2;
         side_t s;
         parse_side(fp + so, nch, lsf, &s);
-        if (lsf && h.mode == 1 && (h.mode_ext & 1)) s.valid = 0;   /* MPEG-2 intensity stereo: not decoded, the frame is dropped */
         size_t mdo = so + h.side_len;
         size_t md_start_ok = s.main_data_begin <= (int)md_len;
         size_t start = md_len - (md_start_ok ? s.main_data_begin : 0);
@@ -605,19 +624,20 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
         /* rows of the band tables: 44100, 48000, 32000 | 22050, 24000, 16000 | 11025, 12000, 8000 */
         int sr_row = (h.ver == 3 ? 0 : (h.ver == 2 ? 3 : 6)) + h.sr_idx;
         bits_t b = {md, md_len + 32, start * 8};
+        if (lsf && nch == 2 && h.mode == 1 && (h.mode_ext & 1)) s.gr[0][1].preflag = 0;   /* intensity right channel: no preflag */
         for (int g = 0; g < ngr; g++) {
             int nz[2] = {0, 0};
             for (int ch = 0; ch < nch; ch++) {
                 const gr_t* q = &s.gr[g][ch];
                 size_t end = b.pos + q->part2_3_length;
-                if (lsf) read_scalefactors_lsf(&b, q, d->sf_l[g][ch], d->sf_s[g][ch]);
+                if (lsf) read_scalefactors_lsf(&b, q, ch == 1 && h.mode == 1 && (h.mode_ext & 1), d->sf_l[g][ch], d->sf_s[g][ch], d->ill_l, d->ill_s);
                 else read_scalefactors(&b, &s, g, ch, d);
                 if (b.pos > end) { memset(is[ch], 0, sizeof is[ch]); b.pos = end; nz[ch] = 0; }
                 else nz[ch] = read_huffman(&b, end, q, sr_row, is[ch]);
                 requantize(q, sr_row, d->sf_l[g][ch], d->sf_s[g][ch], is[ch], xr[ch]);
             }
             if (nch == 2 && h.mode == 1 && h.mode_ext)
-                joint_stereo(&s.gr[g][1], sr_row, h.mode_ext & 2, h.mode_ext & 1, d->sf_l[g][1], d->sf_s[g][1], is[1], xr);
+                joint_stereo(&s.gr[g][1], sr_row, h.mode_ext & 2, h.mode_ext & 1, d->sf_l[g][1], d->sf_s[g][1], is[1], xr, lsf, d->ill_l, d->ill_s);
             for (int ch = 0; ch < nch; ch++) {
                 const gr_t* q = &s.gr[g][ch];
                 if (q->block_type == 2) reorder(q, sr_row, xr[ch]);

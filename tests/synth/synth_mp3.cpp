@@ -308,18 +308,28 @@ void make_granule(Granule& g, Rng& rng, int sr_row, int bt, int mixed, double am
     g.scalefac_compress = rng.below(16);
     int s1 = L3_SLEN[0][g.scalefac_compress], s2 = L3_SLEN[1][g.scalefac_compress];
     auto sfv = [&](int bits) { if (!bits) return 0; int m = (1 << bits) - 1; int v = (int)(-std::log(1.0 - rng.uni()) * 1.2); return std::min(v, m); };
+    const bool lsf_is_right = g_version != 3 && is_cut < 1e8;   // right channel of an MPEG-2 intensity-stereo frame
     if (g_version != 3) {
         // MPEG-2: pick one of the three scalefac_compress ranges, then field widths, then values band by band
         int pick = rng.below(10);
         int* sl = g.lsf_slen;
-        if (pick < 7) { sl[0] = rng.below(5); sl[1] = rng.below(5); sl[2] = rng.below(4); sl[3] = rng.below(4);
+        if (lsf_is_right) {
+            // intensity partition, first range only (every field at least 1 bit wide, at most 4: the other ranges leave
+            // bands without a position, which decoders treat differently); bit 0 of scalefac_compress = intensity_scale
+            sl[0] = 1 + rng.below(4); sl[1] = 1 + rng.below(4); sl[2] = 1 + rng.below(4); sl[3] = 0;
+            g.scalefac_compress = ((sl[0] * 36 + sl[1] * 6 + sl[2]) << 1) | rng.below(2); g.lsf_tbl = 3; g.preflag = 0;
+        } else if (pick < 7) { sl[0] = rng.below(5); sl[1] = rng.below(5); sl[2] = rng.below(4); sl[3] = rng.below(4);
                         g.scalefac_compress = ((sl[0] * 5 + sl[1]) << 4) | (sl[2] << 2) | sl[3]; g.lsf_tbl = 0; g.preflag = 0; }
         else if (pick < 9) { sl[0] = rng.below(5); sl[1] = rng.below(5); sl[2] = rng.below(4); sl[3] = 0;
                              g.scalefac_compress = 400 + (((sl[0] * 5 + sl[1]) << 2) | sl[2]); g.lsf_tbl = 1; g.preflag = 0; }
         else { sl[0] = rng.below(4); sl[1] = rng.below(3); sl[2] = sl[3] = 0;
                g.scalefac_compress = 500 + sl[0] * 3 + sl[1]; g.lsf_tbl = 2; g.preflag = 1; }
         int cls = bt != 2 ? 0 : (g.mixed ? 2 : 1), v[40], k = 0;
-        for (int i = 0; i < 4; i++) for (int j = 0; j < L3_LSF_NSF[g.lsf_tbl][cls][i]; j++) v[k++] = sfv(sl[i]);
+        for (int i = 0; i < 4; i++) for (int j = 0; j < L3_LSF_NSF[g.lsf_tbl][cls][i]; j++) {
+            v[k] = sfv(sl[i]);
+            if (lsf_is_right && sl[i] && v[k] == (1 << sl[i]) - 1) v[k]--;   // never the illegal position (decoders disagree on it)
+            k++;
+        }
         k = 0;
         if (cls == 0) { for (int sfb = 0; sfb < 21; sfb++) g.sf_l[sfb] = v[k++]; }
         else {
@@ -503,7 +513,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         bool js = channels == 2 && rng.chance(0.6);
         bool ms = js && rng.chance(0.7) && !(g_disable & 256);
         // intensity stereo: the right channel is empty above a random bound and its scalefactors there are is_pos values
-        bool ist = js && !lsf && rng.chance(g_is_prob) && !(g_disable & 512);   // (MPEG-2 intensity stereo is not generated)
+        bool ist = js && rng.chance(g_is_prob) && !(g_disable & 512);
         double is_cut = ist ? 20.0 + 300.0 * rng.uni() : 1e9;
         Granule gr[2][2];
         int scfsi[2][4] = {{0}};

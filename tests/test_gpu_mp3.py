@@ -92,6 +92,15 @@ def test_mpeg2_streams_pcm_bit_exact_and_analysis(kw, engine_exact, engine_fast,
     _check_analysis(engine_fast, oracle, img)
 
 
+@pytest.mark.parametrize("kw", [dict(version=2, seed=51), dict(version=2, seed=52, sr_idx=1, br_idx=0), dict(version=0, seed=53, sr_idx=1),
+                                dict(version=0, seed=55, sr_idx=2, br_idx=0)])
+def test_mpeg2_intensity_stereo_pcm_bit_exact(kw, engine_exact, oracle):
+    """MPEG-2 / 2.5 streams whose joint-stereo frames all carry intensity stereo: device PCM == oracle PCM."""
+    img = synth_corpus.make_track(n_frames=400, intensity_prob=1.0, **kw)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 400
+
+
 @pytest.mark.parametrize("kw", SYNTH[:4])
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 def test_synthetic_streams_analysis(kw, mode, engine_exact, engine_fast, oracle):

@@ -152,15 +152,18 @@ def test_mpeg2_streams_decode_like_ffmpeg(oracle, kw):
     assert 0.03 < np.sqrt((pcm.astype(np.float64) ** 2).mean()) < 0.3
 
 
-def test_mpeg2_intensity_stereo_frames_are_dropped(oracle):
-    """MPEG-2 intensity stereo (its own scalefactor partition and ratio tables) is not decoded: such frames are dropped like
-    frames with invalid side info, the rest of the stream decodes."""
-    img = synth_corpus.make_track(n_frames=60, version=2, seed=47).copy()
-    starts, pos, b = [], 0, bytes(img)
-    while pos + 4 <= len(b):
-        starts.append(pos)
-        pos += 72 * [0, 8, 16, 24, 32, 40, 48, 56, 64, 80, 96, 112, 128, 144, 160][b[pos + 2] >> 4] * 1000 // 22050 + ((b[pos + 2] >> 1) & 1)
-    for p0 in starts[10:14]:
-        img[p0 + 3] = (img[p0 + 3] & 0x0F) | 0x50          # joint stereo, mode_extension = intensity only
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", [dict(version=2, seed=51), dict(version=2, seed=52, sr_idx=1, br_idx=0), dict(version=0, seed=53, sr_idx=1),
+                                dict(version=0, seed=55, sr_idx=2, br_idx=0)])
+def test_mpeg2_intensity_stereo_decodes_like_ffmpeg(oracle, kw):
+    """MPEG-2 intensity stereo (ISO 13818-3 2.4.3.2: the right channel's scalefactors come from the intensity partition tables,
+    is_pos selects 2^(-p/4) or 2^(-p/2) steps by intensity_scale, the all-ones position marks a band that is not intensity
+    coded): every joint-stereo frame carries it here, and the oracle agrees with FFmpeg."""
+    img = synth_corpus.make_track(n_frames=400, intensity_prob=1.0, **kw)
+    n, ms, ist = _count_stereo_modes(img)
+    assert n == 400 and ist > 150
     rc, pcm, info = oracle.decode(img)
-    assert rc == 0 and info.n_frames == 56 and info.n_dropped_frames == 4
+    assert rc == 0 and info.n_frames == 400 and info.n_dropped_frames == 0
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6

@@ -132,6 +132,14 @@ isr = np.tan(np.arange(7) * np.pi / 12.0)
 is_l = isr / (1.0 + isr); is_r = 1.0 / (1.0 + isr)
 is_l[6], is_r[6] = 1.0, 0.0
 is_tab = f32(np.stack([is_l, is_r]))
+# MPEG-2 intensity stereo (ISO 13818-3 2.4.3.2): is_pos 0 -> (1, 1); odd -> (i0^((p+1)/2), 1); even -> (1, i0^(p/2)),
+# i0 = 2^(-1/4) (intensity_scale 0) or 2^(-1/2) (intensity_scale 1).  [scale][left/right][is_pos]
+is_lsf = np.ones((2, 2, 32))
+for sc in range(2):
+    for pp in range(1, 32):
+        v = 2.0 ** (-(sc + 1) * ((pp + 1) // 2) / 4.0)
+        is_lsf[sc][0 if pp & 1 else 1][pp] = v
+is_lsf = f32(is_lsf)
 
 # ---------------------------------------------------------------- emit
 def carr_int(name, ctype, a, per=24):
@@ -209,6 +217,7 @@ def emit(path, guard, note):
     o.append(carr_int("L3_SYNTH_IB", "uint8_t", ib))
     o.append(f"#define L3_INV_SQRT2 {float(inv_sqrt2).hex()}f")
     o.append(carr_f32("L3_IS_RATIO", is_tab))
+    o.append(carr_f32("L3_IS_LSF", is_lsf))
     o.append(f"\n#endif /* {guard} */\n")
     pathlib.Path(path).write_text("\n".join(o))
 
