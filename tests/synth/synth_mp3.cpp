@@ -53,6 +53,7 @@ HuffEnc g_enc[16];
 int g_long_start[9][23], g_short_start[9][14];
 bool g_init = false;
 double g_is_prob = 0.25;  // share of joint-stereo frames that use intensity stereo (tests: high, for coverage; bench: 2 %, encoders at 128 kbps rarely use it)
+int g_crc = 0;            // 1: frames carry the 16-bit CRC word after the header (protection_bit = 0); its value is not computed
 int g_version = 3;        // MPEG version field of the streams: 3 = MPEG-1, 2 = MPEG-2 (LSF), 0 = MPEG-2.5 (LSF)
 unsigned g_disable = 0;  // debug: bit0 short blocks, bit1 mixed, bit2 scfsi, bit3 preflag, bit4 sf_scale, bit5 subblock_gain, bit6 escapes, bit7 random tables, bit8 MS, bit9 intensity stereo
 
@@ -472,7 +473,8 @@ extern "C" {
 
 void synth_set_disable(unsigned mask) { g_disable = mask; }
 void synth_set_intensity_prob(double p) { g_is_prob = p; }
-void synth_set_version(int v) { g_version = v; }   // 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5
+void synth_set_version(int v) { g_version = v; }
+void synth_set_crc(int on) { g_crc = on; }   // 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5
 
 // One self-contained group of n_frames frames.  br_idx: 1..14 CBR, 0 = VBR (uniform bitrate index per frame).
 // level_db: target loudness of the PCM (dBFS RMS); the group wanders around it.  Returns bytes written (0 if cap too small).
@@ -502,7 +504,8 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         int pad = 0;
         if (pad_acc >= 1.0) { pad = 1; pad_acc -= 1.0; }
         int flen = base + pad;
-        int cap_f = flen - 4 - side_len;
+        const int hdr_len = 4 + (g_crc ? 2 : 0);
+        int cap_f = flen - hdr_len - side_len;
         size_t P = std::max<size_t>(E, M > mdb_max ? M - mdb_max : 0);
         if (f == 0) P = M;
         int budget = (int)((M + cap_f - P) * 8);
@@ -548,11 +551,12 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
         // header
         BitWriter hw;
         hw.put(0x7FF, 11); hw.put((uint32_t)g_version, 2);                          // sync, MPEG-1 (11) / MPEG-2 (10) / MPEG-2.5 (00)
-        hw.put(1, 2); hw.put(1, 1);                                                 // Layer III, no CRC
+        hw.put(1, 2); hw.put(g_crc ? 0u : 1u, 1);                                   // Layer III, protection bit (0 = CRC word follows)
         hw.put((uint32_t)bri, 4); hw.put((uint32_t)sr_idx, 2); hw.put((uint32_t)pad, 1); hw.put(0, 1);
         hw.put(channels == 1 ? 3u : (js ? 1u : 0u), 2);
         hw.put(js ? ((ms ? 2u : 0u) | (ist ? 1u : 0u)) : 0u, 2);
         hw.put(0, 1); hw.put(1, 1); hw.put(0, 2);
+        if (g_crc) hw.put(0xA55A, 16);                                              // the CRC word (decoders do not verify it by default)
         write_side(hw, channels, (int)(M - P), scfsi, gr);
         // granule data into the main-data stream at P
         BitWriter dw;
@@ -571,7 +575,7 @@ size_t synth_group(uint64_t seed, int n_frames, int sr_idx, int br_idx, int chan
     }
     // scatter the main-data stream back into the frames' payload areas
     for (size_t f = 0; f < frame_off.size(); f++)
-        memcpy(frames.data() + frame_off[f] + 4 + side_len, md.data() + payload_off[f], payload_len[f]);
+        memcpy(frames.data() + frame_off[f] + 4 + (g_crc ? 2 : 0) + side_len, md.data() + payload_off[f], payload_len[f]);
     if (frames.size() > cap) return 0;
     memcpy(out, frames.data(), frames.size());
     return frames.size();

@@ -30,6 +30,7 @@ def _load():
         _lib.synth_track.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_size_t]
         _lib.synth_set_intensity_prob.argtypes = [C.c_double]
         _lib.synth_set_version.argtypes = [C.c_int]
+        _lib.synth_set_crc.argtypes = [C.c_int]
     return _lib
 
 
@@ -46,17 +47,20 @@ def make_group(seed, n_frames=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0
 
 
 def make_track(seed, n_frames=6891, group_len=32, sr_idx=0, br_idx=9, channels=2, level_db=-20.0, intensity_prob=0.25,
-               version=3):
+               version=3, crc=False):
     """One unique track (every group freshly generated). br_idx 0 = VBR. Returns a numpy uint8 array.
     intensity_prob: share of the joint-stereo frames (60 % of stereo frames) that carry intensity stereo.
-    version: 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5 (half / quarter sample rates, 576-sample frames, no intensity stereo)."""
+    version: 3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5 (half / quarter sample rates, 576-sample frames).
+    crc: frames carry the 16-bit CRC word (protection_bit = 0)."""
     lib = _load()
     lib.synth_set_intensity_prob(float(intensity_prob))
     lib.synth_set_version(int(version))
+    lib.synth_set_crc(1 if crc else 0)
     try:
         return _make_track(lib, seed, n_frames, group_len, sr_idx, br_idx, channels, level_db)
     finally:
         lib.synth_set_version(3)
+        lib.synth_set_crc(0)
 
 
 def _make_track(lib, seed, n_frames, group_len, sr_idx, br_idx, channels, level_db):

@@ -196,6 +196,14 @@ def test_keep_info_frame_flag(oracle):
     assert info.n_frames == 41 and gpcm.shape == opcm.shape and (gpcm == opcm).all()
 
 
+@pytest.mark.parametrize("kw", [dict(seed=61), dict(seed=62, channels=1, br_idx=0), dict(seed=63, version=2, sr_idx=1)])
+def test_crc_protected_frames(kw, engine_exact, oracle):
+    img = synth_corpus.make_track(n_frames=200, crc=True, **kw)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 200
+    _check_analysis(engine_exact, oracle, img)
+
+
 def test_clamp_pcm_flag(oracle):
     """RG_FLAG_CLAMP_PCM (the symphonia-behaviour switch of DESIGN.md 4): a loud stream whose samples exceed +-1.0 is clamped
     identically by the oracle and by K2, in the PCM and therefore in peak and histogram."""

@@ -99,6 +99,18 @@ def test_intensity_stereo_decodes_like_ffmpeg(oracle, kw):
     assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
 
 
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", [dict(seed=61), dict(seed=62, channels=1, br_idx=0), dict(seed=63, version=2, sr_idx=1)])
+def test_crc_protected_frames(oracle, kw):
+    """protection_bit = 0: a 16-bit CRC word sits between header and side info (it is not verified, like FFmpeg's default)."""
+    img = synth_corpus.make_track(n_frames=200, crc=True, **kw)
+    assert (img[1] & 1) == 0
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 200
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape and np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+
+
 def test_container_edge_cases(oracle):
     base = synth_corpus.make_track(seed=11, n_frames=50)
     rc0, pcm0, info0 = oracle.decode(base)
