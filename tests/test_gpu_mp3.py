@@ -347,3 +347,24 @@ def test_peak_only_path_equals_the_analysis_peak(oracle):
         assert st == rc, (i, st, rc)
         if rc == 0:
             assert pk.peak == ores.peak and pk.peak_pcm == ores.peak * 32768.0 and pk.sample_rate == info.sample_rate, i
+
+
+def test_full_length_tracks_time_blocked_equals_exact():
+    """BASELINE-sized tracks (3 minutes, 6891 frames, 3612 windows each): the default time-blocked IIR (with its edge-window
+    re-run) and the bit-exact serial IIR give identical per-track histograms, loudness and peaks on every track, and the album
+    histogram equals the sum of the track histograms -- the size-independent properties of the full-size workload."""
+    import mp3rgain_b200 as m
+    pool = synth_corpus.GroupPool(seed=9, n_groups=96, group_len=32, intensity_prob=0.05)
+    imgs = [pool.track(7000 + i, 6891) for i in range(48)]
+    with m.Engine(device=0, exact=False) as fast, m.Engine(device=0, exact=True) as exact:
+        rf, sf = fast.analyze_images(imgs, want_hist=True)
+        re_, se = exact.analyze_images(imgs, want_hist=True)
+        alb = fast.analyze_album_images(imgs, want_hist=True)
+    assert sf == se == [0] * len(imgs)
+    total = np.zeros(12000, np.uint64)
+    for a, b in zip(rf, re_):
+        assert a.n_windows == b.n_windows == 3612 and a.n_frames == 6912   # the pool deals whole 32-frame groups
+        assert (a.histogram == b.histogram).all() and a.loudness_db == b.loudness_db and a.peak == b.peak
+        total += a.histogram.astype(np.uint64)
+    assert (alb.album_histogram == total).all() and int(total.sum()) == 48 * 3612
+    assert alb.album_peak == max(r.peak for r in rf)
