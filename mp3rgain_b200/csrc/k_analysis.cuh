@@ -15,8 +15,8 @@
 //   term erases.
 //   FAST mode: the cascade as a linear transposed-direct-form-II filter evaluated with FMAs (see iir_step_fast);
 //   chains start from zero state n_warm samples early.  Not bit-identical to the reference; K5 flags every
-//   window whose bin decision is within `edge_tol` of flipping and the host re-runs those tracks through the
-//   EXACT kernel.
+//   window whose bin decision is within `edge_tol` of flipping and the host re-decodes and re-runs those tracks
+//   through the EXACT kernel at the end of the call.
 #pragma once
 #include "rg_internal.h"
 

@@ -1,4 +1,5 @@
-// k_hybrid_synth.cuh -- K2: requantise -> MS stereo -> reorder -> alias reduction -> IMDCT/overlap -> polyphase -> PCM.
+// k_hybrid_synth.cuh -- K2: requantise -> MS / intensity stereo -> reorder -> alias reduction -> IMDCT/overlap -> polyphase -> PCM
+// (MPEG-1, 2 and 2.5 Layer III; or, in peak mode, max |sample| per track instead of PCM).
 //
 // One CTA (8 warps) owns a run of consecutive granules of one track and walks it in time order in BATCHES of 8
 // granule-channels (4 stereo granules or 8 mono granules): one granule-channel per warp.  Every stage uses the mapping in
@@ -7,11 +8,11 @@
 //   TMA  the batch's int16 spectra (8 x 1152 B, contiguous in HBM) arrive in shared memory as ONE bulk copy
 //        (cp.async.bulk + mbarrier), issued a batch ahead by one thread,
 //        together with the gain of every scalefactor band that K1 derived from part 2 (8 x 256 B)
-//   P1   requantise + MS + short-block reorder -> xr (slot A)            the warps of one granule, lane = line pair;
+//   P1   requantise + MS / intensity + short-block reorder -> xr (slot A) the warps of one granule, lane = line pair;
 //                                                                        handed to P2 by a 64-thread named barrier
 //   P2   alias butterflies + IMDCT + window + frequency inversion        warp = granule-channel, lane = SUBBAND: the 18
-//        -> F (outputs 0..17, slot A in place), S2 (outputs 18..35)      lines live in registers, the matrices are
-//                                                                        constant-bank operands of the FFMAs
+//        -> F (outputs 0..17, slot A in place), S2 (outputs 18..35)      lines live in registers, the DCT-IV runs as a
+//                                                                        9-point FFT whose twiddles are FFMA immediates
 //   P3   x = F + S2(previous granule); 32-point DCT-II (Lee) in place    thread = (granule-channel, time slot)
 //   P4   16-tap polyphase window over the DCT rows -> PCM                warp = granule-channel, lane = output column
 //

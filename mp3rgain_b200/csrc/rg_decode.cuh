@@ -1,15 +1,16 @@
-// rg_decode.cuh -- stage A on the device: MPEG-1 Layer III file images -> planar f32 PCM in HBM.
+// rg_decode.cuh -- stage A on the device: MPEG-1 / 2 / 2.5 Layer III file images -> planar f32 PCM in HBM.
 //
 // The reference delegates this stage to symphonia-bundle-mp3 (src/replaygain.rs:807-822, 861-863, 882, 896); the kernels
-// below restate ISO/IEC 11172-3 with the arithmetic contract of DESIGN.md ("f32 decode contract"): every table is the
-// frozen float32 data of l3_tables.h, products and sums round separately except where fmaf is written, and every dot
-// product is a sequential fmaf chain in ascending index order from +0.0f.  Compiled with -fmad=false.
+// below restate ISO/IEC 11172-3 and 13818-3 with the arithmetic contract of DESIGN.md ("f32 decode contract"): every table
+// is the frozen float32 data of l3_tables.h, products and sums round separately except where fmaf is written.  Compiled
+// with -fmad=false.
 //
-//   K0  k_frame_index   one warp per track: ID3v2 skip, sync / resync, Xing-Info skip, side-info validity, bit-reservoir
-//                       bookkeeping; compacts every frame's main data into a contiguous per-track stream
-//   K1  k_huffman       one thread per granule-channel: part-3 Huffman decode -> int16 spectra (coalesced via smem staging)
-//   K2  k_hybrid_synth  one CTA per run of granules of one track: scalefactors, requantise, MS stereo, reorder, alias
-//                       reduction, IMDCT + overlap, frequency inversion, 32-point DCT + polyphase window -> PCM
+//   K0  k_index_scan / k_index_merge / k_index_finalize   frame index: ID3v2 skip, sync / resync, Xing-Info skip, side-info
+//                       validity, bit-reservoir bookkeeping -- 64 KiB segments walked speculatively in parallel, stitched per track
+//       k_md_gather     every frame's main data into a contiguous per-track stream (the bit reservoir unrolled)
+//   K1  k_huffman       one thread per granule-channel: scalefactors -> band gains, Huffman decode -> int16 spectra
+//   K2  k_hybrid_synth  one CTA per run of granules of one track: requantise, MS / intensity stereo, reorder, alias
+//                       reduction, IMDCT + overlap, frequency inversion, 32-point DCT + polyphase window -> PCM (or peak)
 #pragma once
 #include <cstdint>
 #include <cstring>
