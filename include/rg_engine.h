@@ -41,7 +41,8 @@ typedef enum {
     RG_ERR_UNKNOWN_SAMPLE_RATE = -8,/* "Unknown sample rate" */
     RG_ERR_UNSUPPORTED_RATE = -9,   /* "Unsupported sample rate: {sr} Hz. Supported rates: ..." */
     RG_ERR_UNSUPPORTED_FORMAT = -10,/* MP4/AAC container (the engine decodes MPEG-1 / 2 / 2.5 Layer III) */
-    RG_ERR_NO_MEMORY = -11
+    RG_ERR_NO_MEMORY = -11,
+    RG_ERR_NO_FRAMES = -12          /* "No valid MP3 frames found" (mp3rgain::analyze, src/lib.rs:498-500) */
 } rg_status;
 
 /* rg_config.flags */
@@ -153,6 +154,42 @@ int rg_analyze_album_shard(rg_engine* e, rg_corpus* c, rg_track_result* out,
 /* get_loudness on the merged histogram + PINK_REF (src/replaygain.rs:1065-1066), computed on the device. */
 int rg_album_finish(rg_engine* e, const uint64_t* d_album_hist, const double* d_album_peak, rg_album_result* album);
 
+/* ---- the global_gain fields: mp3rgain::analyze() and apply_gain*() -------------------------- */
+/* Mp3Analysis (src/lib.rs:57-75).  The reference's strings are enums here: mpeg_version 0 "MPEG1", 1 "MPEG2",
+ * 2 "MPEG2.5" (MpegVersion::as_str, :85-93); channel_mode 0 "Stereo", 1 "Joint Stereo", 2 "Dual Channel", 3 "Mono"
+ * (ChannelMode::as_str, :111-118). */
+typedef struct {
+    uint64_t frame_count;       /* frames the walk counted (Xing/Info frames excluded, :446-451) */
+    uint64_t gain_sum;          /* sum / number of the global_gain values read: avg_gain = gain_sum / gain_count */
+    uint64_t gain_count;
+    double   avg_gain;
+    double   headroom_db;       /* headroom_steps * 1.5 */
+    int32_t  headroom_steps;    /* 255 - max_gain */
+    int32_t  mpeg_version;
+    int32_t  channel_mode;
+    int32_t  status;            /* RG_OK, or RG_ERR_NO_FRAMES */
+    uint8_t  min_gain, max_gain;
+    uint8_t  reserved[2];
+    uint32_t walk_rewalks;      /* 64 KiB segments the merge had to walk again (diagnostic) */
+} rg_gain_stats;
+
+/* mp3rgain::analyze (src/lib.rs:470-514), batched over n file images: the reference's own frame walk (iterate_frames,
+ * :413-466) run as a speculative segmented walk on the device.  Per-entry status in out[i].status. */
+int rg_gain_analyze(rg_engine* e, const rg_input* in, size_t n, rg_gain_stats* out);
+/* The same over a device-resident corpus. */
+int rg_gain_analyze_corpus(rg_engine* e, rg_corpus* c, rg_gain_stats* out);
+
+/* rg_gain_apply.mode */
+#define RG_GAIN_SATURATE 0           /* GainMode::Saturating: apply_gain (src/lib.rs:602-617) */
+#define RG_GAIN_WRAP     1           /* GainMode::Wrapping:   apply_gain_wrap (:1232-1246) */
+/* apply_gain_to_data (src/lib.rs:544-596) / apply_gain_to_channel_data (:668-735), batched: patches the global_gain of
+ * every granule-channel (channel < 0) or of one channel (0 = left, 1 = right; always saturating) by gain_steps and
+ * writes the patched image of file i to out_images[i] (in[i].len bytes; may alias in[i].data).  frames_modified[i] =
+ * the reference's return value.  gain_steps == 0 mirrors the early return of :603-605: images are copied through
+ * unchanged and frames_modified[i] = 0.  The file read / write around it stays in the host wrapper, as in the reference. */
+int rg_gain_apply(rg_engine* e, const rg_input* in, size_t n, int32_t gain_steps, int32_t mode, int32_t channel,
+                  uint8_t* const* out_images, uint32_t* frames_modified);
+
 /* ---- introspection for measurement and parity tests ------------------------------------------- */
 typedef struct {
     uint64_t kernel_launches;   /* kernels launched by this engine since creation */
@@ -163,6 +200,8 @@ typedef struct {
     uint32_t last_batches;      /* decode/analysis batches (= launches of each of K1, K2, K4, K5) in the last analyse call */
     uint32_t last_block_windows;/* windows per time block the time-blocked IIR used in the last batch (0 = exact mode) */
     uint64_t last_iir_samples;  /* channel-samples the time-blocked IIR ran in the last analyse call, warm-up included */
+    float    last_ms_gain_scan, last_ms_gain_merge, last_ms_gain_patch;   /* CUDA-event times of the last rg_gain_* call */
+    uint32_t last_gain_groups;  /* copy / walk groups (= launches of each gain-field kernel) in the last rg_gain_* call */
 } rg_stats;
 int rg_engine_stats(rg_engine* e, rg_stats* out);
 

@@ -30,6 +30,10 @@ RG_ERR_UNKNOWN_SAMPLE_RATE = -8
 RG_ERR_UNSUPPORTED_RATE = -9
 RG_ERR_UNSUPPORTED_FORMAT = -10
 RG_ERR_NO_MEMORY = -11
+RG_ERR_NO_FRAMES = -12
+
+RG_GAIN_SATURATE = 0
+RG_GAIN_WRAP = 1
 
 
 class RgConfig(C.Structure):
@@ -65,6 +69,17 @@ class RgStats(C.Structure):
         ("last_ms_index", C.c_float), ("last_ms_huffman", C.c_float), ("last_ms_hybrid", C.c_float),
         ("last_ms_synth", C.c_float), ("last_ms_iir", C.c_float), ("last_ms_hist", C.c_float),
         ("last_ms_total", C.c_float), ("last_batches", C.c_uint32), ("last_block_windows", C.c_uint32), ("last_iir_samples", C.c_uint64),
+        ("last_ms_gain_scan", C.c_float), ("last_ms_gain_merge", C.c_float), ("last_ms_gain_patch", C.c_float),
+        ("last_gain_groups", C.c_uint32),
+    ]
+
+
+class RgGainStats(C.Structure):
+    _fields_ = [
+        ("frame_count", C.c_uint64), ("gain_sum", C.c_uint64), ("gain_count", C.c_uint64),
+        ("avg_gain", C.c_double), ("headroom_db", C.c_double), ("headroom_steps", C.c_int32),
+        ("mpeg_version", C.c_int32), ("channel_mode", C.c_int32), ("status", C.c_int32),
+        ("min_gain", C.c_uint8), ("max_gain", C.c_uint8), ("reserved", C.c_uint8 * 2), ("walk_rewalks", C.c_uint32),
     ]
 
 
@@ -87,6 +102,9 @@ SYMBOLS = {
     "rg_analyze_corpus": (C.c_int, [_P, _P, C.POINTER(RgTrackResult), _P]),
     "rg_analyze_album_shard": (C.c_int, [_P, _P, C.POINTER(RgTrackResult), _P, _P]),
     "rg_album_finish": (C.c_int, [_P, _P, _P, C.POINTER(RgAlbumResult)]),
+    "rg_gain_analyze": (C.c_int, [_P, C.POINTER(RgInput), C.c_size_t, C.POINTER(RgGainStats)]),
+    "rg_gain_analyze_corpus": (C.c_int, [_P, _P, C.POINTER(RgGainStats)]),
+    "rg_gain_apply": (C.c_int, [_P, C.POINTER(RgInput), C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _P]),
     "rg_engine_stats": (C.c_int, [_P, C.POINTER(RgStats)]),
     "rg_decode_pcm": (C.c_int, [_P, C.POINTER(RgInput), _P, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }

@@ -5,6 +5,7 @@
 #include "rg_coeffs.h"
 #include "k_analysis.cuh"
 #include "rg_decode.cuh"
+#include "k_gain_fields.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -112,13 +113,15 @@ struct rg_engine {
     DevBuf d_pcm_in, d_album, d_album_peak, d_misc;
     DevBuf d_tin, d_fbase, d_frames, d_md, d_meta;
     DevBuf d_tseg, d_segs, d_segout, d_segfin, d_stage;   // speculative segmented frame index (k_frame_index.cuh)
+    DevBuf d_gfseg, d_gfent, d_gfout;     // global_gain walk (k_gain_fields.cuh): per-segment results, entry positions, per-track results
+    HostBuf h_gfout;
     DevBuf d_corpus;                      // file images of rg_analyze_tracks / rg_analyze_album (kept between calls)
     HostBuf h_meta;
     rg_stats stats = {};
     DecodeScratch dec;
     std::vector<DevBuf*> all_bufs() {
         std::vector<DevBuf*> v = {&d_pcm_in, &d_album, &d_album_peak, &d_misc, &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_corpus,
-                                  &d_tseg, &d_segs, &d_segout, &d_segfin, &d_stage};
+                                  &d_tseg, &d_segs, &d_segout, &d_segfin, &d_stage, &d_gfseg, &d_gfent, &d_gfout};
         for (auto& c : ctx) for (DevBuf* b : c.bufs()) v.push_back(b);
         return v;
     }
@@ -170,6 +173,7 @@ extern "C" const char* rg_status_str(int status) {
                    "22050, 16000, 12000, 11025, 8000";
         case RG_ERR_UNSUPPORTED_FORMAT: return "Unsupported format (MP4/AAC container: this engine decodes MPEG-1/2/2.5 Layer III)";
         case RG_ERR_NO_MEMORY: return "out of memory";
+        case RG_ERR_NO_FRAMES: return "No valid MP3 frames found";
         default: return "unknown status";
     }
 }
@@ -243,6 +247,7 @@ extern "C" void rg_engine_destroy(rg_engine* e) {
     cudaDeviceSynchronize();
     for (DevBuf* b : e->all_bufs()) b->release();
     e->h_meta.release();
+    e->h_gfout.release();
     e->dec.release();
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : e->ev_pool) if (ev) cudaEventDestroy(ev);
@@ -559,3 +564,4 @@ extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int 
 }
 
 #include "rg_engine_decode.inl"
+#include "rg_engine_gain.inl"

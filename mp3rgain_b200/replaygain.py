@@ -216,6 +216,30 @@ class Engine:
             raise ReplayGainError(rc, _message(rc, sample_rate=sample_rate))
         return self._result(out, hist)
 
+    # ---- the global_gain fields (mp3rgain::analyze / apply_gain*, src/lib.rs) -------------------------
+    def gain_analyze_images(self, images: Sequence):
+        """rg_gain_analyze over in-memory file images.  Returns the list of RgGainStats (per-entry status inside)."""
+        n = len(images)
+        arr, keep = self._inputs(images, None)
+        out = (_lib.RgGainStats * max(n, 1))()
+        rc = self._lib.rg_gain_analyze(self._h, arr, n, out)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+        return [out[i] for i in range(n)]
+
+    def gain_apply_images(self, images: Sequence, gain_steps: int, wrap: bool = False, channel: int = -1):
+        """rg_gain_apply: returns (patched images as new uint8 arrays, modified frames per image)."""
+        n = len(images)
+        arr, keep = self._inputs(images, None)
+        outs = [np.empty(a.size, np.uint8) for a in keep]
+        ptrs = (C.c_void_p * max(n, 1))(*[o.ctypes.data if o.size else None for o in outs])
+        mod = np.zeros(max(n, 1), np.uint32)
+        rc = self._lib.rg_gain_apply(self._h, arr, n, int(gain_steps), _lib.RG_GAIN_WRAP if wrap else _lib.RG_GAIN_SATURATE,
+                                     int(channel), ptrs, mod.ctypes.data)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+        return outs, [int(x) for x in mod[:n]]
+
     def decode_pcm(self, image) -> tuple:
         """Stage-A parity hook: (planes[nch, frames] float32, sample_rate)."""
         arr, keep = self._inputs([image], None)

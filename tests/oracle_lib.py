@@ -23,9 +23,20 @@ class Mp3Info(C.Structure):
                 ("n_dropped_frames", C.c_uint32)]
 
 
+class GainStats(C.Structure):
+    """gfo_stats (oracle/gain_fields_oracle.h): Mp3Analysis of src/lib.rs:57-75"""
+    _fields_ = [("frame_count", C.c_uint64), ("gain_sum", C.c_uint64), ("gain_count", C.c_uint64),
+                ("avg_gain", C.c_double), ("headroom_db", C.c_double), ("headroom_steps", C.c_int32),
+                ("mpeg_version", C.c_int32), ("channel_mode", C.c_int32), ("min_gain", C.c_uint8), ("max_gain", C.c_uint8)]
+
+
 class Oracle:
     def __init__(self, lib):
         self.lib = lib
+        lib.gfo_analyze.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(GainStats)]
+        lib.gfo_analyze.restype = C.c_int
+        lib.gfo_apply_gain.argtypes = [C.c_void_p, C.c_size_t, C.c_int32, C.c_int, C.c_int]
+        lib.gfo_apply_gain.restype = C.c_size_t
         lib.rgo_analyze_pcm_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_uint, C.POINTER(Res), C.c_void_p]
         lib.rgo_analyze_pcm_f32.restype = C.c_int
         lib.rgo_state_init.argtypes = [C.c_void_p, C.c_uint, C.c_int]
@@ -100,6 +111,20 @@ class Oracle:
         info = Mp3Info()
         rc = self.lib.mp3o_analyze(a.ctypes.data, a.size, flags, C.byref(res), hist.ctypes.data, C.byref(info))
         return rc, res, hist, info
+
+
+    # ---- the first-party frame walk over the global_gain fields (src/lib.rs) ----
+    def gain_analyze(self, image):
+        a = np.ascontiguousarray(np.frombuffer(image, np.uint8) if not isinstance(image, np.ndarray) else image, np.uint8)
+        st = GainStats()
+        rc = self.lib.gfo_analyze(a.ctypes.data, a.size, C.byref(st))
+        return rc, st
+
+    def gain_apply(self, image, steps, wrap=False, channel=-1):
+        """Returns (patched copy of the image, modified frames)."""
+        a = np.array(np.frombuffer(image, np.uint8) if not isinstance(image, np.ndarray) else image, np.uint8, copy=True)
+        n = self.lib.gfo_apply_gain(a.ctypes.data, a.size, steps, 1 if wrap else 0, channel)
+        return a, int(n)
 
 
 _cached = None
