@@ -7,34 +7,35 @@
 // (calculate_gain_locations :262-296, read_gain_at / write_gain_at :299-340).  The walker keeps NO state besides its
 // position, so any two walks that ever stand on the same byte agree from there on.  That makes it exactly parallel:
 //
-//   k_gf_scan    one warp per 64 KiB segment walks speculatively from the segment's first byte; records the first position
-//                it JUMPED from (everything before it was a byte-by-byte scan), where it left the segment, and the gain
-//                statistics of the frames it counted
-//   k_gf_merge   one warp per track stitches the segments: the true walk enters a segment at P (where its predecessor
-//                left); if P <= the segment's first jump, P is on the speculative trajectory and the segment's result
-//                stands; otherwise (a false sync inside the straddling frame) the warp walks the segment again from P.
-//                Emits Mp3Analysis per track and every segment's entry position
-//   k_gf_patch   one warp per segment walks from its entry position (no speculation left) and patches the gain fields
-//                in place (saturating / wrapping / one channel only)
+//   k_gf_scan    one THREAD per 4 KiB sub-segment walks speculatively from the sub-segment's first byte; records the first
+//                position it JUMPED from (everything before it was a byte-by-byte scan), where it left the sub-segment,
+//                and the gain statistics of the frames it counted
+//   k_gf_merge   one warp per track stitches the sub-segments, 32 at a time (lane = sub-segment, a serial resolve over the
+//                lanes by shuffles): the true walk enters a sub-segment at P (where its predecessor left); if P <= the
+//                sub-segment's first jump, P is on the speculative trajectory and the result stands; otherwise (a false
+//                sync inside the straddling frame) that lane walks the sub-segment again from P.  Emits Mp3Analysis per
+//                track and every sub-segment's entry position
+//   k_gf_patch   one thread per sub-segment walks from its entry position (no speculation left) and patches the gain
+//                fields in place (saturating / wrapping / one channel only)
 //
 // A write never changes what the walk reads later: gain bytes lie inside the side info of their own frame (last gain
 // byte <= offset 34 of an MPEG-1 frame, <= 18 of an LSF frame; the smallest frames are 96 and 24 bytes) and frames of one
 // trajectory are disjoint, so walking first and patching in parallel equals the reference's serial read-modify-write.
 //
-// The scan streams the segment through a 4 KiB shared-memory window with coalesced 16-byte loads: the kernel reads every
-// file byte exactly once, its algorithmic traffic, and is bound by HBM bandwidth / load latency.  The byte-by-byte resync
-// is lane-parallel (lane = candidate position, first valid header by ballot).
+// The walker touches ~48 bytes per frame (header, CRC, side info, Xing marker, the next sync word), not the payload.  A
+// first version streamed every file byte through shared memory, one warp per 64 KiB segment, and was bound by instruction
+// issue (~185 warp-instructions per frame, 2.1 TB/s of file bytes).  With one thread per sub-segment the same ~100
+// instructions per frame serve 32 sub-segments at once, the loads go straight to the 32-byte sectors that hold the headers
+// (about a quarter of the file's sectors), and the kernel is bound by scattered-sector HBM bandwidth instead.
 #pragma once
 
-#define GF_SEG (64u * 1024u)
-#define GF_CHUNK 4096
-#define GF_WARPS 4
+#define GF_SUB 4096u            // bytes per speculative sub-segment (one thread each)
+#define GF_THREADS 256
 #define GF_NONE 0xFFFFFFFFu
-#define GF_SPAN 1480            // pos .. pos+31 (candidates) + largest frame (1441) + next sync (2), rounded up
 
 struct GfSeg {
     uint32_t first_jump;   // first position the walk jumped from by a frame length (GF_NONE: it only scanned)
-    uint32_t end_pos;      // first trajectory position at or beyond the segment's end (or where the audio ended)
+    uint32_t end_pos;      // first trajectory position at or beyond the sub-segment's end (or where the audio ended)
     uint32_t n_frames;     // counted frames (Xing/Info frames are jumped over, not counted)
     uint32_t gsum, gcount; // sum / number of the global_gain values read
     uint32_t gminmax;      // min | max << 8
@@ -47,18 +48,18 @@ struct GfTrackOut {
 };
 
 // skip_id3v2 (src/lib.rs:343-354) and find_audio_end (:358-383; APE_FLAG_HEADER_PRESENT = 1 << 31, :844)
-__device__ __forceinline__ void gf_bounds(const uint8_t* __restrict__ d, uint64_t len, uint64_t& a0, uint64_t& audio_end) {
+__device__ __forceinline__ void gf_bounds(const uint8_t* __restrict__ d, uint32_t len, uint32_t& a0, uint32_t& audio_end) {
     a0 = 0;
     if (len >= 10 && d[0] == 'I' && d[1] == 'D' && d[2] == '3')
-        a0 = 10 + (((uint64_t)(d[6] & 0x7F) << 21) | ((uint64_t)(d[7] & 0x7F) << 14) | ((uint64_t)(d[8] & 0x7F) << 7) | (uint64_t)(d[9] & 0x7F));
-    uint64_t end = len;
+        a0 = 10 + (((uint32_t)(d[6] & 0x7F) << 21) | ((uint32_t)(d[7] & 0x7F) << 14) | ((uint32_t)(d[8] & 0x7F) << 7) | (uint32_t)(d[9] & 0x7F));
+    uint32_t end = len;
     if (end >= 128 && d[end - 128] == 'T' && d[end - 127] == 'A' && d[end - 126] == 'G') end -= 128;
     if (end >= 32) {
         const uint8_t* f = d + end - 32;
         if (f[0] == 'A' && f[1] == 'P' && f[2] == 'E' && f[3] == 'T' && f[4] == 'A' && f[5] == 'G' && f[6] == 'E' && f[7] == 'X') {
             const uint64_t tag_size = (uint64_t)f[12] | ((uint64_t)f[13] << 8) | ((uint64_t)f[14] << 16) | ((uint64_t)f[15] << 24);
             const uint64_t header = (f[23] & 0x80) ? 32 : 0;
-            if (end >= tag_size + header) end = end - tag_size - header;
+            if ((uint64_t)end >= tag_size + header) end = (uint32_t)(end - tag_size - header);
         }
     }
     audio_end = end;
@@ -75,173 +76,250 @@ __device__ __forceinline__ uint32_t gf_adjust(uint32_t cur, int steps, int wrap)
     return (uint32_t)((ng + 256) % 256);
 }
 
-// The walk over [pos, bound) of one file image; every lane of the warp executes it with uniform control flow.
+// Frame length without padding by (version, bitrate index, sample-rate index); 0 = not a valid Layer III header
+// (parse_header, src/lib.rs:169-252).  Index: version << 6 | bitrate index << 2 | sample-rate index.
+__device__ __forceinline__ uint32_t gf_lut_index(uint32_t h) { return ((h >> 13) & 0xC0u) | ((h >> 10) & 0x3Fu); }
+__device__ __forceinline__ void gf_fill_lut(uint16_t* lut) {
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t ver = i >> 6, br = (i >> 2) & 15, sr = i & 3;
+        const uint32_t h = 0xFFE20000u | (ver << 19) | (br << 12) | (sr << 10);
+        lut[i] = k0_hdr_valid(h) ? (uint16_t)k0_frame_len(h) : (uint16_t)0;
+    }
+    __syncthreads();
+}
+
+// Image loads.  Images start 16-byte aligned and are followed by >= 16 bytes of slack inside the corpus buffer
+// (corpus_describe), so an aligned word pair that starts below `len` stays inside the allocation; bytes beyond `len` are
+// never consumed by the walk (every read is guarded by len / audio_end).  The patching walk reads with plain loads (it
+// writes the same buffer), the read-only walks through the non-coherent path.
+template <bool PATCH> __device__ __forceinline__ uint32_t gf_ldw(const uint8_t* img, uint32_t a) {   // a % 4 == 0
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(img + a);
+    return PATCH ? *p : __ldg(p);
+}
+// 4 bytes at any offset g, little-endian (first byte in bits 0-7)
+template <bool PATCH> __device__ __forceinline__ uint32_t gf_ld32(const uint8_t* img, uint32_t g) {
+    const uint32_t a = g & ~3u;
+    return __funnelshift_r(gf_ldw<PATCH>(img, a), gf_ldw<PATCH>(img, a + 4), 8 * (g & 3));
+}
+
+// The walk over [pos, bound) of one file image by ONE thread -- but written for the warp: all 32 lanes call it together
+// (`run` = this lane has a sub-segment to walk) and move through two warp-synchronous phases, so that lanes at different
+// points of their walks still execute the same instructions:
+//   SCAN   every scanning lane advances one aligned word per step: bytes that are 0xFF and followed by a byte with its top
+//          three bits set are the only positions parse_header (src/lib.rs:176-178) can accept; such a candidate gets the
+//          full header + next-sync check and either becomes the lane's current frame or the scan resumes one byte later
+//   FRAME  every lane that stands on a validated frame processes it (Xing/Info test, gain fields), jumps, and validates
+//          the header it lands on; a lane that lands on something else goes back to SCAN (one byte later, as the
+//          reference does) once the others have finished their frames
+// A first thread-per-sub-segment version without this structure ran with 5 of 32 lanes active per instruction.
 // PATCH: rewrite the gain fields in place (img must be writable).  channel < 0: every granule-channel (wrap selects
 // GainMode::Wrapping); channel 0 / 1: that channel's fields only, saturating (apply_gain_to_channel_data).
+#define GF_ST_SCAN 0u
+#define GF_ST_FRAME 1u
+#define GF_ST_DONE 2u
 template <bool PATCH>
-__device__ GfSeg gf_walk(uint8_t* img, uint64_t len, uint64_t audio_end, uint8_t* ck, uint64_t pos, uint64_t bound, int lane,
-                         int steps, int wrap, int channel) {
+__device__ GfSeg gf_walk(uint8_t* img, uint32_t len, uint32_t audio_end, const uint16_t* lut, uint32_t pos, uint32_t bound,
+                         int steps, int wrap, int channel, bool run) {
     GfSeg o;
     o.first_jump = GF_NONE; o.n_frames = 0; o.gcount = 0; o.first_hdr = 0; o.pad = 0;
-    uint32_t lsum = 0, lmin = 255, lmax = 0;   // this lane's granule-channel (lanes 0..3)
-    uint64_t cs = ~0ull, ce = 0;               // bytes [cs, ce) of the image are in the window
-    while (pos + 4 <= audio_end && pos < bound) {
-        const uint64_t avail = ce < len ? ce : len;
-        if (pos < cs || pos >= ce || (pos + GF_SPAN > avail && avail < len)) {
-            cs = pos & ~15ull;
-            ce = cs + GF_CHUNK;
-            __syncwarp();
-            for (int i = lane * 16; i < GF_CHUNK; i += 32 * 16) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                const uint64_t g = cs + i;
-                if (g + 16 <= len) v = *reinterpret_cast<const uint4*>(img + g);
-                else if (g < len) {
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    for (int b = 0; b < 16; b++) if (g + b < len) w[b >> 2] |= (uint32_t)img[g + b] << (8 * (b & 3));
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                *reinterpret_cast<uint4*>(ck + i) = v;
-            }
-            __syncwarp();
-        }
-        // lane-parallel resync: the first of the next 32 positions whose 4 bytes parse as a header
-        uint32_t h = 0;
-        if (pos + lane + 4 <= audio_end) {
-            const uint8_t* p = ck + (pos + lane - cs);
-            h = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
-        }
-        const uint32_t cand = __ballot_sync(0xffffffffu, k0_hdr_valid(h));
-        if (!cand) { pos += 32; continue; }
-        const int l = __ffs(cand) - 1;
-        pos += l;
-        if (pos >= bound) break;                      // a scan step of the next segment
-        h = __shfl_sync(0xffffffffu, h, l);
-        const uint64_t next = pos + (uint64_t)k0_frame_len(h);
-        bool valid;
-        if (next + 2 <= audio_end) { const uint8_t* q = ck + (next - cs); valid = q[0] == 0xFF && (q[1] & 0xE0) == 0xE0; }
-        else valid = next <= audio_end;
-        if (!valid) { pos++; continue; }
-        if (o.first_jump == GF_NONE) o.first_jump = (uint32_t)pos;
-        const bool mono = ((h >> 6) & 3) == 3, lsf = ((h >> 19) & 3) != 3;
-        const int so = 4 + ((h & 0x10000u) ? 0 : 2);
-        const uint64_t x = pos + so + k0_side_len(h);
-        if (x + 4 <= len) {
-            const uint8_t* p = ck + (x - cs);
-            if ((p[0] == 'X' && p[1] == 'i' && p[2] == 'n' && p[3] == 'g') || (p[0] == 'I' && p[1] == 'n' && p[2] == 'f' && p[3] == 'o')) { pos = next; continue; }
-        }
-        const int nch = mono ? 1 : 2, n = nch * (lsf ? 1 : 2);
-        if (lane < n) {
-            const int bit = (lsf ? (mono ? 9 : 10) : (mono ? 18 : 20)) + lane * (lsf ? 63 : 59) + 21;
-            const uint64_t idx = pos + so + (bit >> 3);
-            const int sh = bit & 7;
-            uint32_t g = 0, b0 = 0, b1 = 0;
-            if (idx < len) {
-                const uint8_t* p = ck + (idx - cs);
-                b0 = p[0];
-                if (sh == 0) g = b0;
-                else if (idx + 1 < len) { b1 = p[1]; g = ((b0 << sh) | (b1 >> (8 - sh))) & 0xFF; }
-                else g = (b0 << sh) & 0xFF;
-            }
-            lsum += g; lmin = min(lmin, g); lmax = max(lmax, g);
-            if (PATCH && idx < len && (channel < 0 || (lane >= channel && (lane - channel) % nch == 0))) {
-                const uint32_t v = gf_adjust(g, steps, channel < 0 ? wrap : 0);
-                if (sh == 0) img[idx] = (uint8_t)v;
+    uint32_t gsum = 0, gmin = 255, gmax = 0;
+    uint32_t h = 0, next = 0;                        // FRAME state: header at pos, start of the following frame
+    auto in_range = [&](uint32_t p) { return (uint64_t)p + 4 <= audio_end && p < bound; };
+    // header + validity check of the reference's loop body (src/lib.rs:424-443) at p; fills h / next
+    auto check = [&](uint32_t p) -> bool {
+        h = __byte_perm(gf_ld32<PATCH>(img, p), 0, 0x0123);
+        const uint32_t f = lut[gf_lut_index(h)];
+        if ((h & 0xFFE60000u) != 0xFFE20000u || f == 0) return false;
+        next = p + f + ((h >> 9) & 1);
+        if (next + 2 <= audio_end) return (gf_ld32<PATCH>(img, next) & 0xE0FFu) == 0xE0FFu;
+        return next <= audio_end;
+    };
+    uint32_t st = (run && in_range(pos)) ? GF_ST_SCAN : GF_ST_DONE;
+    while (__any_sync(0xffffffffu, st != GF_ST_DONE)) {
+        while (__any_sync(0xffffffffu, st == GF_ST_SCAN)) {
+            if (st == GF_ST_SCAN) {
+                const uint32_t a = pos & ~3u;
+                const uint32_t w = gf_ldw<PATCH>(img, a), wn = gf_ldw<PATCH>(img, a + 4);
+                const uint32_t ff = ((w & 0x7F7F7F7Fu) + 0x01010101u) & w;             // bit 7 of byte i: byte i == 0xFF
+                const uint32_t u = __funnelshift_r(w, wn, 8);                            // byte i = byte i+1 of the stream
+                const uint32_t c = ff & u & (u << 1) & (u << 2) & 0x80808080u & ~((0x80u << (8 * (pos & 3))) - 1u);   // at or after pos
+                if (!c) pos = a + 4;
                 else {
-                    img[idx] = (uint8_t)((b0 & (0xFFu << (8 - sh))) | (v >> sh));
-                    if (idx + 1 < len) img[idx + 1] = (uint8_t)((b1 & (0xFFu >> sh)) | ((v << (8 - sh)) & 0xFF));
+                    pos = a + ((__ffs(c) - 1) >> 3);
+                    if (in_range(pos)) {
+                        if (check(pos)) st = GF_ST_FRAME;
+                        else pos++;
+                    }
                 }
+                if (st == GF_ST_SCAN && !in_range(pos)) st = GF_ST_DONE;   // a scan step of the next sub-segment / the end of the audio
             }
         }
-        if (o.n_frames == 0) o.first_hdr = h;
-        o.n_frames++;
-        o.gcount += n;
-        pos = next;
+        while (__any_sync(0xffffffffu, st == GF_ST_FRAME)) {
+            if (st == GF_ST_FRAME) {
+                if (o.first_jump == GF_NONE) o.first_jump = pos;
+                const bool mono = ((h >> 6) & 3) == 3, lsf = ((h >> 19) & 3) != 3;
+                const uint32_t so = (h & 0x10000u) ? 4 : 6;
+                const uint32_t x = pos + so + (lsf ? (mono ? 9 : 17) : (mono ? 17 : 32));
+                uint32_t m = 0;
+                if (x + 4 <= len) m = gf_ld32<PATCH>(img, x);
+                if (!(x + 4 <= len && (m == 0x676E6958u /* "Xing" */ || m == 0x6F666E49u /* "Info" */))) {
+                    const int nch = mono ? 1 : 2, n = lsf ? nch : 2 * nch;
+                    const uint32_t bit0 = (lsf ? (mono ? 9u : 10u) : (mono ? 18u : 20u)) + 21u, per = lsf ? 63u : 59u;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (k < n) {
+                            const uint32_t bit = bit0 + k * per;
+                            const uint32_t idx = pos + so + (bit >> 3), sh = bit & 7;
+                            uint32_t g = 0, b0 = 0, b1 = 0;
+                            if (idx < len) {
+                                const uint32_t v = gf_ld32<PATCH>(img, idx);
+                                b0 = v & 0xFF;
+                                if (sh == 0) g = b0;
+                                else if (idx + 1 < len) { b1 = (v >> 8) & 0xFF; g = ((b0 << sh) | (b1 >> (8 - sh))) & 0xFF; }
+                                else g = (b0 << sh) & 0xFF;
+                            }
+                            gsum += g; gmin = min(gmin, g); gmax = max(gmax, g);
+                            if (PATCH && idx < len && (channel < 0 || (k >= channel && (k - channel) % nch == 0))) {
+                                const uint32_t v = gf_adjust(g, steps, channel < 0 ? wrap : 0);
+                                if (sh == 0) img[idx] = (uint8_t)v;
+                                else {
+                                    img[idx] = (uint8_t)((b0 & (0xFFu << (8 - sh))) | (v >> sh));
+                                    if (idx + 1 < len) img[idx + 1] = (uint8_t)((b1 & (0xFFu >> sh)) | ((v << (8 - sh)) & 0xFF));
+                                }
+                            }
+                        }
+                    }
+                    if (o.n_frames == 0) o.first_hdr = h;
+                    o.n_frames++;
+                    o.gcount += n;
+                }
+                pos = next;
+                if (!in_range(pos)) st = GF_ST_DONE;
+                else if (!check(pos)) { pos++; st = in_range(pos) ? GF_ST_SCAN : GF_ST_DONE; }
+            }
+        }
     }
-    o.end_pos = (uint32_t)(pos < 0xFFFFFFFFull ? pos : 0xFFFFFFFFull);
-    o.gsum = __reduce_add_sync(0xffffffffu, lsum);
-    o.gminmax = __reduce_min_sync(0xffffffffu, lmin) | (__reduce_max_sync(0xffffffffu, lmax) << 8);
+    o.end_pos = pos;
+    o.gsum = gsum;
+    o.gminmax = gmin | (gmax << 8);
     return o;
 }
 
-// byte range [b, e) of segment `seg` (the last one is open-ended: the walk stops at the end of the audio)
-__device__ __forceinline__ void gf_seg_range(uint32_t seg, uint32_t n_seg, uint64_t& b, uint64_t& e) {
-    b = (uint64_t)seg * GF_SEG;
-    e = (seg + 1 == n_seg) ? ~0ull : (uint64_t)(seg + 1) * GF_SEG;
+// byte range [b, e) of sub-segment `seg` (the last one is open-ended: the walk stops at the end of the audio)
+__device__ __forceinline__ void gf_seg_range(uint32_t seg, uint32_t n_seg, uint32_t& b, uint32_t& e) {
+    b = seg * GF_SUB;
+    e = (seg + 1 == n_seg) ? 0xFFFFFFFFu : (seg + 1) * GF_SUB;
+}
+// the track of [t0, t0 + nt) that owns sub-segment s (TrackSeg.seg_base ascending)
+__device__ __forceinline__ uint32_t gf_find_track(const TrackSeg* __restrict__ tseg, uint32_t nt, uint32_t s) {
+    uint32_t lo = 0, hi = nt;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tseg[mid].seg_base <= s) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
-__global__ void __launch_bounds__(32 * GF_WARPS)
-k_gf_scan(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, const SegDesc* __restrict__ segs,
-          uint32_t seg0, uint32_t n_segs, GfSeg* __restrict__ segout) {
-    __shared__ __align__(16) uint8_t s_chunk[GF_WARPS][GF_CHUNK + 16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t si = blockIdx.x * GF_WARPS + warp;
-    if (si >= n_segs) return;
-    const SegDesc sd = segs[seg0 + si];
-    uint8_t* img = corpus + tin[sd.track].off;
-    const uint64_t len = tin[sd.track].len;
-    uint64_t a0, audio_end, b, e;
+// tin / tseg point at the first track of the group; seg0 = its first sub-segment
+__global__ void __launch_bounds__(GF_THREADS)
+k_gf_scan(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
+          uint32_t n_segs, GfSeg* __restrict__ segout) {
+    __shared__ uint16_t s_lut[256];
+    gf_fill_lut(s_lut);
+    const uint32_t si = blockIdx.x * GF_THREADS + threadIdx.x;
+    const bool have = si < n_segs;
+    const uint32_t t = gf_find_track(tseg, n_tracks, seg0 + (have ? si : 0));
+    const TrackSeg ts = tseg[t];
+    uint8_t* img = corpus + tin[t].off;
+    const uint32_t len = (uint32_t)tin[t].len;
+    uint32_t a0, audio_end, b, e;
     gf_bounds(img, len, a0, audio_end);
-    gf_seg_range(sd.seg, tseg[sd.track].n_seg, b, e);
+    gf_seg_range(seg0 + (have ? si : 0) - ts.seg_base, ts.n_seg, b, e);
     if (b < a0) b = a0;
-    GfSeg o;
-    if (b >= e) { o.first_jump = GF_NONE; o.end_pos = 0; o.n_frames = 0; o.gsum = 0; o.gcount = 0; o.gminmax = 255; o.first_hdr = 0; o.pad = 0; }
-    else o = gf_walk<false>(img, len, audio_end, s_chunk[warp], b, e, lane, 0, 0, -1);
-    if (lane == 0) segout[seg0 + si] = o;
+    const GfSeg o = gf_walk<false>(img, len, audio_end, s_lut, b, e, 0, 0, -1, have && b < e);
+    if (have) segout[seg0 + si] = o;
 }
 
-__global__ void __launch_bounds__(32 * GF_WARPS)
+__global__ void __launch_bounds__(GF_THREADS)
 k_gf_merge(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, const GfSeg* __restrict__ segout,
            uint32_t* __restrict__ entry, GfTrackOut* __restrict__ out, uint32_t n_tracks) {
-    __shared__ __align__(16) uint8_t s_chunk[GF_WARPS][GF_CHUNK + 16];
+    __shared__ uint16_t s_lut[256];
+    gf_fill_lut(s_lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * GF_WARPS + warp;
+    const uint32_t t = blockIdx.x * (GF_THREADS / 32) + warp;
     if (t >= n_tracks) return;
     uint8_t* img = corpus + tin[t].off;
-    const uint64_t len = tin[t].len;
+    const uint32_t len = (uint32_t)tin[t].len;
     const TrackSeg ts = tseg[t];
-    uint64_t a0, audio_end;
+    uint32_t a0, audio_end;
     gf_bounds(img, len, a0, audio_end);
-    uint64_t P = a0;
-    GfTrackOut r;
-    r.frame_count = 0; r.first_hdr = 0; r.n_rewalks = 0; r.gain_sum = 0; r.gain_count = 0;
-    uint32_t gmin = 255, gmax = 0;
-    for (uint32_t s = 0; s < ts.n_seg; s++) {
-        uint64_t b, e;
-        gf_seg_range(s, ts.n_seg, b, e);
+    uint32_t P = a0;                                      // where the true walk stands (warp-uniform)
+    unsigned long long frames = 0, gsum = 0, gcount = 0;  // this lane's sub-segments
+    uint32_t gmin = 255, gmax = 0, rewalks = 0, first_s = GF_NONE, first_hdr = 0;
+    for (uint32_t base = 0; base < ts.n_seg; base += 32) {
+        const uint32_t s = base + lane;
+        GfSeg o;
+        o.first_jump = GF_NONE; o.end_pos = 0; o.n_frames = 0; o.gsum = 0; o.gcount = 0; o.gminmax = 255; o.first_hdr = 0; o.pad = 0;
+        if (s < ts.n_seg) o = segout[ts.seg_base + s];
         uint32_t ent = GF_NONE;
-        if (P < e && P + 4 <= audio_end) {
-            GfSeg o = segout[ts.seg_base + s];
-            if (!(o.first_jump == GF_NONE || P <= (uint64_t)o.first_jump)) {   // P is not on the speculative trajectory
-                o = gf_walk<false>(img, len, audio_end, s_chunk[warp], P, e, lane, 0, 0, -1);
-                r.n_rewalks++;
+        const uint32_t nj = min(32u, ts.n_seg - base);
+        for (uint32_t j = 0; j < nj; j++) {               // serial resolve: lane j's sub-segment against the current P
+            uint32_t b, e;
+            gf_seg_range(base + j, ts.n_seg, b, e);
+            const bool active = P < e && (uint64_t)P + 4 <= audio_end;
+            const uint32_t fj = __shfl_sync(0xffffffffu, o.first_jump, j);
+            if (active && !(fj == GF_NONE || P <= fj)) {  // P is not on the speculative trajectory: lane j walks again from P
+                const GfSeg w = gf_walk<false>(img, len, audio_end, s_lut, P, e, 0, 0, -1, lane == (int)j);
+                if (lane == (int)j) { o = w; rewalks++; }
             }
-            ent = (uint32_t)P;
-            if (r.frame_count == 0 && o.n_frames) r.first_hdr = o.first_hdr;
-            r.frame_count += o.n_frames;
-            r.gain_sum += o.gsum; r.gain_count += o.gcount;
-            if (o.n_frames) { gmin = min(gmin, o.gminmax & 0xFF); gmax = max(gmax, o.gminmax >> 8); }
-            P = o.end_pos;
+            if (lane == (int)j) {
+                if (active) ent = P;
+                else { o.n_frames = 0; o.gsum = 0; o.gcount = 0; }
+            }
+            const uint32_t ep = __shfl_sync(0xffffffffu, o.end_pos, j);
+            if (active) P = ep;
         }
-        if (lane == 0) entry[ts.seg_base + s] = ent;
+        if (s < ts.n_seg) entry[ts.seg_base + s] = ent;
+        if (o.n_frames) {
+            if (first_s == GF_NONE) { first_s = s; first_hdr = o.first_hdr; }
+            frames += o.n_frames; gsum += o.gsum; gcount += o.gcount;
+            gmin = min(gmin, o.gminmax & 0xFF); gmax = max(gmax, o.gminmax >> 8);
+        }
     }
-    r.gminmax = gmin | (gmax << 8);
-    if (lane == 0) out[t] = r;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        frames += __shfl_xor_sync(0xffffffffu, frames, d);
+        gsum += __shfl_xor_sync(0xffffffffu, gsum, d);
+        gcount += __shfl_xor_sync(0xffffffffu, gcount, d);
+    }
+    gmin = __reduce_min_sync(0xffffffffu, gmin);
+    gmax = __reduce_max_sync(0xffffffffu, gmax);
+    rewalks = __reduce_add_sync(0xffffffffu, rewalks);
+    const uint32_t fs = __reduce_min_sync(0xffffffffu, first_s);   // the sub-segment holding the first counted frame
+    const uint32_t src = __ffs(__ballot_sync(0xffffffffu, first_s == fs)) - 1;
+    first_hdr = __shfl_sync(0xffffffffu, first_hdr, src);
+    if (lane == 0) {
+        GfTrackOut r;
+        r.frame_count = (uint32_t)frames; r.first_hdr = fs == GF_NONE ? 0 : first_hdr; r.gminmax = gmin | (gmax << 8); r.n_rewalks = rewalks;
+        r.gain_sum = gsum; r.gain_count = gcount;
+        out[t] = r;
+    }
 }
 
-__global__ void __launch_bounds__(32 * GF_WARPS)
-k_gf_patch(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, const SegDesc* __restrict__ segs,
-           uint32_t seg0, uint32_t n_segs, const uint32_t* __restrict__ entry, int steps, int wrap, int channel) {
-    __shared__ __align__(16) uint8_t s_chunk[GF_WARPS][GF_CHUNK + 16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t si = blockIdx.x * GF_WARPS + warp;
-    if (si >= n_segs) return;
-    const uint32_t ent = entry[seg0 + si];
-    if (ent == GF_NONE) return;
-    const SegDesc sd = segs[seg0 + si];
-    uint8_t* img = corpus + tin[sd.track].off;
-    const uint64_t len = tin[sd.track].len;
-    uint64_t a0, audio_end, b, e;
+__global__ void __launch_bounds__(GF_THREADS)
+k_gf_patch(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
+           uint32_t n_segs, const uint32_t* __restrict__ entry, int steps, int wrap, int channel) {
+    __shared__ uint16_t s_lut[256];
+    gf_fill_lut(s_lut);
+    const uint32_t si = blockIdx.x * GF_THREADS + threadIdx.x;
+    const bool have = si < n_segs;
+    const uint32_t ent = have ? entry[seg0 + si] : GF_NONE;
+    const uint32_t t = gf_find_track(tseg, n_tracks, seg0 + (have ? si : 0));
+    const TrackSeg ts = tseg[t];
+    uint8_t* img = corpus + tin[t].off;
+    const uint32_t len = (uint32_t)tin[t].len;
+    uint32_t a0, audio_end, b, e;
     gf_bounds(img, len, a0, audio_end);
-    gf_seg_range(sd.seg, tseg[sd.track].n_seg, b, e);
-    gf_walk<true>(img, len, audio_end, s_chunk[warp], ent, e, lane, steps, wrap, channel);
+    gf_seg_range(seg0 + (have ? si : 0) - ts.seg_base, ts.n_seg, b, e);
+    gf_walk<true>(img, len, audio_end, s_lut, ent, e, steps, wrap, channel, ent != GF_NONE);
 }

@@ -13,16 +13,16 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
     if (!n) return RG_OK;
     std::vector<TrackIn> tin(n);
     std::vector<TrackSeg> tseg(n);
-    std::vector<SegDesc> segs;
-    uint64_t bytes = 0;
+    uint64_t n_sub = 0, bytes = 0;
     for (size_t i = 0; i < n; i++) {
         if (c->len[i] >= 0xFFFF0000ull) return RG_ERR_INVALID_ARG;   // positions are 32-bit on the device
         tin[i].off = c->off[i]; tin[i].len = c->len[i];
-        tseg[i].seg_base = (uint32_t)segs.size();
-        tseg[i].n_seg = (uint32_t)std::max<uint64_t>(1, (c->len[i] + GF_SEG - 1) / GF_SEG);
-        for (uint32_t sg = 0; sg < tseg[i].n_seg; sg++) segs.push_back(SegDesc{(uint32_t)i, sg});
+        tseg[i].seg_base = (uint32_t)n_sub;
+        tseg[i].n_seg = (uint32_t)std::max<uint64_t>(1, (c->len[i] + GF_SUB - 1) / GF_SUB);
+        n_sub += tseg[i].n_seg;
         bytes += c->len[i];
     }
+    if (n_sub >= 0xFFFFFFFFull) return RG_ERR_INVALID_ARG;          // sub-segment ids are 32-bit (16 TB of file images)
     std::vector<size_t> group_begin;
     const uint64_t gbytes = c->pending_in ? std::max<uint64_t>(bytes / 8 + 1, e->group_bytes_min) : ~0ull;
     uint64_t acc = 0;
@@ -34,17 +34,15 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
     const size_t ng = group_begin.size() - 1;
     CK(e->d_tin.ensure(n * sizeof(TrackIn)));
     CK(e->d_tseg.ensure(n * sizeof(TrackSeg)));
-    CK(e->d_segs.ensure(segs.size() * sizeof(SegDesc)));
-    CK(e->d_gfseg.ensure(segs.size() * sizeof(GfSeg)));
-    CK(e->d_gfent.ensure(segs.size() * sizeof(uint32_t)));
+    CK(e->d_gfseg.ensure(n_sub * sizeof(GfSeg)));
+    CK(e->d_gfent.ensure(n_sub * sizeof(uint32_t)));
     CK(e->d_gfout.ensure(n * sizeof(GfTrackOut)));
     CK(e->h_gfout.ensure(n * sizeof(GfTrackOut)));
     cudaStream_t st = e->stream;
     CK(cudaMemcpyAsync(e->d_tin.p, tin.data(), n * sizeof(TrackIn), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_tseg.p, tseg.data(), n * sizeof(TrackSeg), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_segs.p, segs.data(), segs.size() * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));   // the sources are stack / heap temporaries
-    e->stats.h2d_bytes += n * (sizeof(TrackIn) + sizeof(TrackSeg)) + segs.size() * sizeof(SegDesc);
+    e->stats.h2d_bytes += n * (sizeof(TrackIn) + sizeof(TrackSeg));
     for (size_t g = 0; g < ng; g++) {
         const size_t t0 = group_begin[g], t1 = group_begin[g + 1];
         cudaEvent_t ev_copied = e->pool_event(6 * g), ev0 = e->pool_event(6 * g + 1), ev1 = e->pool_event(6 * g + 2),
@@ -59,19 +57,19 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
             CK(cudaStreamWaitEvent(st, ev_copied, 0));
         }
         const uint32_t seg0 = tseg[t0].seg_base;
-        const uint32_t nsg = (t1 < n ? tseg[t1].seg_base : (uint32_t)segs.size()) - seg0;
-        const unsigned gs = (nsg + GF_WARPS - 1) / GF_WARPS, gt = (unsigned)((t1 - t0 + GF_WARPS - 1) / GF_WARPS);
+        const uint32_t nsg = (t1 < n ? tseg[t1].seg_base : (uint32_t)n_sub) - seg0;
+        const unsigned gs = (nsg + GF_THREADS - 1) / GF_THREADS, gt = (unsigned)((t1 - t0 + GF_THREADS / 32 - 1) / (GF_THREADS / 32));
         CK(cudaEventRecord(ev0, st));
-        k_gf_scan<<<gs, 32 * GF_WARPS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>(), e->d_tseg.as<TrackSeg>(), e->d_segs.as<SegDesc>(), seg0, nsg,
-                                                e->d_gfseg.as<GfSeg>());
+        k_gf_scan<<<gs, GF_THREADS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, (uint32_t)(t1 - t0), seg0, nsg,
+                                             e->d_gfseg.as<GfSeg>());
         CK(cudaEventRecord(ev1, st));
-        k_gf_merge<<<gt, 32 * GF_WARPS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, e->d_gfseg.as<GfSeg>(),
+        k_gf_merge<<<gt, GF_THREADS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, e->d_gfseg.as<GfSeg>(),
                                                  e->d_gfent.as<uint32_t>(), e->d_gfout.as<GfTrackOut>() + t0, (uint32_t)(t1 - t0));
         CK(cudaEventRecord(ev2, st));
         e->stats.kernel_launches += 2;
         if (patch) {
-            k_gf_patch<<<gs, 32 * GF_WARPS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>(), e->d_tseg.as<TrackSeg>(), e->d_segs.as<SegDesc>(), seg0, nsg,
-                                                     e->d_gfent.as<uint32_t>(), steps, wrap, channel);
+            k_gf_patch<<<gs, GF_THREADS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, (uint32_t)(t1 - t0), seg0, nsg,
+                                                  e->d_gfent.as<uint32_t>(), steps, wrap, channel);
             e->stats.kernel_launches++;
         }
         CK(cudaGetLastError());

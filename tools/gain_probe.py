@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""Timing probe of the global_gain walk (k_gain_fields.cuh): N synthetic 3-min tracks resident in HBM, CUDA-event times of
+k_gf_scan / k_gf_merge / k_gf_patch.  usage: gain_probe.py [n_tracks=200] [n_frames=6891]  (development aid; ncu target)"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import mp3rgain_b200 as m  # noqa: E402
+from mp3rgain_b200 import _lib  # noqa: E402
+import synth_corpus  # noqa: E402
+
+n_tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+n_frames = int(sys.argv[2]) if len(sys.argv) > 2 else 6891
+pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
+imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
+total = sum(len(i) for i in imgs)
+lib = _lib.load()
+eng = m.Engine(device=0)
+arr, keep = m.Engine._inputs(imgs, None)
+cor = C.c_void_p()
+assert lib.rg_corpus_upload(eng._h, arr, n_tracks, C.byref(cor)) == 0
+gst = (_lib.RgGainStats * n_tracks)()
+for it in range(4):
+    t = time.time()
+    assert lib.rg_gain_analyze_corpus(eng._h, cor, gst) == 0
+    st = eng.stats()
+    print("analyze: wall %.2f ms | scan %.3f ms (%.0f GB/s) merge %.3f ms | frames[0] %d rewalks %d" % (
+        1e3 * (time.time() - t), st.last_ms_gain_scan, total / st.last_ms_gain_scan / 1e6, st.last_ms_gain_merge,
+        gst[0].frame_count, sum(g.walk_rewalks for g in gst)), flush=True)
+outs = [np.empty(len(i), np.uint8) for i in imgs]
+ptrs = (C.c_void_p * n_tracks)(*[o.ctypes.data for o in outs])
+mod = np.zeros(n_tracks, np.uint32)
+for it in range(2):
+    t = time.time()
+    assert lib.rg_gain_apply(eng._h, arr, n_tracks, 3, 0, -1, ptrs, mod.ctypes.data) == 0
+    st = eng.stats()
+    print("apply (pageable host buffers): wall %.1f ms | scan %.3f merge %.3f patch %.3f ms | groups %d" % (
+        1e3 * (time.time() - t), st.last_ms_gain_scan, st.last_ms_gain_merge, st.last_ms_gain_patch, st.last_gain_groups), flush=True)
