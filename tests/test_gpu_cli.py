@@ -1,0 +1,59 @@
+"""GPU test of the batched CLI glue: the TSV / text lines for the reference's fixtures, built from ONE
+rg_analyze_tracks + ONE rg_gain_analyze call, equal the lines the reference's per-file loop would print from the oracle's
+numbers (src/main.rs:1703-1722, 1941-1968, 1296-1340)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ["test_joint_stereo.mp3", "test_mono.mp3", "test_vbr.mp3", "test_stereo.mp3"]
+
+
+def _round_half_away(x):
+    return int(np.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
+
+def test_info_tsv_matches_the_per_file_loop(oracle, tmp_path, capsys):
+    from mp3rgain_b200 import cli
+    files = [os.path.join(GOLD, n) for n in NAMES] + [str(tmp_path / "missing.mp3")]
+    junk = tmp_path / "junk.mp3"
+    junk.write_bytes(bytes(5000))
+    files.insert(2, str(junk))
+    out, err = cli.info_tsv(files, gain_modifier_db=1.5)
+    exp = [cli.TSV_HEADER]
+    for n in NAMES:
+        img = np.fromfile(os.path.join(GOLD, n), np.uint8)
+        rc, res, hist, info = oracle.analyze_mp3(img)
+        rc2, st = oracle.gain_analyze(img)
+        assert rc == 0 and rc2 == 0
+        g = res.gain_db + 1.5
+        exp.append("{}\t{}\t{:.6f}\t{:.6f}\t{}\t{}".format(n, _round_half_away(g / 1.5), g, res.peak * 32768.0, st.max_gain, st.min_gain))
+    assert out == exp
+    assert err == ["junk.mp3 - Failed to probe format: " + str(junk), "missing.mp3 - Failed to open: " + files[-1]]
+    assert cli.main(["-o", "-d", "1.5"] + files) == 0
+    cap = capsys.readouterr()
+    assert cap.out == "\n".join(exp) + "\n" and cap.err == "\n".join(err) + "\n"
+
+
+def test_track_and_album_lines(oracle):
+    from mp3rgain_b200 import cli
+    files = [os.path.join(GOLD, n) for n in NAMES[:3]]
+    out, err, steps = cli.track_gain_lines(files, gain_modifier=1)
+    assert out[:4] == ["[DRY RUN] mp3rgain Analyzing and would apply track gain to 3 file(s)", "  Target: 89 dB (ReplayGain 1.0)",
+                       "  Gain modifier: +1 steps", ""] and not err
+    hists, peaks = [], []
+    for n, f in zip(NAMES, files):
+        rc, res, hist, info = oracle.analyze_mp3(np.fromfile(f, np.uint8))
+        base = _round_half_away(res.gain_db / 1.5)
+        assert "  -> [DRY RUN] Analyzing %s..." % n in out
+        assert "      Loudness: {:.1f} dB, Gain: {:+.1f} dB ({} steps + 1 = {}), Peak: {:.4f}".format(res.loudness_db, res.gain_db, base, base + 1, res.peak) in out
+        assert steps[NAMES.index(n)] == base + 1
+        hists.append(hist)
+        peaks.append(res.peak)
+    lines, asteps = cli.album_gain_lines(files)
+    _, l, g, p = oracle.album_merge(np.stack(hists), np.array(peaks))
+    assert lines[-5:] == ["", "  Album loudness: {:.1f} dB".format(l), "  Album gain:     {:+.1f} dB ({} steps)".format(g, _round_half_away(g / 1.5)),
+                          "  Album peak:     {:.4f}".format(p), ""]
+    assert asteps == _round_half_away(g / 1.5)
