@@ -42,3 +42,35 @@ for it in range(2):
     st = eng.stats()
     print("apply (pageable host buffers): wall %.1f ms | scan %.3f merge %.3f patch %.3f ms | groups %d" % (
         1e3 * (time.time() - t), st.last_ms_gain_scan, st.last_ms_gain_merge, st.last_ms_gain_patch, st.last_gain_groups), flush=True)
+
+# pinned in / out, and the raw bus next to it: H2D alone, D2H alone, both at once (two streams)
+import torch  # noqa: E402
+offs = np.zeros(n_tracks + 1, np.int64)
+for i, im in enumerate(imgs):
+    offs[i + 1] = offs[i] + ((len(im) + 63) & ~63)
+pin_in = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
+pin_out = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
+arr2 = (_lib.RgInput * n_tracks)()
+for i, im in enumerate(imgs):
+    pin_in.numpy()[offs[i]: offs[i] + len(im)] = im
+    arr2[i].data = pin_in.numpy().ctypes.data + int(offs[i]); arr2[i].len = len(im); arr2[i].track_index = -1
+optr = (C.c_void_p * n_tracks)(*[pin_out.numpy().ctypes.data + int(offs[i]) for i in range(n_tracks)])
+for it in range(3):
+    t = time.time()
+    assert lib.rg_gain_apply(eng._h, arr2, n_tracks, 3, 0, -1, optr, mod.ctypes.data) == 0
+    print("apply (pinned): wall %.1f ms" % (1e3 * (time.time() - t)), flush=True)
+dev_a = torch.empty(int(offs[-1]), dtype=torch.uint8, device="cuda")
+dev_b = torch.empty(int(offs[-1]), dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+for name, up, down in (("H2D alone", True, False), ("D2H alone", False, True), ("H2D + D2H at once", True, True)):
+    torch.cuda.synchronize()
+    t = time.time()
+    if up:
+        with torch.cuda.stream(s1):
+            dev_a.copy_(pin_in, non_blocking=True)
+    if down:
+        with torch.cuda.stream(s2):
+            pin_out.copy_(dev_b, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.time() - t
+    print("%s: %.1f ms (%.1f GB/s per direction)" % (name, 1e3 * dt, total / dt / 1e9), flush=True)
