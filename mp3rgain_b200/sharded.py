@@ -79,3 +79,11 @@ def analyze_album_sharded(engine: Engine, images: Sequence, rank: int, world: in
     tracks = [Engine._result(out[i]) for i in range(n)]
     hist = d_hist.cpu().numpy().view(np.uint64).copy()
     return AlbumGainResult(tracks, alb.album_loudness_db, alb.album_gain_db, alb.album_peak, hist), mine
+
+
+def gain_analyze_sharded(engine: Engine, images: Sequence, rank: int, world: int):
+    """mp3rgain::analyze() (src/lib.rs:470-514) over a file list across `world` GPUs: files are independent, so each rank
+    walks its byte-balanced shard (rg_gain_analyze) and there is no collective.  Returns (this rank's RgGainStats list,
+    shard indices)."""
+    mine = shard_by_bytes([len(im) for im in images], world)[rank]
+    return engine.gain_analyze_images([images[i] for i in mine]), mine
