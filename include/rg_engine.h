@@ -113,7 +113,8 @@ const char* rg_status_str(int status);
  * exact kernel; scaled by max(1, 0.1 * input amplitude / filtered RMS) per window, default 1e-9), "pipeline" (default 1:
  * copy / index / decode / analysis overlap on four streams with two alternating batches; 0 = one batch at a time, every
  * kernel alone on the device, for profiling), "group_bytes_min" (smallest copy / index group of the end-to-end path, default
- * 32 MiB).  Returns RG_ERR_INVALID_ARG for an unknown key. */
+ * 32 MiB), "k4_slim" (default 0; n > 0 launches the time-blocked IIR as waves of n 128-thread CTAs per SM instead of 256-thread
+ * CTAs -- an experiment in co-scheduling with the decode kernels that did not pay).  Returns RG_ERR_INVALID_ARG for an unknown key. */
 int rg_engine_set_option(rg_engine* e, const char* key, double value);
 /* Thread-local detail string for the last failing call (CUDA error text etc.). */
 const char* rg_last_error(void);

@@ -233,6 +233,10 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
 // the instantiation the engine launches (tools/iir_bench.cu times the alternatives)
 #define K4_FAST_THREADS 256
 #define k_iir_fast k_iir_fast_t<3, K4_FAST_THREADS, 2>
+// the "slim" launch: 128-thread CTAs, launched one wave of n_sms CTAs at a time -- one CTA per SM keeps most of the FP64 pipe
+// busy with a quarter of the register file, so that the decode kernels of the next batch stay resident beside it
+#define K4_SLIM_THREADS 128
+#define k_iir_slim k_iir_fast_t<3, K4_SLIM_THREADS, 4>
 
 // ------------------------------------------------------------------------------------------------------------
 // K5: one CTA per track.  Window sums -> bin index -> shared 12000-bin histogram (warp-aggregated atomics)

@@ -103,6 +103,8 @@ struct rg_engine {
     // options
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
     uint32_t k4_round = 0;                // chains in one round of k_iir_fast CTAs: one CTA per SM
+    uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
+    int n_sms = 148;
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
@@ -234,6 +236,7 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         int sms = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         e->k4_round = (uint32_t)(sms * K4_FAST_THREADS);
+        e->n_sms = sms;
     }
     int rc = decode_init_tables(e->dec);
     if (rc != RG_OK) { delete e; return rc; }
@@ -269,6 +272,12 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
+    if (!strcmp(key, "k4_slim")) {
+        if (value < 0 || value > 8) return RG_ERR_INVALID_ARG;
+        e->k4_slim = (uint32_t)value;
+        e->k4_round = (uint32_t)(e->n_sms * (e->k4_slim ? K4_SLIM_THREADS * e->k4_slim : K4_FAST_THREADS));
+        return RG_OK;
+    }
     if (!strcmp(key, "exact_iir")) { if (value != 0) e->flags |= RG_FLAG_EXACT_IIR; else e->flags &= ~RG_FLAG_EXACT_IIR; return RG_OK; }
     return RG_ERR_INVALID_ARG;
 }
@@ -318,8 +327,9 @@ static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTr
     for (uint32_t bw = 8; bw <= 96; bw++) {
         uint64_t chains = 0;
         for (auto& p : nw) chains += (uint64_t)((p.first + bw - 1) / bw) * p.second;
-        const uint64_t ctas = (chains + K4_FAST_THREADS - 1) / K4_FAST_THREADS;
-        const uint64_t rounds = (ctas * K4_FAST_THREADS + unit - 1) / unit;
+        const uint64_t T = e->k4_slim ? K4_SLIM_THREADS : K4_FAST_THREADS;
+        const uint64_t ctas = (chains + T - 1) / T;
+        const uint64_t rounds = (ctas * T + unit - 1) / unit;
         const uint64_t cost = rounds * (bw + e->warm_windows);
         if (cost <= best_cost) { best_cost = cost; best = bw; }
     }
@@ -456,7 +466,16 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
         if (exact)
             k_iir_exact<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_exact[r]);
         else
-            k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
+            if (e->k4_slim) {
+                const uint32_t wave = (uint32_t)e->n_sms * e->k4_slim * K4_SLIM_THREADS;   // chains per launch: k4_slim CTAs per SM
+                for (uint32_t c0 = 0; c0 < cnt; c0 += wave) {
+                    const uint32_t m = std::min(wave, cnt - c0);
+                    k_iir_slim<<<(m + K4_SLIM_THREADS - 1) / K4_SLIM_THREADS, K4_SLIM_THREADS, 0, st>>>(c.d_chains.as<RgChain>() + i0 + c0, m, d_peaks_sorted,
+                                                                                                     (uint32_t)(i0 + c0), e->coef_fast[r]);
+                    if (c0) e->stats.kernel_launches++;
+                }
+            } else
+                k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         e->stats.kernel_launches++;
         i0 = i1;
     }
