@@ -89,11 +89,15 @@ __device__ __forceinline__ void gf_fill_lut(uint16_t* lut) {
 }
 
 // Image loads.  Images start 16-byte aligned and are followed by >= 16 bytes of slack inside the corpus buffer
-// (corpus_describe), so an aligned word pair that starts below `len` stays inside the allocation; bytes beyond `len` are
+// (corpus_describe), so an aligned 16-byte load that starts below `len`, and the word after it, stay inside the allocation; bytes beyond `len` are
 // never consumed by the walk (every read is guarded by len / audio_end).  The patching walk reads with plain loads (it
 // writes the same buffer), the read-only walks through the non-coherent path.
 template <bool PATCH> __device__ __forceinline__ uint32_t gf_ldw(const uint8_t* img, uint32_t a) {   // a % 4 == 0
     const uint32_t* p = reinterpret_cast<const uint32_t*>(img + a);
+    return PATCH ? *p : __ldg(p);
+}
+template <bool PATCH> __device__ __forceinline__ uint4 gf_ld16(const uint8_t* img, uint32_t a) {     // a % 16 == 0
+    const uint4* p = reinterpret_cast<const uint4*>(img + a);
     return PATCH ? *p : __ldg(p);
 }
 // 4 bytes at any offset g, little-endian (first byte in bits 0-7)
@@ -105,7 +109,7 @@ template <bool PATCH> __device__ __forceinline__ uint32_t gf_ld32(const uint8_t*
 // The walk over [pos, bound) of one file image by ONE thread -- but written for the warp: all 32 lanes call it together
 // (`run` = this lane has a sub-segment to walk) and move through two warp-synchronous phases, so that lanes at different
 // points of their walks still execute the same instructions:
-//   SCAN   every scanning lane advances one aligned word per step: bytes that are 0xFF and followed by a byte with its top
+//   SCAN   every scanning lane advances 16 aligned bytes per step: bytes that are 0xFF and followed by a byte with its top
 //          three bits set are the only positions parse_header (src/lib.rs:176-178) can accept; such a candidate gets the
 //          full header + next-sync check and either becomes the lane's current frame or the scan resumes one byte later
 //   FRAME  every lane that stands on a validated frame processes it (Xing/Info test, gain fields), jumps, and validates
@@ -138,14 +142,22 @@ __device__ GfSeg gf_walk(uint8_t* img, uint32_t len, uint32_t audio_end, const u
     while (__any_sync(0xffffffffu, st != GF_ST_DONE)) {
         while (__any_sync(0xffffffffu, st == GF_ST_SCAN)) {
             if (st == GF_ST_SCAN) {
-                const uint32_t a = pos & ~3u;
-                const uint32_t w = gf_ldw<PATCH>(img, a), wn = gf_ldw<PATCH>(img, a + 4);
-                const uint32_t ff = ((w & 0x7F7F7F7Fu) + 0x01010101u) & w;             // bit 7 of byte i: byte i == 0xFF
-                const uint32_t u = __funnelshift_r(w, wn, 8);                            // byte i = byte i+1 of the stream
-                const uint32_t c = ff & u & (u << 1) & (u << 2) & 0x80808080u & ~((0x80u << (8 * (pos & 3))) - 1u);   // at or after pos
-                if (!c) pos = a + 4;
+                // 16 aligned bytes per step.  Bit k of m: byte k is 0xFF and byte k+1 has its top three bits set
+                const uint32_t a = pos & ~15u;
+                const uint4 v = gf_ld16<PATCH>(img, a);
+                const uint32_t w[5] = {v.x, v.y, v.z, v.w, gf_ldw<PATCH>(img, a + 16)};
+                uint32_t m = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t ff = ((w[k] & 0x7F7F7F7Fu) + 0x01010101u) & w[k];       // bit 7 of byte i: byte i == 0xFF
+                    const uint32_t u = __funnelshift_r(w[k], w[k + 1], 8);                  // byte i = byte i+1 of the stream
+                    const uint32_t c = (ff & u & (u << 1) & (u << 2) & 0x80808080u) >> 7;    // bit 0 of byte i: candidate
+                    m |= ((c * 0x01020408u) >> 24) << (4 * k);                               // gather the four flags
+                }
+                m &= ~((1u << (pos & 15u)) - 1u);                                            // at or after pos
+                if (!m) pos = a + 16;
                 else {
-                    pos = a + ((__ffs(c) - 1) >> 3);
+                    pos = a + (__ffs(m) - 1);
                     if (in_range(pos)) {
                         if (check(pos)) st = GF_ST_FRAME;
                         else pos++;
