@@ -430,11 +430,24 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
         rc = index_absorb(e, c, ip, next + 1, true);
         if (rc != RG_OK) return fail(rc);
         const size_t indexed_end = ip.group_begin[ip.groups_absorbed];
+        // Equal batches instead of full ones plus a remainder: the scratch the rest of the call needs (exact for indexed
+        // tracks, by the bytes-to-scratch ratio seen so far for the ones still arriving) is split evenly over the number of
+        // batches it takes anyway, so that no call ends on a sliver of a batch that cannot fill the device.
+        uint64_t need = 0, seen_scratch = 0, seen_len = 0, rest_len = 0;
+        for (size_t i = next; i < n; i++) {
+            if (i < indexed_end) {
+                const uint64_t b = ip.status[i] == RG_OK ? track_scratch_bytes(ip.meta[i]) : 0;
+                need += b; seen_scratch += b; seen_len += c->len[i];
+            } else rest_len += c->len[i];
+        }
+        if (rest_len) need += seen_len ? (uint64_t)((double)seen_scratch / (double)seen_len * (double)rest_len) : rest_len * 37;
+        const uint64_t nb_rest = std::max<uint64_t>(1, (need + budget - 1) / budget);
+        const uint64_t even = std::min<uint64_t>(budget, need / nb_rest + need / nb_rest / 64 + (1ull << 20));
         size_t t1 = next;
         uint64_t bytes = 0;
         while (t1 < indexed_end) {
             const uint64_t b = ip.status[t1] == RG_OK ? track_scratch_bytes(ip.meta[t1]) : 0;
-            if (t1 > next && bytes + b > budget) break;
+            if (t1 > next && bytes + b > even) break;
             bytes += b;
             t1++;
         }
