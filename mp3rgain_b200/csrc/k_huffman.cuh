@@ -93,7 +93,8 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     __shared__ uint32_t s_stage[K1_THREADS / 32][32][17];
     __shared__ uint8_t s_sfl[K1_THREADS][24];     // long scalefactors of every thread's granule-channel (scfsi source)
     __shared__ uint8_t s_c1[2][64];               // count1 tables A / B: 6-bit peek -> (len<<4)|quad
-    __shared__ uint32_t s_key[K1_THREADS];        // big_values of the block's granule-channels (sort key)
+    __shared__ uint32_t s_cnt[512];               // counting sort of the block's granule-channels by big_values: bin sizes, then bin starts
+    __shared__ uint32_t s_wsum[K1_THREADS / 32];
     __shared__ uint8_t s_perm[K1_THREADS];        // worker thread -> granule-channel of the block, ordered by big_values
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -121,14 +122,26 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const uint8_t* s = corpus + tr.corpus_off + rec.file_off + 4 + ((rec.hdr & 0x10000u) ? 0 : 2);
             key = side_field(s, (lsf ? (nch == 1 ? 9 : 10) + 63 * rem : (nch == 1 ? 18 : 20) + 59 * rem) + 12, 9);
         }
-        s_key[tid] = (key << 8) | (uint32_t)tid;   // unique keys: ties keep block order
-    }
-    __syncthreads();
-    {
-        const uint32_t mine = s_key[tid];
-        int rank = 0;
-        for (int j = 0; j < K1_THREADS; j++) rank += s_key[j] < mine ? 1 : 0;   // every lane reads the same word: broadcast
-        s_perm[rank] = (uint8_t)tid;
+        // counting sort over the 9-bit key: my slot inside my bin, then an exclusive prefix over the 512 bins (two per thread)
+        if (tid < 256) { s_cnt[tid] = 0; s_cnt[tid + 256] = 0; }
+        __syncthreads();
+        const uint32_t slot = atomicAdd(&s_cnt[key], 1u);
+        __syncthreads();
+        const uint32_t c0 = s_cnt[2 * tid], c1 = s_cnt[2 * tid + 1];
+        uint32_t incl = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < warp; w++) base += s_wsum[w];
+        s_cnt[2 * tid] = base + incl - c0 - c1;        // bins 2*tid, 2*tid+1: where their first member goes
+        s_cnt[2 * tid + 1] = base + incl - c1;
+        __syncthreads();
+        s_perm[s_cnt[key] + slot] = (uint8_t)tid;
     }
     __syncthreads();
     const int gl = s_perm[tid];                   // my granule-channel within the block
