@@ -120,6 +120,15 @@ def main():
     ap.add_argument("--exact", action="store_true", help="bit-exact serial IIR for every track (parity mode)")
     args = ap.parse_args()
 
+    # stdout carries exactly ONE line, the JSON record: whatever libraries print there (NCCL's version banner ...) goes to
+    # stderr instead -- the real stdout is kept aside and fd 1 points at stderr until the record is written
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -150,7 +159,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "audio-h/s", "cores": ncores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -158,7 +167,6 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     import mp3rgain_b200 as m
@@ -400,7 +408,7 @@ def main():
                                 "sample": f"first {n_sample} tracks of the workload, one pass, {ncores} host threads, {dt:.1f} s",
                                 "loudness_mismatches_vs_gpu": mism}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
