@@ -1,8 +1,8 @@
 """CLI glue for the analysis path: the reference CLI's per-file analysis loops, batched.
 
 The reference's `cmd_info` / `cmd_track_gain` / `cmd_album_gain` (src/main.rs:1119-1150, 1213-1290, 1296-1340) call
-`analyze_track` / `find_max_amplitude` once per file; here the whole file list goes through ONE `rg_analyze_tracks` and ONE
-`rg_gain_analyze` call (the form that fills a GPU), and the lines are formatted exactly as the reference prints them to a
+`analyze_track` / `find_max_amplitude` once per file; here the whole file list is uploaded once and goes through ONE `rg_analyze_corpus`
+and ONE `rg_gain_analyze_corpus` call (the form that fills a GPU), and the lines are formatted exactly as the reference prints them to a
 pipe (the `colored` crate emits no escape codes when stdout is not a terminal):
 
     info_tsv()          `-o` / `-o tsv` (mp3gain-compatible, what beets parses)   src/main.rs:1120-1124, 1703-1722, 1736
@@ -69,8 +69,9 @@ def info_tsv(files: Sequence, gain_modifier_db: float = 0.0, track_index: Option
     for i, msg in errors:
         err_lines[i] = "%s - %s" % (get_filename(files[i]), msg)
     if images:
-        res, sts = eng.analyze_images(images, track_index)
-        gst = eng.gain_analyze_images(images)
+        with eng.upload(images, track_index) as cor:   # the images cross the bus once for both passes
+            res, sts = cor.analyze()
+            gst = cor.gain_analyze()
         for k, i in enumerate(idx):
             if sts[k] != 0:
                 err_lines[i] = "%s - %s" % (get_filename(files[i]), _message(sts[k], os.fspath(files[i]), res[k].sample_rate,

@@ -216,6 +216,11 @@ class Engine:
             raise ReplayGainError(rc, _message(rc, sample_rate=sample_rate))
         return self._result(out, hist)
 
+    # ---- device-resident corpora: copy the file images once, run several passes over them ---------------
+    def upload(self, images: Sequence, track_index: Optional[int] = None) -> "Corpus":
+        """rg_corpus_upload: the images cross the bus once; Corpus.analyze() / Corpus.gain_analyze() then work from HBM."""
+        return Corpus(self, images, track_index)
+
     # ---- the global_gain fields (mp3rgain::analyze / apply_gain*, src/lib.rs) -------------------------
     def gain_analyze_images(self, images: Sequence):
         """rg_gain_analyze over in-memory file images.  Returns the list of RgGainStats (per-entry status inside)."""
@@ -252,6 +257,49 @@ class Engine:
         if rc != 0:
             raise ReplayGainError(rc, _message(rc))
         return buf[: nch.value, : frames.value].copy(), sr.value
+
+
+class Corpus:
+    """A batch of file images resident in device memory (rg_corpus).  Use as a context manager."""
+
+    def __init__(self, engine: Engine, images: Sequence, track_index: Optional[int] = None):
+        self._eng, self._n, self._track_index = engine, len(images), track_index
+        arr, keep = Engine._inputs(images, track_index)
+        self._h = C.c_void_p()
+        rc = engine._lib.rg_corpus_upload(engine._h, arr, self._n, C.byref(self._h))
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._eng._lib.rg_corpus_free(self._eng._h, self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def analyze(self, want_hist: bool = False):
+        """rg_analyze_corpus.  Returns (results, statuses)."""
+        n = self._n
+        out = (_lib.RgTrackResult * max(n, 1))()
+        hist = np.zeros((n, HIST_SIZE), np.uint32) if want_hist else None
+        rc = self._eng._lib.rg_analyze_corpus(self._eng._h, self._h, out, hist.ctypes.data if want_hist else None)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+        return [Engine._result(out[i], hist[i] if want_hist else None) for i in range(n)], [out[i].status for i in range(n)]
+
+    def gain_analyze(self):
+        """rg_gain_analyze_corpus.  Returns the list of RgGainStats."""
+        out = (_lib.RgGainStats * max(self._n, 1))()
+        rc = self._eng._lib.rg_gain_analyze_corpus(self._eng._h, self._h, out)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+        return [out[i] for i in range(self._n)]
 
 
 # ---- module-level functions with the reference's names ------------------------------------------------

@@ -57,3 +57,20 @@ def test_track_and_album_lines(oracle):
     assert lines[-5:] == ["", "  Album loudness: {:.1f} dB".format(l), "  Album gain:     {:+.1f} dB ({} steps)".format(g, _round_half_away(g / 1.5)),
                           "  Album peak:     {:.4f}".format(p), ""]
     assert asteps == _round_half_away(g / 1.5)
+
+
+def test_resident_corpus_gives_the_same_answers_as_the_host_entry_points(engine_fast):
+    """Engine.upload(): the images cross the bus once, rg_analyze_corpus and rg_gain_analyze_corpus both work from HBM."""
+    images = [np.fromfile(os.path.join(GOLD, n), np.uint8) for n in NAMES] + [np.zeros(3000, np.uint8), np.zeros(0, np.uint8)]
+    res, sts = engine_fast.analyze_images(images, want_hist=True)
+    gst = engine_fast.gain_analyze_images(images)
+    with engine_fast.upload(images) as cor:
+        res2, sts2 = cor.analyze(want_hist=True)
+        gst2 = cor.gain_analyze()
+        res3, _ = cor.analyze()          # a second pass over the same resident images
+    assert sts == sts2 and sts[:4] == [0, 0, 0, 0] and sts[4] != 0
+    for a, b, c in zip(res, res2, res3):
+        assert (a.loudness_db, a.gain_db, a.peak, a.n_frames) == (b.loudness_db, b.gain_db, b.peak, b.n_frames) == (c.loudness_db, c.gain_db, c.peak, c.n_frames)
+        assert (a.histogram == b.histogram).all()
+    for a, b in zip(gst, gst2):
+        assert (a.status, a.frame_count, a.gain_sum, a.min_gain, a.max_gain) == (b.status, b.frame_count, b.gain_sum, b.min_gain, b.max_gain)
