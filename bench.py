@@ -394,6 +394,9 @@ def main():
         cpu_val = sum(x[2] for x in o) / 44100.0 / 3600.0 / dt
         # parity spot check of the timed results against the oracle on the sample
         mism = sum(1 for i in range(n_sample) if o[i][1] != out[i].loudness_db)
+        # BASELINE.json's "delta dB vs ref": track loudness of the timed GPU results against the CPU restatement of the reference
+        line["delta_db_vs_ref"] = {"max_abs": max(abs(o[i][1] - out[i].loudness_db) for i in range(n_sample)), "tracks": n_sample,
+                                   "tolerance": 0.01, "ref": "oracle/ (C restatement of src/replaygain.rs + ISO 11172-3 decode)"}
         if gain_fields and "error" not in gain_fields:
             import oracle_lib
             orc = oracle_lib.load()
