@@ -169,6 +169,15 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    if world > 1:
+        # N ranks pull their file images over PCIe at the same time: keep each rank's threads, and with them its pinned staging
+        # buffer (first touch), on the CPUs next to its GPU.  (At N = 1 the CPU baseline needs every core, so nothing is bound.)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:  # noqa: BLE001  (no NVML / restricted cpuset: run unbound)
+            pass
     import mp3rgain_b200 as m
     from mp3rgain_b200 import _lib
     lib = _lib.load()   # raises if the CUDA extension has not been built: there is no fallback
