@@ -416,9 +416,11 @@ def main():
             dtg = time.perf_counter() - t0
             gain_fields["cpu_baseline"] = {"files_per_s": n_sample / dtg, "cores": 1, "kind": "port",
                                            "sample": f"oracle gfo_analyze over the first {n_sample} tracks, one thread, images in RAM"}
+        dt1, o1 = cpu_reference_run(imgs[:2], 1)   # the same restatement on ONE core (the reference itself is single-threaded)
+        one_core = sum(x[2] for x in o1) / 44100.0 / 3600.0 / dt1
         line["cpu_baseline"] = {"value": cpu_val, "unit": "audio-h/s", "cores": ncores, "kind": "port",
                                 "sample": f"first {n_sample} tracks of the workload, one pass, {ncores} host threads, {dt:.1f} s",
-                                "loudness_mismatches_vs_gpu": mism}
+                                "loudness_mismatches_vs_gpu": mism, "one_core": {"value": one_core, "unit": "audio-h/s", "sample": f"first 2 tracks, {dt1:.1f} s"}}
     if rank == 0:
         emit(line)
     eng.close()
