@@ -15,12 +15,18 @@
 //                sub-segment's first jump, P is on the speculative trajectory and the result stands; otherwise (a false
 //                sync inside the straddling frame) that lane walks the sub-segment again from P.  Emits Mp3Analysis per
 //                track and every sub-segment's entry position
-//   k_gf_patch   one thread per sub-segment walks from its entry position (no speculation left) and patches the gain
-//                fields in place (saturating / wrapping / one channel only)
+//   k_gf_patch   one thread per sub-segment walks the ORIGINAL image from its entry position (no speculation left) and writes
+//                the patched gain fields (saturating / wrapping / one channel only) into a COPY of the image
 //
-// A write never changes what the walk reads later: gain bytes lie inside the side info of their own frame (last gain
-// byte <= offset 34 of an MPEG-1 frame, <= 18 of an LSF frame; the smallest frames are 96 and 24 bytes) and frames of one
-// trajectory are disjoint, so walking first and patching in parallel equals the reference's serial read-modify-write.
+// Why a copy: the reference patches in place while it walks, but its cursor only ever reads bytes at or ahead of itself and
+// only ever writes inside frames it has passed, so every decision it takes is a decision about the original bytes.  A
+// parallel in-place patch does not have that property: a false sync at the end of one sub-segment is confirmed or rejected
+// by the two bytes at its frame length, which may be gain bytes that the neighbouring sub-segment's thread has already
+// rewritten (saturation to 255 manufactures 0xFF 0xE? patterns).  tests/dev/gf_kernel_model.c found such a case in its
+// 10,000th image; reading the original and writing the copy makes every walk see what the reference's cursor saw.
+// Within the copy no byte is written twice: gain fields of one frame are 59 / 63 bits apart (different bytes), lie inside
+// the side info of their own frame (last gain byte <= offset 34 of an MPEG-1 frame, <= 18 of an LSF frame; the smallest
+// frames are 96 and 24 bytes), and the frames of one trajectory are disjoint.
 //
 // The walker touches ~48 bytes per frame (header, CRC, side info, Xing marker, the next sync word), not the payload.  A
 // first version streamed every file byte through shared memory, one warp per 64 KiB segment, and was bound by instruction
@@ -90,15 +96,13 @@ __device__ __forceinline__ void gf_fill_lut(uint16_t* lut) {
 
 // Image loads.  Images start 16-byte aligned and are followed by >= 16 bytes of slack inside the corpus buffer
 // (corpus_describe), so an aligned 16-byte load that starts below `len`, and the word after it, stay inside the allocation; bytes beyond `len` are
-// never consumed by the walk (every read is guarded by len / audio_end).  The patching walk reads with plain loads (it
-// writes the same buffer), the read-only walks through the non-coherent path.
+// never consumed by the walk (every read is guarded by len / audio_end).  The image is read-only for every kernel here
+// (the patch goes to a copy), so all loads take the non-coherent path.
 template <bool PATCH> __device__ __forceinline__ uint32_t gf_ldw(const uint8_t* img, uint32_t a) {   // a % 4 == 0
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(img + a);
-    return PATCH ? *p : __ldg(p);
+    return __ldg(reinterpret_cast<const uint32_t*>(img + a));
 }
 template <bool PATCH> __device__ __forceinline__ uint4 gf_ld16(const uint8_t* img, uint32_t a) {     // a % 16 == 0
-    const uint4* p = reinterpret_cast<const uint4*>(img + a);
-    return PATCH ? *p : __ldg(p);
+    return __ldg(reinterpret_cast<const uint4*>(img + a));
 }
 // 4 bytes at any offset g, little-endian (first byte in bits 0-7)
 template <bool PATCH> __device__ __forceinline__ uint32_t gf_ld32(const uint8_t* img, uint32_t g) {
@@ -116,14 +120,15 @@ template <bool PATCH> __device__ __forceinline__ uint32_t gf_ld32(const uint8_t*
 //          the header it lands on; a lane that lands on something else goes back to SCAN (one byte later, as the
 //          reference does) once the others have finished their frames
 // A first thread-per-sub-segment version without this structure ran with 5 of 32 lanes active per instruction.
-// PATCH: rewrite the gain fields in place (img must be writable).  channel < 0: every granule-channel (wrap selects
-// GainMode::Wrapping); channel 0 / 1: that channel's fields only, saturating (apply_gain_to_channel_data).
+// PATCH: write the rewritten gain fields to `outp` (a copy of the image; img itself is only read).  channel < 0: every
+// granule-channel (wrap selects GainMode::Wrapping); channel 0 / 1: that channel's fields only, saturating
+// (apply_gain_to_channel_data).
 #define GF_ST_SCAN 0u
 #define GF_ST_FRAME 1u
 #define GF_ST_DONE 2u
 template <bool PATCH>
-__device__ GfSeg gf_walk(uint8_t* img, uint32_t len, uint32_t audio_end, const uint16_t* lut, uint32_t pos, uint32_t bound,
-                         int steps, int wrap, int channel, bool run) {
+__device__ GfSeg gf_walk(const uint8_t* img, uint8_t* outp, uint32_t len, uint32_t audio_end, const uint16_t* lut, uint32_t pos,
+                         uint32_t bound, int steps, int wrap, int channel, bool run) {
     GfSeg o;
     o.first_jump = GF_NONE; o.n_frames = 0; o.gcount = 0; o.first_hdr = 0; o.pad = 0;
     uint32_t gsum = 0, gmin = 255, gmax = 0;
@@ -193,10 +198,10 @@ __device__ GfSeg gf_walk(uint8_t* img, uint32_t len, uint32_t audio_end, const u
                             gsum += g; gmin = min(gmin, g); gmax = max(gmax, g);
                             if (PATCH && idx < len && (channel < 0 || (k >= channel && (k - channel) % nch == 0))) {
                                 const uint32_t v = gf_adjust(g, steps, channel < 0 ? wrap : 0);
-                                if (sh == 0) img[idx] = (uint8_t)v;
+                                if (sh == 0) outp[idx] = (uint8_t)v;
                                 else {
-                                    img[idx] = (uint8_t)((b0 & (0xFFu << (8 - sh))) | (v >> sh));
-                                    if (idx + 1 < len) img[idx + 1] = (uint8_t)((b1 & (0xFFu >> sh)) | ((v << (8 - sh)) & 0xFF));
+                                    outp[idx] = (uint8_t)((b0 & (0xFFu << (8 - sh))) | (v >> sh));
+                                    if (idx + 1 < len) outp[idx + 1] = (uint8_t)((b1 & (0xFFu >> sh)) | ((v << (8 - sh)) & 0xFF));
                                 }
                             }
                         }
@@ -234,7 +239,7 @@ __device__ __forceinline__ uint32_t gf_find_track(const TrackSeg* __restrict__ t
 
 // tin / tseg point at the first track of the group; seg0 = its first sub-segment
 __global__ void __launch_bounds__(GF_THREADS)
-k_gf_scan(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
+k_gf_scan(const uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
           uint32_t n_segs, GfSeg* __restrict__ segout) {
     __shared__ uint16_t s_lut[256];
     gf_fill_lut(s_lut);
@@ -242,25 +247,25 @@ k_gf_scan(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __re
     const bool have = si < n_segs;
     const uint32_t t = gf_find_track(tseg, n_tracks, seg0 + (have ? si : 0));
     const TrackSeg ts = tseg[t];
-    uint8_t* img = corpus + tin[t].off;
+    const uint8_t* img = corpus + tin[t].off;
     const uint32_t len = (uint32_t)tin[t].len;
     uint32_t a0, audio_end, b, e;
     gf_bounds(img, len, a0, audio_end);
     gf_seg_range(seg0 + (have ? si : 0) - ts.seg_base, ts.n_seg, b, e);
     if (b < a0) b = a0;
-    const GfSeg o = gf_walk<false>(img, len, audio_end, s_lut, b, e, 0, 0, -1, have && b < e);
+    const GfSeg o = gf_walk<false>(img, nullptr, len, audio_end, s_lut, b, e, 0, 0, -1, have && b < e);
     if (have) segout[seg0 + si] = o;
 }
 
 __global__ void __launch_bounds__(GF_THREADS)
-k_gf_merge(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, const GfSeg* __restrict__ segout,
+k_gf_merge(const uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, const GfSeg* __restrict__ segout,
            uint32_t* __restrict__ entry, GfTrackOut* __restrict__ out, uint32_t n_tracks) {
     __shared__ uint16_t s_lut[256];
     gf_fill_lut(s_lut);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t = blockIdx.x * (GF_THREADS / 32) + warp;
     if (t >= n_tracks) return;
-    uint8_t* img = corpus + tin[t].off;
+    const uint8_t* img = corpus + tin[t].off;
     const uint32_t len = (uint32_t)tin[t].len;
     const TrackSeg ts = tseg[t];
     uint32_t a0, audio_end;
@@ -281,7 +286,7 @@ k_gf_merge(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __r
             const bool active = P < e && (uint64_t)P + 4 <= audio_end;
             const uint32_t fj = __shfl_sync(0xffffffffu, o.first_jump, j);
             if (active && !(fj == GF_NONE || P <= fj)) {  // P is not on the speculative trajectory: lane j walks again from P
-                const GfSeg w = gf_walk<false>(img, len, audio_end, s_lut, P, e, 0, 0, -1, lane == (int)j);
+                const GfSeg w = gf_walk<false>(img, nullptr, len, audio_end, s_lut, P, e, 0, 0, -1, lane == (int)j);
                 if (lane == (int)j) { o = w; rewalks++; }
             }
             if (lane == (int)j) {
@@ -319,7 +324,7 @@ k_gf_merge(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __r
 }
 
 __global__ void __launch_bounds__(GF_THREADS)
-k_gf_patch(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
+k_gf_patch(const uint8_t* corpus, uint8_t* out_corpus, const TrackIn* __restrict__ tin, const TrackSeg* __restrict__ tseg, uint32_t n_tracks, uint32_t seg0,
            uint32_t n_segs, const uint32_t* __restrict__ entry, int steps, int wrap, int channel) {
     __shared__ uint16_t s_lut[256];
     gf_fill_lut(s_lut);
@@ -328,10 +333,10 @@ k_gf_patch(uint8_t* corpus, const TrackIn* __restrict__ tin, const TrackSeg* __r
     const uint32_t ent = have ? entry[seg0 + si] : GF_NONE;
     const uint32_t t = gf_find_track(tseg, n_tracks, seg0 + (have ? si : 0));
     const TrackSeg ts = tseg[t];
-    uint8_t* img = corpus + tin[t].off;
+    const uint8_t* img = corpus + tin[t].off;
     const uint32_t len = (uint32_t)tin[t].len;
     uint32_t a0, audio_end, b, e;
     gf_bounds(img, len, a0, audio_end);
     gf_seg_range(seg0 + (have ? si : 0) - ts.seg_base, ts.n_seg, b, e);
-    gf_walk<true>(img, len, audio_end, s_lut, ent, e, steps, wrap, channel, ent != GF_NONE);
+    gf_walk<true>(img, out_corpus + tin[t].off, len, audio_end, s_lut, ent, e, steps, wrap, channel, ent != GF_NONE);
 }

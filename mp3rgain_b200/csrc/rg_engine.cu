@@ -115,7 +115,7 @@ struct rg_engine {
     DevBuf d_pcm_in, d_album, d_album_peak, d_misc;
     DevBuf d_tin, d_fbase, d_frames, d_md, d_meta;
     DevBuf d_tseg, d_segs, d_segout, d_segfin, d_stage;   // speculative segmented frame index (k_frame_index.cuh)
-    DevBuf d_gfseg, d_gfent, d_gfout;     // global_gain walk (k_gain_fields.cuh): per-segment results, entry positions, per-track results
+    DevBuf d_gfseg, d_gfent, d_gfout, d_gfpatch;   // global_gain walk (k_gain_fields.cuh): per-sub-segment results, entry positions, per-track results, patched copy of the images
     HostBuf h_gfout;
     DevBuf d_corpus;                      // file images of rg_analyze_tracks / rg_analyze_album (kept between calls)
     HostBuf h_meta;
@@ -123,7 +123,7 @@ struct rg_engine {
     DecodeScratch dec;
     std::vector<DevBuf*> all_bufs() {
         std::vector<DevBuf*> v = {&d_pcm_in, &d_album, &d_album_peak, &d_misc, &d_tin, &d_fbase, &d_frames, &d_md, &d_meta, &d_corpus,
-                                  &d_tseg, &d_segs, &d_segout, &d_segfin, &d_stage, &d_gfseg, &d_gfent, &d_gfout};
+                                  &d_tseg, &d_segs, &d_segout, &d_segfin, &d_stage, &d_gfseg, &d_gfent, &d_gfout, &d_gfpatch};
         for (auto& c : ctx) for (DevBuf* b : c.bufs()) v.push_back(b);
         return v;
     }

@@ -38,6 +38,7 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
     CK(e->d_gfent.ensure(n_sub * sizeof(uint32_t)));
     CK(e->d_gfout.ensure(n * sizeof(GfTrackOut)));
     CK(e->h_gfout.ensure(n * sizeof(GfTrackOut)));
+    if (patch) CK(e->d_gfpatch.ensure(c->total + 64));   // the patched copy (k_gf_patch reads the original, see k_gain_fields.cuh)
     cudaStream_t st = e->stream;
     CK(cudaMemcpyAsync(e->d_tin.p, tin.data(), n * sizeof(TrackIn), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(e->d_tseg.p, tseg.data(), n * sizeof(TrackSeg), cudaMemcpyHostToDevice, st));
@@ -68,7 +69,9 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
         CK(cudaEventRecord(ev2, st));
         e->stats.kernel_launches += 2;
         if (patch) {
-            k_gf_patch<<<gs, GF_THREADS, 0, st>>>(c->d_bytes, e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, (uint32_t)(t1 - t0), seg0, nsg,
+            const uint64_t off0 = c->off[t0], span = (t1 < n ? c->off[t1] : c->total) - off0;
+            CK(cudaMemcpyAsync(e->d_gfpatch.as<uint8_t>() + off0, c->d_bytes + off0, span, cudaMemcpyDeviceToDevice, st));
+            k_gf_patch<<<gs, GF_THREADS, 0, st>>>(c->d_bytes, e->d_gfpatch.as<uint8_t>(), e->d_tin.as<TrackIn>() + t0, e->d_tseg.as<TrackSeg>() + t0, (uint32_t)(t1 - t0), seg0, nsg,
                                                   e->d_gfent.as<uint32_t>(), steps, wrap, channel);
             e->stats.kernel_launches++;
         }
@@ -80,7 +83,7 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
             CK(cudaStreamWaitEvent(e->s_dec, ev3, 0));
             for (size_t i = t0; i < t1; i++) {
                 if (!c->len[i]) continue;
-                CK(cudaMemcpyAsync(out_images[i], c->d_bytes + c->off[i], c->len[i], cudaMemcpyDeviceToHost, e->s_dec));
+                CK(cudaMemcpyAsync(out_images[i], e->d_gfpatch.as<uint8_t>() + c->off[i], c->len[i], cudaMemcpyDeviceToHost, e->s_dec));
                 e->stats.d2h_bytes += c->len[i];
             }
         }

@@ -118,6 +118,18 @@ def test_false_syncs_after_segment_boundaries_force_rewalks(engine_fast, oracle)
     _check_apply(engine_fast, oracle, [t], 7)
 
 
+def test_patch_decisions_are_taken_on_the_original_bytes(engine_fast, oracle):
+    """Found by tests/test_gain_model.py (seed 9, case 1259): a false header at the end of sub-segment 0 whose frame length
+    points at gain bytes of a frame in sub-segment 1; saturating them to 255 manufactures the sync word that would confirm
+    the false header.  The reference's cursor never sees patched bytes, so neither may the patch kernel (it reads the
+    original image and writes a copy)."""
+    img = np.load(os.path.join(GOLD, "gain_patch_false_sync_case.npy"))
+    for _ in range(5):      # (the in-place version was a race: repeat)
+        _check_apply(engine_fast, oracle, [img] * 8, 80, channel=0)
+        _check_apply(engine_fast, oracle, [img] * 8, 80)
+        _check_apply(engine_fast, oracle, [img] * 8, 255)
+
+
 def test_differential_fuzz(engine_fast, oracle):
     rng = np.random.default_rng(7)
     bases = [synth_corpus.make_track(seed=140 + i, n_frames=500, version=v, channels=c, br_idx=b, sr_idx=s, crc=cr)
