@@ -55,7 +55,8 @@ __device__ __forceinline__ bool k0_compatible(uint32_t a, uint32_t ref) {
 }
 
 #define K0_SEG (64u * 1024u)            // bytes per speculative segment
-#define K0_SEG_RECS (K0_SEG / 96 + 18)  // staged frames per segment (smallest MPEG-1 Layer III frame: 96 bytes)
+#define K0_SEG_RECS (K0_SEG / 24 + 18)  // staged frames per segment (smallest Layer III frame: 24 bytes -- MPEG-2, 8 kbps at 24 kHz;
+                                        // with the MPEG-1 minimum of 96 bytes, low-bitrate LSF streams overflowed the staging)
 
 struct TrackSeg { uint32_t seg_base, n_seg; };     // a track's segments: [seg_base, seg_base + n_seg) of the call's segment arrays
 struct SegDesc { uint32_t track, seg; };           // segment -> (track of the launch's group, index within the track)

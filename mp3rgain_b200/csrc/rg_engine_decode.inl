@@ -111,7 +111,7 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
         tseg[i].n_seg = (uint32_t)std::max<uint64_t>(1, (c->len[i] + K0_SEG - 1) / K0_SEG);
         for (uint32_t sg = 0; sg < tseg[i].n_seg; sg++) segs.push_back(SegDesc{(uint32_t)i, sg});
         ip.frame_base[i] = fb; ip.md_base[i] = mb;
-        fb += c->len[i] / 96 + 2;                      // smallest MPEG-1 Layer III frame is 96 bytes
+        fb += c->len[i] / 24 + 2;                      // smallest Layer III frame: 24 bytes (MPEG-2, 8 kbps at 24 kHz)
         mb += (c->len[i] + 32 + 15) & ~15ull;
         bytes += c->len[i];
     }

@@ -666,6 +666,58 @@ static int decode_stream(const uint8_t* data, size_t len, uint32_t flags, pcm_si
     return status;
 }
 
+/* ------------------------------------------------------------------ frame index only (the demux half of decode_stream)
+ * The same walk as decode_stream, statement for statement, without the decoding: which frames become audio, where each
+ * frame's granule data starts in the concatenated main-data stream (the bit reservoir unrolled) and what that stream holds.
+ * Checker for the device's speculative frame index (k_frame_index.cuh) and its CPU model (tests/dev/k0_index_model.c). */
+int mp3o_index(const uint8_t* data, size_t len, uint32_t flags, mp3o_frame* recs, size_t max_recs, uint8_t* md, size_t* md_len_out,
+               mp3o_info* info) {
+    init_once();
+    memset(info, 0, sizeof *info);
+    size_t pos = skip_id3v2(data, len);
+    hdr_t ref;
+    int have_ref = 0, in_sync = 0, first = 1;
+    size_t md_len = 0, n = 0;
+    int status = MP3O_ERR_PROBE;
+    while (pos + 4 <= len) {
+        hdr_t h;
+        int ok = parse_hdr(data + pos, &h) && (!have_ref || compatible(&h, &ref));
+        if (ok && pos + (size_t)h.frame_len > len) break;
+        if (ok && !in_sync) {
+            size_t nx = pos + h.frame_len;
+            hdr_t h2;
+            if (nx + 4 <= len && !(parse_hdr(data + nx, &h2) && compatible(&h2, &h))) ok = 0;
+        }
+        if (!ok) { in_sync = 0; pos++; continue; }
+        in_sync = 1;
+        if (!have_ref) { ref = h; have_ref = 1; info->sample_rate = h.sr; info->channels = h.channels; status = 0; }
+        const uint8_t* fp = data + pos;
+        const size_t fpos = pos;
+        pos += h.frame_len;
+        if (first) {
+            first = 0;
+            if (!(flags & MP3O_FLAG_KEEP_INFO_FRAME) && is_info_frame(fp, &h)) { info->skipped_info_frame = 1; continue; }
+        }
+        size_t so = 4 + (h.crc ? 2 : 0);
+        side_t s;
+        parse_side(fp + so, h.channels, h.ver != 3, &s);
+        size_t mdo = so + h.side_len;
+        size_t md_start_ok = s.main_data_begin <= (int)md_len;
+        size_t start = md_len - (md_start_ok ? s.main_data_begin : 0);
+        if ((size_t)h.frame_len > mdo) { memcpy(md + md_len, fp + mdo, h.frame_len - mdo); md_len += h.frame_len - mdo; }
+        if (!s.valid || !md_start_ok) { info->n_dropped_frames++; continue; }
+        if (n < max_recs) {
+            recs[n].file_off = (uint32_t)fpos; recs[n].md_start = (uint32_t)start; recs[n].md_end = (uint32_t)md_len;
+            recs[n].hdr = ((uint32_t)fp[0] << 24) | ((uint32_t)fp[1] << 16) | ((uint32_t)fp[2] << 8) | fp[3];
+        }
+        n++;
+        info->n_frames++;
+    }
+    *md_len_out = md_len;
+    info->status = status;
+    return status;
+}
+
 /* ------------------------------------------------------------------ public entry points */
 typedef struct { float* pcm; size_t max_frames, n; } copy_ctx;
 static void sink_copy(void* c, const float* l, const float* r, int n) {

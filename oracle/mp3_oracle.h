@@ -23,6 +23,13 @@ typedef struct {
     uint32_t n_dropped_frames;    /* frames dropped as DecodeError (reservoir underflow / invalid side info) */
 } mp3o_info;
 
+/* One PCM-producing frame of the index: where it starts in the file, where its granule data starts / how many bytes the
+ * concatenated main-data stream holds once the frame is read, and its 4 header bytes (big-endian). */
+typedef struct { uint32_t file_off, md_start, hdr, md_end; } mp3o_frame;
+/* The demux half of mp3o_decode only.  md: len + 64 bytes. */
+int mp3o_index(const uint8_t* data, size_t len, uint32_t flags, mp3o_frame* recs, size_t max_recs, uint8_t* md, size_t* md_len_out,
+               mp3o_info* info);
+
 /* MP3 file image -> planar f32 PCM.  pcm holds 2 planes of max_frames floats (plane 1 unused for mono). */
 int mp3o_decode(const uint8_t* data, size_t len, uint32_t flags, float* pcm, size_t max_frames, mp3o_info* info);
 /* analyze_track_internal (src/replaygain.rs:796-925): decode + stage B. hist_out NULL or 12000 u32. */

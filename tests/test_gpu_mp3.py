@@ -92,6 +92,25 @@ def test_mpeg2_streams_pcm_bit_exact_and_analysis(kw, engine_exact, engine_fast,
     _check_analysis(engine_fast, oracle, img)
 
 
+@pytest.mark.parametrize("kw", [dict(version=2, seed=47, channels=1, br_idx=2), dict(version=2, seed=48, channels=1, br_idx=1, sr_idx=1),
+                                dict(version=0, seed=49, channels=1, br_idx=1, sr_idx=2), dict(version=2, seed=50, channels=2, br_idx=3)])
+def test_low_bitrate_lsf_streams_with_frames_below_96_bytes(kw, engine_exact, engine_fast, oracle):
+    """8-24 kbps MPEG-2 / 2.5: frames of 52, 24, 72 and 78 bytes, several 64 KiB index segments each.  The frame-record
+    capacities used to assume the MPEG-1 minimum of 96 bytes per frame (len/96 records per track, 64Ki/96 staged frames per
+    segment); these streams hold up to four times as many."""
+    img = synth_corpus.make_track(n_frames=7000, **kw)
+    assert len(img) / 7000 < 96 and len(img) > 2 * 65536
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.n_frames == 7000
+    _check_analysis(engine_exact, oracle, img)
+    _check_analysis(engine_fast, oracle, img)
+    # and next to other tracks in one call (the records of one track must not run into the next one's)
+    other = synth_corpus.make_track(seed=3, n_frames=200)
+    res, sts = engine_fast.analyze_images([img, other, img], want_hist=True)
+    rc, ores, ohist, _ = oracle.analyze_mp3(other)
+    assert sts == [0, 0, 0] and (res[1].histogram == ohist).all() and (res[0].histogram == res[2].histogram).all()
+
+
 @pytest.mark.parametrize("kw", [dict(version=2, seed=51), dict(version=2, seed=52, sr_idx=1, br_idx=0), dict(version=0, seed=53, sr_idx=1),
                                 dict(version=0, seed=55, sr_idx=2, br_idx=0)])
 def test_mpeg2_intensity_stereo_pcm_bit_exact(kw, engine_exact, oracle):

@@ -148,6 +148,23 @@ LSF = [dict(version=2, seed=41), dict(version=2, seed=42, channels=1, sr_idx=1, 
        dict(version=0, seed=44), dict(version=0, seed=45, sr_idx=1, br_idx=0), dict(version=0, seed=46, sr_idx=2, br_idx=2, channels=1)]
 
 
+LOW_BITRATE = [dict(version=2, seed=47, channels=1, br_idx=2), dict(version=2, seed=48, channels=1, br_idx=1, sr_idx=1),
+               dict(version=0, seed=49, channels=1, br_idx=1, sr_idx=2), dict(version=2, seed=50, channels=2, br_idx=3)]
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", LOW_BITRATE)
+def test_low_bitrate_lsf_streams_decode_like_ffmpeg(oracle, kw):
+    """Frames shorter than the MPEG-1 minimum of 96 bytes (52, 24, 72 and 78 bytes here: 8-24 kbps MPEG-2 / 2.5)."""
+    img = synth_corpus.make_track(n_frames=400, **kw)
+    assert len(img) / 400 < 96
+    rc, pcm, info = oracle.decode(img)
+    assert rc == 0 and info.n_frames == 400 and info.n_dropped_frames == 0
+    ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
+    assert pcm.shape == ff.shape == (kw["channels"], 400 * 576)
+    assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+
+
 @pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
 @pytest.mark.parametrize("kw", LSF)
 def test_mpeg2_streams_decode_like_ffmpeg(oracle, kw):
