@@ -11,6 +11,14 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("RG_SIMT_EMU") == "1":
+        # Development aid (tests/dev/simt_emu): run the -m gpu tests' logic without a GPU by pointing the ctypes binding at
+        # the engine sources compiled against the CPU SIMT interpreter.  Only this test session is affected; the product's
+        # loader (mp3rgain_b200/_lib.py) knows nothing about it, and the driver's GPU run never sets the variable.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "dev", "simt_emu"))
+        import build_emu
+        from mp3rgain_b200 import _lib
+        _lib.LIB_PATH = build_emu.build()
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,105 @@
+"""Builds tests/dev/simt_emu/librg_engine_emu.so: the engine's CUDA sources compiled by g++ against the SIMT interpreter in
+cuda_runtime.h (this directory).  TEST INFRASTRUCTURE ONLY -- see the header of cuda_runtime.h.
+
+The sources under mp3rgain_b200/csrc are copied to a scratch directory with three mechanical rewrites, none of which touches
+kernel logic:
+  1. `kernel<<<grid, block, smem, stream>>>(args);`  ->  `EMU_LAUNCH(grid, block, smem, stream, kernel(args));`
+  2. `extern __shared__ <attrs> T name[];`           ->  `T* name = EMU_DYN_SMEM(T);`
+  3. the bodies of the five inline-PTX helpers of K2 (mbarrier init / expect_tx / try_wait, cp.async.bulk, bar.sync id, 64)
+     are replaced by calls into the interpreter's rendezvous primitives of the same meaning.
+"""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
+CSRC = os.path.join(ROOT, "mp3rgain_b200", "csrc")
+OUT = os.path.join(HERE, "librg_engine_emu.so")
+SCRATCH = os.path.join(HERE, "_build")
+
+PTX_HELPERS = {
+    "k2_mbar_init": "emu::mbar_init(bar, count);",
+    "k2_mbar_expect": "emu::mbar_expect(bar, bytes);",
+    "k2_bulk_load": "emu::bulk_load(dst, src, bytes, bar);",
+    "k2_mbar_wait": "emu::mbar_wait(bar, parity);",
+    "k2_pair_sync": "emu::barrier(1 + (pair < 3 ? pair : 3), 64);",
+}
+
+
+def _match(src, i, open_ch, close_ch):
+    """index just past the bracket that closes the one at src[i]"""
+    depth = 0
+    while True:
+        c = src[i]
+        if c == open_ch:
+            depth += 1
+        elif c == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+
+
+def rewrite(src, name):
+    # 1. launches
+    out = []
+    pos = 0
+    for m in re.finditer(r"([A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<", src):
+        if m.start() < pos:
+            continue
+        cfg_end = src.index(">>>", m.end())
+        cfg = src[m.end():cfg_end]
+        j = cfg_end + 3
+        while src[j].isspace():
+            j += 1
+        assert src[j] == "(", f"{name}: launch of {m.group(1)} without an argument list"
+        args_end = _match(src, j, "(", ")")
+        out.append(src[pos:m.start()])
+        out.append(f"EMU_LAUNCH({cfg}, {m.group(1)}{src[j:args_end]})")
+        pos = args_end
+    out.append(src[pos:])
+    src = "".join(out)
+    assert "<<<" not in src, f"{name}: a launch was not rewritten"
+    # 2. dynamic shared memory
+    src = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];", r"\1* \2 = EMU_DYN_SMEM(\1);", src)
+    # 3. inline-PTX helpers
+    for fn, body in PTX_HELPERS.items():
+        m = re.search(r"\b" + fn + r"\s*\([^)]*\)\s*\{", src)
+        if not m:
+            continue
+        end = _match(src, m.end() - 1, "{", "}")
+        src = src[:m.end()] + " " + body + " }" + src[end:]
+    assert "asm volatile" not in src and "asm(" not in src, f"{name}: inline PTX without an interpreter counterpart"
+    return src
+
+
+def build(force=False):
+    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl", ".h")))
+    deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(HERE, "cuda_runtime.h"), os.path.abspath(__file__),
+                                                    os.path.join(ROOT, "include", "rg_engine.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    shutil.rmtree(SCRATCH, ignore_errors=True)
+    os.makedirs(os.path.join(SCRATCH, "mp3rgain_b200", "csrc"))
+    os.makedirs(os.path.join(SCRATCH, "include"))
+    shutil.copy(os.path.join(ROOT, "include", "rg_engine.h"), os.path.join(SCRATCH, "include"))
+    for f in srcs:
+        with open(os.path.join(CSRC, f)) as fh:
+            text = rewrite(fh.read(), f)
+        dst = f[:-3] + ".cpp" if f.endswith(".cu") else f
+        with open(os.path.join(SCRATCH, "mp3rgain_b200", "csrc", dst), "w") as fh:
+            fh.write(text)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+           "-I", HERE, "-o", OUT, os.path.join(SCRATCH, "mp3rgain_b200", "csrc", "rg_engine.cpp")]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stderr[-6000:])
+        raise RuntimeError("simt_emu build failed")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))
