@@ -67,8 +67,21 @@ static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char
 // ---------------------------------------------------------------------------------------------------------------------
 namespace emu {
 
+// Context switch: a hand-written callee-saved-register switch on x86-64 (swapcontext costs a sigprocmask system call per
+// switch, a third of the run time of a collective-heavy kernel); ucontext elsewhere.
+#if defined(__x86_64__)
+#define EMU_ASM_SWITCH 1
+extern "C" void emu_switch_ctx(void** save_sp, void* new_sp);
+asm(".text\n.local emu_switch_ctx\n.type emu_switch_ctx,@function\nemu_switch_ctx:\n"
+    "pushq %rbp\npushq %rbx\npushq %r12\npushq %r13\npushq %r14\npushq %r15\n"
+    "movq %rsp, (%rdi)\nmovq %rsi, %rsp\n"
+    "popq %r15\npopq %r14\npopq %r13\npopq %r12\npopq %rbx\npopq %rbp\nret\n"
+    ".size emu_switch_ctx, .-emu_switch_ctx\n");
+#endif
+
 struct Fiber {
     ucontext_t ctx;
+    void* sp;
     uint3 tid;
     unsigned lin;          // linear thread id
     bool done, waiting;
@@ -84,6 +97,7 @@ struct State {
     std::vector<Fiber> fib;
     std::vector<char*> stacks;
     ucontext_t sched;
+    void* sched_sp = nullptr;
     Fiber* cur = nullptr;
     unsigned nthreads = 0, live = 0;
     dim3 blockDim, gridDim;
@@ -105,14 +119,21 @@ inline void die(const char* msg) {
     fprintf(stderr, "simt_emu: %s (block %u, thread %u)\n", msg, s.blockIdx.x, s.cur ? s.cur->lin : 0);
     abort();
 }
-inline void yield() { State& s = S(); Fiber* f = s.cur; swapcontext(&f->ctx, &s.sched); }
+#ifdef EMU_ASM_SWITCH
+inline void to_sched(Fiber* f) { emu_switch_ctx(&f->sp, S().sched_sp); }
+inline void to_fiber(Fiber* f) { emu_switch_ctx(&S().sched_sp, f->sp); }
+#else
+inline void to_sched(Fiber* f) { swapcontext(&f->ctx, &S().sched); }
+inline void to_fiber(Fiber* f) { swapcontext(&S().sched, &f->ctx); }
+#endif
+inline void yield() { to_sched(S().cur); }
 inline void entry() {
     State& s = S();
     s.thunk(s.body);
     s.cur->done = true;
     s.live--;
     s.progress++;
-    swapcontext(&s.cur->ctx, &s.sched);
+    to_sched(s.cur);
 }
 
 template <class F> void thunk_of(const void* p) { (*static_cast<const F*>(p))(); }
@@ -137,11 +158,22 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, const F& body
         memset(s.dyn_smem, 0xCD, smem);
         for (unsigned t = 0; t < nt; t++) {
             Fiber& f = s.fib[t];
+#ifdef EMU_ASM_SWITCH
+            {
+                uintptr_t top = ((uintptr_t)s.stacks[t] + STACK) & ~(uintptr_t)15;
+                void** P = (void**)(top - 16);     // `ret` pops the entry address from P; entry then sees rsp = 8 mod 16
+                P[0] = (void*)&entry; P[1] = nullptr;
+                void** sp = P - 6;                 // r15 r14 r13 r12 rbx rbp
+                for (int k = 0; k < 6; k++) sp[k] = nullptr;
+                f.sp = sp;
+            }
+#else
             getcontext(&f.ctx);
             f.ctx.uc_stack.ss_sp = s.stacks[t];
             f.ctx.uc_stack.ss_size = STACK;
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, (void (*)())entry, 0);
+#endif
             f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
             f.lin = t; f.done = false; f.waiting = false; f.c_wait = f.c_done = false;
         }
@@ -155,7 +187,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, const F& body
                 if (f.done) continue;
                 if (!f.waiting) ran_free = true;
                 s.cur = &f;
-                swapcontext(&s.sched, &f.ctx);
+                to_fiber(&f);
             }
             s.cur = nullptr;
             if (s.live && !ran_free && s.progress == p0) { s.cur = &s.fib[0]; die("deadlock: every live thread waits and nothing completes"); }
