@@ -156,7 +156,9 @@ static int decode_init_tables(DecodeScratch& ds) {
             uint8_t* ls = mixed ? T.line_sfb_mixed[r] : T.line_sfb_short[r];
             uint16_t* ro = mixed ? T.scatter_mixed[r] : T.scatter_short[r];
             for (int i = 0; i < 576; i++) ro[i] = (uint16_t)i;
-            if (mixed) for (int i = 0; i < 36; i++) ls[i] = T.line_sfb_long[r][i];
+            // mixed: 8 long bands in MPEG-1, 6 in LSF (what the scalefactor partitions carry): the lines below 36 at every rate
+            // but 8 kHz, whose 6 long bands span 72 lines and meet short band 3 there (FFmpeg's compute_band_indexes does the same)
+            if (mixed) for (int i = 0; i < T.long_start[r][r < 3 ? 8 : 6]; i++) ls[i] = T.line_sfb_long[r][i];
             for (int sfb = mixed ? 3 : 0; sfb < 13; sfb++) {
                 int st = T.short_start[r][sfb], w = L3_SFB_SHORT_W[r][sfb];
                 for (int win = 0; win < 3; win++)

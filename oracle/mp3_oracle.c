@@ -349,7 +349,11 @@ static void requantize(const gr_t* q, int sr_row, const int* sf_l, int (*sf_s)[3
     int i = 0;
     if (q->block_type != 2 || q->mixed) {
         int nl = 22;
-        if (q->block_type == 2) for (nl = 0; g_long_start[sr_row][nl] < 36; nl++) {}   /* mixed: the long bands below line 36 (8 in MPEG-1, 6 in LSF) */
+        /* mixed: 8 long bands in MPEG-1, 6 in LSF (what the scalefactor partitions carry) = the lines below 36 at every rate
+         * but 8 kHz, whose 6 long bands span 72 lines and meet short band 3 there (FFmpeg's compute_band_indexes: "For
+         * 8000Hz, we handle the 72 first exponents as long blocks"; counting the bands below line 36 instead gave 3 at 8 kHz
+         * and left the short part 36 lines early) */
+        if (q->block_type == 2) nl = sr_row < 3 ? 8 : 6;
         for (int sfb = 0; sfb < nl; sfb++) {
             int e = q->global_gain - 210 - mult * (sf_l[sfb] + (q->preflag ? L3_PRETAB[sfb] : 0));
             float g = L3_GAIN[e - L3_GAIN_MIN];

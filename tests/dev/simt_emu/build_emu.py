@@ -92,7 +92,7 @@ def build(force=False):
         dst = f[:-3] + ".cpp" if f.endswith(".cu") else f
         with open(os.path.join(SCRATCH, "mp3rgain_b200", "csrc", dst), "w") as fh:
             fh.write(text)
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
            "-I", HERE, "-o", OUT, os.path.join(SCRATCH, "mp3rgain_b200", "csrc", "rg_engine.cpp")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:

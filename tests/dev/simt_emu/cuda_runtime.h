@@ -21,6 +21,7 @@
 #include <math.h>
 #include <time.h>
 #include <type_traits>
+#include <source_location>
 #include <vector>
 
 #define RG_SIMT_EMU 1
@@ -91,6 +92,7 @@ struct Fiber {
     int c_op;
     uint64_t c_val, c_res;
     int c_arg;
+    const char* c_file; unsigned c_line;
 };
 
 struct State {
@@ -109,6 +111,7 @@ struct State {
     void (*thunk)(const void*) = nullptr;
     unsigned char* dyn_smem = nullptr;
     uint64_t launches = 0, fibers_run = 0;
+    const char* kernel = "";
 };
 inline State& S() { static State s; return s; }
 static const size_t STACK = 192 * 1024;
@@ -116,7 +119,7 @@ static const size_t DYN_SMEM = 256 * 1024;
 
 inline void die(const char* msg) {
     State& s = S();
-    fprintf(stderr, "simt_emu: %s (block %u, thread %u)\n", msg, s.blockIdx.x, s.cur ? s.cur->lin : 0);
+    fprintf(stderr, "simt_emu: %s (kernel %s, block %u, thread %u)\n", msg, s.kernel, s.blockIdx.x, s.cur ? s.cur->lin : 0);
     abort();
 }
 #ifdef EMU_ASM_SWITCH
@@ -190,7 +193,15 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, const F& body
                 to_fiber(&f);
             }
             s.cur = nullptr;
-            if (s.live && !ran_free && s.progress == p0) { s.cur = &s.fib[0]; die("deadlock: every live thread waits and nothing completes"); }
+            if (s.live && !ran_free && s.progress == p0) {
+                for (unsigned t = 0; t < nt; t++) {
+                    const Fiber& f = s.fib[t];
+                    if (!f.done && f.c_wait) fprintf(stderr, "simt_emu: thread %u waits at %s:%u (op %d, mask %08x)\n", t, f.c_file, f.c_line, f.c_op, f.c_mask);
+                    else if (!f.done) fprintf(stderr, "simt_emu: thread %u waits at a barrier / mbarrier\n", t);
+                }
+                s.cur = &s.fib[0];
+                die("deadlock: every live thread waits and nothing completes");
+            }
         }
     }
     s.cur = nullptr;
@@ -212,14 +223,15 @@ inline void barrier(int id, unsigned count) {
 
 enum { OP_SHFL, OP_SHFL_XOR, OP_SHFL_UP, OP_SHFL_DOWN, OP_BALLOT, OP_ADD, OP_MIN, OP_MAX, OP_SMIN, OP_SMAX, OP_MATCH, OP_SYNC };
 
-inline uint64_t collective(uint32_t mask, int op, uint64_t val, int arg, int width = 32) {
+typedef std::source_location SL;
+inline uint64_t collective(uint32_t mask, int op, uint64_t val, int arg, int width, const SL& loc) {
     State& s = S();
     Fiber* f = s.cur;
     const unsigned w0 = f->lin & ~31u, lane = f->lin & 31u;
     const unsigned wn = (s.nthreads - w0) < 32 ? (s.nthreads - w0) : 32;
     if (!(mask >> lane & 1)) die("collective: the calling lane is not in its own mask");
     if (wn < 32) mask &= (1u << wn) - 1;
-    f->c_wait = true; f->c_done = false; f->c_mask = mask; f->c_op = op; f->c_val = val; f->c_arg = arg;
+    f->c_wait = true; f->c_done = false; f->c_mask = mask; f->c_op = op; f->c_val = val; f->c_arg = arg; f->c_file = loc.file_name(); f->c_line = loc.line();
     for (;;) {
         if (f->c_done) break;
         bool all = true;
@@ -228,7 +240,10 @@ inline uint64_t collective(uint32_t mask, int op, uint64_t val, int arg, int wid
                 Fiber& g = s.fib[w0 + l];
                 if (g.done) die("collective: a lane named in the mask has exited");
                 if (!g.c_wait || g.c_done) all = false;
-                else if (g.c_mask != mask || g.c_op != op) die("collective: lanes of one mask meet at different operations");
+                // a lane waiting at ANOTHER collective (other mask, operation or call site) has not arrived at this one: legal when
+                // its mask does not name this lane (disjoint groups of a diverged warp); if it does, both wait for ever and
+                // the scheduler's deadlock check reports the two call sites
+                else if (g.c_mask != mask || g.c_op != op || g.c_line != f->c_line || g.c_file != f->c_file) all = false;
             }
         if (all) {
             uint64_t red = 0; bool first = true;
@@ -309,29 +324,29 @@ inline void mbar_wait(unsigned long long* bar, uint32_t parity) {
 #define blockIdx (emu::S().blockIdx)
 #define blockDim (emu::S().blockDim)
 #define gridDim (emu::S().gridDim)
-#define EMU_LAUNCH(grid, block, smem, stream, ...) emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { __VA_ARGS__; })
+#define EMU_LAUNCH(grid, block, smem, stream, ...) emu::S().kernel = #__VA_ARGS__, emu::launch(dim3(grid), dim3(block), (size_t)(smem), [&]() { __VA_ARGS__; })
 #define EMU_DYN_SMEM(T) reinterpret_cast<T*>(emu::S().dyn_smem)
 
 static inline void __syncthreads() { emu::barrier(0, 0); }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::collective(mask, emu::OP_SYNC, 0, 0); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu, const emu::SL& loc = emu::SL::current()) { emu::collective(mask, emu::OP_SYNC, 0, 0, 32, loc); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
-template <class T> static inline T __shfl_sync(unsigned m, T v, int src, int w = 32) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL, emu::to_bits(v), src, w)); }
-template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int x, int w = 32) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_XOR, emu::to_bits(v), x, w)); }
-template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d, int w = 32) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_UP, emu::to_bits(v), (int)d, w)); }
-template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d, int w = 32) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_DOWN, emu::to_bits(v), (int)d, w)); }
-static inline unsigned __ballot_sync(unsigned m, int p) { return (unsigned)emu::collective(m, emu::OP_BALLOT, p != 0, 0); }
-static inline int __any_sync(unsigned m, int p) { return emu::collective(m, emu::OP_BALLOT, p != 0, 0) != 0; }
-static inline int __all_sync(unsigned m, int p) { return emu::collective(m, emu::OP_BALLOT, p == 0, 0) == 0; }
+template <class T> static inline T __shfl_sync(unsigned m, T v, int src, int w = 32, const emu::SL& loc = emu::SL::current()) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL, emu::to_bits(v), src, w, loc)); }
+template <class T> static inline T __shfl_xor_sync(unsigned m, T v, int x, int w = 32, const emu::SL& loc = emu::SL::current()) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_XOR, emu::to_bits(v), x, w, loc)); }
+template <class T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d, int w = 32, const emu::SL& loc = emu::SL::current()) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_UP, emu::to_bits(v), (int)d, w, loc)); }
+template <class T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d, int w = 32, const emu::SL& loc = emu::SL::current()) { return emu::from_bits<T>(emu::collective(m, emu::OP_SHFL_DOWN, emu::to_bits(v), (int)d, w, loc)); }
+static inline unsigned __ballot_sync(unsigned m, int p, const emu::SL& loc = emu::SL::current()) { return (unsigned)emu::collective(m, emu::OP_BALLOT, p != 0, 0, 32, loc); }
+static inline int __any_sync(unsigned m, int p, const emu::SL& loc = emu::SL::current()) { return emu::collective(m, emu::OP_BALLOT, p != 0, 0, 32, loc) != 0; }
+static inline int __all_sync(unsigned m, int p, const emu::SL& loc = emu::SL::current()) { return emu::collective(m, emu::OP_BALLOT, p == 0, 0, 32, loc) == 0; }
 static inline unsigned __activemask() { return 0xffffffffu; }
-static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { return (unsigned)emu::collective(m, emu::OP_ADD, v, 0); }
-static inline int __reduce_add_sync(unsigned m, int v) { return (int)(unsigned)emu::collective(m, emu::OP_ADD, (unsigned)v, 0); }
-static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return (unsigned)emu::collective(m, emu::OP_MIN, v, 0); }
-static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return (unsigned)emu::collective(m, emu::OP_MAX, v, 0); }
-static inline int __reduce_min_sync(unsigned m, int v) { return (int)(unsigned)emu::collective(m, emu::OP_SMIN, (unsigned)v, 0); }
-static inline int __reduce_max_sync(unsigned m, int v) { return (int)(unsigned)emu::collective(m, emu::OP_SMAX, (unsigned)v, 0); }
-static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { unsigned r = 0; for (int b = 0; b < 32; b++) if (emu::collective(m, emu::OP_BALLOT, v >> b & 1, 0)) r |= 1u << b; return r; }
-template <class T> static inline unsigned __match_any_sync(unsigned m, T v) { return (unsigned)emu::collective(m, emu::OP_MATCH, emu::to_bits(v), 0); }
+static inline unsigned __reduce_add_sync(unsigned m, unsigned v, const emu::SL& loc = emu::SL::current()) { return (unsigned)emu::collective(m, emu::OP_ADD, v, 0, 32, loc); }
+static inline int __reduce_add_sync(unsigned m, int v, const emu::SL& loc = emu::SL::current()) { return (int)(unsigned)emu::collective(m, emu::OP_ADD, (unsigned)v, 0, 32, loc); }
+static inline unsigned __reduce_min_sync(unsigned m, unsigned v, const emu::SL& loc = emu::SL::current()) { return (unsigned)emu::collective(m, emu::OP_MIN, v, 0, 32, loc); }
+static inline unsigned __reduce_max_sync(unsigned m, unsigned v, const emu::SL& loc = emu::SL::current()) { return (unsigned)emu::collective(m, emu::OP_MAX, v, 0, 32, loc); }
+static inline int __reduce_min_sync(unsigned m, int v, const emu::SL& loc = emu::SL::current()) { return (int)(unsigned)emu::collective(m, emu::OP_SMIN, (unsigned)v, 0, 32, loc); }
+static inline int __reduce_max_sync(unsigned m, int v, const emu::SL& loc = emu::SL::current()) { return (int)(unsigned)emu::collective(m, emu::OP_SMAX, (unsigned)v, 0, 32, loc); }
+static inline unsigned __reduce_or_sync(unsigned m, unsigned v, const emu::SL& loc = emu::SL::current()) { unsigned r = 0; for (int b = 0; b < 32; b++) if (emu::collective(m, emu::OP_BALLOT, v >> b & 1, 0, 32, loc)) r |= 1u << b; return r; }
+template <class T> static inline unsigned __match_any_sync(unsigned m, T v, const emu::SL& loc = emu::SL::current()) { return (unsigned)emu::collective(m, emu::OP_MATCH, emu::to_bits(v), 0, 32, loc); }
 
 template <class T> static inline T __ldg(const T* p) { return *p; }
 template <class T> static inline T __ldcs(const T* p) { return *p; }

@@ -89,6 +89,7 @@ with m.Engine(device=0, exact=True) as eng:
         if why is None:
             (gs,) = eng.gain_analyze_images([img])
             grc, ost = orc.gain_analyze(img)
+            grc = -12 if grc == -1 else grc    # the oracle's -1 is "No valid MP3 frames found" = RG_ERR_NO_FRAMES
             if gs.status != grc:
                 why = f"gain status {gs.status} vs {grc}"
             elif grc == 0 and (gs.frame_count, gs.gain_sum, gs.gain_count, gs.min_gain, gs.max_gain) != (

@@ -117,3 +117,33 @@ def info_frame(first_frame_header, tag=b"Info"):
 
 def id3v1_trailer():
     return b"TAG" + bytes(125)
+
+
+def set_mixed_block_flags(img):
+    """Sets mixed_block_flag in every short-block granule-channel of an MPEG-2 / 2.5 stream (the synthesiser emits pure short
+    blocks only at those versions).  The granule's scalefactor partition and band layout change with the flag, so the payload
+    decodes to different -- but still well-defined -- values.  Returns (image, granule-channels changed)."""
+    import ffmpeg_ref   # the pure-Python frame splitter of the harness
+    out, n = [], 0
+    for fb in ffmpeg_ref.split_frames(img):
+        fr = bytearray(fb)
+        h = int.from_bytes(fr[:4], "big")
+        assert ((h >> 19) & 3) != 3, "MPEG-2 / 2.5 streams only"
+        mono = ((h >> 6) & 3) == 3
+        base = 4 + (0 if (h >> 16) & 1 else 2)
+        for ch in range(1 if mono else 2):
+            b0 = (9 if mono else 10) + 63 * ch          # this channel's 63 granule bits (main_data_begin 8 + private 1 / 2)
+
+            def get(o, w):
+                v = 0
+                for k in range(w):
+                    bit = b0 + o + k
+                    v = (v << 1) | ((fr[base + bit // 8] >> (7 - bit % 8)) & 1)
+                return v
+            if get(38, 1) and get(39, 2) == 2:            # window_switching_flag, block_type == 2
+                bit = b0 + 41                             # mixed_block_flag
+                if not (fr[base + bit // 8] >> (7 - bit % 8)) & 1:
+                    fr[base + bit // 8] |= 1 << (7 - bit % 8)
+                    n += 1
+        out.append(bytes(fr))
+    return np.frombuffer(b"".join(out), np.uint8).copy(), n

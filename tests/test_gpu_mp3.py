@@ -92,6 +92,17 @@ def test_mpeg2_streams_pcm_bit_exact_and_analysis(kw, engine_exact, engine_fast,
     _check_analysis(engine_fast, oracle, img)
 
 
+@pytest.mark.parametrize("kw", [dict(version=v, sr_idx=sr, br_idx=6 if v == 2 else 2, seed=77 + sr + 3 * v, channels=c)
+                                for v, sr, c in [(2, 0, 2), (2, 1, 1), (2, 2, 2), (0, 0, 2), (0, 1, 2), (0, 2, 2), (0, 2, 1)]])
+def test_lsf_mixed_blocks(kw, engine_exact, oracle):
+    """Mixed blocks at every MPEG-2 / 2.5 rate (6 long bands, then short band 3 onwards; at 8 kHz the long part is 72 lines):
+    the band-code / reorder tables of K2 against the oracle, bit-exact PCM and histogram."""
+    img, n = synth_corpus.set_mixed_block_flags(synth_corpus.make_track(n_frames=160, **kw))
+    assert n >= 2
+    _check_pcm(engine_exact, oracle, img)
+    _check_analysis(engine_exact, oracle, img)
+
+
 @pytest.mark.parametrize("kw", [dict(version=2, seed=47, channels=1, br_idx=2), dict(version=2, seed=48, channels=1, br_idx=1, sr_idx=1),
                                 dict(version=0, seed=49, channels=1, br_idx=1, sr_idx=2), dict(version=2, seed=50, channels=2, br_idx=3)])
 def test_low_bitrate_lsf_streams_with_frames_below_96_bytes(kw, engine_exact, engine_fast, oracle):

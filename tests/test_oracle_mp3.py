@@ -196,3 +196,26 @@ def test_mpeg2_intensity_stereo_decodes_like_ffmpeg(oracle, kw):
     ff = ffmpeg_ref.decode_frames(ffmpeg_ref.split_frames(img))
     assert pcm.shape == ff.shape
     assert np.abs(pcm.astype(np.float64) - ff).max() < 5e-6
+
+
+LSF_RATES = [dict(version=v, sr_idx=sr, br_idx=6 if v == 2 else 2, seed=79 if (v, sr) == (0, 1) else 78, intensity_prob=0.0)
+             for v, sr in [(2, 0), (2, 1), (2, 2), (0, 0), (0, 1), (0, 2)]]
+
+
+@pytest.mark.skipif(not ffmpeg_ref.available(), reason="bundled libavcodec not present")
+@pytest.mark.parametrize("kw", LSF_RATES)
+def test_lsf_mixed_blocks_decode_like_ffmpeg(oracle, kw):
+    """Mixed blocks at the six MPEG-2 / 2.5 rates: 6 long bands, then short band 3 onwards.  At 8 kHz those 6 bands span 72
+    lines, not 36 (the band tables of that rate are twice as wide at the bottom); the restatement used to count the long
+    bands below line 36 (3 at 8 kHz) and start the short part 36 lines early.  Found by tests/dev/simt_emu/fuzz_emu.py.
+    The flag is set on streams that were generated as pure short blocks, so the payload is re-interpreted: seeds are chosen
+    so that no re-interpreted granule overruns its part2_3_length (what a decoder does then is a separate question), and the
+    streams carry no intensity stereo (a mixed right channel inside an intensity frame leaves the oracle ~1e-3 away from
+    FFmpeg in the following granule: open)."""
+    img, n = synth_corpus.set_mixed_block_flags(synth_corpus.make_track(n_frames=160, channels=2, **kw))
+    assert n >= 4
+    frames = ffmpeg_ref.split_frames(img)
+    ref = ffmpeg_ref.decode_frames(frames)
+    rc, pcm, _ = oracle.decode(img)
+    assert rc == 0 and pcm.shape == ref.shape
+    assert np.abs(pcm - ref).max() < 3e-6
