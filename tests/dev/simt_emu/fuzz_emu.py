@@ -38,7 +38,7 @@ for i, (v, c, b, s, cr) in enumerate(CONFIGS):
 
 
 def corrupt(img):
-    kind = int(rng.integers(0, 7))
+    kind = int(rng.integers(0, 9))
     img = img.copy()
     if kind == 0:
         for _ in range(int(rng.integers(1, 40))):
@@ -59,6 +59,35 @@ def corrupt(img):
         p = int(rng.integers(0, len(img)))
         junk = rng.choice(np.array([0xFF, 0xFB, 0xE3, 0xF3, 0x90, 0x00, 0x64], dtype=np.uint8), int(rng.integers(1, 600)))
         img = np.concatenate([img[:p], junk, img[p:]])
+    elif kind == 7:    # an ID3v2 tag in front: honest, short, longer than the file, with the footer flag, with non-syncsafe size bytes
+        body = int(rng.integers(0, 700))
+        claim = body if rng.integers(0, 3) else int(rng.integers(0, 2 * len(img) + 4000))
+        flags = int(rng.choice([0x00, 0x10, 0x40, 0x80]))
+        size = [(claim >> 21) & 0x7F, (claim >> 14) & 0x7F, (claim >> 7) & 0x7F, claim & 0x7F]
+        if rng.integers(0, 8) == 0:
+            size[int(rng.integers(0, 4))] |= 0x80
+        tag = np.array([0x49, 0x44, 0x33, int(rng.choice([2, 3, 4])), 0, flags] + size, dtype=np.uint8)
+        fill = rng.choice(np.array([0x00, 0xFF, 0xFB, 0x54, 0x90], dtype=np.uint8), body)
+        img = np.concatenate([tag, fill, np.zeros(10 if flags & 0x10 else 0, np.uint8), img[int(rng.integers(0, 3)) * int(rng.integers(0, 50)):]])
+    elif kind == 8:    # trailers: ID3v1, APEv2 (+ ID3v1), with honest and dishonest sizes, possibly after a cut
+        if rng.integers(0, 2):
+            img = img[: int(rng.integers(len(img) // 2, len(img) + 1))]
+        parts = [img]
+        if rng.integers(0, 2):
+            n_items = int(rng.integers(0, 300))
+            sz = n_items + 32 if rng.integers(0, 4) else int(rng.integers(0, 2 * len(img)))
+            foot = np.zeros(32, np.uint8)
+            foot[:8] = np.frombuffer(b"APETAGEX", np.uint8)
+            foot[8:12] = np.frombuffer(int(2000).to_bytes(4, "little"), np.uint8)
+            foot[12:16] = np.frombuffer(int(sz).to_bytes(4, "little"), np.uint8)
+            foot[20:24] = np.frombuffer(int(rng.choice([0, 0x80000000, 0xA0000000])).to_bytes(4, "little"), np.uint8)
+            hdr = foot.copy()
+            parts += ([hdr] if rng.integers(0, 2) else []) + [rng.choice(np.array([0x00, 0xFF, 0xFB, 0x41], dtype=np.uint8), n_items), foot]
+        if rng.integers(0, 3):
+            t = rng.choice(np.array([0x00, 0x20, 0xFF, 0xFB, 0x61], dtype=np.uint8), 128)
+            t[:3] = np.frombuffer(b"TAG", np.uint8)
+            parts.append(t)
+        img = np.concatenate(parts)
     else:              # a second stream of another version spliced behind a cut
         other = bases[int(rng.integers(0, len(bases)))]
         p = int(rng.integers(1, len(img))); q = int(rng.integers(0, len(other)))
@@ -67,7 +96,9 @@ def corrupt(img):
 
 
 bad = 0
-with m.Engine(device=0, exact=True) as eng:
+recent = []      # (image, status, histogram, peak, gain stats) of the last cases, for the batch check
+with m.Engine(device=0, exact=True) as eng, m.Engine(device=0, exact=False) as fast:
+    fast.set_option("group_bytes_min", 4096)     # several copy / index groups even for these small corpora
     for case in range(n_cases):
         base = case % len(bases)
         kind, img = corrupt(bases[base])
@@ -107,6 +138,23 @@ with m.Engine(device=0, exact=True) as eng:
                     oimg, on = orc.gain_apply(img, steps, wrap=bool(mode))
                 if nmod != on or not (patched == oimg).all():
                     why = f"patch steps={steps} mode={mode}: {nmod} vs {on}"
+        if why is None:
+            recent.append((img, sts[0], res[0].histogram.copy() if sts[0] == 0 else None, res[0].peak if sts[0] == 0 else None))
+            if len(recent) == 7:
+                # the same images side by side in one call of the time-blocked engine (pipelined groups, shared batches):
+                # every track must come out as it did alone -- corrupt neighbours must not leak into each other
+                imgs = [r[0] for r in recent]
+                bres, bsts = fast.analyze_images(imgs, want_hist=True)
+                for k, r in enumerate(recent):
+                    if bsts[k] != r[1] or (r[1] == 0 and (not (bres[k].histogram == r[2]).all() or bres[k].peak != r[3])):
+                        why = f"batch entry {k} differs from the same image analysed alone"
+                        np.save(f"/tmp/fuzz_emu_batch_{seed}_{case}_{k}.npy", r[0])
+                gb = fast.gain_analyze_images(imgs)
+                for k, r in enumerate(recent):
+                    grc1, ost1 = orc.gain_analyze(r[0])
+                    if gb[k].status != (-12 if grc1 == -1 else grc1) or (grc1 == 0 and (gb[k].frame_count, gb[k].gain_sum) != (ost1.frame_count, ost1.gain_sum)):
+                        why = f"batch gain entry {k}"
+                recent.clear()
         if why:
             bad += 1
             print("MISMATCH case", case, "kind", kind, "base", base, "len", len(img), why, flush=True)
