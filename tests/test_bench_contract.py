@@ -36,3 +36,28 @@ def test_last_gpu_bench_line_has_the_contract_keys():
     for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
         assert k in d["e2e"], k
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_gpu_arm_runs_end_to_end_on_the_interpreted_kernels():
+    """bench.py's own arm at toy sizes, with the engine built from the kernel sources by the CPU SIMT interpreter
+    (tests/dev/simt_emu/run_bench_emu.py): every code path of the arm runs and the record carries the contract's keys.  The
+    numbers mean nothing; the parity fields must still be clean."""
+    import shutil
+    import pytest
+    if shutil.which("g++") is None or os.uname().machine != "x86_64":
+        pytest.skip("needs g++ on x86-64")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dev", "simt_emu", "run_bench_emu.py"), "--tracks", "8", "--frames", "64",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "delta_db_vs_ref", "gain_fields"):
+        assert k in d, k
+    assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    assert "error" not in d["gain_fields"], d["gain_fields"]
+    assert d["gain_fields"]["frames_modified"] == 8 * 64
+    assert d["delta_db_vs_ref"]["max_abs"] == 0.0 and d["cpu_baseline"]["loudness_mismatches_vs_gpu"] == 0
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
