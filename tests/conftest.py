@@ -18,7 +18,7 @@ def pytest_configure(config):
         sys.path.insert(0, os.path.join(ROOT, "tests", "dev", "simt_emu"))
         import build_emu
         from mp3rgain_b200 import _lib
-        _lib.LIB_PATH = build_emu.build()
+        _lib.LIB_PATH = os.environ.get("RG_SIMT_EMU_LIB") or build_emu.build()   # (an instrumented build made by hand: coverage, ...)
 
 
 @pytest.fixture(scope="session")

@@ -17,8 +17,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(HERE)))
 CSRC = os.path.join(ROOT, "mp3rgain_b200", "csrc")
-OUT = os.path.join(HERE, "librg_engine_emu.so")
-SCRATCH = os.path.join(HERE, "_build")
+# SIMT_EMU_ASAN=1: the same build under AddressSanitizer (global memory is heap memory and __shared__ arrays are statics here,
+# so an out-of-bounds access of a kernel lands in a redzone).  The process that loads it needs
+#   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
+ASAN = os.environ.get("SIMT_EMU_ASAN") == "1"
+OUT = os.path.join(HERE, "librg_engine_emu_asan.so" if ASAN else "librg_engine_emu.so")
+SCRATCH = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 
 PTX_HELPERS = {
     "k2_mbar_init": "emu::mbar_init(bar, count);",
@@ -92,7 +96,8 @@ def build(force=False):
         dst = f[:-3] + ".cpp" if f.endswith(".cu") else f
         with open(os.path.join(SCRATCH, "mp3rgain_b200", "csrc", dst), "w") as fh:
             fh.write(text)
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w"] + (
+           ["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + [
            "-I", HERE, "-o", OUT, os.path.join(SCRATCH, "mp3rgain_b200", "csrc", "rg_engine.cpp")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:

@@ -158,7 +158,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, const F& body
     for (unsigned bx = 0; bx < grid.x; bx++) {
         s.blockIdx = uint3{bx, by, bz};
         for (auto& b : s.bar_arrived) b = 0;
-        memset(s.dyn_smem, 0xCD, smem);
+        memset(s.dyn_smem, getenv("SIMT_EMU_POISON") ? (int)strtol(getenv("SIMT_EMU_POISON"), nullptr, 0) : 0xCD, smem);
         for (unsigned t = 0; t < nt; t++) {
             Fiber& f = s.fib[t];
 #ifdef EMU_ASM_SWITCH
@@ -465,9 +465,12 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr a, int) 
 static inline cudaError_t emu_alloc(void** p, size_t n) {
     void* q = nullptr;
     if (posix_memalign(&q, 256, n ? n : 1)) { *p = nullptr; return cudaErrorMemoryAllocation; }
-    // poison in page-sized strides only beyond 64 MiB (big scratch buffers of the engine are mostly never touched)
-    if (n <= (64u << 20)) memset(q, 0xA5, n);
-    else for (size_t i = 0; i < n; i += 4096) ((unsigned char*)q)[i] = 0xA5;
+    // fresh device memory holds no particular value: poison it (SIMT_EMU_POISON=<byte>, default 0xA5), so that a result that
+    // depends on memory nobody wrote changes with the poison; in page-sized strides only beyond 64 MiB (the big scratch
+    // buffers of the engine are mostly never touched)
+    static const int poison = getenv("SIMT_EMU_POISON") ? (int)strtol(getenv("SIMT_EMU_POISON"), nullptr, 0) : 0xA5;
+    if (n <= (64u << 20)) memset(q, poison, n);
+    else for (size_t i = 0; i < n; i += 4096) ((unsigned char*)q)[i] = (unsigned char)poison;
     *p = q;
     return cudaSuccess;
 }

@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, HERE)
 import build_emu  # noqa: E402
 from mp3rgain_b200 import _lib  # noqa: E402
-_lib.LIB_PATH = build_emu.build()
+_lib.LIB_PATH = os.environ.get("RG_SIMT_EMU_LIB") or build_emu.build()
 import mp3rgain_b200 as m  # noqa: E402
 import oracle_lib  # noqa: E402
 import synth_corpus  # noqa: E402

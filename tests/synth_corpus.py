@@ -147,3 +147,26 @@ def set_mixed_block_flags(img):
                     n += 1
         out.append(bytes(fr))
     return np.frombuffer(b"".join(out), np.uint8).copy(), n
+
+
+def set_intensity_scalefac_compress(img, values):
+    """Overwrites scalefac_compress of the RIGHT channel in every intensity-stereo frame of an MPEG-2 / 2.5 stream with the
+    next entry of `values` (cycled): reaches the three intensity partition ranges of ISO 13818-3 2.4.3.2 (sfc >> 1 below
+    180, below 244, up to 255), of which the synthesiser only emits the first.  The payload is re-interpreted, as in
+    set_mixed_block_flags.  Returns (image, frames changed)."""
+    import ffmpeg_ref
+    out, n = [], 0
+    for fb in ffmpeg_ref.split_frames(img):
+        fr = bytearray(fb)
+        h = int.from_bytes(fr[:4], "big")
+        assert ((h >> 19) & 3) != 3, "MPEG-2 / 2.5 streams only"
+        if ((h >> 6) & 3) == 1 and ((h >> 4) & 1):          # joint stereo with the intensity bit
+            base = 4 + (0 if (h >> 16) & 1 else 2)
+            v = int(values[n % len(values)])
+            for k in range(9):
+                bit = 10 + 63 + 29 + k                       # main_data_begin 8, private 2, channel 0's 63 bits, 12 + 9 + 8
+                byte, m = base + bit // 8, 1 << (7 - bit % 8)
+                fr[byte] = (fr[byte] | m) if (v >> (8 - k)) & 1 else (fr[byte] & ~m)
+            n += 1
+        out.append(bytes(fr))
+    return np.frombuffer(b"".join(out), np.uint8).copy(), n

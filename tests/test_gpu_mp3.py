@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+import mp3rgain_b200 as m
 import oracle_lib
 import synth_corpus
 
@@ -410,3 +411,64 @@ def test_differential_fuzz_against_the_oracle():
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "90", "11"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "90 cases, 0 mismatches" in p.stdout
+
+
+def test_edge_flagged_tracks_are_decoded_again_with_the_exact_filter(oracle):
+    """The time-blocked IIR flags a track whose window lands within edge_tol of a bin boundary and the call decodes it again
+    with the serial filter (analyze_corpus_impl's `flagged` loop).  Real corpora flag ~1e-5 of their tracks, so neither the
+    bench nor any other test ever entered that loop: a tolerance of 1 flags every window, which must turn the time-blocked
+    engine into the exact one -- per-track histograms, album histogram (the flagged tracks' album adds are deferred to the
+    second pass and must be counted exactly once) and statistics."""
+    imgs = [synth_corpus.make_track(seed=300 + i, n_frames=70 + 9 * i, **kw) for i, kw in enumerate(
+        [dict(), dict(channels=1, br_idx=5), dict(version=2, sr_idx=1), dict(sr_idx=1), dict(version=0, sr_idx=2, br_idx=2)])]
+    want = [oracle.analyze_mp3(im) for im in imgs]
+    with m.Engine(device=0, exact=False) as eng:
+        eng.set_option("edge_tol", 1.0)
+        eng.set_option("group_bytes_min", 8192)
+        before = eng.stats().exact_reruns
+        res, sts = eng.analyze_images(imgs, want_hist=True)
+        assert sts == [0] * len(imgs)
+        assert eng.stats().exact_reruns - before == len(imgs)
+        for r, (rc, ores, ohist, info) in zip(res, want):
+            assert r.exact_rerun == 1 and (r.histogram == ohist).all() and r.loudness_db == ores.loudness_db and r.peak == ores.peak
+        # album mode: the sum of the track histograms, every flagged track counted once
+        album = eng.analyze_album_images(imgs, want_hist=True)
+        total = sum(w[2].astype(np.uint64) for w in want)
+        assert (album.album_histogram == total).all()
+        assert album.album_peak == max(w[1].peak for w in want)
+        # a resident corpus takes the same path
+        with eng.upload(imgs) as cor:
+            res2, sts2 = cor.analyze(want_hist=True)
+        assert sts2 == sts and all((a.histogram == b.histogram).all() for a, b in zip(res, res2))
+        # and with the tolerance back to its default nothing is flagged on this corpus, with the same results
+        eng.set_option("edge_tol", 1e-9)
+        res3, _ = eng.analyze_images(imgs, want_hist=True)
+        assert all(r.exact_rerun == 0 for r in res3) and all((a.histogram == b.histogram).all() for a, b in zip(res, res3))
+
+
+def test_slim_iir_launch_shape_gives_the_same_results(oracle):
+    """k4_slim (k_iir_fast as waves of 128-thread CTAs, an option kept from the co-scheduling experiments): same chains, same
+    arithmetic, other launch shape."""
+    imgs = [synth_corpus.make_track(seed=320 + i, n_frames=90) for i in range(3)]
+    with m.Engine(device=0, exact=False) as eng:
+        ref, sts = eng.analyze_images(imgs, want_hist=True)
+        for slim in (1, 2):
+            eng.set_option("k4_slim", slim)
+            res, sts2 = eng.analyze_images(imgs, want_hist=True)
+            assert sts2 == sts == [0, 0, 0]
+            assert all((a.histogram == b.histogram).all() and a.peak == b.peak for a, b in zip(ref, res))
+        for r, im in zip(ref, imgs):
+            assert (r.histogram == oracle.analyze_mp3(im)[2]).all()
+
+
+@pytest.mark.parametrize("kw", [dict(version=2, sr_idx=0, br_idx=6, seed=90), dict(version=2, sr_idx=1, br_idx=6, seed=91),
+                                dict(version=0, sr_idx=2, br_idx=2, seed=92)])
+def test_lsf_intensity_partitions_of_every_range(kw, engine_exact, oracle):
+    """ISO 13818-3 2.4.3.2, right channel of an intensity frame: the scalefactor partition comes from scalefac_compress >> 1
+    in three ranges (< 180, < 244, <= 255).  The synthesiser only emits the first; the other two arms of K1 had never run
+    (line coverage of the interpreted kernels)."""
+    base = synth_corpus.make_track(n_frames=120, channels=2, intensity_prob=0.9, **kw)
+    img, n = synth_corpus.set_intensity_scalefac_compress(base, [360, 401, 447, 487, 488, 495, 503, 511, 366, 490])
+    assert n >= 40
+    _check_pcm(engine_exact, oracle, img)
+    _check_analysis(engine_exact, oracle, img)
