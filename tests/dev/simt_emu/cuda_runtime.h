@@ -497,7 +497,9 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { r
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = emu_now(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
+// a query may always answer "not yet": SIMT_EMU_QUERY_NOT_READY=1 makes it do so, which drives the host code down the paths it
+// takes when the device is still busy (e.g. batches planned while later index groups are outstanding)
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { static const bool nr = getenv("SIMT_EMU_QUERY_NOT_READY") != nullptr; return nr ? cudaErrorNotReady : cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
     if (!a || !b || a->t < 0 || b->t < 0) { *ms = 0; return cudaErrorInvalidValue; }
     *ms = (float)(b->t - a->t);

@@ -17,7 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SLOW_OR_SUBPROCESS = [
     "tests/test_gpu_mp3.py::test_full_length_tracks_time_blocked_equals_exact",
     "tests/test_gpu_stage_b.py::test_long_track_fast_equals_exact",
-    "tests/test_gpu_mp3.py::test_differential_fuzz_against_the_oracle",      # runs tools/fuzz_parity.py on the real library
     "tests/test_gpu_mp3.py::test_mixed_corpus_through_the_pipeline",
     "tests/test_gpu_gain_fields.py::test_three_minute_track_and_analysis_consistency",
     "tests/test_gpu_mp3.py::test_segmented_frame_index_equals_serial_walk",

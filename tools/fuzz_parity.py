@@ -10,6 +10,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("RG_SIMT_EMU") == "1":   # development aid: the interpreted kernel sources instead of a GPU (tests/dev/simt_emu)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "dev", "simt_emu"))
+    import build_emu  # noqa: E402
+    from mp3rgain_b200 import _lib  # noqa: E402
+    _lib.LIB_PATH = os.environ.get("RG_SIMT_EMU_LIB") or build_emu.build()
 import mp3rgain_b200 as m  # noqa: E402
 import oracle_lib  # noqa: E402
 import synth_corpus  # noqa: E402
@@ -53,6 +58,7 @@ with m.Engine(device=0, exact=True) as eng:
             bad += 1
             print("MISMATCH case", case, "kind", int(kind), "base", case % len(bases), "len", len(img), "status gpu/oracle", sts[0], rc,
                   "frames", res[0].n_frames if sts[0] == 0 else None, info.n_frames, "dropped", info.n_dropped_frames, flush=True)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             np.save(os.path.join(ROOT, "gpurun_out", f"fuzz_case_{seed}_{case}.npy"), img)
 print("fuzz_parity: %d cases, %d mismatches" % (n_cases, bad))
 sys.exit(1 if bad else 0)
