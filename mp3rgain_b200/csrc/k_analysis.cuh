@@ -290,12 +290,19 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
             // rounding differences move trunc(val) across a bin boundary that matters?  The tolerance grows with the
             // ratio of input amplitude to filtered RMS (heavily attenuated windows carry larger relative error), and
             // windows far outside the histogram can never change bin membership.
+            // the filter state entering a window carries the previous window's level, so take the louder of the two
+            float a = 0.0f;
+            if (scale_tol) {
+                a = fmaxf(t.wmax0[w], t.wmax1[w]);
+                if (w > 0) a = fmaxf(a, fmaxf(t.wmax0[w - 1], t.wmax1[w - 1]));
+                // Outside what one warm-up window can forget: samples beyond +120 dBFS (no Layer III stream decodes to them
+                // short of global_gain 255 throughout; caller-supplied PCM can hold anything), infinities, and NaNs, which the
+                // serial filter carries to the end of the track.  Flag the track: it is filtered again serially.
+                if (!(a <= 1.0e6f) || !(ms - ms == 0.0)) edge++;
+            }
             if (val > -2002.0 && val < 10001.0) {
                 double tol = edge_tol;
                 if (scale_tol) {
-                    // the filter state entering a window carries the previous window's level, so take the louder of the two
-                    float a = fmaxf(t.wmax0[w], t.wmax1[w]);
-                    if (w > 0) a = fmaxf(a, fmaxf(t.wmax0[w - 1], t.wmax1[w - 1]));
                     const double amp = 32768.0 * (double)a;
                     const double ratio = amp / sqrt(ms + 1e-300);
                     tol = edge_tol * fmax(1.0, 0.1 * ratio);

@@ -83,3 +83,26 @@ def test_long_track_fast_equals_exact(engine_exact, engine_fast):
     assert a.n_windows == 3600
     assert (a.histogram == b.histogram).all()
     assert a.loudness_db == b.loudness_db and a.peak == b.peak
+
+
+@pytest.mark.parametrize("spike", [np.inf, -np.inf, 3.0e38, 2.0e7])
+def test_caller_pcm_beyond_what_a_warm_up_window_forgets(spike, engine_exact, engine_fast, oracle):
+    """rg_analyze_pcm_f32 takes whatever the caller holds.  One sample at +146 dBFS or beyond leaves the serial filter ringing
+    for several 50 ms windows, and an infinity leaves it at NaN to the end of the track (every later window then lands in
+    bin 2000: `NaN as i32` = 0) -- more than the single warm-up window of the time-blocked kernel can reproduce, so K5 flags
+    such tracks and they are filtered again serially.  Found by tests/dev/simt_emu/fuzz_stage_b_emu.py (the decoder cannot
+    produce such samples: |PCM| stays below 1e9 even with every global_gain at 255)."""
+    l, r = oracle_lib.lcg_pcm(44100, 11, 0, 2)
+    l = np.array(l, np.float32)
+    l[9000] = spike
+    for eng in (engine_exact, engine_fast):
+        g = _check(eng, oracle, [l, np.array(r, np.float32)], 44100)
+    assert g.exact_rerun == 1
+
+
+def test_nan_samples_poison_the_rest_of_the_track_like_the_reference(engine_exact, engine_fast, oracle):
+    x = np.array(oracle_lib.lcg_pcm(3 * 16000, 5, 0, 1)[0], np.float32)
+    x[20000] = np.nan          # f64::max ignores the NaN for the peak; the filter state does not recover
+    for eng in (engine_exact, engine_fast):
+        g = _check(eng, oracle, [x], 16000)
+        assert g.histogram[2000] == g.n_windows - 20000 // 800 and np.isfinite(g.peak)
