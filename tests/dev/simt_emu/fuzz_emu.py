@@ -117,6 +117,11 @@ with m.Engine(device=0, exact=True) as eng, m.Engine(device=0, exact=False) as f
                 gpcm, _sr = eng.decode_pcm(img)
                 if gpcm.shape != opcm.shape or not bool((gpcm == opcm).all()):
                     why = "pcm"
+                else:   # find_peak_amplitude: the peak-only pipeline (K2 in peak mode, no PCM stored) against max |sample|
+                    (pk, pst), = eng.find_peak_images([img])
+                    want = float(np.abs(opcm).max()) if opcm.size else 0.0
+                    if pst != 0 or pk.peak != want or pk.peak != ores.peak or pk.sample_rate != info.sample_rate:
+                        why = f"find_peak {pst} {pk.peak} vs {want}"
         if why is None:
             (gs,) = eng.gain_analyze_images([img])
             grc, ost = orc.gain_analyze(img)
