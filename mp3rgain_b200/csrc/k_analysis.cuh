@@ -284,7 +284,10 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
             // (lsum + rsum) / totsamp * 0.5 ; 1000*log10(ms + 1e-37) ; `as i32` (saturating, NaN -> 0)
             const double ms = __dmul_rn(__ddiv_rn(__dadd_rn(l, r), tot), 0.5);
             const double val = __dmul_rn(1000.0, log10(__dadd_rn(ms, 1e-37)));
-            const int v = __double2int_rz(val);  // cvt.rzi.s32.f64: truncates, saturates, NaN -> 0
+            // Rust `val as i32` (src/replaygain.rs:755): truncates, saturates, NaN -> 0.  Spelled out: cvt.rzi.s32.f64 maps a
+            // NaN *f64* source to MININT (PTX ISA, cvt: "zero if the source is not .f64 ..., otherwise 1 << (bits-1)"), which
+            // round 1's hardware run showed as windows missing from bin 2000.
+            const int v = (val != val) ? 0 : (val >= 2147483647.0) ? 2147483647 : (val <= -2147483648.0) ? (-2147483647 - 1) : (int)val;
             const long long li = (long long)v + RG_HIST_OFF;
             // Edge test: would a perturbation of the window's mean square at the level of the time-blocked kernel's
             // rounding differences move trunc(val) across a bin boundary that matters?  The tolerance grows with the

@@ -398,9 +398,10 @@ static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); re
 static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
 static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }
 static inline double __longlong_as_double(long long u) { double d; memcpy(&d, &u, 8); return d; }
-static inline int __double2int_rz(double d) { if (d != d) return 0; if (d >= 2147483647.0) return 2147483647; if (d <= -2147483648.0) return (-2147483647 - 1); return (int)d; }
-static inline int __float2int_rz(float d) { return __double2int_rz((double)d); }
-static inline int __float2int_rn(float d) { return __double2int_rz(nearbyint((double)d)); }
+// cvt.rzi.s32.f64 on silicon: a NaN with an .f64 source converts to MININT, not 0 (PTX ISA, cvt; seen on B200 in round 1)
+static inline int __double2int_rz(double d) { if (d != d) return (-2147483647 - 1); if (d >= 2147483647.0) return 2147483647; if (d <= -2147483648.0) return (-2147483647 - 1); return (int)d; }
+static inline int __float2int_rz(float d) { if (d != d) return 0; return __double2int_rz((double)d); }
+static inline int __float2int_rn(float d) { if (d != d) return 0; return __double2int_rz(nearbyint((double)d)); }
 static inline float __int2float_rn(int i) { return (float)i; }
 static inline float __uint2float_rn(unsigned i) { return (float)i; }
 static inline double __int2double_rn(int i) { return (double)i; }
