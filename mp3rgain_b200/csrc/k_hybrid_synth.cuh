@@ -41,7 +41,9 @@ struct K2Smem {
     alignas(16) float A[K2_SLOTS][SLOTF];     // per granule-channel: xr[576] -> F[18][ROW] -> DCT rows [18][ROW], in place
     float S2[K2_SLOTS][SLOTF];                // IMDCT outputs 18..35 of the granule-channel (added by the NEXT granule)
     alignas(16) uint32_t stage[K2_GC][288];   // the batch's int16 line pairs, written by the TMA unit
-    alignas(16) float bandgain[K2_GC][64];    // per band: 2^(exponent/4) ([0..21] long sfb, [22..60] short sfb*3+win), by TMA
+    alignas(16) uint8_t banddelta[K2_GC][K1_GAIN_ROW];   // per band: what to subtract from the granule-channel's gain exponent
+                                              // ([0..21] long sfb, [22..60] short sfb*3+win, [62..63] the exponent itself), by TMA
+    float gaintab[L3_GAIN_MAX - L3_GAIN_MIN + 1];   // 2^(e/4)
     float wa[8][32], wb[8][32];
     GranInfo gi[K2_MAX_G][2];                 // side info of every granule-channel of the run
     uint32_t p1w[K2_MAX_G][2];                // tsel | ms<<2 | (nz!=0)<<3 | intensity<<4 | (9*max sb_limit of the granule)<<8
@@ -116,39 +118,6 @@ __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corp
     if (gi.ms) nzm = max(nzm, (uint32_t)nz_in[gcb + (ch ^ 1)]);
     gi.sb_limit = nzm == 0 ? 0 : (gi.bt == 2 ? 32 : (uint8_t)min(32u, (nzm + 17) / 18 + 1));
     return gi;
-}
-
-// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+)
-__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void k2_mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void k2_mbar_expect(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void k2_bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(k2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k2_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void k2_mbar_wait(unsigned long long* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "K2_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra K2_DONE;\n"
-        "bra K2_WAIT;\n"
-        "K2_DONE:\n"
-        "}" ::"r"(k2_smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void k2_pair_sync(int pair) {   // immediate ids, so that ptxas reserves 5 barriers and not 16
-    switch (pair) {
-        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-    }
 }
 
 // 3-point DFT of complex numbers (W3 = e^{-2 pi i/3}): X0 = x0 + s, X1 = m - i q, X2 = m + i q with s = x1 + x2,
@@ -257,7 +226,7 @@ template <int NCH>
 __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus,
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
-                                        const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
+                                        const uint16_t* __restrict__ nz_in, const uint8_t* __restrict__ gains,
                                         const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits,
                                         uint32_t flags) {
     constexpr int G = K2_GC / NCH;      // granules per batch
@@ -271,6 +240,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 
     // ---- one-time table staging and state reset
     for (int i = tid; i < 256; i += K2_THREADS) { (&S.wa[0][0])[i] = (&T->synth_wa[0][0])[i]; (&S.wb[0][0])[i] = (&T->synth_wb[0][0])[i]; }
+    for (int i = tid; i < L3_GAIN_MAX - L3_GAIN_MIN + 1; i += K2_THREADS) S.gaintab[i] = T->gain[i];
     for (int i = tid; i < 576; i += K2_THREADS) {
         S.code[0][i] = T->line_sfb_long[sr][i];
         S.code[1][i] = 22 + T->line_sfb_short[sr][i];
@@ -303,9 +273,9 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         const uint32_t gl0 = b * G;
         const uint32_t ngc = min((uint32_t)G, gcount - gl0) * NCH;
         const size_t gc0 = (size_t)tr.gc_base + (size_t)(gfirst + gl0) * NCH;
-        k2_mbar_expect(&S.mbar, ngc * (1152u + 4u * K1_GAIN_ROW));
+        k2_mbar_expect(&S.mbar, ngc * (1152u + K1_GAIN_ROW));
         k2_bulk_load(&S.stage[0][0], spectra + gc0 * 576, ngc * 1152u, &S.mbar);
-        k2_bulk_load(&S.bandgain[0][0], gains + gc0 * K1_GAIN_ROW, ngc * 4u * K1_GAIN_ROW, &S.mbar);
+        k2_bulk_load(&S.banddelta[0][0], gains + gc0 * K1_GAIN_ROW, ngc * K1_GAIN_ROW, &S.mbar);
     };
 
     if (tid == 0) issue_copy(0);
@@ -326,11 +296,13 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
             const int lim9 = (int)(w0 >> 8);
             const int tsel0 = w0 & 3, tsel1 = w1 & 3;
             const bool ms = (w0 >> 2) & 1;
-            const bool nzf0 = (w0 >> 3) & 1, nzf1 = (w1 >> 3) & 1;
+            // K1 writes a row only up to its last decoded line (nz): everything beyond reads as zero
+            const uint32_t nz0 = S.gi[gl][0].nz, nz1 = S.gi[gl][NCH - 1].nz;
             const uint32_t* st0 = S.stage[my_gi * NCH];
             const uint32_t* st1 = S.stage[my_gi * NCH + NCH - 1];
-            const float* bg0 = S.bandgain[my_gi * NCH];
-            const float* bg1 = S.bandgain[my_gi * NCH + NCH - 1];
+            const uint8_t* bd0 = S.banddelta[my_gi * NCH];
+            const uint8_t* bd1 = S.banddelta[my_gi * NCH + NCH - 1];
+            const int be0 = *reinterpret_cast<const uint16_t*>(bd0 + 62), be1 = *reinterpret_cast<const uint16_t*>(bd1 + 62);
             float* x0 = S.A[(gl % NS) * NCH];
             float* x1 = S.A[(gl % NS) * NCH + NCH - 1];
             const bool ist = NCH == 2 && ((w0 >> 4) & 1);
@@ -342,7 +314,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 if (my_ch == 0 && lane < 4) top[lane] = -1;
                 k2_pair_sync(my_gi);
                 for (int pr = lane + 32 * my_ch; pr < 288; pr += 64) {
-                    if (nzf1 && st1[pr] != 0u) {
+                    if ((uint32_t)(2 * pr) < nz1 && st1[pr] != 0u) {
                         const int code = S.code[tsel1][2 * pr];
                         if (code < 22) atomicMax(&top[0], code);
                         else atomicMax(&top[1 + (code - 22) % 3], (code - 22) / 3);
@@ -369,8 +341,9 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 float v[2][2];
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++) {
-                    const uint32_t packed = (ch ? nzf1 : nzf0) ? (ch ? st1 : st0)[pr] : 0u;
-                    const float gn = (ch ? nzf1 : nzf0) ? (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]] : 0.0f;
+                    const bool coded = (uint32_t)(2 * pr) < (ch ? nz1 : nz0);
+                    const uint32_t packed = coded ? (ch ? st1 : st0)[pr] : 0u;
+                    const float gn = coded ? S.gaintab[(ch ? be1 : be0) - (int)(ch ? bd1 : bd0)[S.code[ch ? tsel1 : tsel0][2 * pr]]] : 0.0f;
                     const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
                     const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
                     const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
@@ -533,7 +506,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
-               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const float* __restrict__ gains,
+               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const uint8_t* __restrict__ gains,
                const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits /* [track] or null */,
                uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];

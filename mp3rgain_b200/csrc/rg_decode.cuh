@@ -77,6 +77,7 @@ struct DecTrack {   // per-track addressing shared by K1/K2 (device array)
     uint32_t pad;
 };
 
+#include "k_ptx.cuh"
 #include "k_frame_index.cuh"
 #include "k_huffman.cuh"
 #include "k_hybrid_synth.cuh"

@@ -232,6 +232,7 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
+    CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     {
         int sms = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
