@@ -28,53 +28,68 @@
 
 #define K1_THREADS 256
 #define K1_GAIN_ROW 64        // BYTES per granule-channel: [0..21] long sfb, [22..60] short sfb*3+win, [62..63] gain exponent base (u16)
-#define K1_STAGE 28672u       // bytes of main data staged per window
+#define K1_STAGE 28672u       // bytes of main data staged per window (256 granule-channels at 128 kbps: 24.4 KB)
 #define K1_SLACK 16u          // the bit window prefetches up to 12 bytes past the last bit it needs
 
-struct K1Smem {
-    alignas(16) uint8_t stage[K1_STAGE];
-    uint16_t huff[8192];
-    uint32_t tile[K1_THREADS / 32][32][17];
-    uint32_t side[K1_THREADS][3];    // pre-pass -> main pass (indexed by granule-channel of the block, stream order)
+struct K1Pre {                       // pre-pass -> main pass, indexed by granule-channel of the block in stream order
+    uint32_t side[K1_THREADS][3];    //   its side-info bits, left-aligned
     uint32_t start[K1_THREADS];      //   first bit of the granule-channel in the track's main-data stream
     uint32_t mdend[K1_THREADS];      //   bytes of main data readable for its frame
     uint32_t info[K1_THREADS];       //   active | ch<<1 | gr<<2 | is_right<<3 | scfsi<<4 | part2_3_length<<8
-    uint32_t rowoff[K1_THREADS];     // (worker order) word offset of the worker's spectrum row in the block, 0xFFFFFFFF = none
-    uint32_t lim[K1_THREADS];        // (worker order) words of the row that this flush may write
-    uint8_t sfl[K1_THREADS][24];     // long scalefactors of every granule-channel (scfsi source)
-    uint2 quad[256];                 // (count1 pattern << 4 | next four bits) -> the quad as two int16 pairs
-    uint8_t c1[2][64];               // count1 tables A / B: 6-bit peek -> (len << 4) | pattern
     uint32_t cnt[512];               // counting sort: bin sizes, then bin starts
     uint32_t wsum[K1_THREADS / 32];
     uint8_t perm[K1_THREADS];        // worker thread -> granule-channel of the block, ordered by big_values
+};
+struct K1Smem {
+    alignas(16) uint8_t stage[K1_STAGE];
+    uint16_t huff[8192];
+    union {
+        alignas(16) uint32_t tile[K1_THREADS / 32][32 * 17];   // per warp: 32 gain rows of 17 words, then 32 spectrum rows of 16 (swizzled)
+        K1Pre pre;                   // (every worker has taken its values into registers before the first tile row is written)
+    };
+    uint32_t rowoff[K1_THREADS];     // (worker order) word offset in the block of the next 16 words the worker's row flushes, 0xFFFFFFFF = none
+    uint32_t lim[K1_THREADS];        // (worker order) words of that stretch that are complete
+    uint8_t sfl[K1_THREADS][24];     // long scalefactors of every granule-channel (scfsi source)
+    uint32_t quad[256];              // (count1 pattern << 4 | next four bits) -> v w x y as four int8
+    uint8_t c1[2][64];               // count1 tables A / B: 6-bit peek -> (len << 4) | pattern
     uint32_t base;                   // first main-data byte wanted by a granule-channel that is still pending
     alignas(8) unsigned long long mbar;
 };
+static_assert(sizeof(K1Pre) <= sizeof(uint32_t) * (K1_THREADS / 32) * 32 * 17, "pre-pass scratch must fit under the tiles");
 
-// Big-endian bit window over the staged main data: words wi, wi+1 (hi, lo) and the prefetched wi+2 (nx).
+// Big-endian bit window over the staged main data: the words at pos>>5, +1, +2 (hi, lo, nx) in registers.
 struct BitWin {
-    const uint32_t* st;    // staged words, indexed by (absolute word index - w0)
-    uint32_t w0;           // absolute index of the first staged word
-    uint32_t hi, lo, nx, wi;
+    const uint8_t* st;     // the staged bytes
+    uint32_t hi, lo, nx;
+    uint32_t off;          // offset in `st` of the word that follows nx
     uint32_t pos;          // absolute position of the next unread bit
-    uint32_t lim;          // bytes readable for this frame (later bytes read as zero, like the oracle's reservoir)
-    __device__ __forceinline__ uint32_t load(uint32_t i) const {
-        uint32_t v = __byte_perm(st[i - w0], 0, 0x0123);
-        if (i >= (lim >> 2)) {   // the word reaches past the readable bytes (only at the very end of a frame's data)
-            const uint32_t b = i * 4;
-            v = b >= lim ? 0u : (v & (0xFFFFFFFFu << (8 * (b + 4 - lim))));
-        }
+    uint32_t lim_rel;      // bytes of `st` readable for this frame (later bytes read as zero, like the oracle's reservoir)
+    __device__ __forceinline__ uint32_t next() {
+        uint32_t v = __byte_perm(*reinterpret_cast<const uint32_t*>(st + off), 0, 0x0123);
+        if (off + 4 > lim_rel)   // the word reaches past the readable bytes (only at the very end of a frame's data)
+            v = off >= lim_rel ? 0u : (v & (0xFFFFFFFFu << (8 * (off + 4 - lim_rel))));
+        off += 4;
         return v;
     }
-    __device__ __forceinline__ void init(const uint32_t* staged, uint32_t first_word, uint32_t lim_bytes, uint32_t bitpos) {
-        st = staged; w0 = first_word; lim = lim_bytes; pos = bitpos;
-        wi = bitpos >> 5;
-        hi = load(wi); lo = load(wi + 1); nx = load(wi + 2);
+    __device__ __forceinline__ void init(const uint8_t* staged, uint32_t base_byte, uint32_t lim_bytes, uint32_t bitpos) {
+        st = staged; lim_rel = lim_bytes - base_byte; pos = bitpos;
+        off = ((bitpos >> 5) << 2) - base_byte;
+        hi = next(); lo = next(); nx = next();
     }
-    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }   // 32 bits from `pos` on
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }    // bits pos .. pos+31
+    __device__ __forceinline__ uint32_t peek2() const { return __funnelshift_l(nx, lo, pos); }   // bits pos+32 .. pos+63
     __device__ __forceinline__ void skip(uint32_t n) {   // n <= 32: at most one word boundary is crossed
-        pos += n;
-        if ((pos >> 5) != wi) { hi = lo; lo = nx; wi++; nx = load(wi + 2); }
+        const uint32_t np = pos + n;
+        if ((np ^ pos) & 32u) { hi = lo; lo = nx; nx = next(); }
+        pos = np;
+    }
+    __device__ __forceinline__ void skip64(uint32_t n) {   // n <= 64
+        const uint32_t np = pos + n, adv = (np >> 5) - (pos >> 5);
+        if (adv) {
+            hi = lo; lo = nx; nx = next();
+            if (adv > 1) { hi = lo; lo = nx; nx = next(); }
+        }
+        pos = np;
     }
     __device__ __forceinline__ uint32_t get(int n) {     // n <= 16, 0 allowed
         const uint32_t v = (peek() >> 1) >> (31 - n);
@@ -97,7 +112,7 @@ __device__ __forceinline__ uint32_t k1_bits(uint32_t W0, uint32_t W1, uint32_t W
     return __funnelshift_l(b, a, o) >> (32 - n);
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 2)
+__global__ void __launch_bounds__(K1_THREADS, 3)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
           int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
@@ -115,13 +130,11 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             S.c1[1][tid] = (uint8_t)((4u << 4) | (15u - (tid >> 2)));
         }
         // the quad table: pattern bits v w x y (v = bit 3); the sign bits of the non-zero values follow the code in that order
-        uint32_t val[4], used = 0;
+        uint32_t v4 = 0, used = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            val[k] = 0;
-            if ((tid >> (7 - k)) & 1) { val[k] = ((tid >> (3 - used)) & 1) ? 0xFFFFu : 1u; used++; }
-        }
-        S.quad[tid] = make_uint2(val[0] | (val[1] << 16), val[2] | (val[3] << 16));
+        for (int k = 0; k < 4; k++)
+            if ((tid >> (7 - k)) & 1) { v4 |= (((tid >> (3 - used)) & 1) ? 0xFFu : 1u) << (8 * k); used++; }
+        S.quad[tid] = v4;
         if (tid == 0) k2_mbar_init(&S.mbar, 1);
     }
     const HuffBlock blk = blocks[blockIdx.x];
@@ -163,54 +176,54 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const uint32_t up = __shfl_up_sync(0xffffffffu, p23, o);
             if ((uint32_t)o <= rem) before += up;
         }
-        S.side[tid][0] = W0; S.side[tid][1] = W1; S.side[tid][2] = W2;
-        S.start[tid] = md_start * 8 + before;
-        S.mdend[tid] = md_end;
-        S.info[tid] = inf;
+        S.pre.side[tid][0] = W0; S.pre.side[tid][1] = W1; S.pre.side[tid][2] = W2;
+        S.pre.start[tid] = md_start * 8 + before;
+        S.pre.mdend[tid] = md_end;
+        S.pre.info[tid] = inf;
 #pragma unroll
         for (int i = 0; i < 6; i++) reinterpret_cast<uint32_t*>(S.sfl[tid])[i] = 0;
     }
     // ---- counting sort of the block's granule-channels over the 9-bit big_values: my slot inside my bin, then an exclusive
     // prefix over the 512 bins (two per thread)
     {
-        S.cnt[tid] = 0; S.cnt[tid + 256] = 0;
+        S.pre.cnt[tid] = 0; S.pre.cnt[tid + 256] = 0;
         __syncthreads();
-        const uint32_t slot = atomicAdd(&S.cnt[key], 1u);
+        const uint32_t slot = atomicAdd(&S.pre.cnt[key], 1u);
         __syncthreads();
-        const uint32_t c0 = S.cnt[2 * tid], c1 = S.cnt[2 * tid + 1];
+        const uint32_t c0 = S.pre.cnt[2 * tid], c1 = S.pre.cnt[2 * tid + 1];
         uint32_t incl = c0 + c1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += up;
         }
-        if (lane == 31) S.wsum[warp] = incl;
+        if (lane == 31) S.pre.wsum[warp] = incl;
         __syncthreads();
         uint32_t base = 0;
-        for (int w = 0; w < warp; w++) base += S.wsum[w];
-        S.cnt[2 * tid] = base + incl - c0 - c1;        // bins 2*tid, 2*tid+1: where their first member goes
-        S.cnt[2 * tid + 1] = base + incl - c1;
+        for (int w = 0; w < warp; w++) base += S.pre.wsum[w];
+        S.pre.cnt[2 * tid] = base + incl - c0 - c1;        // bins 2*tid, 2*tid+1: where their first member goes
+        S.pre.cnt[2 * tid + 1] = base + incl - c1;
         __syncthreads();
-        S.perm[S.cnt[key] + slot] = (uint8_t)tid;
+        S.pre.perm[S.pre.cnt[key] + slot] = (uint8_t)tid;
     }
     __syncthreads();
 
     // ---- main pass, thread = worker: side info of my granule-channel
-    const int gl = S.perm[tid];                   // my granule-channel within the block
+    const int gl = S.pre.perm[tid];                   // my granule-channel within the block
     const uint32_t gc = blk.gc0 + gl;
-    const uint32_t inf = S.info[gl];
+    const uint32_t inf = S.pre.info[gl];
     const bool active = inf & 1u;
     const uint32_t ch = (inf >> 1) & 1, gr = (inf >> 2) & 1;
     const bool is_right = (inf >> 3) & 1;   // right channel of an intensity-stereo frame: K2 needs its raw scalefactors (is_pos)
     const int scfsi = (int)((inf >> 4) & 15);
-    const uint32_t my_start = S.start[gl], my_end = my_start + (inf >> 8);
+    const uint32_t my_start = S.pre.start[gl], my_end = my_start + (inf >> 8), my_mdend = S.pre.mdend[gl];
     int bv = 0, r0 = 0, r1 = 0, c1tab = 0;
     uint32_t reg0 = 0, reg1 = 0, reg2 = 0;   // per region: first-level table base << 8 | linbits
     bool silent = true;
     int bt = 0, mixed = 0, slen1 = 0, slen2 = 0, base_e = 0, sf_shift = 2, preflag = 0, sbg0 = 0, sbg1 = 0, sbg2 = 0;
     int ls[4] = {0, 0, 0, 0}, ltbl = 0, cls = 0;   // MPEG-2: field widths and partition table from scalefac_compress
     if (active) {
-        const uint32_t W0 = S.side[gl][0], W1 = S.side[gl][1], W2 = S.side[gl][2];
+        const uint32_t W0 = S.pre.side[gl][0], W1 = S.pre.side[gl][1], W2 = S.pre.side[gl][2];
         auto fld = [&](int o, int n) { return (int)k1_bits(W0, W1, W2, o, n); };
         const uint32_t p23 = inf >> 8;
         bv = fld(12, 9);
@@ -278,11 +291,13 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     uint32_t* blk_gains = reinterpret_cast<uint32_t*>(gains + ((size_t)tr.gc_base + blk.gc0) * K1_GAIN_ROW);
     uint8_t* srow = sfraw + ((size_t)tr.gc_base + gc) * K1_GAIN_ROW;
     uint8_t* sfl = S.sfl[gl];
-    uint32_t* trow = S.tile[warp][lane];
-    uint8_t* grow = reinterpret_cast<uint8_t*>(trow);   // part 2 parks the 64-byte gain row in the same tile row
+    uint8_t* grow = reinterpret_cast<uint8_t*>(&S.tile[warp][lane * 17]);   // part 2 parks the 64-byte gain row in the warp's tile
+    uint4* t4 = reinterpret_cast<uint4*>(S.tile[warp]);   // parts 3: 32 rows of four 16-byte chunks, chunk c of row r at c ^ ((r >> 1) & 3)
+    const int swz = (lane >> 1) & 3;
     const uint8_t* c1 = S.c1[c1tab];
     const uint32_t avail = (tr.md_bytes + 16 + 15) & ~15u;   // bytes of the track's stream that may be copied (its region is longer)
     const uint8_t* md_track = md + tr.md_off;
+    const uint32_t my_row = (uint32_t)gl * 288u;
 
     // ---- windows over the block's slice of the stream: all of it at once unless the slice exceeds K1_STAGE bytes
     bool pending = active;
@@ -296,18 +311,19 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         const uint32_t base = first & ~15u;
         // the granule-channel with the smallest start always fits: part2_3_length < 4096 bits
         const bool in = pending && (my_end >> 3) + K1_SLACK <= base + K1_STAGE;
+        const int last_pass = __syncthreads_and(!pending || in);   // (also: everybody has read S.base)
         if (tid == 0) {
             const uint32_t bytes = base < avail ? min(K1_STAGE, avail - base) : 16u;
             k2_mbar_expect(&S.mbar, bytes);
             k2_bulk_load(S.stage, md_track + base, bytes, &S.mbar);
         }
-        S.rowoff[tid] = in ? (uint32_t)gl * 288u : 0xFFFFFFFFu;
+        S.rowoff[tid] = in ? my_row : 0xFFFFFFFFu;
         k2_mbar_wait(&S.mbar, pass & 1);
 
         BitWin br;
-        br.st = reinterpret_cast<const uint32_t*>(S.stage); br.w0 = base >> 2; br.lim = 0; br.pos = 0; br.wi = 0; br.hi = br.lo = br.nx = 0;
+        br.st = S.stage; br.lim_rel = 0; br.pos = 0; br.off = 0; br.hi = br.lo = br.nx = 0;
         if (in) {
-            br.init(reinterpret_cast<const uint32_t*>(S.stage), base >> 2, S.mdend[gl], my_start);
+            br.init(S.stage, base, my_mdend, my_start);
             // ---- part 2 (ISO 11172-3 2.4.2.7): my own scalefactors.  Long ones go to shared memory (granule 1 may need them),
             // short ones straight into their band's byte.
             if (lsf) {
@@ -378,11 +394,13 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         for (int k = 0; k < 16; k++) {
             const int row = 2 * k + (lane >> 4), col = lane & 15;
             const uint32_t ro = S.rowoff[warp * 32 + row];
-            if (ro != 0xFFFFFFFFu) blk_gains[(ro / 288u) * (K1_GAIN_ROW / 4) + col] = S.tile[warp][row][col];
+            if (ro != 0xFFFFFFFFu) blk_gains[(ro / 288u) * (K1_GAIN_ROW / 4) + col] = S.tile[warp][row * 17 + col];
         }
         __syncwarp();
 
-        // ---- phase 1: big values.  Every lane emits one pair per iteration while it has any.
+        // ---- phase 1: big values.  Every lane decodes one pair per step while it has any; four pairs make a 16-byte chunk of
+        // the lane's tile row, four chunks (16 pairs) a flush.  A lane's last, incomplete chunk stays in registers (c0..c2): the
+        // count1 words that follow complete it.
         const int mybv = in ? bv : 0;
         const int wmin = __reduce_min_sync(0xffffffffu, mybv);
         const int wmax = __reduce_max_sync(0xffffffffu, mybv);
@@ -392,16 +410,16 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             const int line = 2 * p;
             const uint32_t reg = line < r0 ? reg0 : (line < r1 ? reg1 : reg2);
             const int linbits = (int)(reg & 0xFFu);
-            uint32_t w = br.peek();
-            uint32_t e = S.huff[(reg >> 8) + (w >> (32 - HUF_L1))];
+            const uint32_t wh = br.peek(), wl = br.peek2();
+            uint32_t e = S.huff[(reg >> 8) + (wh >> (32 - HUF_L1))];
             if (e & 0x8000u) {
                 const uint32_t nb2 = (e >> 11) & 15;
-                e = S.huff[((e & 0x7FFu) << 2) + ((w << HUF_L1) >> (32 - nb2))];
+                e = S.huff[((e & 0x7FFu) << 2) + ((wh << HUF_L1) >> (32 - nb2))];
             }
-            br.skip(e >> 8);
+            const uint32_t len = e >> 8;   // <= 19
             int x = (e >> 4) & 15, y = e & 15;
-            // linbits(x) sign(x) linbits(y) sign(y): at most 28 bits, peeled off one peek
-            w = br.peek();
+            // linbits(x) sign(x) linbits(y) sign(y): at most 28 bits after the code word, all inside the 64-bit peek
+            uint32_t w = __funnelshift_l(wl, wh, len);
             const int lbx = (x == 15) ? linbits : 0;
             x += (int)((w >> 1) >> (31 - lbx));
             w <<= lbx;
@@ -413,79 +431,110 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             w <<= lby;
             const int sy = y != 0;
             const bool negy = sy && (w >> 31);
-            br.skip((uint32_t)(lbx + sx + lby + sy));
+            br.skip64(len + (uint32_t)(lbx + sx + lby + sy));
             x = negx ? -x : x;
             y = negy ? -y : y;
             return ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);
         };
+        uint32_t c0 = 0, c1w = 0, c2 = 0;
         for (int p0 = 0; p0 < wmax; p0 += 16) {
             const bool full = p0 + 16 <= wmin;   // every lane is inside its big-values region for the whole block of 16
-            if (full) {
 #pragma unroll 1
-                for (int pp = 0; pp < 16; pp++) trow[pp] = big_pair(p0 + pp);
-            } else {
-                const int n = min(16, wmax - p0);
-#pragma unroll 1
-                for (int pp = 0; pp < n; pp++)
-                    if (p0 + pp < mybv) trow[pp] = big_pair(p0 + pp);
+            for (int g = 0; g < 4; g++) {
+                const int pb = p0 + 4 * g;
+                if (pb >= wmax) break;
+                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (full || pb < mybv) v0 = big_pair(pb);
+                if (full || pb + 1 < mybv) v1 = big_pair(pb + 1);
+                if (full || pb + 2 < mybv) v2 = big_pair(pb + 2);
+                if (full || pb + 3 < mybv) v3 = big_pair(pb + 3);
+                if (pb == (mybv & ~3)) { c0 = v0; c1w = v1; c2 = v2; }
+                t4[lane * 4 + (g ^ swz)] = make_uint4(v0, v1, v2, v3);
             }
             __syncwarp();
-#pragma unroll 4
-            for (int k = 0; k < 16; k++) {
-                const int row = 2 * k + (lane >> 4), col = lane & 15;
-                const uint32_t v = S.tile[warp][row][col];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int row = 8 * k + (lane >> 2), chunk = lane & 3;
                 const uint32_t ro = S.rowoff[warp * 32 + row];
-                if (ro != 0xFFFFFFFFu && (full || (uint32_t)(p0 + col) < S.lim[warp * 32 + row])) blk_words[ro + p0 + col] = v;
+                if (ro != 0xFFFFFFFFu && (full || (uint32_t)(p0 + 4 * chunk + 4) <= S.lim[warp * 32 + row]))
+                    *reinterpret_cast<uint4*>(blk_words + ro + p0 + 4 * chunk) = t4[row * 4 + (chunk ^ ((row >> 1) & 3))];
             }
             __syncwarp();
         }
 
-        // ---- phase 2: count1 quads, one per lane and iteration, from pair `bv` on (oracle: while (pos < end && line <= 572));
-        // a quad that straddles the end of the granule-channel's bits is discarded.  An overrun of the big-values region
-        // silences the granule-channel (oracle: read_huffman).
+        // ---- phase 2: count1 quads from pair `bv` on (oracle: while (pos < end && line <= 572)), two per lane and step; a quad
+        // that straddles the end of the granule-channel's bits is discarded.  An overrun of the big-values region silences the
+        // granule-channel (oracle: read_huffman).  The four new words are rotated behind the r = bv % 4 words the lane carries,
+        // so that complete 16-byte chunks keep leaving through the tile; a lane's last 0..5 words leave one by one.
         bool overrun = false;
         uint32_t nz = 0;
-        bool more = false;
+        bool live = false;
         int q = mybv;
         if (in && !silent) {
             if (br.pos > my_end) overrun = true;
-            else { nz = 2u * (uint32_t)bv; more = true; }
+            else { nz = 2u * (uint32_t)bv; live = true; }
         }
-        if (in) S.rowoff[tid] = (uint32_t)gl * 288u + (uint32_t)mybv;   // phase-2 rows start at the lane's own pair `bv`
-        while (__any_sync(0xffffffffu, more)) {
-            int produced = 0;
+        const uint32_t r = live ? (uint32_t)(mybv & 3) : 0u;
+        uint32_t gpos = (uint32_t)(mybv & ~3);
+        if (in) S.rowoff[tid] = my_row + gpos;
+        auto quad = [&](uint32_t& a, uint32_t& b) -> bool {
+            if (!(br.pos < my_end && q <= 286)) return false;
+            const uint32_t w = br.peek();
+            const uint32_t e = c1[w >> 26];
+            const uint32_t len = e >> 4, pat = e & 15u;
+            const uint32_t tot = len + (uint32_t)__popc(pat);
+            if (br.pos + tot > my_end) return false;   // straddles the end: discarded
+            const uint32_t v4 = S.quad[(pat << 4) | ((w << len) >> 28)];   // v w x y as four int8
+            br.skip(tot);
+            a = __byte_perm(v4, 0, 0x9180);   // (v, w) as int16 pair: bytes b0, sign(b0), b1, sign(b1)
+            b = __byte_perm(v4, 0, 0xB3A2);   // (x, y)
+            q += 2; nz += 4;
+            return true;
+        };
+        while (__any_sync(0xffffffffu, live)) {
+            uint32_t nvalid = 0;
 #pragma unroll 1
-            for (int k = 0; k < 8; k++) {
-                if (more) {
-                    if (br.pos < my_end && q <= 286) {
-                        const uint32_t w = br.peek();
-                        const uint32_t e = c1[w >> 26];
-                        const uint32_t len = e >> 4, pat = e & 15u;
-                        const uint32_t tot = len + (uint32_t)__popc(pat);
-                        if (br.pos + tot > my_end) more = false;   // straddles the end: discarded
-                        else {
-                            const uint2 o = S.quad[(pat << 4) | ((w << len) >> 28)];
-                            br.skip(tot);
-                            trow[2 * k] = o.x;
-                            trow[2 * k + 1] = o.y;
-                            q += 2; nz += 4; produced += 2;
-                        }
-                    } else more = false;
+            for (int it = 0; it < 4; it++) {
+                if (live) {
+                    uint32_t a = 0, b = 0, c = 0, d = 0;
+                    int n = 0;
+                    if (quad(a, b)) { n = 2; if (quad(c, d)) n = 4; }
+                    const uint32_t o0 = r == 0 ? a : c0;
+                    const uint32_t o1 = r == 0 ? b : (r == 1 ? a : c1w);
+                    const uint32_t o2 = r == 0 ? c : (r == 1 ? b : (r == 2 ? a : c2));
+                    const uint32_t o3 = r == 0 ? d : (r == 1 ? c : (r == 2 ? b : a));
+                    const uint32_t n0 = r == 1 ? d : (r == 2 ? c : b);
+                    if (n == 4) {
+                        t4[lane * 4 + (it ^ swz)] = make_uint4(o0, o1, o2, o3);
+                        nvalid += 4;
+                        c0 = n0; c1w = r == 2 ? d : c; c2 = d;
+                    } else {
+                        const uint32_t tot = r + (uint32_t)n;   // the lane is done: its last words leave one by one
+                        uint32_t* dst = blk_words + my_row + gpos + nvalid;
+                        if (tot > 0) dst[0] = o0;
+                        if (tot > 1) dst[1] = o1;
+                        if (tot > 2) dst[2] = o2;
+                        if (tot > 3) dst[3] = o3;
+                        if (tot > 4) dst[4] = n0;
+                        live = false;
+                    }
                 }
             }
-            S.lim[tid] = (uint32_t)produced;
+            S.lim[tid] = nvalid;
             __syncwarp();
-#pragma unroll 4
-            for (int k = 0; k < 16; k++) {
-                const int row = 2 * k + (lane >> 4), col = lane & 15;
-                const uint32_t v = S.tile[warp][row][col];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int row = 8 * k + (lane >> 2), chunk = lane & 3;
                 const uint32_t ro = S.rowoff[warp * 32 + row];
-                if (ro != 0xFFFFFFFFu && (uint32_t)col < S.lim[warp * 32 + row]) blk_words[ro + col] = v;
+                if (ro != 0xFFFFFFFFu && (uint32_t)(4 * chunk + 4) <= S.lim[warp * 32 + row])
+                    *reinterpret_cast<uint4*>(blk_words + ro + 4 * chunk) = t4[row * 4 + (chunk ^ ((row >> 1) & 3))];
             }
             __syncwarp();
-            if (in) S.rowoff[tid] += 16;
+            gpos += nvalid;
+            if (in) S.rowoff[tid] = my_row + gpos;
         }
         if (in) nz_out[tr.gc_base + gc] = (overrun || silent) ? 0 : (uint16_t)nz;
+        if (last_pass) break;
         pending = pending && !in;
         __syncthreads();   // the staging buffer and S.base are reused by the next window
     }

@@ -103,6 +103,7 @@ struct rg_engine {
     // options
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
     uint32_t k4_round = 0;                // chains in one round of k_iir_fast CTAs: one CTA per SM
+    uint32_t k2_smem_pad = 0;             // profiling: extra dynamic shared memory per K2 CTA (lowers K2's CTAs per SM)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
@@ -231,7 +232,7 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         f.u0[0] += f.uz[0]; f.u0[1] += f.uz[1];
         f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
-    CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
+    CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem) + 40 * 1024));
     CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     {
         int sms = 0;
@@ -273,6 +274,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
+    if (!strcmp(key, "k2_smem_pad")) { if (value < 0 || value > 40 * 1024) return RG_ERR_INVALID_ARG; e->k2_smem_pad = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "k4_slim")) {
         if (value < 0 || value > 8) return RG_ERR_INVALID_ARG;
         e->k4_slim = (uint32_t)value;

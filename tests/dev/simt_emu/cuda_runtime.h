@@ -93,6 +93,7 @@ struct Fiber {
     uint64_t c_val, c_res;
     int c_arg;
     const char* c_file; unsigned c_line;
+    unsigned stc_calls;    // __syncthreads_count / _and / _or calls of this thread (they alternate between two accumulators)
 };
 
 struct State {
@@ -106,6 +107,7 @@ struct State {
     uint3 blockIdx;
     // block barrier 0 and named barriers 1..15
     unsigned bar_arrived[16] = {}, bar_gen[16] = {};
+    int stc_acc[2] = {0, 0};
     uint64_t progress = 0;
     const void* body = nullptr;
     void (*thunk)(const void*) = nullptr;
@@ -178,7 +180,7 @@ template <class F> void launch(dim3 grid, dim3 block, size_t smem, const F& body
             makecontext(&f.ctx, (void (*)())entry, 0);
 #endif
             f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-            f.lin = t; f.done = false; f.waiting = false; f.c_wait = f.c_done = false;
+            f.lin = t; f.done = false; f.waiting = false; f.c_wait = f.c_done = false; f.stc_calls = 0;
         }
         s.live = nt;
         s.fibers_run += nt;
@@ -328,6 +330,20 @@ inline void mbar_wait(unsigned long long* bar, uint32_t parity) {
 #define EMU_DYN_SMEM(T) reinterpret_cast<T*>(emu::S().dyn_smem)
 
 static inline void __syncthreads() { emu::barrier(0, 0); }
+// block-wide vote: every thread adds its predicate to one of two alternating accumulators, a barrier, everybody reads, a second
+// barrier, everybody clears (a thread can only reach the accumulator's next use after all threads have passed the call in between)
+static inline int __syncthreads_count(int pred) {
+    emu::State& s = emu::S();
+    const unsigned slot = s.cur->stc_calls++ & 1;
+    s.stc_acc[slot] += pred ? 1 : 0;
+    emu::barrier(0, 0);
+    const int r = s.stc_acc[slot];
+    emu::barrier(0, 0);
+    s.stc_acc[slot] = 0;
+    return r;
+}
+static inline int __syncthreads_and(int pred) { const int live = (int)emu::S().live; return __syncthreads_count(pred) == live; }
+static inline int __syncthreads_or(int pred) { return __syncthreads_count(pred) != 0; }
 static inline void __syncwarp(unsigned mask = 0xffffffffu, const emu::SL& loc = emu::SL::current()) { emu::collective(mask, emu::OP_SYNC, 0, 0, 32, loc); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}

@@ -23,6 +23,9 @@ imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
 print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
 lib = _lib.load()
 eng = m.Engine(device=0, exact=exact)
+for kv in os.environ.get("RG_OPTS", "").split(","):   # e.g. RG_OPTS=k2_smem_pad=30000,iir_block_windows=16
+    if "=" in kv:
+        eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
 if os.environ.get("RG_PIPELINE") == "0":
     eng.set_option("pipeline", 0)   # one batch at a time, every kernel alone on the device
 arr, keep = m.Engine._inputs(imgs, None)
