@@ -28,6 +28,7 @@
 
 #define K1_THREADS 256
 #define K1_GAIN_ROW 64        // BYTES per granule-channel: [0..21] long sfb, [22..60] short sfb*3+win, [62..63] gain exponent base (u16)
+#define K1_C1_ROW 144         // bytes per granule-channel: at most (576 - 2 * big_values) / 4 quads
 #define K1_STAGE 28672u       // bytes of main data staged per window (256 granule-channels at 128 kbps: 24.4 KB)
 #define K1_SLACK 16u          // the bit window prefetches up to 12 bytes past the last bit it needs
 
@@ -50,12 +51,20 @@ struct K1Smem {
     uint32_t rowoff[K1_THREADS];     // (worker order) word offset in the block of the next 16 words the worker's row flushes, 0xFFFFFFFF = none
     uint32_t lim[K1_THREADS];        // (worker order) words of that stretch that are complete
     uint8_t sfl[K1_THREADS][24];     // long scalefactors of every granule-channel (scfsi source)
-    uint32_t quad[256];              // (count1 pattern << 4 | next four bits) -> v w x y as four int8
     uint8_t c1[2][64];               // count1 tables A / B: 6-bit peek -> (len << 4) | pattern
     uint32_t base;                   // first main-data byte wanted by a granule-channel that is still pending
     alignas(8) unsigned long long mbar;
 };
 static_assert(sizeof(K1Pre) <= sizeof(uint32_t) * (K1_THREADS / 32) * 32 * 17, "pre-pass scratch must fit under the tiles");
+
+#ifdef __CUDACC__
+#define K1_NOINLINE __noinline__
+#else
+#define K1_NOINLINE __attribute__((noinline))
+#endif
+__device__ K1_NOINLINE uint32_t k1_mask_tail(uint32_t v, uint32_t off, uint32_t lim_rel) {
+    return off >= lim_rel ? 0u : (v & (0xFFFFFFFFu << (8 * (off + 4 - lim_rel))));
+}
 
 // Big-endian bit window over the staged main data: the words at pos>>5, +1, +2 (hi, lo, nx) in registers.
 struct BitWin {
@@ -66,13 +75,15 @@ struct BitWin {
     uint32_t lim_rel;      // bytes of `st` readable for this frame (later bytes read as zero, like the oracle's reservoir)
     __device__ __forceinline__ uint32_t next() {
         uint32_t v = __byte_perm(*reinterpret_cast<const uint32_t*>(st + off), 0, 0x0123);
-        if (off + 4 > lim_rel)   // the word reaches past the readable bytes (only at the very end of a frame's data)
-            v = off >= lim_rel ? 0u : (v & (0xFFFFFFFFu << (8 * (off + 4 - lim_rel))));
+        if (off + 4 > lim_rel) v = k1_mask_tail(v, off, lim_rel);   // (a real branch: never taken by a sound stream)
         off += 4;
         return v;
     }
-    __device__ __forceinline__ void init(const uint8_t* staged, uint32_t base_byte, uint32_t lim_bytes, uint32_t bitpos) {
-        st = staged; lim_rel = lim_bytes - base_byte; pos = bitpos;
+    // Bytes at or beyond lim_bytes read as zero -- which can only matter to a granule-channel whose part2_3_length claims
+    // bits beyond them (a damaged stream: end_bit > 8 * lim_bytes).  Every other granule-channel either stops at its last bit
+    // or is discarded / silenced once it has run past it, whatever the bits beyond were, so it reads the staged bytes as they are.
+    __device__ __forceinline__ void init(const uint8_t* staged, uint32_t base_byte, uint32_t lim_bytes, uint32_t bitpos, uint32_t end_bit) {
+        st = staged; lim_rel = end_bit > 8u * lim_bytes ? lim_bytes - base_byte : 0xFFFFFFF0u; pos = bitpos;
         off = ((bitpos >> 5) << 2) - base_byte;
         hi = next(); lo = next(); nx = next();
     }
@@ -116,6 +127,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
           int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
+          uint8_t* __restrict__ c1q /* [gc][K1_C1_ROW]: one byte per count1 quad, pattern << 4 | the four bits after its code */,
           uint8_t* __restrict__ gains /* [gc][K1_GAIN_ROW] */,
           uint8_t* __restrict__ sfraw /* [gc][K1_GAIN_ROW]: raw scalefactors = is_pos, right channel of intensity-stereo frames only */) {
     extern __shared__ __align__(16) unsigned char k1_raw[];
@@ -129,12 +141,6 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             S.c1[0][tid] = T->c1a_lut[tid];
             S.c1[1][tid] = (uint8_t)((4u << 4) | (15u - (tid >> 2)));
         }
-        // the quad table: pattern bits v w x y (v = bit 3); the sign bits of the non-zero values follow the code in that order
-        uint32_t v4 = 0, used = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if ((tid >> (7 - k)) & 1) { v4 |= (((tid >> (3 - used)) & 1) ? 0xFFu : 1u) << (8 * k); used++; }
-        S.quad[tid] = v4;
         if (tid == 0) k2_mbar_init(&S.mbar, 1);
     }
     const HuffBlock blk = blocks[blockIdx.x];
@@ -323,7 +329,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         BitWin br;
         br.st = S.stage; br.lim_rel = 0; br.pos = 0; br.off = 0; br.hi = br.lo = br.nx = 0;
         if (in) {
-            br.init(S.stage, base, my_mdend, my_start);
+            br.init(S.stage, base, my_mdend, my_start, my_end);
             // ---- part 2 (ISO 11172-3 2.4.2.7): my own scalefactors.  Long ones go to shared memory (granule 1 may need them),
             // short ones straight into their band's byte.
             if (lsf) {
@@ -399,8 +405,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         __syncwarp();
 
         // ---- phase 1: big values.  Every lane decodes one pair per step while it has any; four pairs make a 16-byte chunk of
-        // the lane's tile row, four chunks (16 pairs) a flush.  A lane's last, incomplete chunk stays in registers (c0..c2): the
-        // count1 words that follow complete it.
+        // the lane's tile row, four chunks (16 pairs) a flush (a lane's last chunk may be partly zero: K2 knows big_values).
         const int mybv = in ? bv : 0;
         const int wmin = __reduce_min_sync(0xffffffffu, mybv);
         const int wmax = __reduce_max_sync(0xffffffffu, mybv);
@@ -436,7 +441,6 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             y = negy ? -y : y;
             return ((uint32_t)(uint16_t)(int16_t)x) | ((uint32_t)(uint16_t)(int16_t)y << 16);
         };
-        uint32_t c0 = 0, c1w = 0, c2 = 0;
         for (int p0 = 0; p0 < wmax; p0 += 16) {
             const bool full = p0 + 16 <= wmin;   // every lane is inside its big-values region for the whole block of 16
 #pragma unroll 1
@@ -448,7 +452,6 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 if (full || pb + 1 < mybv) v1 = big_pair(pb + 1);
                 if (full || pb + 2 < mybv) v2 = big_pair(pb + 2);
                 if (full || pb + 3 < mybv) v3 = big_pair(pb + 3);
-                if (pb == (mybv & ~3)) { c0 = v0; c1w = v1; c2 = v2; }
                 t4[lane * 4 + (g ^ swz)] = make_uint4(v0, v1, v2, v3);
             }
             __syncwarp();
@@ -456,16 +459,16 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             for (int k = 0; k < 4; k++) {
                 const int row = 8 * k + (lane >> 2), chunk = lane & 3;
                 const uint32_t ro = S.rowoff[warp * 32 + row];
-                if (ro != 0xFFFFFFFFu && (full || (uint32_t)(p0 + 4 * chunk + 4) <= S.lim[warp * 32 + row]))
+                if (ro != 0xFFFFFFFFu && (full || (uint32_t)(p0 + 4 * chunk) < S.lim[warp * 32 + row]))
                     *reinterpret_cast<uint4*>(blk_words + ro + p0 + 4 * chunk) = t4[row * 4 + (chunk ^ ((row >> 1) & 3))];
             }
             __syncwarp();
         }
 
-        // ---- phase 2: count1 quads from pair `bv` on (oracle: while (pos < end && line <= 572)), two per lane and step; a quad
-        // that straddles the end of the granule-channel's bits is discarded.  An overrun of the big-values region silences the
-        // granule-channel (oracle: read_huffman).  The four new words are rotated behind the r = bv % 4 words the lane carries,
-        // so that complete 16-byte chunks keep leaving through the tile; a lane's last 0..5 words leave one by one.
+        // ---- phase 2: count1 quads from pair `bv` on (oracle: while (pos < end && line <= 572)); a quad that straddles the end of
+        // the granule-channel's bits is discarded.  An overrun of the big-values region silences the granule-channel (oracle:
+        // read_huffman).  A quad leaves as ONE byte -- its pattern (which of v w x y are +-1) and the four bits after the code
+        // word, the first popc(pattern) of which are the signs -- sixteen quads per 16-byte store; K2 expands them.
         bool overrun = false;
         uint32_t nz = 0;
         bool live = false;
@@ -474,64 +477,29 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             if (br.pos > my_end) overrun = true;
             else { nz = 2u * (uint32_t)bv; live = true; }
         }
-        const uint32_t r = live ? (uint32_t)(mybv & 3) : 0u;
-        uint32_t gpos = (uint32_t)(mybv & ~3);
-        if (in) S.rowoff[tid] = my_row + gpos;
-        auto quad = [&](uint32_t& a, uint32_t& b) -> bool {
-            if (!(br.pos < my_end && q <= 286)) return false;
-            const uint32_t w = br.peek();
-            const uint32_t e = c1[w >> 26];
-            const uint32_t len = e >> 4, pat = e & 15u;
-            const uint32_t tot = len + (uint32_t)__popc(pat);
-            if (br.pos + tot > my_end) return false;   // straddles the end: discarded
-            const uint32_t v4 = S.quad[(pat << 4) | ((w << len) >> 28)];   // v w x y as four int8
-            br.skip(tot);
-            a = __byte_perm(v4, 0, 0x9180);   // (v, w) as int16 pair: bytes b0, sign(b0), b1, sign(b1)
-            b = __byte_perm(v4, 0, 0xB3A2);   // (x, y)
-            q += 2; nz += 4;
-            return true;
-        };
+        uint4* qrow = reinterpret_cast<uint4*>(c1q + ((size_t)tr.gc_base + gc) * K1_C1_ROW);
         while (__any_sync(0xffffffffu, live)) {
-            uint32_t nvalid = 0;
-#pragma unroll 1
-            for (int it = 0; it < 4; it++) {
+            uint32_t acc[4] = {0, 0, 0, 0};
+            const bool was_live = live;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
                 if (live) {
-                    uint32_t a = 0, b = 0, c = 0, d = 0;
-                    int n = 0;
-                    if (quad(a, b)) { n = 2; if (quad(c, d)) n = 4; }
-                    const uint32_t o0 = r == 0 ? a : c0;
-                    const uint32_t o1 = r == 0 ? b : (r == 1 ? a : c1w);
-                    const uint32_t o2 = r == 0 ? c : (r == 1 ? b : (r == 2 ? a : c2));
-                    const uint32_t o3 = r == 0 ? d : (r == 1 ? c : (r == 2 ? b : a));
-                    const uint32_t n0 = r == 1 ? d : (r == 2 ? c : b);
-                    if (n == 4) {
-                        t4[lane * 4 + (it ^ swz)] = make_uint4(o0, o1, o2, o3);
-                        nvalid += 4;
-                        c0 = n0; c1w = r == 2 ? d : c; c2 = d;
-                    } else {
-                        const uint32_t tot = r + (uint32_t)n;   // the lane is done: its last words leave one by one
-                        uint32_t* dst = blk_words + my_row + gpos + nvalid;
-                        if (tot > 0) dst[0] = o0;
-                        if (tot > 1) dst[1] = o1;
-                        if (tot > 2) dst[2] = o2;
-                        if (tot > 3) dst[3] = o3;
-                        if (tot > 4) dst[4] = n0;
-                        live = false;
+                    live = false;
+                    if (br.pos < my_end && q <= 286) {
+                        const uint32_t w = br.peek();
+                        const uint32_t e = c1[w >> 26];
+                        const uint32_t len = e >> 4, pat = e & 15u;
+                        const uint32_t tot = len + (uint32_t)__popc(pat);
+                        if (br.pos + tot <= my_end) {   // (else: straddles the end, discarded)
+                            acc[k >> 2] |= ((pat << 4) | ((w << len) >> 28)) << (8 * (k & 3));
+                            br.skip(tot);
+                            q += 2; nz += 4;
+                            live = true;
+                        }
                     }
                 }
             }
-            S.lim[tid] = nvalid;
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int row = 8 * k + (lane >> 2), chunk = lane & 3;
-                const uint32_t ro = S.rowoff[warp * 32 + row];
-                if (ro != 0xFFFFFFFFu && (uint32_t)(4 * chunk + 4) <= S.lim[warp * 32 + row])
-                    *reinterpret_cast<uint4*>(blk_words + ro + 4 * chunk) = t4[row * 4 + (chunk ^ ((row >> 1) & 3))];
-            }
-            __syncwarp();
-            gpos += nvalid;
-            if (in) S.rowoff[tid] = my_row + gpos;
+            if (was_live) *qrow++ = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         }
         if (in) nz_out[tr.gc_base + gc] = (overrun || silent) ? 0 : (uint16_t)nz;
         if (last_pass) break;

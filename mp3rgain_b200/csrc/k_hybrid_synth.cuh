@@ -34,6 +34,7 @@
 
 struct __align__(2) GranInfo {
     uint16_t nz;          // lines decoded by K1 (0 = silent)
+    uint16_t bvp;         // pairs of the big-values region: int16 pairs in the spectrum row; the lines from there to nz are count1 quads
     uint8_t bt, mixed, ms /* bit0 MS stereo, bit1 intensity stereo (frame level) */, sb_limit /* subbands with possibly non-zero IMDCT input */;
 };
 
@@ -41,6 +42,7 @@ struct K2Smem {
     alignas(16) float A[K2_SLOTS][SLOTF];     // per granule-channel: xr[576] -> F[18][ROW] -> DCT rows [18][ROW], in place
     float S2[K2_SLOTS][SLOTF];                // IMDCT outputs 18..35 of the granule-channel (added by the NEXT granule)
     alignas(16) uint32_t stage[K2_GC][288];   // the batch's int16 line pairs, written by the TMA unit
+    alignas(16) uint8_t c1q[K2_GC][K1_C1_ROW];   // the batch's count1 quads, one byte each (pattern << 4 | the four bits after the code)
     alignas(16) uint8_t banddelta[K2_GC][K1_GAIN_ROW];   // per band: what to subtract from the granule-channel's gain exponent
                                               // ([0..21] long sfb, [22..60] short sfb*3+win, [62..63] the exponent itself), by TMA
     float gaintab[L3_GAIN_MAX - L3_GAIN_MIN + 1];   // 2^(e/4)
@@ -110,6 +112,7 @@ __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corp
     gi.mixed = (gi.bt == 2) ? (uint8_t)(f & 1) : 0;
     const size_t gcb = (size_t)tr.gc_base + (size_t)g * nch;
     gi.nz = nz_in[gcb + ch];
+    gi.bvp = (uint16_t)min(side_field(s, b0 + 12 - (gpf == 1 ? 5 : 0), 9), (uint32_t)gi.nz >> 1);   // (b0 carries the 5 extra bits of the MPEG-2 scalefac_compress)
     const bool joint = nch == 2 && ((rec.hdr >> 6) & 3) == 1;
     gi.ms = (uint8_t)((joint && ((rec.hdr >> 4) & 2) ? 1 : 0) | (joint && ((rec.hdr >> 4) & 1) ? 2 : 0));
     // subbands whose IMDCT input can be non-zero: the coded lines (of either channel under MS / intensity stereo), one more
@@ -226,7 +229,7 @@ template <int NCH>
 __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ corpus,
                                         const FrameRec* __restrict__ frames, const DecTrack& tr, const RunDesc& run,
                                         const L3Dev* __restrict__ T, const int16_t* __restrict__ spectra,
-                                        const uint16_t* __restrict__ nz_in, const uint8_t* __restrict__ gains,
+                                        const uint8_t* __restrict__ c1q, const uint16_t* __restrict__ nz_in, const uint8_t* __restrict__ gains,
                                         const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits,
                                         uint32_t flags) {
     constexpr int G = K2_GC / NCH;      // granules per batch
@@ -273,8 +276,9 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         const uint32_t gl0 = b * G;
         const uint32_t ngc = min((uint32_t)G, gcount - gl0) * NCH;
         const size_t gc0 = (size_t)tr.gc_base + (size_t)(gfirst + gl0) * NCH;
-        k2_mbar_expect(&S.mbar, ngc * (1152u + K1_GAIN_ROW));
+        k2_mbar_expect(&S.mbar, ngc * (1152u + K1_GAIN_ROW + K1_C1_ROW));
         k2_bulk_load(&S.stage[0][0], spectra + gc0 * 576, ngc * 1152u, &S.mbar);
+        k2_bulk_load(&S.c1q[0][0], c1q + gc0 * K1_C1_ROW, ngc * K1_C1_ROW, &S.mbar);
         k2_bulk_load(&S.banddelta[0][0], gains + gc0 * K1_GAIN_ROW, ngc * K1_GAIN_ROW, &S.mbar);
     };
 
@@ -296,8 +300,12 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
             const int lim9 = (int)(w0 >> 8);
             const int tsel0 = w0 & 3, tsel1 = w1 & 3;
             const bool ms = (w0 >> 2) & 1;
-            // K1 writes a row only up to its last decoded line (nz): everything beyond reads as zero
-            const uint32_t nz0 = S.gi[gl][0].nz, nz1 = S.gi[gl][NCH - 1].nz;
+            // K1 writes int16 pairs up to big_values, one byte per count1 quad from there to its last decoded line (nz), and
+            // nothing beyond: the rest reads as zero
+            const int nzp0 = S.gi[gl][0].nz >> 1, nzp1 = S.gi[gl][NCH - 1].nz >> 1;
+            const int bvp0 = S.gi[gl][0].bvp, bvp1 = S.gi[gl][NCH - 1].bvp;
+            const uint8_t* cq0 = S.c1q[my_gi * NCH];
+            const uint8_t* cq1 = S.c1q[my_gi * NCH + NCH - 1];
             const uint32_t* st0 = S.stage[my_gi * NCH];
             const uint32_t* st1 = S.stage[my_gi * NCH + NCH - 1];
             const uint8_t* bd0 = S.banddelta[my_gi * NCH];
@@ -314,7 +322,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 if (my_ch == 0 && lane < 4) top[lane] = -1;
                 k2_pair_sync(my_gi);
                 for (int pr = lane + 32 * my_ch; pr < 288; pr += 64) {
-                    if ((uint32_t)(2 * pr) < nz1 && st1[pr] != 0u) {
+                    if (pr < nzp1 && (pr < bvp1 ? st1[pr] != 0u : ((cq1[(pr - bvp1) >> 1] >> (((pr - bvp1) & 1) ? 4 : 6)) & 3u) != 0u)) {
                         const int code = S.code[tsel1][2 * pr];
                         if (code < 22) atomicMax(&top[0], code);
                         else atomicMax(&top[1 + (code - 22) % 3], (code - 22) / 3);
@@ -341,14 +349,27 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 float v[2][2];
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++) {
-                    const bool coded = (uint32_t)(2 * pr) < (ch ? nz1 : nz0);
-                    const uint32_t packed = coded ? (ch ? st1 : st0)[pr] : 0u;
-                    const float gn = coded ? S.gaintab[(ch ? be1 : be0) - (int)(ch ? bd1 : bd0)[S.code[ch ? tsel1 : tsel0][2 * pr]]] : 0.0f;
-                    const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
-                    const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
-                    const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
-                    v[ch][0] = q0 < 0 ? -m0 : m0;
-                    v[ch][1] = q1 < 0 ? -m1 : m1;
+                    const int nzp = ch ? nzp1 : nzp0, bvp = ch ? bvp1 : bvp0;
+                    const float gn = pr < nzp ? S.gaintab[(ch ? be1 : be0) - (int)(ch ? bd1 : bd0)[S.code[ch ? tsel1 : tsel0][2 * pr]]] : 0.0f;
+                    if (pr < bvp || pr >= nzp) {
+                        const uint32_t packed = pr < bvp ? (ch ? st1 : st0)[pr] : 0u;
+                        const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
+                        const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
+                        const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
+                        v[ch][0] = q0 < 0 ? -m0 : m0;
+                        v[ch][1] = q1 < 0 ? -m1 : m1;
+                    } else {
+                        // count1 pair: values 0 / +-1, |1|^(4/3) * gain = gain.  The quad's byte holds the pattern v w x y (bit 7 =
+                        // v) and the four bits that followed its code word: the sign bits of the non-zero values, in that order
+                        const int t = pr - bvp;
+                        const uint32_t byte = (ch ? cq1 : cq0)[t >> 1];
+                        const uint32_t k0 = (t & 1) ? 2u : 0u;                  // this pair is (v, w) or (x, y)
+                        const uint32_t a0 = (byte >> (7 - k0)) & 1u, a1 = (byte >> (6 - k0)) & 1u;
+                        const uint32_t i0 = (uint32_t)__popc((byte >> 4) >> (4 - k0)), i1 = i0 + a0;   // non-zero values before each
+                        const uint32_t n0 = (byte >> (3 - i0)) & 1u, n1 = (byte >> (3 - i1)) & 1u;
+                        v[ch][0] = a0 ? (n0 ? -gn : gn) : 0.0f;
+                        v[ch][1] = a1 ? (n1 ? -gn : gn) : 0.0f;
+                    }
                 }
                 uint32_t ipos = 255;
                 if (NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
@@ -506,13 +527,14 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
 __global__ void __launch_bounds__(K2_THREADS, 3)
 k_hybrid_synth(const uint8_t* __restrict__ corpus, const FrameRec* __restrict__ frames,
                const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs, const L3Dev* __restrict__ T,
-               const int16_t* __restrict__ spectra, const uint16_t* __restrict__ nz_in, const uint8_t* __restrict__ gains,
+               const int16_t* __restrict__ spectra, const uint8_t* __restrict__ c1q, const uint16_t* __restrict__ nz_in,
+               const uint8_t* __restrict__ gains,
                const uint8_t* __restrict__ sfraw, float* __restrict__ pcm, uint32_t* __restrict__ peak_bits /* [track] or null */,
                uint32_t flags) {
     extern __shared__ __align__(16) unsigned char k2_raw[];
     K2Smem& S = *reinterpret_cast<K2Smem*>(k2_raw);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
-    if (tr.channels == 1) k2_body<1>(S, corpus, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
-    else k2_body<2>(S, corpus, frames, tr, run, T, spectra, nz_in, gains, sfraw, pcm, peak_bits, flags);
+    if (tr.channels == 1) k2_body<1>(S, corpus, frames, tr, run, T, spectra, c1q, nz_in, gains, sfraw, pcm, peak_bits, flags);
+    else k2_body<2>(S, corpus, frames, tr, run, T, spectra, c1q, nz_in, gains, sfraw, pcm, peak_bits, flags);
 }

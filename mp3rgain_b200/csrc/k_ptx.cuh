@@ -35,3 +35,10 @@ __device__ __forceinline__ void k2_pair_sync(int pair) {   // immediate ids, so 
         default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
     }
 }
+// prmt.b32 with the selector's replicate-sign bits honoured (bit 3 of a nibble: the result byte is the selected byte's sign,
+// 0x00 or 0xFF).  The CUDA intrinsic __byte_perm masks those bits away.
+__device__ __forceinline__ uint32_t k2_prmt(uint32_t a, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0u), "r"(sel));
+    return r;
+}

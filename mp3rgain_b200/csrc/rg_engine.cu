@@ -74,7 +74,7 @@ struct PcmTrack {
 // (integer / f32 work) run while the IIR of batch k keeps the FP64 pipe busy, and the host plans batch k+1 meanwhile.
 struct BatchCtx {
     // stage A scratch
-    DevBuf d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_gains, d_sfraw, d_pcm;
+    DevBuf d_dtracks, d_hblocks, d_runs, d_spectra, d_nz, d_c1q, d_gains, d_sfraw, d_pcm;
     // stage B scratch
     DevBuf d_chains, d_wsum, d_wmax, d_peaks, d_twin, d_tout, d_hist, d_perm, d_tpeak;
     HostBuf h_desc_a, h_desc, h_tout;      // pinned: descriptor staging (decode / analysis), results
@@ -87,7 +87,7 @@ struct BatchCtx {
     size_t n_chains = 0;
     uint32_t* hist_host = nullptr;         // where this batch's per-track histograms go (n x 12000), or null
     std::vector<DevBuf*> bufs() {
-        return {&d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_gains, &d_sfraw, &d_pcm, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_perm, &d_tpeak};
+        return {&d_dtracks, &d_hblocks, &d_runs, &d_spectra, &d_nz, &d_c1q, &d_gains, &d_sfraw, &d_pcm, &d_chains, &d_wsum, &d_wmax, &d_peaks, &d_twin, &d_tout, &d_hist, &d_perm, &d_tpeak};
     }
 };
 

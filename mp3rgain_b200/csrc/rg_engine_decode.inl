@@ -286,6 +286,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     CK(x.d_runs.ensure(std::max<size_t>(runs.size(), 1) * sizeof(RunDesc)));
     CK(x.d_spectra.ensure(std::max<uint64_t>(gc_total, 1) * 576 * sizeof(int16_t) + 64));
     CK(x.d_nz.ensure(std::max<uint64_t>(gc_total, 1) * sizeof(uint16_t) + 64));
+    CK(x.d_c1q.ensure(std::max<uint64_t>(gc_total, 1) * K1_C1_ROW + 64));
     CK(x.d_gains.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW + 64));
     CK(x.d_sfraw.ensure(std::max<uint64_t>(gc_total, 1) * K1_GAIN_ROW + 64));
     if (!peak_only) CK(x.d_pcm.ensure(std::max<uint64_t>(pcm_total, 4) * sizeof(float) + 64));
@@ -322,7 +323,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     if (!hb.empty()) {
         k_huffman<<<(unsigned)hb.size(), K1_THREADS, sizeof(K1Smem), st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                            x.d_dtracks.as<DecTrack>(), x.d_hblocks.as<HuffBlock>(), e->dec.d_tab,
-                                                           x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(), x.d_gains.as<uint8_t>(), x.d_sfraw.as<uint8_t>());
+                                                           x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(), x.d_c1q.as<uint8_t>(), x.d_gains.as<uint8_t>(), x.d_sfraw.as<uint8_t>());
         e->stats.kernel_launches++;
         CK(cudaGetLastError());
     }
@@ -330,7 +331,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     if (!runs.empty()) {
         k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem) + e->k2_smem_pad, st>>>(c->d_bytes, e->d_frames.as<FrameRec>(),
                                                                                x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>(), e->dec.d_tab,
-                                                                               x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(),
+                                                                               x.d_spectra.as<int16_t>(), x.d_c1q.as<uint8_t>(), x.d_nz.as<uint16_t>(),
                                                                                x.d_gains.as<uint8_t>(), x.d_sfraw.as<uint8_t>(), peak_only ? nullptr : x.d_pcm.as<float>(),
                                                                                peak_only ? x.d_tpeak.as<uint32_t>() : nullptr, e->flags);
         e->stats.kernel_launches++;
@@ -357,7 +358,7 @@ static void collect_decode_timing(rg_engine* e, BatchCtx& x) {
 
 // Bytes of device scratch one track needs in a batch (spectra + nz + band gains + PCM)
 static uint64_t track_scratch_bytes(const TrackMeta& m) {
-    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * ((576 * 2 + 2 + 2 * K1_GAIN_ROW) + 576ull * 4) + 4096;
+    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * ((576 * 2 + 2 + 2 * K1_GAIN_ROW + K1_C1_ROW) + 576ull * 4) + 4096;
 }
 
 static void drain_streams(rg_engine* e) {
@@ -583,7 +584,7 @@ extern "C" int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_t
 
 // Bytes of device scratch one track needs in a peak-only batch (no PCM is stored)
 static uint64_t track_scratch_bytes_peak(const TrackMeta& m) {
-    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * (576 * 2 + 2 + 2 * K1_GAIN_ROW) + 4096;
+    return (uint64_t)m.n_frames * meta_gpf(m) * m.channels * (576 * 2 + 2 + 2 * K1_GAIN_ROW + K1_C1_ROW) + 4096;
 }
 
 extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_result* out) {

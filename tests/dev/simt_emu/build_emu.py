@@ -30,6 +30,7 @@ PTX_HELPERS = {
     "k2_bulk_load": "emu::bulk_load(dst, src, bytes, bar);",
     "k2_mbar_wait": "emu::mbar_wait(bar, parity);",
     "k2_pair_sync": "emu::barrier(1 + (pair < 3 ? pair : 3), 64);",
+    "k2_prmt": "return emu::prmt(a, 0u, sel);",
 }
 
 

@@ -382,7 +382,9 @@ static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v
 static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
 static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++) r |= (v >> i & 1) << (31 - i); return r; }
-static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
+namespace emu {
+// prmt.b32, default mode: nibble bits 0..2 select a byte of {b, a}, bit 3 replaces it by its sign (0x00 / 0xFF)
+static inline unsigned prmt(unsigned a, unsigned b, unsigned s) {
     const uint64_t ab = ((uint64_t)b << 32) | a;
     unsigned r = 0;
     for (int i = 0; i < 4; i++) {
@@ -393,6 +395,9 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
     }
     return r;
 }
+}
+// the CUDA intrinsic uses only three bits of each selector nibble (nvcc masks the rest away: seen in the SASS, round 2)
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) { return emu::prmt(a, b, s & 0x7777u); }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 static inline int __mulhi(int a, int b) { return (int)(((int64_t)a * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
