@@ -52,6 +52,7 @@ struct K1Smem {
     uint32_t lim[K1_THREADS];        // (worker order) words of that stretch that are complete
     uint8_t sfl[K1_THREADS][24];     // long scalefactors of every granule-channel (scfsi source)
     uint8_t c1[2][64];               // count1 tables A / B: 6-bit peek -> (len << 4) | pattern
+    uint8_t c1res[256];              // (pattern << 4 | the four bits after the code word) -> v w x y as 2-bit two's complement, v in bits 0-1
     uint32_t base;                   // first main-data byte wanted by a granule-channel that is still pending
     alignas(8) unsigned long long mbar;
 };
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3)
 k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
           const DecTrack* __restrict__ tracks, const HuffBlock* __restrict__ blocks, const L3Dev* __restrict__ T,
           int16_t* __restrict__ spectra /* [gc][576] */, uint16_t* __restrict__ nz_out /* [gc] */,
-          uint8_t* __restrict__ c1q /* [gc][K1_C1_ROW]: one byte per count1 quad, pattern << 4 | the four bits after its code */,
+          uint8_t* __restrict__ c1q /* [gc][K1_C1_ROW]: one byte per count1 quad, v w x y as 2-bit two's complement */,
           uint8_t* __restrict__ gains /* [gc][K1_GAIN_ROW] */,
           uint8_t* __restrict__ sfraw /* [gc][K1_GAIN_ROW]: raw scalefactors = is_pos, right channel of intensity-stereo frames only */) {
     extern __shared__ __align__(16) unsigned char k1_raw[];
@@ -140,6 +141,13 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         if (tid < 64) {
             S.c1[0][tid] = T->c1a_lut[tid];
             S.c1[1][tid] = (uint8_t)((4u << 4) | (15u - (tid >> 2)));
+        }
+        {   // pattern bits v w x y (v = bit 3); the sign bits of the non-zero values follow the code word in that order
+            uint32_t res = 0, used = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((tid >> (7 - k)) & 1) { res |= (((tid >> (3 - used)) & 1) ? 3u : 1u) << (2 * k); used++; }
+            S.c1res[tid] = (uint8_t)res;
         }
         if (tid == 0) k2_mbar_init(&S.mbar, 1);
     }
@@ -467,8 +475,8 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
 
         // ---- phase 2: count1 quads from pair `bv` on (oracle: while (pos < end && line <= 572)); a quad that straddles the end of
         // the granule-channel's bits is discarded.  An overrun of the big-values region silences the granule-channel (oracle:
-        // read_huffman).  A quad leaves as ONE byte -- its pattern (which of v w x y are +-1) and the four bits after the code
-        // word, the first popc(pattern) of which are the signs -- sixteen quads per 16-byte store; K2 expands them.
+        // read_huffman).  A quad leaves as ONE byte -- v w x y as 2-bit two's complement, through a 256-entry table indexed
+        // by its pattern and the four bits after the code word -- sixteen quads per 16-byte store; K2 expands them.
         bool overrun = false;
         uint32_t nz = 0;
         bool live = false;
@@ -491,7 +499,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                         const uint32_t len = e >> 4, pat = e & 15u;
                         const uint32_t tot = len + (uint32_t)__popc(pat);
                         if (br.pos + tot <= my_end) {   // (else: straddles the end, discarded)
-                            acc[k >> 2] |= ((pat << 4) | ((w << len) >> 28)) << (8 * (k & 3));
+                            acc[k >> 2] |= (uint32_t)S.c1res[(pat << 4) | ((w << len) >> 28)] << (8 * (k & 3));
                             br.skip(tot);
                             q += 2; nz += 4;
                             live = true;

@@ -42,10 +42,11 @@ struct K2Smem {
     alignas(16) float A[K2_SLOTS][SLOTF];     // per granule-channel: xr[576] -> F[18][ROW] -> DCT rows [18][ROW], in place
     float S2[K2_SLOTS][SLOTF];                // IMDCT outputs 18..35 of the granule-channel (added by the NEXT granule)
     alignas(16) uint32_t stage[K2_GC][288];   // the batch's int16 line pairs, written by the TMA unit
-    alignas(16) uint8_t c1q[K2_GC][K1_C1_ROW];   // the batch's count1 quads, one byte each (pattern << 4 | the four bits after the code)
+    alignas(16) uint8_t c1q[K2_GC][K1_C1_ROW];   // the batch's count1 quads, one byte each (v w x y as 2-bit two's complement, v in bits 0-1)
     alignas(16) uint8_t banddelta[K2_GC][K1_GAIN_ROW];   // per band: what to subtract from the granule-channel's gain exponent
                                               // ([0..21] long sfb, [22..60] short sfb*3+win, [62..63] the exponent itself), by TMA
     float gaintab[L3_GAIN_MAX - L3_GAIN_MIN + 1];   // 2^(e/4)
+    float bgain[K2_GC][64];                   // the batch's band gains, looked up from the bytes above at the start of P1
     float wa[8][32], wb[8][32];
     GranInfo gi[K2_MAX_G][2];                 // side info of every granule-channel of the run
     uint32_t p1w[K2_MAX_G][2];                // tsel | ms<<2 | (nz!=0)<<3 | intensity<<4 | (9*max sb_limit of the granule)<<8
@@ -308,9 +309,16 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
             const uint8_t* cq1 = S.c1q[my_gi * NCH + NCH - 1];
             const uint32_t* st0 = S.stage[my_gi * NCH];
             const uint32_t* st1 = S.stage[my_gi * NCH + NCH - 1];
-            const uint8_t* bd0 = S.banddelta[my_gi * NCH];
-            const uint8_t* bd1 = S.banddelta[my_gi * NCH + NCH - 1];
-            const int be0 = *reinterpret_cast<const uint16_t*>(bd0 + 62), be1 = *reinterpret_cast<const uint16_t*>(bd1 + 62);
+            const float* bg0 = S.bgain[my_gi * NCH];
+            const float* bg1 = S.bgain[my_gi * NCH + NCH - 1];
+            {   // this warp's granule-channel: band byte -> band gain, 2^((exponent - byte) / 4)
+                const uint8_t* bd = S.banddelta[my_gi * NCH + my_ch];
+                const int be = *reinterpret_cast<const uint16_t*>(bd + 62);
+                float* bg = S.bgain[my_gi * NCH + my_ch];
+                bg[lane] = S.gaintab[be - (int)bd[lane]];
+                bg[lane + 32] = S.gaintab[be - (int)bd[lane + 32]];   // (entries 61..63 are never read)
+            }
+            if (NCH == 2) k2_pair_sync(my_gi); else __syncwarp();
             float* x0 = S.A[(gl % NS) * NCH];
             float* x1 = S.A[(gl % NS) * NCH + NCH - 1];
             const bool ist = NCH == 2 && ((w0 >> 4) & 1);
@@ -322,7 +330,7 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 if (my_ch == 0 && lane < 4) top[lane] = -1;
                 k2_pair_sync(my_gi);
                 for (int pr = lane + 32 * my_ch; pr < 288; pr += 64) {
-                    if (pr < nzp1 && (pr < bvp1 ? st1[pr] != 0u : ((cq1[(pr - bvp1) >> 1] >> (((pr - bvp1) & 1) ? 4 : 6)) & 3u) != 0u)) {
+                    if (pr < nzp1 && (pr < bvp1 ? st1[pr] != 0u : ((cq1[(pr - bvp1) >> 1] >> (4 * ((pr - bvp1) & 1))) & 15u) != 0u)) {
                         const int code = S.code[tsel1][2 * pr];
                         if (code < 22) atomicMax(&top[0], code);
                         else atomicMax(&top[1 + (code - 22) % 3], (code - 22) / 3);
@@ -345,31 +353,48 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 }
                 k2_pair_sync(my_gi);
             }
-            for (int pr = lane + 32 * my_ch; pr < lim9; pr += 32 * NCH) {
-                float v[2][2];
+            // Two passes over the lane's (at most NIT) line pairs, both fully unrolled: every load first, then the arithmetic, so
+            // that the dependent shared-memory lookups (line -> band -> gain) of all pairs are in flight together.
+            constexpr int NIT = (288 + 32 * NCH - 1) / (32 * NCH);
+            uint32_t pk[NIT][2];
+            float gq[NIT][2];
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int pr = lane + 32 * my_ch + 32 * NCH * it;
 #pragma unroll
                 for (int ch = 0; ch < NCH; ch++) {
                     const int nzp = ch ? nzp1 : nzp0, bvp = ch ? bvp1 : bvp0;
-                    const float gn = pr < nzp ? S.gaintab[(ch ? be1 : be0) - (int)(ch ? bd1 : bd0)[S.code[ch ? tsel1 : tsel0][2 * pr]]] : 0.0f;
-                    if (pr < bvp || pr >= nzp) {
-                        const uint32_t packed = pr < bvp ? (ch ? st1 : st0)[pr] : 0u;
-                        const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
-                        const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
-                        const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
-                        v[ch][0] = q0 < 0 ? -m0 : m0;
-                        v[ch][1] = q1 < 0 ? -m1 : m1;
-                    } else {
-                        // count1 pair: values 0 / +-1, |1|^(4/3) * gain = gain.  The quad's byte holds the pattern v w x y (bit 7 =
-                        // v) and the four bits that followed its code word: the sign bits of the non-zero values, in that order
-                        const int t = pr - bvp;
-                        const uint32_t byte = (ch ? cq1 : cq0)[t >> 1];
-                        const uint32_t k0 = (t & 1) ? 2u : 0u;                  // this pair is (v, w) or (x, y)
-                        const uint32_t a0 = (byte >> (7 - k0)) & 1u, a1 = (byte >> (6 - k0)) & 1u;
-                        const uint32_t i0 = (uint32_t)__popc((byte >> 4) >> (4 - k0)), i1 = i0 + a0;   // non-zero values before each
-                        const uint32_t n0 = (byte >> (3 - i0)) & 1u, n1 = (byte >> (3 - i1)) & 1u;
-                        v[ch][0] = a0 ? (n0 ? -gn : gn) : 0.0f;
-                        v[ch][1] = a1 ? (n1 ? -gn : gn) : 0.0f;
+                    uint32_t packed = 0u;
+                    float gn = 0.0f;
+                    if (pr < lim9 && pr < nzp) {
+                        gn = (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]];
+                        if (pr < bvp) packed = (ch ? st1 : st0)[pr];
+                        else {
+                            // count1 pair: K1 left one byte per quad, v w x y as 2-bit two's complement (0, +1, -1) from bit 0 up
+                            const int t = pr - bvp;
+                            const uint32_t nib = ((ch ? cq1 : cq0)[t >> 1] >> (4 * (t & 1))) & 15u;
+                            const uint32_t c0 = nib & 3u, c1 = nib >> 2;
+                            packed = (((c0 ^ 2u) - 2u) & 0xFFFFu) | (((c1 ^ 2u) - 2u) << 16);
+                        }
                     }
+                    pk[it][ch] = packed;
+                    gq[it][ch] = gn;
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; it++) {
+                const int pr = lane + 32 * my_ch + 32 * NCH * it;
+                if (pr >= lim9) break;
+                float v[2][2];
+#pragma unroll
+                for (int ch = 0; ch < NCH; ch++) {
+                    const uint32_t packed = pk[it][ch];
+                    const float gn = gq[it][ch];
+                    const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
+                    const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
+                    const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
+                    v[ch][0] = q0 < 0 ? -m0 : m0;
+                    v[ch][1] = q1 < 0 ? -m1 : m1;
                 }
                 uint32_t ipos = 255;
                 if (NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
