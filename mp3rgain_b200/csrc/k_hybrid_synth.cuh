@@ -272,6 +272,18 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
         S.p1w[gl][ch] = tsel | ((uint32_t)(gi.ms & 1) << 2) | ((gi.nz != 0 ? 1u : 0u) << 3) | ((uint32_t)(gi.ms >> 1) << 4) | ((uint32_t)(9 * lim) << 8);
     }
 
+    // long-block band of this lane's line pairs (P1), one byte per pass
+    constexpr int NIT = (288 + 32 * NCH - 1) / (32 * NCH);
+    unsigned long long codeL = 0;
+    uint32_t codeH = 0;   // (mono: nine passes)
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const int pr = lane + 32 * my_ch + 32 * NCH * it;
+        const uint32_t cd = pr < 288 ? S.code[0][2 * pr] : 0u;
+        if (it < 8) codeL |= (unsigned long long)cd << (8 * (it & 7));
+        else codeH = cd;
+    }
+
     // spectra and band gains of batch b: granule-channels are contiguous in HBM, 1152 + 256 bytes each
     auto issue_copy = [&](uint32_t b) {
         const uint32_t gl0 = b * G;
@@ -354,75 +366,82 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 k2_pair_sync(my_gi);
             }
             // Two passes over the lane's (at most NIT) line pairs, both fully unrolled: every load first, then the arithmetic, so
-            // that the dependent shared-memory lookups (line -> band -> gain) of all pairs are in flight together.
-            constexpr int NIT = (288 + 32 * NCH - 1) / (32 * NCH);
-            uint32_t pk[NIT][2];
-            float gq[NIT][2];
+            // that the dependent shared-memory lookups (line -> band -> gain) of all pairs are in flight together.  PLAIN = both
+            // channels are long blocks and the frame has no intensity stereo (97 % of all granules): the band of a pair is then
+            // a per-lane constant (codeL, set up once per CTA) and the stores are in line order.
+            auto pairs = [&](auto plain_c) {
+                constexpr bool PLAIN = decltype(plain_c)::value;
+                uint32_t pk[NIT][2];
+                float gq[NIT][2];
 #pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                const int pr = lane + 32 * my_ch + 32 * NCH * it;
+                for (int it = 0; it < NIT; it++) {
+                    const int pr = lane + 32 * my_ch + 32 * NCH * it;
+                    const uint32_t codeP = it < 8 ? (uint32_t)(codeL >> (8 * (it & 7))) & 0xFFu : codeH;
 #pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
-                    const int nzp = ch ? nzp1 : nzp0, bvp = ch ? bvp1 : bvp0;
-                    uint32_t packed = 0u;
-                    float gn = 0.0f;
-                    if (pr < lim9 && pr < nzp) {
-                        gn = (ch ? bg1 : bg0)[S.code[ch ? tsel1 : tsel0][2 * pr]];
-                        if (pr < bvp) packed = (ch ? st1 : st0)[pr];
-                        else {
-                            // count1 pair: K1 left one byte per quad, v w x y as 2-bit two's complement (0, +1, -1) from bit 0 up
-                            const int t = pr - bvp;
-                            const uint32_t nib = ((ch ? cq1 : cq0)[t >> 1] >> (4 * (t & 1))) & 15u;
-                            const uint32_t c0 = nib & 3u, c1 = nib >> 2;
-                            packed = (((c0 ^ 2u) - 2u) & 0xFFFFu) | (((c1 ^ 2u) - 2u) << 16);
+                    for (int ch = 0; ch < NCH; ch++) {
+                        const int nzp = ch ? nzp1 : nzp0, bvp = ch ? bvp1 : bvp0;
+                        uint32_t packed = 0u;
+                        float gn = 0.0f;
+                        if (pr < nzp) {   // (nz never reaches beyond the granule's last subband: nzp <= lim9)
+                            gn = (ch ? bg1 : bg0)[PLAIN ? codeP : (uint32_t)S.code[ch ? tsel1 : tsel0][2 * pr]];
+                            if (pr < bvp) packed = (ch ? st1 : st0)[pr];
+                            else {
+                                // count1 pair: K1 left one byte per quad, v w x y as 2-bit two's complement (0, +1, -1) from bit 0 up
+                                const int t = pr - bvp;
+                                const uint32_t nib = ((ch ? cq1 : cq0)[t >> 1] >> (4 * (t & 1))) & 15u;
+                                const uint32_t c0 = nib & 3u, c1 = nib >> 2;
+                                packed = (((c0 ^ 2u) - 2u) & 0xFFFFu) | (((c1 ^ 2u) - 2u) << 16);
+                            }
+                        }
+                        pk[it][ch] = packed;
+                        gq[it][ch] = gn;
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < NIT; it++) {
+                    const int pr = lane + 32 * my_ch + 32 * NCH * it;
+                    if (pr >= lim9) break;
+                    float v[2][2];
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++) {
+                        const uint32_t packed = pk[it][ch];
+                        const float gn = gq[it][ch];
+                        const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
+                        const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
+                        const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
+                        v[ch][0] = q0 < 0 ? -m0 : m0;
+                        v[ch][1] = q1 < 0 ? -m1 : m1;
+                    }
+                    uint32_t ipos = 255;
+                    if (!PLAIN && NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
+                    if (!PLAIN && NCH == 2 && ipos != 255) {
+                        const float kl = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][0][ipos & 31] : S.isr[0][ipos & 7];
+                        const float kr = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][1][ipos & 31] : S.isr[1][ipos & 7];
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float l = v[0][h];
+                            v[0][h] = __fmul_rn(l, kl);
+                            v[NCH - 1][h] = __fmul_rn(l, kr);
+                        }
+                    } else if (NCH == 2 && ms) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const float a = v[0][h], c = v[NCH - 1][h];
+                            v[0][h] = __fmul_rn(__fadd_rn(a, c), L3_INV_SQRT2);
+                            v[NCH - 1][h] = __fmul_rn(__fsub_rn(a, c), L3_INV_SQRT2);
                         }
                     }
-                    pk[it][ch] = packed;
-                    gq[it][ch] = gn;
-                }
-            }
 #pragma unroll
-            for (int it = 0; it < NIT; it++) {
-                const int pr = lane + 32 * my_ch + 32 * NCH * it;
-                if (pr >= lim9) break;
-                float v[2][2];
-#pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
-                    const uint32_t packed = pk[it][ch];
-                    const float gn = gq[it][ch];
-                    const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
-                    const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
-                    const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
-                    v[ch][0] = q0 < 0 ? -m0 : m0;
-                    v[ch][1] = q1 < 0 ? -m1 : m1;
-                }
-                uint32_t ipos = 255;
-                if (NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
-                if (NCH == 2 && ipos != 255) {
-                    const float kl = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][0][ipos & 31] : S.isr[0][ipos & 7];
-                    const float kr = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][1][ipos & 31] : S.isr[1][ipos & 7];
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float l = v[0][h];
-                        v[0][h] = __fmul_rn(l, kl);
-                        v[NCH - 1][h] = __fmul_rn(l, kr);
-                    }
-                } else if (NCH == 2 && ms) {
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const float a = v[0][h], c = v[NCH - 1][h];
-                        v[0][h] = __fmul_rn(__fadd_rn(a, c), L3_INV_SQRT2);
-                        v[NCH - 1][h] = __fmul_rn(__fsub_rn(a, c), L3_INV_SQRT2);
+                    for (int ch = 0; ch < NCH; ch++) {
+                        float* x = ch ? x1 : x0;
+                        const int tsel = ch ? tsel1 : tsel0;
+                        if (PLAIN || tsel == 0) *reinterpret_cast<float2*>(x + 2 * pr) = make_float2(v[ch][0], v[ch][1]);
+                        else { x[S.scat[tsel - 1][2 * pr]] = v[ch][0]; x[S.scat[tsel - 1][2 * pr + 1]] = v[ch][1]; }
                     }
                 }
-#pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
-                    float* x = ch ? x1 : x0;
-                    const int tsel = ch ? tsel1 : tsel0;
-                    if (tsel == 0) *reinterpret_cast<float2*>(x + 2 * pr) = make_float2(v[ch][0], v[ch][1]);
-                    else { x[S.scat[tsel - 1][2 * pr]] = v[ch][0]; x[S.scat[tsel - 1][2 * pr + 1]] = v[ch][1]; }
-                }
-            }
+            };
+            if (!ist && tsel0 == 0 && tsel1 == 0) pairs(std::true_type{});
+            else pairs(std::false_type{});
         }
         if (NCH == 2) k2_pair_sync(my_gi); else __syncwarp();
 

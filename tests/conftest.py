@@ -39,5 +39,8 @@ def engine_exact():
 def engine_fast():
     import mp3rgain_b200 as m
     e = m.Engine(device=0, exact=False)
+    for kv in os.environ.get("RG_TEST_OPTS", "").split(","):   # development: e.g. RG_TEST_OPTS=k4_lean=1
+        if "=" in kv:
+            e.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     yield e
     e.close()
