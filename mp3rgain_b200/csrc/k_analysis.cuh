@@ -238,73 +238,6 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
 #define K4_SLIM_THREADS 128
 #define k_iir_slim k_iir_fast_t<3, K4_SLIM_THREADS, 4>
 
-// The same chains in under 80 registers, so that three CTAs of any mix of this kernel, K1 and K2 share an SM (the FP64 pipe is
-// a resource of its own: decode work issues beside it).  A chain is ONE float4 stream from a 16-byte aligned start (the host
-// cuts blocks at multiples of four windows and rounds the warm-up up to a multiple of four samples): four samples per step
-// with the next float4 in flight; a step that holds the end of the warm-up, the end of a window or the end of the chain
-// takes a sample-by-sample path.  Sample for sample the arithmetic of k_iir_fast_t.
-#define K4_LEAN_THREADS 256
-__global__ void __launch_bounds__(K4_LEAN_THREADS, 3)
-k_iir_lean(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base,
-           const __grid_constant__ RgCoefFast c) {
-  // grid-stride over the chains: the host may launch fewer CTAs than there are groups of chains (one per SM, so that the
-  // kernel never holds more than a third of an SM)
-  for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_chains; ci += gridDim.x * blockDim.x) {
-    const RgChain ch = chains[ci];
-    TdfState s;
-    const bool head = ch.flags & 1u;   // chain starts at the first sample of the track
-#pragma unroll
-    for (int i = 0; i < 10; i++) s.s[i] = head ? c.s0[i] : 0.0;
-    s.u[0] = head ? c.u0[0] : c.uz[0];
-    s.u[1] = head ? c.u0[1] : c.uz[1];
-    const float4* p4 = reinterpret_cast<const float4*>(ch.src);
-    double sum = 0.0;
-    float m = 0.0f, peak = 0.0f;
-    double* out = ch.wsum;
-    float* mout = ch.wmax;
-    uint32_t skip = ch.n_warm;   // samples still to run without accumulating
-    uint32_t tot = 0;            // samples accumulated in the current window
-    const uint32_t win = ch.win;
-    uint32_t left = ch.n_warm + ch.n_main;
-    const uint32_t nit = (left + 3) >> 2;
-    float4 nxt = nit ? __ldg(p4) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#pragma unroll 1
-    for (uint32_t it = 0; it < nit; it++) {
-        const float4 cur = nxt;
-        if (it + 1 < nit) nxt = __ldg(p4 + it + 1);
-        if (skip >= 4) {
-            iir_step_fast(s, c, cur.x); iir_step_fast(s, c, cur.y); iir_step_fast(s, c, cur.z); iir_step_fast(s, c, cur.w);
-            skip -= 4; left -= 4;
-        } else if (skip == 0 && tot + 4 < win && left >= 4) {
-            double z = iir_step_fast(s, c, cur.x); sum = __fma_rn(z, z, sum);
-            z = iir_step_fast(s, c, cur.y); sum = __fma_rn(z, z, sum);
-            z = iir_step_fast(s, c, cur.z); sum = __fma_rn(z, z, sum);
-            z = iir_step_fast(s, c, cur.w); sum = __fma_rn(z, z, sum);
-            m = fmaxf(fmaxf(m, fmaxf(fabsf(cur.x), fabsf(cur.y))), fmaxf(fabsf(cur.z), fabsf(cur.w)));
-            tot += 4; left -= 4;
-        } else {
-#pragma unroll 1
-            for (int q = 0; q < 4 && left; q++, left--) {
-                const float x = q == 0 ? cur.x : (q == 1 ? cur.y : (q == 2 ? cur.z : cur.w));
-                const double z = iir_step_fast(s, c, x);
-                if (skip) skip--;
-                else {
-                    sum = __fma_rn(z, z, sum);
-                    m = fmaxf(m, fabsf(x));
-                    if (++tot == win) { *out++ = sum; *mout++ = m; peak = fmaxf(peak, m); sum = 0.0; m = 0.0f; tot = 0; }
-                }
-            }
-        }
-    }
-    if (tot) {   // the track's final partial window (src/replaygain.rs:907)
-        *out = sum;
-        *mout = m;
-        peak = fmaxf(peak, m);
-    }
-    peaks[chain_base + ci] = peak;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // K5: one CTA per track.  Window sums -> bin index -> shared 12000-bin histogram (warp-aggregated atomics)
 // -> suffix scan for the 95th percentile -> optional flush to the global per-track / album histograms.

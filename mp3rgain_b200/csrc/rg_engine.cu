@@ -103,11 +103,6 @@ struct rg_engine {
     // options
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
     uint32_t k4_round = 0;                // chains in one round of k_iir_fast CTAs: one CTA per SM
-    uint32_t k4_lean = 0;                 // 1: k_iir_lean (80 registers) instead of k_iir_fast (128)
-    uint32_t k4_per_sm = 0;               // > 0: k_iir_lean launches at most this many CTAs per SM (grid-stride over the chains)
-    uint32_t k4_smem = 0;                 // dynamic shared memory per k_iir_lean CTA: none is used, it only shapes how CTAs pack onto an SM
-    uint32_t k1_smem_pad = 0;
-    uint32_t k2_smem_pad = 0;             // profiling: extra dynamic shared memory per K2 CTA (lowers K2's CTAs per SM)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
@@ -236,9 +231,8 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         f.u0[0] += f.uz[0]; f.u0[1] += f.uz[1];
         f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
-    CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem) + 40 * 1024));
-    CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem) + 40 * 1024));
-    CK(cudaFuncSetAttribute(k_iir_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
+    CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     {
         int sms = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -279,16 +273,6 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
-    if (!strcmp(key, "k4_lean")) { e->k4_lean = value != 0; return RG_OK; }
-    if (!strcmp(key, "k4_per_sm")) {
-        if (value < 0 || value > 8) return RG_ERR_INVALID_ARG;
-        e->k4_per_sm = (uint32_t)value;
-        if (e->k4_lean) e->k4_round = (uint32_t)(e->n_sms * (e->k4_per_sm ? e->k4_per_sm : 1) * K4_LEAN_THREADS);
-        return RG_OK;
-    }
-    if (!strcmp(key, "k4_smem")) { if (value < 0 || value > 100 * 1024) return RG_ERR_INVALID_ARG; e->k4_smem = (uint32_t)value; return RG_OK; }
-    if (!strcmp(key, "k1_smem_pad")) { if (value < 0 || value > 40 * 1024) return RG_ERR_INVALID_ARG; e->k1_smem_pad = (uint32_t)value; return RG_OK; }
-    if (!strcmp(key, "k2_smem_pad")) { if (value < 0 || value > 40 * 1024) return RG_ERR_INVALID_ARG; e->k2_smem_pad = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "k4_slim")) {
         if (value < 0 || value > 8) return RG_ERR_INVALID_ARG;
         e->k4_slim = (uint32_t)value;
@@ -328,7 +312,7 @@ static inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 
 // Windows per time block of the time-blocked IIR.
 static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTrack>& tracks) {
-    if (e->block_windows) return e->k4_lean ? (e->block_windows + 3) & ~3u : e->block_windows;
+    if (e->block_windows) return e->block_windows;
     std::vector<std::pair<uint32_t, uint32_t>> nw;   // (windows, channels) per track
     for (const PcmTrack& t : tracks) {
         const uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
@@ -341,7 +325,7 @@ static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTr
     const uint64_t unit = e->k4_round ? e->k4_round : 148 * K4_FAST_THREADS;
     uint32_t best = 16;
     uint64_t best_cost = ~0ull;
-    for (uint32_t bw = 8; bw <= 96; bw += (e->k4_lean ? 4 : 1)) {
+    for (uint32_t bw = 8; bw <= 96; bw++) {
         uint64_t chains = 0;
         for (auto& p : nw) chains += (uint64_t)((p.first + bw - 1) / bw) * p.second;
         const uint64_t T = e->k4_slim ? K4_SLIM_THREADS : K4_FAST_THREADS;
@@ -393,7 +377,6 @@ static void build_chains(rg_engine* e, const std::vector<PcmTrack>& tracks, bool
                         uint64_t s0 = (uint64_t)w0 * win;
                         uint64_t s1 = std::min<uint64_t>((uint64_t)w1 * win, t.frames);
                         uint64_t warm = std::min<uint64_t>(s0, (uint64_t)ww * win);
-                        if (e->k4_lean) warm = std::min<uint64_t>(s0, (warm + 3) & ~3ull);   // k_iir_lean reads float4s: s0 is a multiple of 4
                         RgChain ch{};
                         ch.src = t.d_ch[c] + (s0 - warm);
                         ch.wsum = wbase + w0;
@@ -492,9 +475,7 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
                                                                                                      (uint32_t)(i0 + c0), e->coef_fast[r]);
                     if (c0) e->stats.kernel_launches++;
                 }
-            } else if (e->k4_lean)
-                k_iir_lean<<<std::min<uint32_t>((cnt + K4_LEAN_THREADS - 1) / K4_LEAN_THREADS, e->k4_per_sm ? e->k4_per_sm * (uint32_t)e->n_sms : ~0u), K4_LEAN_THREADS, e->k4_smem, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
-            else
+            } else
                 k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         e->stats.kernel_launches++;
         i0 = i1;

@@ -321,7 +321,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     }
     CK(cudaEventRecord(x.ev_a[3], st));
     if (!hb.empty()) {
-        k_huffman<<<(unsigned)hb.size(), K1_THREADS, sizeof(K1Smem) + e->k1_smem_pad, st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
+        k_huffman<<<(unsigned)hb.size(), K1_THREADS, sizeof(K1Smem), st>>>(c->d_bytes, e->d_md.as<uint8_t>(), e->d_frames.as<FrameRec>(),
                                                            x.d_dtracks.as<DecTrack>(), x.d_hblocks.as<HuffBlock>(), e->dec.d_tab,
                                                            x.d_spectra.as<int16_t>(), x.d_nz.as<uint16_t>(), x.d_c1q.as<uint8_t>(), x.d_gains.as<uint8_t>(), x.d_sfraw.as<uint8_t>());
         e->stats.kernel_launches++;
@@ -329,7 +329,7 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
     }
     CK(cudaEventRecord(x.ev_a[1], st));
     if (!runs.empty()) {
-        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem) + e->k2_smem_pad, st>>>(c->d_bytes, e->d_frames.as<FrameRec>(),
+        k_hybrid_synth<<<(unsigned)runs.size(), K2_THREADS, sizeof(K2Smem), st>>>(c->d_bytes, e->d_frames.as<FrameRec>(),
                                                                                x.d_dtracks.as<DecTrack>(), x.d_runs.as<RunDesc>(), e->dec.d_tab,
                                                                                x.d_spectra.as<int16_t>(), x.d_c1q.as<uint8_t>(), x.d_nz.as<uint16_t>(),
                                                                                x.d_gains.as<uint8_t>(), x.d_sfraw.as<uint8_t>(), peak_only ? nullptr : x.d_pcm.as<float>(),

@@ -13,7 +13,7 @@ import mp3rgain_b200 as m  # noqa: E402
 from mp3rgain_b200 import _lib  # noqa: E402
 import synth_corpus  # noqa: E402
 
-BASE = {"pipeline": 1, "k4_lean": 0, "k4_per_sm": 0, "k4_smem": 0, "k1_smem_pad": 0, "k2_smem_pad": 0, "iir_block_windows": 0}
+BASE = {"pipeline": 1, "k4_slim": 0, "iir_block_windows": 0, "iir_warm_windows": 1}
 n_tracks = int(sys.argv[1])
 sets = sys.argv[2:] or [""]
 pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
@@ -30,7 +30,7 @@ for spec in sets:
     for kv in spec.split(","):
         if "=" in kv:
             opts[kv.split("=")[0]] = float(kv.split("=")[1])
-    for k in ("pipeline", "k4_lean", "k4_per_sm", "k4_smem", "k1_smem_pad", "k2_smem_pad", "iir_block_windows"):
+    for k in BASE:
         eng.set_option(k, opts[k])
     best = None
     for it in range(4):
