@@ -7,10 +7,15 @@
  * shim maps those pub fns 1:1 onto these symbols.
  *
  * Conventions: plain pointers and sizes, no torch / CUDA types; every call returns 0 (RG_OK) or
- * a negative rg_status and never unwinds; all outputs are caller-allocated; no callbacks.
+ * a negative rg_status and never unwinds; all outputs are caller-allocated; no callbacks
+ * (one exception: a host that brings its own transport for the album exchange attaches a function, see rg_exchange_fn).
  * Host pointers unless a parameter is explicitly documented as a DEVICE pointer.
  * The library has no CPU compute path: without a usable CUDA device rg_engine_create fails with
  * RG_ERR_NO_DEVICE and nothing else can be called.
+ *
+ * Threading: the reference's functions are re-entrant (every call owns its decoder and analyser).  An rg_engine owns one
+ * set of streams and device buffers, so calls on the SAME engine serialise on an internal lock (any thread may call at
+ * any time; they queue); callers that want calls to overlap create one engine per thread.  rg_last_error is thread-local.
  */
 #ifndef MP3RGAIN_B200_RG_ENGINE_H
 #define MP3RGAIN_B200_RG_ENGINE_H
@@ -145,7 +150,36 @@ void rg_corpus_free(rg_engine* e, rg_corpus* c);
 uint64_t rg_corpus_bytes(const rg_corpus* c);
 int rg_analyze_corpus(rg_engine* e, rg_corpus* c, rg_track_result* out, uint32_t* hist_out);
 
-/* ---- album mode across GPUs (one engine per rank) --------------------------------------------- */
+/* ---- album mode across GPUs: one engine per rank, the engine owns the exchange ---------------------------------- */
+/* analyze_album (src/replaygain.rs:1033-1074) over a file list that is split across `nranks` processes, one GPU each:
+ * every rank analyses its shard and accumulates its tracks' histograms on its device; ONE exchange follows -- all-reduce
+ * (sum) of the RG_HIST_SIZE u64 counters and all-reduce(max) of {peak, error key}, one NCCL group on the engine's stream
+ * -- and every rank computes the album loudness from the merged histogram.  Every rank returns the same album result (or
+ * the same error: a failing file anywhere fails the album everywhere, with the status of the failing file that comes
+ * first in the global list, :1055).
+ *
+ * The communicator: rank 0 calls rg_comm_unique_id and hands the 128 bytes to the other ranks by any means (the host
+ * program's own launcher, a file, torch.distributed ...); every rank then calls rg_engine_comm_init (ncclCommInitRank on
+ * the engine's device).  A host that already holds an ncclComm_t for this device passes it to rg_engine_comm_attach
+ * instead (borrowed, not destroyed by the engine).  NCCL is loaded at run time (libnccl.so.2); a host with another
+ * transport attaches an exchange function (rg_engine_comm_attach_host): it is called once per album with the two host
+ * buffers and must return them reduced over all ranks (sum / max), 0 on success. */
+#define RG_COMM_ID_BYTES 128
+typedef int (*rg_exchange_fn)(void* ctx, uint64_t* sum_u64, size_t n_sum, uint64_t* max_u64, size_t n_max);
+int rg_comm_unique_id(uint8_t id[RG_COMM_ID_BYTES]);
+int rg_engine_comm_init(rg_engine* e, int rank, int nranks, const uint8_t id[RG_COMM_ID_BYTES]);
+int rg_engine_comm_attach(rg_engine* e, void* nccl_comm, int rank, int nranks);
+int rg_engine_comm_attach_host(rg_engine* e, int rank, int nranks, rg_exchange_fn fn, void* ctx);
+int rg_engine_comm_release(rg_engine* e);
+/* `in` / `c` = THIS rank's shard (contiguous in the global file list, starting at global index shard_offset).
+ * album_hist_out: NULL or RG_HIST_SIZE u64 (the merged histogram).  first_bad_global: NULL or the global index of the file
+ * that failed the album (-1 if none).  With nranks == 1 (no communicator) this is rg_analyze_album. */
+int rg_analyze_album_sharded(rg_engine* e, const rg_input* in, size_t n, uint64_t shard_offset, rg_track_result* out,
+                             rg_album_result* album, uint64_t* album_hist_out, int64_t* first_bad_global);
+int rg_analyze_album_sharded_corpus(rg_engine* e, rg_corpus* c, uint64_t shard_offset, rg_track_result* out,
+                                    rg_album_result* album, uint64_t* album_hist_out, int64_t* first_bad_global);
+
+/* ---- the same in two steps, for a caller that runs the exchange itself (device buffers) -------------------------- */
 /* Analyse this rank's shard and ADD its tracks' histograms into d_album_hist (DEVICE pointer, RG_HIST_SIZE u64,
  * caller-zeroed) and fold its peak into *d_album_peak (DEVICE pointer, one f64, caller-zeroed).  The caller then
  * all-reduces both buffers (sum / max) over NCCL and calls rg_album_finish on every rank: the accumulate loop of
@@ -203,6 +237,8 @@ typedef struct {
     uint64_t last_iir_samples;  /* channel-samples the time-blocked IIR ran in the last analyse call, warm-up included */
     float    last_ms_gain_scan, last_ms_gain_merge, last_ms_gain_patch;   /* CUDA-event times of the last rg_gain_* call */
     uint32_t last_gain_groups;  /* copy / walk groups (= launches of each gain-field kernel) in the last rg_gain_* call */
+    float    last_ms_exchange;  /* CUDA-event time of the album exchange (the NCCL group) in the last rg_analyze_album_sharded* call */
+    uint32_t reserved;
 } rg_stats;
 int rg_engine_stats(rg_engine* e, rg_stats* out);
 

@@ -70,7 +70,7 @@ class RgStats(C.Structure):
         ("last_ms_synth", C.c_float), ("last_ms_iir", C.c_float), ("last_ms_hist", C.c_float),
         ("last_ms_total", C.c_float), ("last_batches", C.c_uint32), ("last_block_windows", C.c_uint32), ("last_iir_samples", C.c_uint64),
         ("last_ms_gain_scan", C.c_float), ("last_ms_gain_merge", C.c_float), ("last_ms_gain_patch", C.c_float),
-        ("last_gain_groups", C.c_uint32),
+        ("last_gain_groups", C.c_uint32), ("last_ms_exchange", C.c_float), ("reserved", C.c_uint32),
     ]
 
 
@@ -85,6 +85,8 @@ class RgGainStats(C.Structure):
 
 # every symbol include/rg_engine.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
+COMM_ID_BYTES = 128
+ExchangeFn = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t, C.POINTER(C.c_uint64), C.c_size_t)
 SYMBOLS = {
     "rg_is_available": (C.c_int, []),
     "rg_engine_create": (C.c_int, [C.POINTER(RgConfig), C.POINTER(_P)]),
@@ -102,6 +104,13 @@ SYMBOLS = {
     "rg_analyze_corpus": (C.c_int, [_P, _P, C.POINTER(RgTrackResult), _P]),
     "rg_analyze_album_shard": (C.c_int, [_P, _P, C.POINTER(RgTrackResult), _P, _P]),
     "rg_album_finish": (C.c_int, [_P, _P, _P, C.POINTER(RgAlbumResult)]),
+    "rg_comm_unique_id": (C.c_int, [_P]),
+    "rg_engine_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "rg_engine_comm_attach": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "rg_engine_comm_attach_host": (C.c_int, [_P, C.c_int, C.c_int, ExchangeFn, _P]),
+    "rg_engine_comm_release": (C.c_int, [_P]),
+    "rg_analyze_album_sharded": (C.c_int, [_P, C.POINTER(RgInput), C.c_size_t, C.c_uint64, C.POINTER(RgTrackResult), C.POINTER(RgAlbumResult), _P, C.POINTER(C.c_int64)]),
+    "rg_analyze_album_sharded_corpus": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(RgTrackResult), C.POINTER(RgAlbumResult), _P, C.POINTER(C.c_int64)]),
     "rg_gain_analyze": (C.c_int, [_P, C.POINTER(RgInput), C.c_size_t, C.POINTER(RgGainStats)]),
     "rg_gain_analyze_corpus": (C.c_int, [_P, _P, C.POINTER(RgGainStats)]),
     "rg_gain_apply": (C.c_int, [_P, C.POINTER(RgInput), C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P), _P]),

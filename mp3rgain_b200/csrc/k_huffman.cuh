@@ -22,7 +22,7 @@
 //              64-byte segments.  Nothing is written beyond the last decoded line: K2 reads `nz` and treats the rest of
 //              the row as zero.
 //
-// Follows ISO/IEC 11172-3 2.4.2.7 / 2.4.3.4 and 13818-3 2.4.3.2 exactly as the oracle (oracle/mp3_oracle.c: read_scalefactors,
+// Follows ISO/IEC 11172-3 2.4.2.7 / 2.4.3.4 and 13818-3 2.4.3.2 exactly as the CPU restatement the tests check against (read_scalefactors,
 // read_huffman) does; the reference delegates this stage to symphonia-bundle-mp3 (src/replaygain.rs:861-863, 896).
 #pragma once
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -92,6 +93,10 @@ struct BatchCtx {
 };
 
 struct rg_engine {
+    // The reference's functions are re-entrant (each call owns its decoder and analyser); an engine owns ONE set of streams,
+    // batch contexts and growable device buffers, so its entry points serialise on this lock (recursive: rg_analyze_album
+    // finishes through rg_album_finish).  Callers that want concurrency create one engine per thread.
+    std::recursive_mutex mu;
     int device = 0;
     uint32_t flags = 0;
     uint64_t scratch_bytes = 0;
@@ -118,7 +123,13 @@ struct rg_engine {
     DevBuf d_gfseg, d_gfent, d_gfout, d_gfpatch;   // global_gain walk (k_gain_fields.cuh): per-sub-segment results, entry positions, per-track results, patched copy of the images
     HostBuf h_gfout;
     DevBuf d_corpus;                      // file images of rg_analyze_tracks / rg_analyze_album (kept between calls)
-    HostBuf h_meta;
+    HostBuf h_meta, h_xchg;
+    // album mode across GPUs (rg_engine_comm.inl): this engine is rank `rank` of `nranks`
+    void* comm = nullptr;                 // ncclComm_t
+    bool comm_owned = false;
+    rg_exchange_fn xchg_fn = nullptr;     // or a host-side exchange
+    void* xchg_ctx = nullptr;
+    int rank = 0, nranks = 1;
     rg_stats stats = {};
     DecodeScratch dec;
     std::vector<DevBuf*> all_bufs() {
@@ -127,10 +138,16 @@ struct rg_engine {
         for (auto& c : ctx) for (DevBuf* b : c.bufs()) v.push_back(b);
         return v;
     }
-    cudaEvent_t pool_event(size_t i) {
-        while (ev_pool.size() <= i) { cudaEvent_t x = nullptr; cudaEventCreate(&x); ev_pool.push_back(x); }
-        return ev_pool[i];
+    cudaError_t reserve_events(size_t n) {   // ev_pool[0 .. n) exist afterwards
+        while (ev_pool.size() < n) {
+            cudaEvent_t x = nullptr;
+            const cudaError_t err = cudaEventCreate(&x);
+            if (err != cudaSuccess) return err;
+            ev_pool.push_back(x);
+        }
+        return cudaSuccess;
     }
+    cudaEvent_t pool_event(size_t i) { return ev_pool[i]; }   // (reserved by the caller)
 };
 
 struct rg_corpus {
@@ -180,6 +197,9 @@ extern "C" const char* rg_status_str(int status) {
     }
 }
 
+static int engine_init(rg_engine* e, const rg_config* cfg, int dev);
+extern "C" void rg_engine_destroy(rg_engine* e);
+
 extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     if (!out) return RG_ERR_INVALID_ARG;
     *out = nullptr;
@@ -194,6 +214,13 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
     if (dev < 0 || dev >= n) return RG_ERR_INVALID_ARG;
     CK(cudaSetDevice(dev));
     rg_engine* e = new rg_engine();
+    const int rc = engine_init(e, cfg, dev);
+    if (rc != RG_OK) { rg_engine_destroy(e); return rc; }   // (streams, events and buffers created so far are released)
+    *out = e;
+    return RG_OK;
+}
+
+static int engine_init(rg_engine* e, const rg_config* cfg, int dev) {
     e->device = dev;
     e->flags = cfg ? cfg->flags : 0;
     e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (24ull << 30);
@@ -239,18 +266,18 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
         e->k4_round = (uint32_t)(sms * K4_FAST_THREADS);
         e->n_sms = sms;
     }
-    int rc = decode_init_tables(e->dec);
-    if (rc != RG_OK) { delete e; return rc; }
-    *out = e;
-    return RG_OK;
+    return decode_init_tables(e->dec);
 }
 
+static void comm_drop(rg_engine* e);
 extern "C" void rg_engine_destroy(rg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (DevBuf* b : e->all_bufs()) b->release();
+    comm_drop(e);
     e->h_meta.release();
+    e->h_xchg.release();
     e->h_gfout.release();
     e->dec.release();
     for (auto& ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -268,6 +295,7 @@ extern "C" void rg_engine_destroy(rg_engine* e) {
 
 extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value) {
     if (!e || !key) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     if (!strcmp(key, "iir_block_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->block_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
@@ -285,6 +313,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
 
 extern "C" int rg_engine_stats(rg_engine* e, rg_stats* out) {
     if (!e || !out) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     *out = e->stats;
     return RG_OK;
 }
@@ -540,6 +569,7 @@ static void fill_result(rg_track_result* o, const PcmTrack& t, const RgTrackOut&
 extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int nch, size_t frames, uint32_t sample_rate,
                                   rg_track_result* out, uint32_t* hist_out) {
     if (!e || !out || !planes || nch < 1 || !planes[0] || (nch >= 2 && !planes[1])) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     e->stats.last_ms_iir = e->stats.last_ms_hist = 0;
     PcmTrack t;
@@ -585,3 +615,4 @@ extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int 
 
 #include "rg_engine_decode.inl"
 #include "rg_engine_gain.inl"
+#include "rg_engine_comm.inl"

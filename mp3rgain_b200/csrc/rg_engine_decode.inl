@@ -46,6 +46,7 @@ static int corpus_describe(rg_corpus* c, const rg_input* in, size_t n) {
 
 extern "C" int rg_corpus_upload(rg_engine* e, const rg_input* in, size_t n, rg_corpus** out) {
     if (!e || !out || (n && !in)) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     *out = nullptr;
     CK(cudaSetDevice(e->device));
     rg_corpus* c = new rg_corpus();
@@ -68,7 +69,8 @@ extern "C" int rg_corpus_upload(rg_engine* e, const rg_input* in, size_t n, rg_c
 
 extern "C" void rg_corpus_free(rg_engine* e, rg_corpus* c) {
     if (!c) return;
-    if (e) cudaSetDevice(e->device);
+    std::unique_lock<std::recursive_mutex> lock;
+    if (e) { lock = std::unique_lock<std::recursive_mutex>(e->mu); cudaSetDevice(e->device); }
     c->d_own.release();
     delete c;
 }
@@ -164,6 +166,7 @@ static int index_enqueue_group(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t
         const size_t t0 = ip.group_begin[g], t1 = ip.group_begin[g + 1];
         cudaStream_t si = (g & 3) == 0 ? e->s_index : e->s_index_x[(g & 3) - 1];
         if (si != e->s_index) CK(cudaStreamWaitEvent(si, e->ev[1], 0));
+        CK(e->reserve_events(4 * g + 4));
         cudaEvent_t ev_copied = e->pool_event(4 * g), ev_k0a = e->pool_event(4 * g + 1), ev_k0b = e->pool_event(4 * g + 2),
                     ev_done = e->pool_event(4 * g + 3);
         if (c->pending_in) {
@@ -503,6 +506,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
 
 extern "C" int rg_analyze_corpus(rg_engine* e, rg_corpus* c, rg_track_result* out, uint32_t* hist_out) {
     if (!e || !c || (!out && !c->len.empty())) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     return analyze_corpus_impl(e, c, out, hist_out, nullptr, nullptr, false, nullptr);
 }
 
@@ -520,6 +524,7 @@ static int host_corpus(rg_engine* e, const rg_input* in, size_t n, rg_corpus& c)
 
 extern "C" int rg_analyze_tracks(rg_engine* e, const rg_input* in, size_t n, rg_track_result* out, uint32_t* hist_out) {
     if (!e || (n && (!in || !out))) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     rg_corpus c;
     int rc = host_corpus(e, in, n, c);
     if (rc != RG_OK) return rc;
@@ -533,6 +538,7 @@ static int album_buffers(rg_engine* e) {
 
 extern "C" int rg_album_finish(rg_engine* e, const uint64_t* d_album_hist, const double* d_album_peak, rg_album_result* album) {
     if (!e || !d_album_hist || !d_album_peak || !album) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     CK(cudaSetDevice(e->device));
     CK(e->d_misc.ensure(64));
     k_album_percentile<<<1, K5_THREADS, 0, e->stream>>>(reinterpret_cast<const unsigned long long*>(d_album_hist),
@@ -551,6 +557,7 @@ extern "C" int rg_album_finish(rg_engine* e, const uint64_t* d_album_hist, const
 
 extern "C" int rg_analyze_album_shard(rg_engine* e, rg_corpus* c, rg_track_result* out, uint64_t* d_album_hist, double* d_album_peak) {
     if (!e || !c || !d_album_hist || !d_album_peak || (!out && !c->len.empty())) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     int bad = -1;
     return analyze_corpus_impl(e, c, out, nullptr, reinterpret_cast<unsigned long long*>(d_album_hist),
                                reinterpret_cast<unsigned long long*>(d_album_peak), true, &bad);
@@ -559,6 +566,7 @@ extern "C" int rg_analyze_album_shard(rg_engine* e, rg_corpus* c, rg_track_resul
 extern "C" int rg_analyze_album(rg_engine* e, const rg_input* in, size_t n, rg_track_result* out, rg_album_result* album,
                                 uint64_t* album_hist_out) {
     if (!e || !album || (n && (!in || !out))) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     int rc = album_buffers(e);
     if (rc != RG_OK) return rc;
     unsigned long long* d_hist = e->d_album.as<unsigned long long>();
@@ -588,6 +596,7 @@ static uint64_t track_scratch_bytes_peak(const TrackMeta& m) {
 }
 
 extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_result* out) {
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     // find_peak_amplitude (src/replaygain.rs:1140-1249): max |sample| over all channels of the decoded stream.  The same
     // copy / index / decode pipeline as the analysis, but K2 folds |sample| into one word per track instead of storing PCM,
     // and there is no filter / histogram stage.
@@ -654,6 +663,7 @@ extern "C" int rg_find_peak(rg_engine* e, const rg_input* in, size_t n, rg_peak_
 extern "C" int rg_decode_pcm(rg_engine* e, const rg_input* in, float* pcm, size_t max_frames, size_t* frames_out,
                              uint32_t* channels_out, uint32_t* sample_rate_out) {
     if (!e || !in || !pcm || !frames_out) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     rg_corpus c;
     int rc = host_corpus(e, in, 1, c);
     if (rc != RG_OK) return rc;

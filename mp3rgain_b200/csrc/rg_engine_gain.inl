@@ -46,6 +46,7 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
     e->stats.h2d_bytes += n * (sizeof(TrackIn) + sizeof(TrackSeg));
     for (size_t g = 0; g < ng; g++) {
         const size_t t0 = group_begin[g], t1 = group_begin[g + 1];
+        CK(e->reserve_events(6 * g + 6));
         cudaEvent_t ev_copied = e->pool_event(6 * g), ev0 = e->pool_event(6 * g + 1), ev1 = e->pool_event(6 * g + 2),
                     ev2 = e->pool_event(6 * g + 3), ev3 = e->pool_event(6 * g + 4);
         if (c->pending_in) {
@@ -121,6 +122,7 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
 
 extern "C" int rg_gain_analyze(rg_engine* e, const rg_input* in, size_t n, rg_gain_stats* out) {
     if (!e || (n && (!in || !out))) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     rg_corpus c;
     int rc = host_corpus(e, in, n, c);
     if (rc != RG_OK) return rc;
@@ -131,6 +133,7 @@ extern "C" int rg_gain_analyze(rg_engine* e, const rg_input* in, size_t n, rg_ga
 
 extern "C" int rg_gain_analyze_corpus(rg_engine* e, rg_corpus* c, rg_gain_stats* out) {
     if (!e || !c || (!out && !c->len.empty())) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     int rc = gain_impl(e, c, out, false, 0, 0, -1, nullptr, nullptr);
     if (rc != RG_OK) drain_streams(e);
     return rc;
@@ -139,6 +142,7 @@ extern "C" int rg_gain_analyze_corpus(rg_engine* e, rg_corpus* c, rg_gain_stats*
 extern "C" int rg_gain_apply(rg_engine* e, const rg_input* in, size_t n, int32_t gain_steps, int32_t mode, int32_t channel,
                              uint8_t* const* out_images, uint32_t* frames_modified) {
     if (!e || (n && (!in || !out_images)) || channel > 1 || (mode != RG_GAIN_SATURATE && mode != RG_GAIN_WRAP)) return RG_ERR_INVALID_ARG;
+    std::lock_guard<std::recursive_mutex> lock(e->mu);
     for (size_t i = 0; i < n; i++) if (in[i].len && (!in[i].data || !out_images[i])) return RG_ERR_INVALID_ARG;
     if (gain_steps == 0) {   // apply_gain returns Ok(0) before it reads the file (src/lib.rs:603-605)
         for (size_t i = 0; i < n; i++) {

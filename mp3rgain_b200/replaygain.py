@@ -15,6 +15,7 @@ import ctypes as C
 import dataclasses
 import enum
 import os
+import threading
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -27,9 +28,10 @@ GAIN_STEP_DB = 1.5              # src/lib.rs:48
 
 
 class ReplayGainError(RuntimeError):
-    def __init__(self, status: int, message: str):
+    def __init__(self, status: int, message: str, index: Optional[int] = None):
         super().__init__(message)
         self.status = status
+        self.index = index      # album mode: position in the input list of the file that failed the album
 
 
 class AudioFileType(enum.Enum):  # src/replaygain.rs:47-53
@@ -179,7 +181,10 @@ class Engine:
             res.append(self._result(out[i], hist[i] if want_hist else None))
         return res, sts
 
-    def analyze_album_images(self, images: Sequence, track_index: Optional[int] = None, want_hist: bool = False) -> AlbumGainResult:
+    def analyze_album_images(self, images: Sequence, track_index: Optional[int] = None, want_hist: bool = False,
+                             names: Optional[Sequence] = None) -> AlbumGainResult:
+        """rg_analyze_album.  `names` (the files' paths) only serve the error message: the reference fails the album with the
+        first failing file's error, which names that file (src/replaygain.rs:1055, :822)."""
         n = len(images)
         arr, keep = self._inputs(images, track_index)
         out = (_lib.RgTrackResult * max(n, 1))()
@@ -187,9 +192,64 @@ class Engine:
         ah = np.zeros(HIST_SIZE, np.uint64) if want_hist else None
         rc = self._lib.rg_analyze_album(self._h, arr, n, out, C.byref(alb), ah.ctypes.data if want_hist else None)
         if rc != 0:
-            bad = next((out[i] for i in range(n) if out[i].status != 0), None)
-            raise ReplayGainError(rc, _message(rc, sample_rate=bad.sample_rate if bad else 0,
-                                               track_index=-1 if track_index is None else track_index))
+            bad = next((i for i in range(n) if out[i].status != 0), None)
+            raise ReplayGainError(rc, _message(rc, path=os.fspath(names[bad]) if names is not None and bad is not None else "",
+                                               sample_rate=out[bad].sample_rate if bad is not None else 0,
+                                               track_index=-1 if track_index is None else track_index), index=bad)
+        return AlbumGainResult([self._result(out[i]) for i in range(n)], alb.album_loudness_db, alb.album_gain_db,
+                               alb.album_peak, ah)
+
+    # ---- album mode across GPUs: this engine is one rank of several (the engine owns the exchange) ----------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rg_comm_unique_id (ncclGetUniqueId): rank 0 creates it and hands it to the other ranks."""
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES)()
+        rc = _lib.load().rg_comm_unique_id(buf)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+        return bytes(buf)
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        buf = (C.c_uint8 * _lib.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        rc = self._lib.rg_engine_comm_init(self._h, rank, nranks, buf)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+
+    def comm_attach_host(self, rank: int, nranks: int, fn):
+        """Another transport for the exchange: fn(sum_array_u64, max_array_u64) reduces both numpy arrays in place over all ranks."""
+        def tramp(ctx, psum, nsum, pmax, nmax):
+            try:
+                fn(np.ctypeslib.as_array(psum, (nsum,)), np.ctypeslib.as_array(pmax, (nmax,)))
+                return 0
+            except Exception:   # noqa: BLE001 -- must not unwind through the C frame
+                return 1
+        self._xchg = _lib.ExchangeFn(tramp)   # keep the trampoline alive as long as the engine uses it
+        rc = self._lib.rg_engine_comm_attach_host(self._h, rank, nranks, self._xchg, None)
+        if rc != 0:
+            raise ReplayGainError(rc, _message(rc))
+
+    def comm_release(self):
+        self._lib.rg_engine_comm_release(self._h)
+        self._xchg = None
+
+    def analyze_album_sharded_images(self, images: Sequence, shard_offset: int, track_index: Optional[int] = None,
+                                     want_hist: bool = True, names: Optional[Sequence] = None) -> AlbumGainResult:
+        """rg_analyze_album_sharded: `images` = this rank's shard, which starts at `shard_offset` in the global file list;
+        `names` = the GLOBAL list of paths (for the error message).  Every rank gets the same album numbers or the same error."""
+        n = len(images)
+        arr, keep = self._inputs(images, track_index)
+        out = (_lib.RgTrackResult * max(n, 1))()
+        alb = _lib.RgAlbumResult()
+        ah = np.zeros(HIST_SIZE, np.uint64) if want_hist else None
+        bad = C.c_int64(-1)
+        rc = self._lib.rg_analyze_album_sharded(self._h, arr, n, int(shard_offset), out, C.byref(alb),
+                                                ah.ctypes.data if want_hist else None, C.byref(bad))
+        if rc != 0:
+            g = int(bad.value)
+            local = g - int(shard_offset)
+            raise ReplayGainError(rc, _message(rc, path=os.fspath(names[g]) if names is not None and g >= 0 else "",
+                                               sample_rate=out[local].sample_rate if 0 <= local < n else 0,
+                                               track_index=-1 if track_index is None else track_index), index=g if g >= 0 else None)
         return AlbumGainResult([self._result(out[i]) for i in range(n)], alb.album_loudness_db, alb.album_gain_db,
                                alb.album_peak, ah)
 
@@ -304,13 +364,16 @@ class Corpus:
 
 # ---- module-level functions with the reference's names ------------------------------------------------
 _default_engine: Optional[Engine] = None
+_default_engine_lock = threading.Lock()
 
 
 def _engine() -> Engine:
+    """The module-level functions share one engine; calls from several threads queue on the engine's own lock."""
     global _default_engine
-    if _default_engine is None:
-        _default_engine = Engine(device=int(os.environ.get("LOCAL_RANK", "0")))
-    return _default_engine
+    with _default_engine_lock:
+        if _default_engine is None:
+            _default_engine = Engine(device=int(os.environ.get("LOCAL_RANK", "0")))
+        return _default_engine
 
 
 def is_available() -> bool:
@@ -343,7 +406,7 @@ def analyze_track(file_path) -> ReplayGainResult:
 
 def analyze_album_with_index(files: Sequence, track_index: Optional[int] = None) -> AlbumGainResult:
     images = [_read(f) for f in files]  # an unreadable file aborts the album, like the `?` at :1055
-    return _engine().analyze_album_images(images, track_index)
+    return _engine().analyze_album_images(images, track_index, names=list(files))
 
 
 def analyze_album(files: Sequence) -> AlbumGainResult:

@@ -1,20 +1,14 @@
-"""Multi-GPU driver: one process per GPU (torch.distributed), tracks sharded by bytes, no data-path collective in track
-mode; album mode adds exactly one exchange -- all-reduce(sum) of the 12000-bin histogram and all-reduce(max) of the peak
-(the accumulate loop of the reference, src/replaygain.rs:1053-1066, with the cross-device step in the middle).
-
-torch is plumbing here (device buffers for the collective, process group); the analysis itself runs in librg_engine.so.
+"""Multi-GPU launcher: one process per GPU, tracks sharded by bytes.  Track mode has no data-path collective; album mode has
+exactly one exchange, and the ENGINE owns it (rg_analyze_album_sharded: all-reduce(sum) of the 12000-bin histogram +
+all-reduce(max) of {peak, error key} as one NCCL group on the engine's stream -- the accumulate loop of the reference,
+src/replaygain.rs:1053-1066, with the cross-device step in the middle).  What is left here is the launch protocol: split
+the list, hand rank 0's NCCL unique id to the other ranks, call the engine.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import List, Optional, Sequence, Tuple
 
-import numpy as np
-
-from . import _lib
-from .replaygain import AlbumGainResult, Engine, ReplayGainError, ReplayGainResult, _message
-
-HIST = _lib.HIST_SIZE
+from .replaygain import AlbumGainResult, Engine
 
 
 def shard_by_bytes(sizes: Sequence[int], world: int) -> List[List[int]]:
@@ -31,54 +25,46 @@ def shard_by_bytes(sizes: Sequence[int], world: int) -> List[List[int]]:
     return shards
 
 
-def album_reduce(hist, peak, group=None):
-    """The one collective of the path.  hist: int64 tensor [12000] (u64 counters reinterpreted), peak: float64 tensor [1],
-    both resident where the process group's backend wants them (CUDA for NCCL over NVLink, CPU for gloo).  In place."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=group)
-    return hist, peak
+def shard_offsets(shards: Sequence[Sequence[int]]) -> List[int]:
+    """Global index of each shard's first file (shards are contiguous and in input order)."""
+    offs, acc = [], 0
+    for s in shards:
+        offs.append(acc)
+        acc += len(s)
+    return offs
 
 
-def analyze_album_sharded(engine: Engine, images: Sequence, rank: int, world: int, group=None,
-                          track_index: Optional[int] = None) -> Tuple[AlbumGainResult, List[int]]:
-    """analyze_album across `world` GPUs.  Every rank passes the SAME list of file images (or at least the same sizes);
-    each analyses its byte-balanced shard on its own GPU, the partial album histogram / peak are all-reduced over NCCL,
-    and every rank finishes the percentile on its device.  Returns (album result with this rank's tracks, shard indices).
-    A failing file aborts the album on every rank (src/replaygain.rs:1055)."""
+def connect(engine: Engine, rank: int, world: int, group=None, transport: str = "nccl"):
+    """Make `engine` rank `rank` of `world`.  transport "nccl": the engine creates its own communicator (rank 0's unique id
+    is broadcast over the torch.distributed group, any backend); transport "host": the exchange goes through
+    torch.distributed on host tensors (gloo: the CPU tests, or a host without NCCL)."""
+    if world <= 1:
+        return
+    import numpy as np
     import torch
     import torch.distributed as dist
-    lib = engine._lib
-    mine = shard_by_bytes([len(im) for im in images], world)[rank]
-    dev = torch.device("cuda", torch.cuda.current_device())
-    d_hist = torch.zeros(HIST, dtype=torch.int64, device=dev)
-    d_peak = torch.zeros(1, dtype=torch.float64, device=dev)
-    n = len(mine)
-    arr, keep = Engine._inputs([images[i] for i in mine], track_index)
-    out = (_lib.RgTrackResult * max(n, 1))()
-    status = torch.zeros(1, dtype=torch.int64, device=dev)
-    cor = C.c_void_p()
-    rc = lib.rg_corpus_upload(engine._h, arr, n, C.byref(cor))
-    if rc == 0:
-        torch.cuda.synchronize()
-        rc = lib.rg_analyze_album_shard(engine._h, cor, out, d_hist.data_ptr(), d_peak.data_ptr())
-        lib.rg_corpus_free(engine._h, cor)
-    status[0] = -rc  # statuses are <= 0: the max over ranks of -rc finds any failure
-    if world > 1:
-        dist.all_reduce(status, op=dist.ReduceOp.MAX, group=group)
-    if int(status.item()) != 0:
-        st = -int(status.item())
-        raise ReplayGainError(st, _message(st))
-    album_reduce(d_hist, d_peak, group)
-    torch.cuda.synchronize()   # the collective ran on torch's streams; rg_album_finish reads the buffers on the engine's
-    alb = _lib.RgAlbumResult()
-    rc = lib.rg_album_finish(engine._h, d_hist.data_ptr(), d_peak.data_ptr(), C.byref(alb))
-    if rc != 0:
-        raise ReplayGainError(rc, _message(rc))
-    tracks = [Engine._result(out[i]) for i in range(n)]
-    hist = d_hist.cpu().numpy().view(np.uint64).copy()
-    return AlbumGainResult(tracks, alb.album_loudness_db, alb.album_gain_db, alb.album_peak, hist), mine
+    if transport == "host":
+        def xchg(sum_u64, max_u64):
+            s = torch.from_numpy(sum_u64.view(np.int64))     # counters stay far below 2^63
+            m = torch.from_numpy(max_u64.view(np.int64))     # non-negative doubles and error keys (< 2^63) order like int64
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+        engine.comm_attach_host(rank, world, xchg)
+        return
+    box = [Engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.comm_init(rank, world, box[0])
+
+
+def analyze_album_sharded(engine: Engine, images: Sequence, rank: int, world: int, track_index: Optional[int] = None,
+                          names: Optional[Sequence] = None) -> Tuple[AlbumGainResult, List[int]]:
+    """analyze_album across `world` GPUs (call connect() once before).  Every rank passes the SAME list of file images (or at
+    least the same sizes); each analyses its byte-balanced shard on its own GPU.  Returns (album result with this rank's
+    tracks, shard indices).  A failing file aborts the album on every rank with that file's error (src/replaygain.rs:1055)."""
+    shards = shard_by_bytes([len(im) for im in images], world)
+    mine = shards[rank]
+    return engine.analyze_album_sharded_images([images[i] for i in mine], shard_offsets(shards)[rank], track_index,
+                                               names=names), mine
 
 
 def gain_analyze_sharded(engine: Engine, images: Sequence, rank: int, world: int):

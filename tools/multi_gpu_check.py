@@ -3,8 +3,8 @@
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
 
-Every rank builds the same seeded corpus, analyses its byte-balanced shard, the 12000-bin album histogram and the peak are
-all-reduced over NCCL, and rank 0 compares the merged histogram / album loudness with the sum of the oracle's per-track
+Every rank builds the same seeded corpus and analyses its byte-balanced shard; the engine all-reduces the 12000-bin album
+histogram and {peak, error key} over its own NCCL communicator (rg_analyze_album_sharded), and rank 0 compares the merged histogram / album loudness with the sum of the oracle's per-track
 histograms (tests/ oracle: checker only)."""
 import os
 import sys
@@ -31,7 +31,17 @@ n_tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 pool = synth_corpus.GroupPool(seed=7, n_groups=64, group_len=16)
 imgs = [pool.track(500 + i, 300 + 37 * (i % 5)) for i in range(n_tracks)]
 with m.Engine(device=local) as eng:
+    sharded.connect(eng, rank, world)       # the engine creates its own NCCL communicator from rank 0's unique id
     alb, mine = sharded.analyze_album_sharded(eng, imgs, rank, world)
+    exch_ms = eng.stats().last_ms_exchange
+    # a failing file on the LAST rank fails the album on every rank, with that file's index
+    broken = list(imgs)
+    broken[-1] = np.zeros(len(imgs[-1]), np.uint8)
+    try:
+        sharded.analyze_album_sharded(eng, broken, rank, world)
+        err = None
+    except m.ReplayGainError as ex:
+        err = (ex.status, ex.index)
 ok = True
 if rank == 0:
     orc = oracle_lib.load()
@@ -47,7 +57,9 @@ if rank == 0:
     print(f"world {world}: album histogram identical to the oracle sum: {same}; windows {int(total.sum())}; "
           f"album loudness {alb.album_loudness_db} (oracle {o_loud}); peak {alb.album_peak} vs {peak}; shard sizes "
           f"{[len(s) for s in sharded.shard_by_bytes([len(i) for i in imgs], world)]}", flush=True)
+    print(f"exchange (NCCL group: all-reduce sum u64[12000] + max u64[2]) {exch_ms:.3f} ms on the engine's stream; failing-file case -> {err}", flush=True)
     ok = same and alb.album_peak == peak and (o_loud is None or o_loud == alb.album_loudness_db)
+ok = ok and err == (-5, n_tracks - 1)
 if world > 1:
     t = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(t)
