@@ -30,14 +30,52 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FRAMES_3MIN = 6891          # 3 min of 44.1 kHz MPEG-1 Layer III frames
+GROUP_LEN = 32              # frames per self-contained group of the synthetic pool
 METRIC = "audio-hours/sec analysed"
 
 
 def build_corpus(n_tracks, n_frames, seed):
     """n_tracks distinct tracks: seeded random sequences of self-contained frame groups from a seeded pool."""
     import synth_corpus
-    pool = synth_corpus.GroupPool(seed=seed, n_groups=256, group_len=32, intensity_prob=0.02)
+    pool = synth_corpus.GroupPool(seed=seed, n_groups=256, group_len=GROUP_LEN, intensity_prob=0.02)
     return [pool.track(seed * 100003 + i, n_frames) for i in range(n_tracks)]
+
+
+def build_mixed_corpus(n_tracks, seed, seconds=180.0):
+    """BASELINE.json configs[3]: 3-minute tracks of divergent frame sizes -- VBR 32-320 kbps and CBR 32 / 128 / 320, 44.1 and
+    48 kHz (two IIR coefficient sets in one batch), one track in five mono.  Returns (images, audio seconds)."""
+    import synth_corpus
+    kinds = [(0, 0, 2), (1, 0, 2), (0, 0, 1), (1, 14, 2), (0, 1, 2), (0, 9, 2), (1, 0, 1), (1, 9, 2), (0, 14, 2), (0, 0, 2)]   # (sr_idx, br_idx (0 = VBR), channels)
+    pools = {}
+    imgs, secs = [], 0.0
+    for i in range(n_tracks):
+        k = kinds[i % len(kinds)]
+        if k not in pools:
+            pools[k] = synth_corpus.GroupPool(seed=seed * 31 + len(pools), n_groups=64, group_len=GROUP_LEN, sr_idx=k[0], br_idx=k[1],
+                                              channels=k[2], intensity_prob=0.02)
+        rate = synth_corpus.RATES[k[0]]
+        n_frames = max(1, int(seconds * rate / 1152.0))
+        imgs.append(pools[k].track(seed * 7 + i, n_frames))
+        secs += (n_frames + GROUP_LEN - 1) // GROUP_LEN * GROUP_LEN * 1152.0 / rate
+    return imgs, secs
+
+
+def pin_images(imgs, _lib):
+    """Pinned host copies of the file images + the rg_input array over them (the e2e paths DMA straight out of these)."""
+    import torch
+    n = len(imgs)
+    offs = np.zeros(n + 1, np.int64)
+    for i, im in enumerate(imgs):
+        offs[i + 1] = offs[i] + ((len(im) + 63) & ~63)
+    pinned = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
+    pnp = pinned.numpy()
+    arr = (_lib.RgInput * n)()
+    for i, im in enumerate(imgs):
+        pnp[offs[i]: offs[i] + len(im)] = im
+        arr[i].data = pnp.ctypes.data + int(offs[i])
+        arr[i].len = len(im)
+        arr[i].track_index = -1
+    return pinned, arr
 
 
 def audio_seconds(n_tracks, n_frames):
@@ -133,10 +171,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ncores = os.cpu_count() or 1
+    # (the same dict in both arms: the reference arm times a bounded sample of exactly this workload)
     config = {"workload": f"configs[1]: {args.tracks} synthetic 3-min 44.1 kHz stereo CBR-128 MP3 tracks per GPU, track-mode",
-              "tracks_per_gpu": args.tracks, "frames_per_track": args.frames, "sample_rate": 44100, "channels": 2,
-              "bitrate_kbps": 128, "sharding": f"by-track x{world}", "iir_mode": "exact" if args.exact else "time-blocked+edge-rerun",
-              "l2": "inputs (2.9 GB compressed per GPU, 95 GB of intermediates) are far larger than the 126 MB L2"}
+              "tracks_per_gpu": args.tracks, "frames_per_track": args.frames,
+              "frames_decoded_per_track": (args.frames + GROUP_LEN - 1) // GROUP_LEN * GROUP_LEN,   # the pool deals whole groups
+              "sample_rate": 44100, "channels": 2,
+              "bitrate_kbps": 128, "sharding": f"by-track x{args.gpus}", "iir_mode": "exact" if args.exact else "time-blocked+edge-rerun",
+              "l2": "inputs (2.9 GB compressed per GPU, 60 GB of intermediates) are far larger than the 126 MB L2"}
 
     # ------------------------------------------------------------------ reference arm: CPU only, rank 0 only
     if args.impl == "reference":
@@ -190,18 +231,7 @@ def main():
     imgs = build_corpus(args.tracks, args.frames, seed=1 + rank)
     n = len(imgs)
     total_bytes = int(sum(len(i) for i in imgs))
-    # pinned host copies of every file image (the e2e path DMA's straight out of these)
-    offs = np.zeros(n + 1, np.int64)
-    for i, im in enumerate(imgs):
-        offs[i + 1] = offs[i] + ((len(im) + 63) & ~63)
-    pinned = torch.empty(int(offs[-1]), dtype=torch.uint8, pin_memory=True)
-    pnp = pinned.numpy()
-    arr = (_lib.RgInput * n)()
-    for i, im in enumerate(imgs):
-        pnp[offs[i]: offs[i] + len(im)] = im
-        arr[i].data = pnp.ctypes.data + int(offs[i])
-        arr[i].len = len(im)
-        arr[i].track_index = -1
+    pinned, arr = pin_images(imgs, _lib)
     imgs = imgs[: max(2 * ncores, 8)]   # only the CPU-baseline sample is needed from here on (host RAM: N ranks share one box)
     eng = m.Engine(device=local_rank, exact=args.exact)
     out = (_lib.RgTrackResult * n)()
@@ -227,7 +257,7 @@ def main():
         assert lib.rg_analyze_corpus(eng._h, cor, out, None) == 0
     if args.warmup > 0:
         asec = sum(out[i].n_frames for i in range(n)) * 1152 / 44100.0   # audio actually decoded: the pool deals whole 32-frame groups
-        config["frames_decoded_per_track"] = int(out[0].n_frames)
+        assert int(out[0].n_frames) == config["frames_decoded_per_track"]
     st0 = eng.stats()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -259,7 +289,6 @@ def main():
              "k_iir": sa.last_ms_iir, "k_hist": sa.last_ms_hist, "launches_per_step": int(sa.last_batches),
              "iir_samples": int(sa.last_iir_samples)}
     eng.set_option("pipeline", 1)
-    lib.rg_corpus_free(eng._h, cor)
 
     # ---- e2e: host buffers in, results out, copies inside the timed region
     for _ in range(max(1, args.warmup // 3)):
@@ -273,6 +302,103 @@ def main():
 
     value = world * asec / 3600.0 / (wall_ms / 1000.0)
     e2e = world * asec / 3600.0 / (e2e_ms / 1000.0)
+
+    # ---- the other BASELINE.json configs beside the headline (not part of `value`), each a short run of its own:
+    #   album  configs[2]: album mode over the same resident corpus, sharded over all ranks; the timed region holds the whole
+    #          call -- analysis, the engine's exchange (one NCCL group: all-reduce sum u64[12000] + max u64[2]) and the percentile
+    #   mixed  configs[3]: VBR 32-320 + CBR, 44.1 / 48 kHz, 20 % mono (divergent frame sizes, two coefficient sets per batch)
+    #   stream configs[4]: 30-second clips out of pinned host memory, copies overlapped with the kernels; H2D GB/s beside it
+    extra = {}
+    xsteps = max(1, min(args.steps, 3))
+    try:
+        from mp3rgain_b200 import sharded
+        sharded.connect(eng, rank, world)
+        alb = _lib.RgAlbumResult()
+        bad = C.c_int64(-1)
+        ahist = np.zeros(_lib.HIST_SIZE, np.uint64)
+        xch = []
+        assert lib.rg_analyze_album_sharded_corpus(eng._h, cor, rank * n, out, C.byref(alb), ahist.ctypes.data, C.byref(bad)) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(xsteps):
+            assert lib.rg_analyze_album_sharded_corpus(eng._h, cor, rank * n, out, C.byref(alb), ahist.ctypes.data, C.byref(bad)) == 0
+            xch.append(eng.stats().last_ms_exchange)
+        barrier()
+        a_ms = maxr(1000.0 * (time.perf_counter() - t0) / xsteps)
+        # the merged histogram holds every window of every rank's tracks exactly once
+        n_win = float(sum(out[i].n_windows - out[i].n_dropped_windows for i in range(n)))
+        if world > 1:
+            t = torch.tensor([n_win], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            n_win = float(t.item())
+        extra["album"] = {"workload": f"configs[2]: album mode, {n} tracks per GPU x {world} GPU(s), histogram merge over NCCL inside the timed call",
+                          "value": world * asec / 3600.0 / (a_ms / 1000.0), "unit": "audio-h/s", "ms_per_step": a_ms,
+                          "exchange_ms": float(np.mean(xch)), "exchange": "one NCCL group on the engine's stream: all-reduce(sum) u64[12000] + all-reduce(max) u64[2]" if world > 1 else "none (one rank)",
+                          "album_loudness_db": alb.album_loudness_db, "album_peak": alb.album_peak,
+                          "merged_windows": int(ahist.sum()), "windows_of_all_tracks": int(n_win), "histogram_is_the_sum": bool(int(ahist.sum()) == int(n_win))}
+    except Exception as ex:  # noqa: BLE001  (a secondary measurement must never take the headline line down)
+        extra["album"] = {"error": repr(ex)}
+    lib.rg_corpus_free(eng._h, cor)
+    try:
+        mimgs, msec = build_mixed_corpus(args.tracks, seed=11 + rank, seconds=180.0 * args.frames / FRAMES_3MIN)   # (3 min unless a toy run)
+        mbytes = int(sum(len(i) for i in mimgs))
+        mpin, marr = pin_images(mimgs, _lib)
+        nm = len(mimgs)
+        mout = (_lib.RgTrackResult * nm)()
+        mcor = C.c_void_p()
+        assert lib.rg_corpus_upload(eng._h, marr, nm, C.byref(mcor)) == 0
+        assert lib.rg_analyze_corpus(eng._h, mcor, mout, None) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(xsteps):
+            assert lib.rg_analyze_corpus(eng._h, mcor, mout, None) == 0
+        barrier()
+        m_ms = maxr(1000.0 * (time.perf_counter() - t0) / xsteps)
+        lib.rg_corpus_free(eng._h, mcor)
+        assert lib.rg_analyze_tracks(eng._h, marr, nm, mout, None) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(xsteps):
+            assert lib.rg_analyze_tracks(eng._h, marr, nm, mout, None) == 0
+        barrier()
+        me_ms = maxr(1000.0 * (time.perf_counter() - t0) / xsteps)
+        assert all(mout[i].status == 0 for i in range(nm))
+        rates = sorted({int(mout[i].sample_rate) for i in range(nm)})
+        extra["mixed"] = {"workload": f"configs[3]: {nm} 3-min tracks per GPU, VBR 32-320 / CBR 32, 128, 320 kbps, 44.1 + 48 kHz, 20 % mono; sharded by bytes",
+                          "value": world * msec / 3600.0 / (m_ms / 1000.0), "unit": "audio-h/s", "ms_per_step": m_ms,
+                          "e2e": {"value": world * msec / 3600.0 / (me_ms / 1000.0), "ms_per_step": me_ms, "h2d_bytes_per_step": mbytes * world},
+                          "sample_rates": rates, "mono_tracks": int(sum(1 for i in range(nm) if mout[i].channels == 1)),
+                          "compressed_bytes_per_gpu": mbytes, "exact_reruns": int(sum(mout[i].exact_rerun for i in range(nm)))}
+        del mpin, marr
+    except Exception as ex:  # noqa: BLE001
+        extra["mixed"] = {"error": repr(ex)}
+    try:
+        import synth_corpus
+        clip_frames = min(int(30.0 * 44100 / 1152.0), args.frames)   # (30 s unless a toy run)
+        n_clips = 6 * args.tracks                      # the same 50 audio-hours per GPU, in 30-second pieces
+        pool = synth_corpus.GroupPool(seed=101 + rank, n_groups=128, group_len=GROUP_LEN, intensity_prob=0.02)
+        cimgs = [pool.track(977 * rank + i, clip_frames) for i in range(n_clips)]
+        cbytes = int(sum(len(i) for i in cimgs))
+        csec = n_clips * ((clip_frames + GROUP_LEN - 1) // GROUP_LEN * GROUP_LEN) * 1152.0 / 44100.0
+        cpin, carr = pin_images(cimgs, _lib)
+        del cimgs
+        cout = (_lib.RgTrackResult * n_clips)()
+        assert lib.rg_analyze_tracks(eng._h, carr, n_clips, cout, None) == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(xsteps):
+            assert lib.rg_analyze_tracks(eng._h, carr, n_clips, cout, None) == 0
+        barrier()
+        c_ms = maxr(1000.0 * (time.perf_counter() - t0) / xsteps)
+        assert all(cout[i].status == 0 for i in range(n_clips))
+        extra["stream"] = {"workload": f"configs[4]: {n_clips} 30-second clips per GPU out of pinned host memory, copy / index / decode / analysis overlapped",
+                           "value": world * csec / 3600.0 / (c_ms / 1000.0), "unit": "audio-h/s", "ms_per_step": c_ms,
+                           "clips_per_s": world * n_clips / (c_ms / 1000.0), "h2d_gbs_per_gpu": cbytes / (c_ms / 1000.0) / 1e9,
+                           "h2d_bytes_per_step": cbytes * world, "hbm_peak_gbs": float(peaks_early.get("hbm_gbs", 6650.0)),
+                           "note": "the compressed stream is what crosses the bus: H2D GB/s is bounded by PCIe (~55 GB/s per GPU), 1 % of the HBM peak"}
+        del cpin, carr
+    except Exception as ex:  # noqa: BLE001
+        extra["stream"] = {"error": repr(ex)}
 
     # ---- row f1 beside it (not part of `value`): the global_gain walk of mp3rgain::analyze() / apply_gain() over the same
     # corpus.  Its scan kernel streams every file byte once through shared memory -- the one kernel of this repo whose
@@ -316,11 +442,14 @@ def main():
         gain_fields = {"workload": "mp3rgain::analyze() / apply_gain(+3) over the same corpus (SURVEY 8 row f1)",
                        "frames_per_track": int(gst[0].frame_count),
                        "kernel_ms": {"k_gf_scan": scan_ms, "k_gf_merge": float(np.mean(merge)), "k_gf_patch": patch_ms},
-                       "roofline": {"bound": "hbm", "kernel": "k_gf_scan", "achieved": total_bytes / (scan_ms / 1000.0) / 1e9,
-                                    "peak": hbm, "unit": "GB/s", "frac": total_bytes / (scan_ms / 1000.0) / 1e9 / hbm,
+                       "roofline": {"bound": "hbm", "kernel": "k_gf_scan",
+                                    "achieved": (gf_traffic / (scan_ms / 1000.0) / 1e9) if gf_traffic else None,
+                                    "peak": hbm, "unit": "GB/s", "frac": (gf_traffic / (scan_ms / 1000.0) / 1e9 / hbm) if gf_traffic else None,
                                     "algorithmic_bytes_per_launch": total_bytes, "traffic": gf_traffic,
-                                    "note": "algorithmic bytes = the file bytes; the walk reads only the sectors holding headers and "
-                                            "side info, so DRAM traffic (ncu, profiles/traffic.json) is below the file bytes"},
+                                    "file_bytes_gbs": total_bytes / (scan_ms / 1000.0) / 1e9,
+                                    "note": "achieved / frac = DRAM bytes of the launch (ncu, profiles/traffic.json) over its CUDA-event time: the "
+                                            "walk reads only the sectors that hold headers and side info, about half of the file; file_bytes_gbs "
+                                            "= the rate a caller sees (file bytes / time)"},
                        "frames_modified": int(mod.sum())}
     except Exception as ex:  # noqa: BLE001  (a secondary measurement must never take the headline line down)
         gain_fields = {"error": repr(ex)}
@@ -363,8 +492,8 @@ def main():
                 "kernel_ms_alone": alone,
                 "achieved_alone": total_bytes / (alone["k_hybrid_synth"] / 1000.0) / 1e9,
                 "staged_dram_gbs_whole_step": (staged * n / (wall_ms / 1000.0) / 1e9) if staged else None,
-                "note": "no kernel of this path is HBM-bound: k_hybrid_synth is instruction-issue bound (74 % issue-active in "
-                        "profiles/), k_iir FP64-pipe bound (74 %); the compressed stream is ~0.5 % of HBM peak by construction "
+                "note": "no kernel of this path is HBM-bound: k_hybrid_synth is instruction-issue bound (70 % issue-active in "
+                        "profiles/), k_iir FP64-pipe bound (88 %); the compressed stream is ~1 % of HBM peak by construction "
                         "(DESIGN.md 6). staged_dram_gbs_whole_step = ncu DRAM bytes of all kernels (spectra, PCM round trips) / step time"}
 
     # ---- the roofline that actually binds the second-largest kernel: k_iir is FP64-pipe bound.  28 FP64 instructions per
@@ -394,7 +523,7 @@ def main():
             "exact_reruns": reruns,
             "e2e": {"value": e2e, "unit": "audio-h/s", "h2d_bytes_per_step": total_bytes * world,
                     "d2h_bytes_per_step": n * C.sizeof(_lib.RgTrackResult) * world, "ms_per_step": e2e_ms},
-            "roofline": roofline, "gain_fields": gain_fields}
+            "roofline": roofline, "configs": extra, "gain_fields": gain_fields}
 
     if rank == 0 and world == 1:
         # CPU baseline beside it: the oracle (C restatement of the reference path) on a bounded sample, all host threads

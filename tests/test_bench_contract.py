@@ -20,6 +20,16 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "audio-h/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms describe the workload with the same dict
+    import shutil
+    if shutil.which("g++") is not None and os.uname().machine == "x86_64":
+        q = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dev", "simt_emu", "run_bench_emu.py"), "--tracks", "2", "--frames", "64",
+                            "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=900)
+        assert q.returncode == 0, q.stderr[-3000:]
+        g = json.loads(q.stdout.splitlines()[0])
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--frames", "64",
+                            "--tracks", "2"], capture_output=True, text=True, timeout=600)
+        assert json.loads(r.stdout.splitlines()[0])["config"] == g["config"]
 
 
 def test_last_gpu_bench_line_has_the_contract_keys():
@@ -57,6 +67,10 @@ def test_gpu_arm_runs_end_to_end_on_the_interpreted_kernels():
         assert k in d, k
     assert d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert "error" not in d["gain_fields"], d["gain_fields"]
+    for k in ("album", "mixed", "stream"):        # BASELINE.json configs[2..4] beside the headline
+        assert "error" not in d["configs"][k] and d["configs"][k]["value"] > 0, d["configs"][k]
+    assert d["configs"]["album"]["histogram_is_the_sum"] and d["configs"]["mixed"]["sample_rates"] == [44100, 48000]
+    assert d["configs"]["mixed"]["mono_tracks"] > 0
     assert d["gain_fields"]["frames_modified"] == 8 * 64
     assert d["delta_db_vs_ref"]["max_abs"] == 0.0 and d["cpu_baseline"]["loudness_mismatches_vs_gpu"] == 0
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
