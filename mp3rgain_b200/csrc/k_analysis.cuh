@@ -293,11 +293,16 @@ k_hist_percentile(const RgTrackWin* __restrict__ tracks, const float* __restrict
             // rounding differences move trunc(val) across a bin boundary that matters?  The tolerance grows with the
             // ratio of input amplitude to filtered RMS (heavily attenuated windows carry larger relative error), and
             // windows far outside the histogram can never change bin membership.
-            // the filter state entering a window carries the previous window's level, so take the louder of the two
+            // The filter state entering a window carries the level of the windows before it, and a chain that restarts from
+            // zero state one (two, below 32 kHz) windows early forgets what came before its warm-up only down to
+            // pole^(warm-up samples) of that level: take the loudest of this window and the three before it
+            // (tests/test_iir_bound.py: a +90 dBFS burst two windows before a block start is otherwise 150x over tolerance).
             float a = 0.0f;
             if (scale_tol) {
                 a = fmaxf(t.wmax0[w], t.wmax1[w]);
-                if (w > 0) a = fmaxf(a, fmaxf(t.wmax0[w - 1], t.wmax1[w - 1]));
+#pragma unroll
+                for (uint32_t j = 1; j <= 3; j++)
+                    if (w >= j) a = fmaxf(a, fmaxf(t.wmax0[w - j], t.wmax1[w - j]));
                 // Outside what one warm-up window can forget: samples beyond +120 dBFS (no Layer III stream decodes to them
                 // short of global_gain 255 throughout; caller-supplied PCM can hold anything), infinities, and NaNs, which the
                 // serial filter carries to the end of the track.  Flag the track: it is filtered again serially.

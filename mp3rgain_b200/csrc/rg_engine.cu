@@ -400,7 +400,9 @@ static void build_chains(rg_engine* e, const std::vector<PcmTrack>& tracks, bool
                     ch.win = win; ch.rate_idx = (uint32_t)t.rate_idx; ch.flags = 1;
                     chains.push_back(ch);
                 } else {
-                    const uint32_t ww = e->warm_windows;
+                    // warm-up windows: the slowest pole of the cascade decays to 3e-15 within one 50 ms window at 32 kHz and
+                    // above, but only to 1e-13 .. 2e-10 at the MPEG-2 / 2.5 rates (fewer samples per window): two windows there
+                    const uint32_t ww = std::max<uint32_t>(e->warm_windows, t.sample_rate <= 24000 ? 2u : 1u);
                     for (uint32_t w0 = 0; w0 < n_win; w0 += bw) {
                         uint32_t w1 = std::min(n_win, w0 + bw);
                         uint64_t s0 = (uint64_t)w0 * win;
@@ -595,7 +597,9 @@ extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int 
     BatchCtx& c = e->ctx[0];
     c.pt.assign(1, t);
     c.hist_host = hist_out;
-    const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0;
+    // (the reference's 88.2 kHz coefficient row has poles outside the unit circle: nothing is ever forgotten, so that rate is
+    // always filtered serially -- no Layer III stream has it, only caller-supplied PCM)
+    const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0 || sample_rate == 88200;
     std::vector<RgTrackOut> res;
     int rc = stage_b_enqueue(e, c, exact, hist_out != nullptr, nullptr, nullptr, false, false);
     if (rc == RG_OK) rc = stage_b_collect(e, c, res);
