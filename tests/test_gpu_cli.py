@@ -74,3 +74,55 @@ def test_resident_corpus_gives_the_same_answers_as_the_host_entry_points(engine_
         assert (a.histogram == b.histogram).all()
     for a, b in zip(gst, gst2):
         assert (a.status, a.frame_count, a.gain_sum, a.min_gain, a.max_gain) == (b.status, b.frame_count, b.gain_sum, b.min_gain, b.max_gain)
+
+
+def test_json_reports_match_the_per_file_loop(oracle, tmp_path, capsys):
+    """`-o json` for cmd_info, `-r` and `-a` (src/main.rs:101-165, 1119-1150, 1213-1290, 1296-1455): the documents built from ONE
+    batched engine call each equal the documents the reference's loops would serialise from the oracle's numbers."""
+    import json
+    from mp3rgain_b200 import cli
+    files = [os.path.join(GOLD, n) for n in NAMES[:3]]
+    junk = tmp_path / "junk.mp3"
+    junk.write_bytes(bytes(3000))
+    doc = json.loads(cli.info_json(files + [str(junk)]))
+    assert list(doc) == ["files"] and len(doc["files"]) == 4
+    for f, d in zip(files, doc["files"]):
+        rc, st = oracle.gain_analyze(np.fromfile(f, np.uint8))
+        assert rc == 0
+        assert d == {"file": f, "frames": st.frame_count, "mpeg_version": ["MPEG1", "MPEG2", "MPEG2.5"][st.mpeg_version],
+                     "channel_mode": ["Stereo", "Joint Stereo", "Dual Channel", "Mono"][st.channel_mode], "min_gain": st.min_gain,
+                     "max_gain": st.max_gain, "avg_gain": st.gain_sum / st.gain_count, "headroom_steps": 255 - st.max_gain,
+                     "headroom_db": (255 - st.max_gain) * 1.5}
+    assert doc["files"][3] == {"file": str(junk), "status": "error", "error": "No valid MP3 frames found"}
+
+    doc = json.loads(cli.track_gain_json(files + [str(junk)], gain_modifier=1))
+    hists, peaks = [], []
+    for f, d in zip(files, doc["files"]):
+        rc, res, hist, info = oracle.analyze_mp3(np.fromfile(f, np.uint8))
+        steps = _round_half_away(res.gain_db / 1.5) + 1
+        assert d["file"] == f and d["loudness_db"] == res.loudness_db and d["peak"] == res.peak and d["status"] == "dry_run" and d["dry_run"] is True
+        assert d["gain_applied_steps"] == steps and d["gain_applied_db"] == steps * 1.5
+        assert ("warning" in d) == (steps > 0 and res.peak * 10 ** (res.gain_db / 20) > 1.0)
+        hists.append(hist)
+        peaks.append(res.peak)
+    assert doc["files"][3] == {"file": str(junk), "status": "error", "error": "Failed to probe format: " + str(junk)}
+    assert doc["summary"] == {"total_files": 4, "successful": 0, "failed": 1, "dry_run": True}
+
+    text, rc = cli.album_gain_json(files)
+    doc = json.loads(text)
+    _, l, g, p = oracle.album_merge(np.stack(hists), np.array(peaks))
+    assert rc == 0 and doc["album"] == {"loudness_db": l, "gain_db": g, "gain_steps": _round_half_away(g / 1.5), "peak": p}
+    assert [d["file"] for d in doc["files"]] == files and doc["summary"] == {"total_files": 3, "successful": 0, "failed": 0, "dry_run": True}
+    text, rc = cli.album_gain_json(files + [str(junk)])      # the first failing file fails the album (src/main.rs:1428-1450)
+    assert rc == 1 and json.loads(text) == {"summary": {"total_files": 4, "successful": 0, "failed": 4, "dry_run": True}}
+
+    # -R over a directory, through main()
+    d = tmp_path / "lib" / "sub"
+    d.mkdir(parents=True)
+    import shutil
+    shutil.copy(files[0], d / "b.MP3")
+    shutil.copy(files[1], tmp_path / "lib" / "a.mp3")
+    (tmp_path / "lib" / "cover.jpg").write_bytes(b"x")
+    assert cli.main(["-R", "-o", "json", str(tmp_path / "lib")]) == 0
+    got = json.loads(capsys.readouterr().out)
+    assert [x["file"] for x in got["files"]] == [str(tmp_path / "lib" / "a.mp3"), str(d / "b.MP3")]
