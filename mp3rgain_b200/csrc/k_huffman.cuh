@@ -90,17 +90,26 @@ struct BitWin {
     }
     __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, pos); }    // bits pos .. pos+31
     __device__ __forceinline__ uint32_t peek2() const { return __funnelshift_l(nx, lo, pos); }   // bits pos+32 .. pos+63
+    // The refill is written without a branch: lanes cross their word boundaries at different symbols, so a branch would run
+    // its body for a handful of lanes at nearly every symbol.  The word after nx is loaded every time (a shared-memory read)
+    // and taken only by the lanes that crossed.
+    __device__ __forceinline__ void advance_if(bool cross) {
+        uint32_t v = __byte_perm(*reinterpret_cast<const uint32_t*>(st + off), 0, 0x0123);
+        if (cross && off + 4 > lim_rel) v = k1_mask_tail(v, off, lim_rel);   // (a real branch: never taken by a sound stream)
+        hi = cross ? lo : hi;
+        lo = cross ? nx : lo;
+        nx = cross ? v : nx;
+        off += cross ? 4u : 0u;
+    }
     __device__ __forceinline__ void skip(uint32_t n) {   // n <= 32: at most one word boundary is crossed
         const uint32_t np = pos + n;
-        if ((np ^ pos) & 32u) { hi = lo; lo = nx; nx = next(); }
+        advance_if(((np ^ pos) & 32u) != 0);
         pos = np;
     }
     __device__ __forceinline__ void skip64(uint32_t n) {   // n <= 64
         const uint32_t np = pos + n, adv = (np >> 5) - (pos >> 5);
-        if (adv) {
-            hi = lo; lo = nx; nx = next();
-            if (adv > 1) { hi = lo; lo = nx; nx = next(); }
-        }
+        advance_if(adv != 0);
+        if (adv > 1) advance_if(true);   // (rare: more than 32 bits in one symbol takes linbits on both values)
         pos = np;
     }
     __device__ __forceinline__ uint32_t get(int n) {     // n <= 16, 0 allowed
@@ -374,9 +383,27 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                 for (int win = 0; win < 3; win++)   // sfb 12 carries no scalefactor; a mixed block has no short sfb 0..2
                     grow[22 + 36 + win] = (uint8_t)(8 * (win == 0 ? sbg0 : (win == 1 ? sbg1 : sbg2)));
             } else {
-                for (int sfb = 0; sfb < 21; sfb++) {
-                    const int grp = sfb < 6 ? 0 : (sfb < 11 ? 1 : (sfb < 16 ? 2 : 3));
-                    if (!(scfsi & (8 >> grp))) sfl[sfb] = (uint8_t)br.get(grp < 2 ? slen1 : slen2);
+                // long blocks: up to 11 fields of slen1 bits (<= 44 bits), then up to 10 of slen2 (<= 30): two 64-bit peeks, the
+                // fields sliced out with shifts (a band group that scfsi copies from granule 0 occupies no bits)
+                {
+                    const unsigned long long w64 = ((unsigned long long)br.peek() << 32) | br.peek2();
+                    uint32_t o = 0;
+                    if (slen1) {
+#pragma unroll 1
+                        for (int sfb = 0; sfb < 11; sfb++)
+                            if (!(scfsi & (sfb < 6 ? 8 : 4))) { sfl[sfb] = (uint8_t)((w64 << o) >> (64 - slen1)); o += slen1; }
+                    }
+                    br.skip64(o);
+                }
+                {
+                    const unsigned long long w64 = ((unsigned long long)br.peek() << 32) | br.peek2();
+                    uint32_t o = 0;
+                    if (slen2) {
+#pragma unroll 1
+                        for (int sfb = 11; sfb < 21; sfb++)
+                            if (!(scfsi & (sfb < 16 ? 2 : 1))) { sfl[sfb] = (uint8_t)((w64 << o) >> (64 - slen2)); o += slen2; }
+                    }
+                    br.skip64(o);
                 }
             }
         }
@@ -451,16 +478,26 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         };
         for (int p0 = 0; p0 < wmax; p0 += 16) {
             const bool full = p0 + 16 <= wmin;   // every lane is inside its big-values region for the whole block of 16
+            if (full) {
 #pragma unroll 1
-            for (int g = 0; g < 4; g++) {
-                const int pb = p0 + 4 * g;
-                if (pb >= wmax) break;
-                uint32_t v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                if (full || pb < mybv) v0 = big_pair(pb);
-                if (full || pb + 1 < mybv) v1 = big_pair(pb + 1);
-                if (full || pb + 2 < mybv) v2 = big_pair(pb + 2);
-                if (full || pb + 3 < mybv) v3 = big_pair(pb + 3);
-                t4[lane * 4 + (g ^ swz)] = make_uint4(v0, v1, v2, v3);
+                for (int g = 0; g < 4; g++) {
+                    const int pb = p0 + 4 * g;
+                    const uint32_t v0 = big_pair(pb), v1 = big_pair(pb + 1), v2 = big_pair(pb + 2), v3 = big_pair(pb + 3);
+                    t4[lane * 4 + (g ^ swz)] = make_uint4(v0, v1, v2, v3);
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    const int pb = p0 + 4 * g;
+                    if (pb >= wmax) break;
+                    uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll 1
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t w = pb + k < mybv ? big_pair(pb + k) : 0u;
+                        v[0] = k == 0 ? w : v[0]; v[1] = k == 1 ? w : v[1]; v[2] = k == 2 ? w : v[2]; v[3] = k == 3 ? w : v[3];
+                    }
+                    t4[lane * 4 + (g ^ swz)] = make_uint4(v[0], v[1], v[2], v[3]);
+                }
             }
             __syncwarp();
 #pragma unroll

@@ -28,7 +28,7 @@
 #define K2_THREADS 256
 #define K2_GC 8            // granule-channels per batch, one per warp
 #define K2_SLOTS 10        // slots of A / S2: (G+1) granules x channels = 5x2 (stereo) or 9x1 (mono)
-#define K2_MAX_G 128       // granules per run, including the two replayed ones
+#define K2_MAX_G 256       // granules per run, including the two replayed ones
 #define ROW 33             // padded row of 32 values
 #define SLOTF (18 * ROW)   // floats per slot
 

@@ -108,6 +108,7 @@ struct rg_engine {
     // options
     uint32_t block_windows = 0 /* 0 = chosen per batch to fill whole waves */, warm_windows = 1;
     uint32_t k4_round = 0;                // chains in one round of k_iir_fast CTAs: one CTA per SM
+    uint32_t run_granules = 254;          // granules per K2 CTA (a run re-decodes the two granules before it; setup is per run)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
@@ -301,6 +302,11 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
+    if (!strcmp(key, "run_granules")) {
+        if (value < 2 || value > K2_MAX_G - 2) return RG_ERR_INVALID_ARG;
+        e->run_granules = (uint32_t)value & ~1u;
+        return RG_OK;
+    }
     if (!strcmp(key, "k4_slim")) {
         if (value < 0 || value > 8) return RG_ERR_INVALID_ARG;
         e->k4_slim = (uint32_t)value;

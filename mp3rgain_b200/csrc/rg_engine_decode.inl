@@ -9,7 +9,7 @@
 // The host plans batch k+1 (run / chain descriptors need K0's frame counts) while the device works on batch k; two
 // BatchCtx alternate, each with half of the scratch budget.
 
-#define RUN_GRANULES 126  // granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
+#define RUN_GRANULES 254  // default granules per K2 CTA (even: runs start on granule 0 of a frame; +2 replayed = K2_MAX_G)
 
 static const uint32_t MPEG1_RATES[3] = {44100, 48000, 32000};
 // TrackMeta.sr_idx = sample-rate index | MPEG version << 4 (3 = MPEG-1, 2 = MPEG-2, 0 = MPEG-2.5)
@@ -278,8 +278,8 @@ static int decode_enqueue(rg_engine* e, rg_corpus* c, const IndexPlan& ip, Batch
         t.pcm_off = pcm_total; t.pcm_plane = plane;
         const uint32_t n_gc = n_gran * m.channels;
         for (uint32_t g0 = 0; g0 < n_gc; g0 += K1_THREADS) hb.push_back(HuffBlock{(uint32_t)k, g0});
-        for (uint32_t g0 = 0; g0 < n_gran; g0 += RUN_GRANULES)
-            runs.push_back(RunDesc{(uint32_t)k, g0, std::min<uint32_t>(RUN_GRANULES, n_gran - g0), 0});
+        for (uint32_t g0 = 0; g0 < n_gran; g0 += e->run_granules)
+            runs.push_back(RunDesc{(uint32_t)k, g0, std::min<uint32_t>(e->run_granules, n_gran - g0), 0});
         gc_total += n_gc;
         pcm_total += plane * m.channels;
         p.frames = plane;

@@ -13,7 +13,7 @@ import mp3rgain_b200 as m  # noqa: E402
 from mp3rgain_b200 import _lib  # noqa: E402
 import synth_corpus  # noqa: E402
 
-BASE = {"pipeline": 1, "k4_slim": 0, "iir_block_windows": 0, "iir_warm_windows": 1}
+BASE = {"pipeline": 1, "k4_slim": 0, "iir_block_windows": 0, "iir_warm_windows": 1, "run_granules": 254}
 n_tracks = int(sys.argv[1])
 sets = sys.argv[2:] or [""]
 pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
