@@ -62,7 +62,7 @@ typedef struct rg_corpus rg_corpus;   /* opaque: a batch of file images resident
 typedef struct {
     int32_t  device;            /* CUDA ordinal (one engine per GPU; one process per GPU when sharded) */
     uint32_t flags;             /* RG_FLAG_* */
-    uint64_t scratch_bytes;     /* device scratch budget for decoded PCM + intermediates; 0 = default (24 GiB) */
+    uint64_t scratch_bytes;     /* device scratch budget for decoded PCM + intermediates; 0 = default (48 GiB) */
 } rg_config;
 
 /* One file image.  Stands in for the `&Path` argument of analyze_track (src/replaygain.rs:929):

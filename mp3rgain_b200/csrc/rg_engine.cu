@@ -224,7 +224,7 @@ extern "C" int rg_engine_create(const rg_config* cfg, rg_engine** out) {
 static int engine_init(rg_engine* e, const rg_config* cfg, int dev) {
     e->device = dev;
     e->flags = cfg ? cfg->flags : 0;
-    e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (24ull << 30);
+    e->scratch_bytes = (cfg && cfg->scratch_bytes) ? cfg->scratch_bytes : (48ull << 30);
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->s_index, cudaStreamNonBlocking));

@@ -19,7 +19,7 @@ sets = sys.argv[2:] or [""]
 pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
 imgs = [pool.track(1000 + i, 6891) for i in range(n_tracks)]
 lib = _lib.load()
-eng = m.Engine(device=0, exact=False)
+eng = m.Engine(device=0, exact=False, scratch_bytes=int(float(os.environ.get("RG_SCRATCH_GB", "0")) * (1 << 30)))
 arr, keep = m.Engine._inputs(imgs, None)
 cor = C.c_void_p()
 assert lib.rg_corpus_upload(eng._h, arr, n_tracks, C.byref(cor)) == 0
