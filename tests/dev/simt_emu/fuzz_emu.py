@@ -28,7 +28,9 @@ orc = oracle_lib.load()
 # (version, channels, bitrate index, sample-rate index, crc): MPEG-1 128k / 32k mono, MPEG-2 48k, MPEG-2.5 8k (24-byte-class
 # frames), MPEG-1 with CRC, MPEG-2 mono with CRC, MPEG-2 8 kbps at 24 kHz (the smallest Layer III frame)
 CONFIGS = [(3, 2, 9, 0, False), (3, 1, 1, 1, False), (2, 2, 6, 0, False), (0, 2, 1, 2, False), (3, 2, 5, 2, True), (2, 1, 4, 1, True),
-           (2, 1, 1, 1, False), (0, 1, 1, 0, False)]
+           (2, 1, 1, 1, False), (0, 1, 1, 0, False),
+           # 320 kbps at 32 kHz (the largest frames: K1 walks its slice of the main data in several windows) and VBR
+           (3, 2, 14, 2, False), (3, 2, 0, 0, False)]
 bases = []
 for i, (v, c, b, s, cr) in enumerate(CONFIGS):
     try:

@@ -42,7 +42,7 @@ for it in range(3):
     st = eng.stats()
     print("rc", rc, "wall %.3fs  dev total %.1f ms | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f | reruns %d launches %d" % (
         dt, st.last_ms_total, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist,
-        audio_s / 3600.0 / dt, st.exact_reruns, st.kernel_launches), flush=True)
+        audio_s / 3600.0 / dt, st.exact_reruns, st.kernel_launches), "batches", st.last_batches, "bw", st.last_block_windows, flush=True)
 print("sample result", out[0].loudness_db, out[0].peak, out[0].n_windows, out[0].n_edge_windows, out[0].exact_rerun)
 
 if len(sys.argv) > 4 and sys.argv[4] == "e2e":
@@ -68,8 +68,9 @@ if len(sys.argv) > 4 and sys.argv[4] == "e2e":
         rc = lib.rg_analyze_tracks(eng._h, arr2, n_tracks, out, None)
         dt = time.time() - t
         st = eng.stats()
-        print("e2e rc", rc, "wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f" % (
-            dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt), flush=True)
+        print("e2e rc", rc, "wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f | batches %d bw %d" % (
+            dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt,
+            st.last_batches, st.last_block_windows), flush=True)
 
 if len(sys.argv) > 4 and sys.argv[4] == "peak":
     pk = (_lib.RgPeakResult * n_tracks)()
@@ -80,3 +81,14 @@ if len(sys.argv) > 4 and sys.argv[4] == "peak":
         st = eng.stats()
         print("peak-only rc", rc, "wall %.3fs (pageable host buffers) | index %.1f huff %.1f hybrid %.1f | audio-h/s %.1f | peak[0] %.6f" % (
             dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, audio_s / 3600.0 / dt, pk[0].peak), flush=True)
+
+if len(sys.argv) > 4 and sys.argv[4] == "e2e_pageable":
+    # the same call from PAGEABLE host buffers: the copies go through the driver's staging at a fraction of the pinned rate, i.e.
+    # the call is bound by the host link -- a one-GPU stand-in for eight ranks sharing the host's PCIe complex
+    for it in range(4):
+        t = time.time()
+        rc = lib.rg_analyze_tracks(eng._h, arr, n_tracks, out, None)
+        dt = time.time() - t
+        st = eng.stats()
+        print("e2e(pageable) rc", rc, "wall %.3fs | audio-h/s %.1f | batches %d | %.1f GB/s" % (
+            dt, audio_s / 3600.0 / dt, st.last_batches, sum(len(i) for i in imgs) / dt / 1e9), flush=True)
