@@ -112,7 +112,6 @@ struct rg_engine {
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
-    bool group_tail = true;               // the last copy / index groups of the end-to-end path shrink (a half, a quarter, eighths)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
     RgCoefFast coef_fast[12];
@@ -303,7 +302,6 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
-    if (!strcmp(key, "group_tail")) { e->group_tail = value != 0; return RG_OK; }
     if (!strcmp(key, "run_granules")) {
         if (value < 2 || value > K2_MAX_G - 2) return RG_ERR_INVALID_ARG;
         e->run_granules = (uint32_t)value & ~1u;

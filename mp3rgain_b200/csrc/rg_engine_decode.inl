@@ -122,25 +122,15 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     // the number of tracks); about eight, never smaller than 32 MiB, when the bytes are still arriving from the host, so
     // that indexing starts as soon as the first group has landed
     const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, e->group_bytes_min) : ~0ull;
-    // (the first two groups are a quarter and a half of that: the pipeline starts as soon as a few files have landed; and the
-    // last groups shrink again -- a half, a quarter, eighths: when the host link is the bottleneck (eight ranks pulling at
-    // once get 23-35 GB/s each instead of 55, profiles/r2_h2d_concurrent_8gpu.log) the call ends one group's worth of compute
-    // after the last byte has landed, so the last group should be small)
-    uint64_t acc = 0, done_bytes = 0;
+    // (the first two groups are a quarter and a half of that: the pipeline starts as soon as a few files have landed.  Shrinking
+    // the LAST groups as well -- so that a copy-bound call ends sooner after its last byte -- was tried and changed nothing
+    // measurable on one GPU, pinned or pageable: profiles/r2_e2e_group_sweep.log)
+    uint64_t acc = 0;
     for (size_t i = 0; i < n; i++) {
         const size_t k = ip.group_begin.size();   // groups started so far
-        uint64_t lim = gbytes;
-        if (gbytes != ~0ull) {
-            const uint64_t left = bytes - (done_bytes - acc);   // bytes from the start of the current group to the end
-            lim = k <= 1 ? gbytes / 4 : (k == 2 ? gbytes / 2 : gbytes);
-            if (!e->group_tail) { }
-            else if (left <= gbytes / 2) lim = std::min(lim, gbytes / 8);
-            else if (left <= gbytes) lim = std::min(lim, gbytes / 4);
-            else if (left <= 2 * gbytes) lim = std::min(lim, gbytes / 2);
-        }
+        const uint64_t lim = gbytes == ~0ull ? gbytes : (k <= 1 ? gbytes / 4 : (k == 2 ? gbytes / 2 : gbytes));
         if (i == 0 || acc >= lim) { ip.group_begin.push_back(i); acc = 0; }
         acc += c->len[i];
-        done_bytes += c->len[i];
     }
     ip.group_begin.push_back(n);
     if (!n) return RG_OK;
