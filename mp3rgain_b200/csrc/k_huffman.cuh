@@ -525,7 +525,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
         uint4* qrow = reinterpret_cast<uint4*>(c1q + ((size_t)tr.gc_base + gc) * K1_C1_ROW);
         while (__any_sync(0xffffffffu, live)) {
             uint32_t acc[4] = {0, 0, 0, 0};
-            const bool was_live = live;
+            const int q_before = q;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 if (live) {
@@ -544,7 +544,10 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
                     }
                 }
             }
-            if (was_live) *qrow++ = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            // (only a group that holds a quad is stored: a granule-channel whose count1 region ends exactly on a group boundary
+            // -- big_values 0 and all 144 quads present fills its row to the last byte -- must not write a tenth, empty group
+            // into its neighbour's row)
+            if (q != q_before) *qrow++ = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         }
         if (in) nz_out[tr.gc_base + gc] = (overrun || silent) ? 0 : (uint16_t)nz;
         if (last_pass) break;

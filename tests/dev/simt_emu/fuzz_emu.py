@@ -165,6 +165,7 @@ with m.Engine(device=0, exact=True) as eng, m.Engine(device=0, exact=False) as f
         if why:
             bad += 1
             print("MISMATCH case", case, "kind", kind, "base", base, "len", len(img), why, flush=True)
+            if os.environ.get("FUZZ_DUMP"): img.tofile(os.path.join(os.environ["FUZZ_DUMP"], "fuzz_fail_%d_%d.mp3" % (seed, case)))
             os.makedirs("/tmp/fuzz_emu", exist_ok=True)
             np.save(f"/tmp/fuzz_emu/case_{seed}_{case}.npy", img)
 print("fuzz_emu: %d cases, %d mismatches (seed %d)" % (n_cases, bad, seed))

@@ -446,6 +446,17 @@ def test_edge_flagged_tracks_are_decoded_again_with_the_exact_filter(oracle):
         assert all(r.exact_rerun == 0 for r in res3) and all((a.histogram == b.histogram).all() for a, b in zip(res, res3))
 
 
+def test_count1_region_that_fills_its_row_to_the_last_byte(engine_exact, oracle):
+    """K1 hands the count1 quads to K2 as one byte each, sixteen to a 16-byte store, in a 144-byte row per granule-channel.  A
+    granule-channel with big_values = 0 and all 144 quads present fills its row exactly -- and round 2's first version then
+    stored a tenth, empty group into the NEXT granule-channel's row, zeroing its first sixteen quads (found by the differential
+    fuzz on a 320 kbps stream with sync-like junk spliced in: PCM off by 7e-15, histogram unchanged).  The image is that case."""
+    img = np.fromfile(os.path.join(GOLD, "count1_fills_its_row.mp3"), np.uint8)
+    info = _check_pcm(engine_exact, oracle, img)
+    assert info.sample_rate == 32000 and info.n_frames == 72
+    _check_analysis(engine_exact, oracle, img)
+
+
 def test_a_realistic_share_of_flagged_tracks_is_rerun_beside_unflagged_ones(oracle):
     """The same loop at a flag rate between none and all: with the tolerance at 5e-4 a track of ~200 windows is flagged with
     probability ~0.2, so one call holds tracks that keep their time-blocked result and tracks that are decoded again with the
