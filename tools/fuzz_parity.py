@@ -25,7 +25,9 @@ rng = np.random.default_rng(seed)
 orc = oracle_lib.load()
 bases = [synth_corpus.make_track(seed=900 + i, n_frames=120, version=v, channels=c, br_idx=b, sr_idx=s, crc=cr)
          for i, (v, c, b, s, cr) in enumerate([(3, 2, 9, 0, False), (3, 1, 0, 1, False), (2, 2, 6, 0, False), (0, 2, 0, 2, False),
-                                               (3, 2, 5, 2, True), (2, 1, 4, 1, True)])]
+                                               (3, 2, 5, 2, True), (2, 1, 4, 1, True),
+                                               # 320 kbps at 32 kHz (K1 walks its slice of the main data in several windows), 256 kbps
+                                               (3, 2, 14, 2, False), (3, 2, 13, 0, False)])]
 bad = 0
 with m.Engine(device=0, exact=True) as eng:
     for case in range(n_cases):
