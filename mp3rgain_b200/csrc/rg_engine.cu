@@ -111,6 +111,7 @@ struct rg_engine {
     uint32_t run_granules = 254;          // granules per K2 CTA (a run re-decodes the two granules before it; setup is per run)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
+    bool timeline = false;                // development aid: print every batch's kernel intervals to stderr
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
@@ -301,6 +302,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
+    if (!strcmp(key, "timeline")) { e->timeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
     if (!strcmp(key, "run_granules")) {
         if (value < 2 || value > K2_MAX_G - 2) return RG_ERR_INVALID_ARG;

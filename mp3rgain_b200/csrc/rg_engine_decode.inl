@@ -359,6 +359,15 @@ static void collect_decode_timing(rg_engine* e, BatchCtx& x) {
     if (cudaEventElapsedTime(&ms, x.ev_a[0], x.ev_a[3]) == cudaSuccess) e->stats.last_ms_index += ms;
     if (cudaEventElapsedTime(&ms, x.ev_a[3], x.ev_a[1]) == cudaSuccess) e->stats.last_ms_huffman += ms;
     if (cudaEventElapsedTime(&ms, x.ev_a[1], x.ev_a[2]) == cudaSuccess) e->stats.last_ms_hybrid += ms;
+    if (e->timeline) {   // development aid: where the batch's kernels sat in the call (ms since the call's first event)
+        float t[8] = {};
+        cudaEventElapsedTime(&t[0], e->ev[7], x.ev_a[0]); cudaEventElapsedTime(&t[1], e->ev[7], x.ev_a[3]);
+        cudaEventElapsedTime(&t[2], e->ev[7], x.ev_a[1]); cudaEventElapsedTime(&t[3], e->ev[7], x.ev_a[2]);
+        cudaEventElapsedTime(&t[4], e->ev[7], x.ev_b[0]); cudaEventElapsedTime(&t[5], e->ev[7], x.ev_b[1]);
+        cudaEventElapsedTime(&t[6], e->ev[7], x.ev_b[2]); cudaEventElapsedTime(&t[7], e->ev[7], x.ev_b[3]);
+        fprintf(stderr, "[rg timeline] batch of %4zu tracks: gather %6.2f K1 %6.2f-%6.2f K2 -%6.2f | K4 %6.2f-%6.2f K5 -%6.2f results %6.2f\n",
+                x.ids.size(), t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
+    }
 }
 
 // Bytes of device scratch one track needs in a batch (spectra + nz + band gains + PCM)

@@ -92,3 +92,35 @@ if len(sys.argv) > 4 and sys.argv[4] == "e2e_pageable":
         st = eng.stats()
         print("e2e(pageable) rc", rc, "wall %.3fs | audio-h/s %.1f | batches %d | %.1f GB/s" % (
             dt, audio_s / 3600.0 / dt, st.last_batches, sum(len(i) for i in imgs) / dt / 1e9), flush=True)
+
+if len(sys.argv) > 4 and sys.argv[4] == "resident_with_h2d":
+    # does a host->device copy running beside the kernels slow them down?  The resident corpus again, with an unrelated pinned
+    # buffer streaming to the device on another stream for the whole call
+    import threading
+    import torch
+    side = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+    dst = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    cs = torch.cuda.Stream()
+    stop = threading.Event()
+
+    def pump():
+        with torch.cuda.stream(cs):
+            while not stop.is_set():
+                dst.copy_(side, non_blocking=True)
+                cs.synchronize()
+    for with_copy in (False, True, False, True):
+        th = None
+        if with_copy:
+            stop.clear()
+            th = threading.Thread(target=pump)
+            th.start()
+            time.sleep(0.05)
+        t = time.time()
+        rc = lib.rg_analyze_corpus(eng._h, cor, out, None)
+        dt = time.time() - t
+        st = eng.stats()
+        if th:
+            stop.set()
+            th.join()
+        print("resident, H2D beside it: %s | wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f" % (
+            with_copy, dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist), flush=True)
