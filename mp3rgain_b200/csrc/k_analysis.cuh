@@ -19,6 +19,7 @@
 //   through the EXACT kernel at the end of the call.
 #pragma once
 #include "rg_internal.h"
+#include "k_ptx.cuh"
 
 // Coefficients travel as a by-value kernel parameter (constant bank 0), so every coefficient is a uniform operand at a
 // compile-time offset -- no coefficient registers, no shared device symbol between engines.
@@ -230,7 +231,94 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
     peaks[chain_base + ci] = peak;
 }
 
-// the instantiation the engine launches (tools/iir_bench.cu times the alternatives)
+// The time-blocked kernel the engine launches: the same chains and the same arithmetic, but the samples reach the thread through
+// a private ring of two 128-byte lines in shared memory filled by cp.async (eight 16-byte copies per line, issued back to back,
+// one line ahead) instead of float4 loads that rely on the line surviving in L1 from one load to the next.  Alone the kernel is
+// FP64-bound either way; beside the frame-index kernels of the end-to-end path (which stream the file images through the same
+// L1) the L1-dependent form took 6.1 ms per batch instead of 3.6 (profiles/r2_timeline_e2e.log).
+#define K4_RING_BYTES (2 * 8 * 256 * 16)
+template <bool ACCUM>
+__device__ __forceinline__ void iir_run_staged(TdfState& s, const RgCoefFast& c, WinAcc& w, float& peak, const float* __restrict__ p,
+                                               uint32_t n, float4* __restrict__ ring /* + threadIdx.x */) {
+    // head: up to the next 128-byte line
+    uint32_t head = (uint32_t)((128u - (reinterpret_cast<uintptr_t>(p) & 127u)) & 127u) >> 2;
+    if (head > n) head = n;
+#pragma unroll 1
+    for (uint32_t i = 0; i < head; i++) iir_sample<true, ACCUM>(s, c, w, peak, __ldg(p + i));
+    p += head; n -= head;
+    const uint32_t nlines = n >> 5;
+    if (nlines) {
+        const float4* g = reinterpret_cast<const float4*>(p);
+        auto issue = [&](uint32_t line) {
+            float4* dst = ring + (line & 1u) * (8 * 256);
+            const float4* src = g + (size_t)line * 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++) k2_cp_async16(dst + j * 256, src + j);
+        };
+        issue(0);
+        k2_cp_async_commit();
+        if (nlines > 1) issue(1);
+        k2_cp_async_commit();
+#pragma unroll 1
+        for (uint32_t l = 0; l < nlines; l++) {
+            k2_cp_async_wait1();   // every group but the newest has landed: line l is in its slot
+            const float4* cur4 = ring + (l & 1u) * (8 * 256);
+#pragma unroll 1
+            for (int j = 0; j < 8; j++) {
+                const float4 a = cur4[j * 256];
+                const float xs[4] = {a.x, a.y, a.z, a.w};
+                if (!ACCUM || w.tot + 4 < w.win) {
+                    // the window cannot end inside this group: no per-sample bookkeeping
+                    float m = w.wmax;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const double z = iir_step_fast(s, c, xs[q]);
+                        if (ACCUM) { m = fmaxf(m, fabsf(xs[q])); w.sum = __fma_rn(z, z, w.sum); }
+                    }
+                    if (ACCUM) { w.wmax = m; w.tot += 4; }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) iir_sample<true, ACCUM>(s, c, w, peak, xs[q]);
+                }
+            }
+            if (l + 2 < nlines) issue(l + 2);   // into the slot that was just consumed
+            k2_cp_async_commit();
+        }
+        k2_cp_async_wait0();
+    }
+    p += (size_t)nlines * 32; n -= nlines * 32;
+#pragma unroll 1
+    for (uint32_t i = 0; i < n; i++) iir_sample<true, ACCUM>(s, c, w, peak, __ldg(p + i));
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_iir_staged(const RgChain* __restrict__ chains, uint32_t n_chains, float* __restrict__ peaks, uint32_t chain_base,
+             const __grid_constant__ RgCoefFast c) {
+    extern __shared__ __align__(16) unsigned char k4_raw[];
+    float4* ring = reinterpret_cast<float4*>(k4_raw) + threadIdx.x;
+    uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chains) return;
+    const RgChain ch = chains[ci];
+    TdfState s;
+    const bool head = ch.flags & 1u;   // chain starts at the first sample of the track
+#pragma unroll
+    for (int i = 0; i < 10; i++) s.s[i] = head ? c.s0[i] : 0.0;
+    s.u[0] = head ? c.u0[0] : c.uz[0];
+    s.u[1] = head ? c.u0[1] : c.uz[1];
+    WinAcc w;
+    w.sum = 0.0; w.out = ch.wsum; w.mout = ch.wmax; w.wmax = 0.0f; w.tot = 0; w.win = ch.win;
+    float peak = 0.0f;
+    if (ch.n_warm) iir_run_staged<false>(s, c, w, peak, ch.src, ch.n_warm, ring);
+    iir_run_staged<true>(s, c, w, peak, ch.src + ch.n_warm, ch.n_main, ring);
+    if (w.tot) {
+        *w.out = w.sum;
+        *w.mout = w.wmax;
+        peak = fmaxf(peak, w.wmax);
+    }
+    peaks[chain_base + ci] = peak;
+}
+
+// the register-prefetch instantiations (tools/iir_bench.cu times the alternatives; `k4_slim` launches the second)
 #define K4_FAST_THREADS 256
 #define k_iir_fast k_iir_fast_t<3, K4_FAST_THREADS, 2>
 // the "slim" launch: 128-thread CTAs, launched one wave of n_sms CTAs at a time -- one CTA per SM keeps most of the FP64 pipe

@@ -42,3 +42,10 @@ __device__ __forceinline__ uint32_t k2_prmt(uint32_t a, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(0u), "r"(sel));
     return r;
 }
+// cp.async: 16 bytes global -> shared without a register round trip (LDGSTS), tracked in per-thread groups
+__device__ __forceinline__ void k2_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(k2_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void k2_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void k2_cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }

@@ -111,6 +111,7 @@ struct rg_engine {
     uint32_t run_granules = 254;          // granules per K2 CTA (a run re-decodes the two granules before it; setup is per run)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
+    bool k4_staged = true;                // K4 reads its samples through a shared-memory ring (cp.async) instead of float4 loads through L1
     bool timeline = false;                // development aid: print every batch's kernel intervals to stderr
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
@@ -261,6 +262,7 @@ static int engine_init(rg_engine* e, const rg_config* cfg, int dev) {
         f.k2 = c2 * (1.0 + row[23] + row[24]);
     }
     CK(cudaFuncSetAttribute(k_hybrid_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K2Smem)));
+    CK(cudaFuncSetAttribute(k_iir_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, K4_RING_BYTES));
     CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     {
         int sms = 0;
@@ -302,6 +304,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
+    if (!strcmp(key, "k4_staged")) { e->k4_staged = value != 0; return RG_OK; }
     if (!strcmp(key, "timeline")) { e->timeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
     if (!strcmp(key, "run_granules")) {
@@ -515,7 +518,8 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
                     if (c0) e->stats.kernel_launches++;
                 }
             } else
-                k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
+                if (e->k4_staged) k_iir_staged<<<blocks, T, K4_RING_BYTES, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
+                else k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         e->stats.kernel_launches++;
         i0 = i1;
     }

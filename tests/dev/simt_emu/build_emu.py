@@ -31,6 +31,10 @@ PTX_HELPERS = {
     "k2_mbar_wait": "emu::mbar_wait(bar, parity);",
     "k2_pair_sync": "emu::barrier(1 + (pair < 3 ? pair : 3), 64);",
     "k2_prmt": "return emu::prmt(a, 0u, sel);",
+    "k2_cp_async16": "memcpy(smem_dst, gsrc, 16);",      # (the interpreter copies at once: wait / commit have nothing to do)
+    "k2_cp_async_commit": "",
+    "k2_cp_async_wait1": "",
+    "k2_cp_async_wait0": "",
 }
 
 
