@@ -231,11 +231,13 @@ k_iir_fast_t(const RgChain* __restrict__ chains, uint32_t n_chains, float* __res
     peaks[chain_base + ci] = peak;
 }
 
-// The time-blocked kernel the engine launches: the same chains and the same arithmetic, but the samples reach the thread through
-// a private ring of two 128-byte lines in shared memory filled by cp.async (eight 16-byte copies per line, issued back to back,
-// one line ahead) instead of float4 loads that rely on the line surviving in L1 from one load to the next.  Alone the kernel is
-// FP64-bound either way; beside the frame-index kernels of the end-to-end path (which stream the file images through the same
-// L1) the L1-dependent form took 6.1 ms per batch instead of 3.6 (profiles/r2_timeline_e2e.log).
+// The time-blocked kernel of the END-TO-END path: the same chains and the same arithmetic, but the samples reach the thread
+// through a private ring of two 128-byte lines in shared memory filled by cp.async (eight 16-byte copies per line, issued back
+// to back, one line ahead) instead of float4 loads that rely on the line surviving in L1 from one load to the next.  While file
+// images are still arriving, the frame-index kernels of the later groups run beside K4 and stream those images through the same
+// L1: the register-prefetch kernel then took 6.1 ms per batch instead of 3.6, this one 4.8 (profiles/r2_timeline_e2e.log:
+// 112.5 -> 106.0 ms per 1000 tracks end to end).  Alone it is 6 % slower than k_iir_fast (28.6 vs 26.9 ms: four samples per
+// loop trip instead of twelve), so resident corpora keep that one.
 #define K4_RING_BYTES (2 * 8 * 256 * 16)
 template <bool ACCUM>
 __device__ __forceinline__ void iir_run_staged(TdfState& s, const RgCoefFast& c, WinAcc& w, float& peak, const float* __restrict__ p,
@@ -263,7 +265,7 @@ __device__ __forceinline__ void iir_run_staged(TdfState& s, const RgCoefFast& c,
         for (uint32_t l = 0; l < nlines; l++) {
             k2_cp_async_wait1();   // every group but the newest has landed: line l is in its slot
             const float4* cur4 = ring + (l & 1u) * (8 * 256);
-#pragma unroll 1
+#pragma unroll 1   // (measured: unrolling this loop by 2 or 4 makes the kernel 17 % slower)
             for (int j = 0; j < 8; j++) {
                 const float4 a = cur4[j * 256];
                 const float xs[4] = {a.x, a.y, a.z, a.w};

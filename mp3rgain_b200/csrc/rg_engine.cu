@@ -83,6 +83,7 @@ struct BatchCtx {
     cudaEvent_t ev_b[4] = {};              // analysis stream: K4 start, K4 end = K5 start, K5 end, results on the host
     // host bookkeeping of the batch in flight
     bool busy = false, decoded = false, exact = false;
+    bool images_arriving = false;          // the batch belongs to a call whose file images are still crossing the bus (K4 then reads through its ring)
     std::vector<uint32_t> ids;             // caller-side index of every track of the batch
     std::vector<PcmTrack> pt;
     size_t n_chains = 0;
@@ -111,7 +112,7 @@ struct rg_engine {
     uint32_t run_granules = 254;          // granules per K2 CTA (a run re-decodes the two granules before it; setup is per run)
     uint32_t k4_slim = 0;                 // > 0: k_iir_fast as waves of k4_slim 128-thread CTAs per SM (see k_analysis.cuh)
     int n_sms = 148;
-    bool k4_staged = true;                // K4 reads its samples through a shared-memory ring (cp.async) instead of float4 loads through L1
+    int k4_staged = -1;                   // K4 through the shared-memory ring: 1 always, 0 never, -1 (default) while file images are still arriving
     bool timeline = false;                // development aid: print every batch's kernel intervals to stderr
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
@@ -304,7 +305,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
-    if (!strcmp(key, "k4_staged")) { e->k4_staged = value != 0; return RG_OK; }
+    if (!strcmp(key, "k4_staged")) { e->k4_staged = (int)value; return RG_OK; }
     if (!strcmp(key, "timeline")) { e->timeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
     if (!strcmp(key, "run_granules")) {
@@ -518,7 +519,7 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
                     if (c0) e->stats.kernel_launches++;
                 }
             } else
-                if (e->k4_staged) k_iir_staged<<<blocks, T, K4_RING_BYTES, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
+                if (e->k4_staged == 1 || (e->k4_staged < 0 && c.images_arriving)) k_iir_staged<<<blocks, T, K4_RING_BYTES, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
                 else k_iir_fast<<<blocks, T, 0, st>>>(c.d_chains.as<RgChain>() + i0, cnt, d_peaks_sorted, (uint32_t)i0, e->coef_fast[r]);
         e->stats.kernel_launches++;
         i0 = i1;
@@ -609,6 +610,7 @@ extern "C" int rg_analyze_pcm_f32(rg_engine* e, const float* const* planes, int 
     BatchCtx& c = e->ctx[0];
     c.pt.assign(1, t);
     c.hist_host = hist_out;
+    c.images_arriving = false;
     // (the reference's 88.2 kHz coefficient row has poles outside the unit circle: nothing is ever forgotten, so that rate is
     // always filtered serially -- no Layer III stream has it, only caller-supplied PCM)
     const bool exact = (e->flags & RG_FLAG_EXACT_IIR) != 0 || sample_rate == 88200;

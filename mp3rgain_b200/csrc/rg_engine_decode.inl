@@ -472,6 +472,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
         x.ids.resize(t1 - next);
         for (size_t i = next; i < t1; i++) x.ids[i - next] = (uint32_t)i;
         x.hist_host = hist_out ? hist_out + next * RG_HIST_BINS : nullptr;
+        x.images_arriving = c->pending_in != nullptr;
         rc = decode_enqueue(e, c, ip, x);
         if (rc == RG_OK) rc = stage_b_enqueue(e, x, exact_all, hist_out != nullptr, d_album_hist, d_album_peak, !exact_all, true);
         if (rc != RG_OK) return fail(rc);
