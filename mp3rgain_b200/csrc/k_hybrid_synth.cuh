@@ -29,7 +29,8 @@
 #define K2_GC 8            // granule-channels per batch, one per warp
 #define K2_SLOTS 10        // slots of A / S2: (G+1) granules x channels = 5x2 (stereo) or 9x1 (mono)
 #define K2_MAX_G 256       // granules per run, including the two replayed ones
-#define ROW 33             // padded row of 32 values
+#define ROW 34             // padded row of 32 values: 8-byte aligned for the float2 accesses of P3, whose threads (one row each, 136 bytes
+                           // apart, slots 2448 bytes apart) then fall on distinct bank pairs; P2 and P4 access a row across the lanes
 #define SLOTF (18 * ROW)   // floats per slot
 
 struct __align__(2) GranInfo {
@@ -56,10 +57,10 @@ struct K2Smem {
     uint8_t istab[K2_GC / 2][64];             // intensity stereo: is_pos per band of the right channel's partition, 255 = not intensity coded
     int istop[K2_GC / 2][4];                  // highest non-zero band of the right channel: [0] long sfb, [1..3] short sfb per window
     float isr[2][8];                          // MPEG-1: is_pos -> left / right factor
-    float isl[2][2][32];                      // MPEG-2: [intensity_scale][left / right][is_pos]
     uint8_t iscale[K2_GC / 2];                // MPEG-2: intensity_scale of the granule's right channel
     alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
 };
+static_assert(3 * (sizeof(K2Smem) + 1024) <= 228 * 1024, "three CTAs of K2 must fit one SM's shared memory");
 
 // Compile-time loop: the body receives its index as an integral_constant, so table entries indexed with it are constant
 // expressions and reach the SASS as instruction immediates (FFMA/FMUL imm32) -- no constant-bank or uniform-register
@@ -72,29 +73,49 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
+// Lee's recursive DCT-II split on float2: two independent transforms of the same size side by side (the two halves of a
+// 32-point transform after its first split use the same secants), every operation one packed instruction with the secant as
+// the broadcast operand:  g[i] = x[i] + x[N-1-i],  h[i] = (x[i] - x[N-1-i]) * sec[i],  X[2k] = G[k],  X[2k+1] = H[k] + H[k+1].
 template <int N, int OFF>
-struct Dct2 {
-    static __device__ __forceinline__ void run(float (&x)[N]) {
-        float g[N / 2], h[N / 2];
+struct Dct2x2 {
+    static __device__ __forceinline__ void run(float2 (&x)[N]) {
+        float2 g[N / 2], h[N / 2];
         static_for<0, N / 2>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             constexpr float sec = L3_DCT_SEC[OFF + i];
-            g[i] = __fadd_rn(x[i], x[N - 1 - i]);
-            h[i] = __fmul_rn(__fsub_rn(x[i], x[N - 1 - i]), sec);
+            g[i] = k2_fadd2(x[i], x[N - 1 - i]);
+            h[i] = k2_fmul2(k2_fsub2(x[i], x[N - 1 - i]), make_float2(sec, sec));
         });
-        Dct2<N / 2, OFF + N / 2>::run(g);
-        Dct2<N / 2, OFF + N / 2>::run(h);
+        Dct2x2<N / 2, OFF + N / 2>::run(g);
+        Dct2x2<N / 2, OFF + N / 2>::run(h);
 #pragma unroll
         for (int k = 0; k < N / 2; k++) {
             x[2 * k] = g[k];
-            x[2 * k + 1] = (k + 1 < N / 2) ? __fadd_rn(h[k], h[k + 1]) : h[k];
+            x[2 * k + 1] = (k + 1 < N / 2) ? k2_fadd2(h[k], h[k + 1]) : h[k];
         }
     }
 };
 template <int OFF>
-struct Dct2<1, OFF> {
-    static __device__ __forceinline__ void run(float (&)[1]) {}
+struct Dct2x2<1, OFF> {
+    static __device__ __forceinline__ void run(float2 (&)[1]) {}
 };
+// 32-point transform of one row: the first split in scalar form, then both 16-point halves as ONE packed transform
+// (the halves never mix before the final interleave, so each half of a packed operation is the scalar recursion's operation)
+__device__ __forceinline__ void k2_dct32(float (&x)[32]) {
+    float2 z[16];
+    static_for<0, 16>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        constexpr float sec = L3_DCT_SEC[i];
+        z[i].x = __fadd_rn(x[i], x[31 - i]);
+        z[i].y = __fmul_rn(__fsub_rn(x[i], x[31 - i]), sec);
+    });
+    Dct2x2<16, 16>::run(z);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        x[2 * k] = z[k].x;
+        x[2 * k + 1] = (k + 1 < 16) ? __fadd_rn(z[k].y, z[k + 1].y) : z[k].y;
+    }
+}
 
 // position of IMDCT-36 output i in the 18-point DCT-IV vector u: i<9: u[i+9]; 9..26: u[26-i]; 27..35: u[i-27]
 __device__ __forceinline__ constexpr int idx36(int i) { return i < 9 ? i + 9 : (i < 27 ? 26 - i : i - 27); }
@@ -124,58 +145,59 @@ __device__ __forceinline__ GranInfo k2_parse_gi(const uint8_t* __restrict__ corp
     return gi;
 }
 
-// 3-point DFT of complex numbers (W3 = e^{-2 pi i/3}): X0 = x0 + s, X1 = m - i q, X2 = m + i q with s = x1 + x2,
-// m = x0 - s/2 (one fmaf per component), q = (sqrt3/2)(x1 - x2).  Operation for operation the oracle's dft3().
-__device__ __forceinline__ void k2_dft3(float x0r, float x0i, float x1r, float x1i, float x2r, float x2i,
-                                        float& y0r, float& y0i, float& y1r, float& y1i, float& y2r, float& y2i) {
-    const float sr = __fadd_rn(x1r, x2r), si = __fadd_rn(x1i, x2i), dr = __fsub_rn(x1r, x2r), di = __fsub_rn(x1i, x2i);
-    y0r = __fadd_rn(x0r, sr); y0i = __fadd_rn(x0i, si);
-    const float mr = fmaf(-0.5f, sr, x0r), mi = fmaf(-0.5f, si, x0i);
-    const float qr = __fmul_rn(L3_SQRT3_2, dr), qi = __fmul_rn(L3_SQRT3_2, di);
-    y1r = __fadd_rn(mr, qi); y1i = __fsub_rn(mi, qr);
-    y2r = __fsub_rn(mr, qi); y2i = __fadd_rn(mi, qr);
+// Complex numbers are float2 {re, im}; every operation below is one packed f32x2 instruction on both components.  Swapping the
+// halves of an operand and negating one of them (multiplication by -i or +i) are operand modifiers of those instructions, not
+// instructions of their own.
+// 3-point DFT (W3 = e^{-2 pi i/3}): X0 = x0 + s, X1 = m - i q, X2 = m + i q with s = x1 + x2, m = x0 - s/2 (one fma per
+// component), q = (sqrt3/2)(x1 - x2).  Operation for operation the f32 decode contract's dft3.
+__device__ __forceinline__ void k2_dft3(float2 x0, float2 x1, float2 x2, float2& y0, float2& y1, float2& y2) {
+    const float2 s = k2_fadd2(x1, x2), d = k2_fsub2(x1, x2);
+    y0 = k2_fadd2(x0, s);
+    const float2 m = k2_ffma2(make_float2(-0.5f, -0.5f), s, x0);
+    const float2 q = k2_fmul2(make_float2(L3_SQRT3_2, L3_SQRT3_2), d);
+    const float2 miq = make_float2(q.y, -q.x);   // -i q
+    y1 = k2_fadd2(m, miq);                       // (mr + qi, mi - qr)
+    y2 = k2_fsub2(m, miq);                       // (mr - qi, mi + qr)
 }
 
-// 18-point DCT-IV u[m] = sum_k X[k] cos(pi/72 (2m+1)(2k+1)) through a 9-point complex FFT (3 x 3 Cooley-Tukey), 172 FP
-// instructions instead of the 324 FFMAs of the matrix form; all twiddles are instruction immediates:
+// 18-point DCT-IV u[m] = sum_k X[k] cos(pi/72 (2m+1)(2k+1)) through a 9-point complex FFT (3 x 3 Cooley-Tukey), 84 packed
+// instructions (172 in scalar form, 324 FFMAs in matrix form); all twiddles are instruction immediates:
 //   v[n] = (X[2n] + i X[17-2n]) e^{-i pi (4n+1)/72},  V = FFT9(v),  y[k] = V[k] e^{-i pi k/18},  u[2k] = Re y[k], u[17-2k] = -Im y[k]
-// A complex product (a + i b)(c + i d) is evaluated as (fmaf(-b, d, a*c), fmaf(a, d, b*c)) -- the oracle's dct4_18().
+// A complex product (a + i b)(c + i d) is evaluated as (fmaf(-b, d, a*c), fmaf(a, d, b*c)): one packed multiplication by c and
+// one packed fma of (-b, a) with d.
 __device__ __forceinline__ void k2_dct4_18(const float (&X)[18], float (&u)[18]) {
-    float vr[9], vi[9];
+    float2 v[9];
     static_for<0, 9>([&](auto nc) {
         constexpr int n = decltype(nc)::value;
         constexpr float c = L3_D4_PRE[0][n], s = L3_D4_PRE[1][n];
         const float a = X[2 * n], b = X[17 - 2 * n];
-        vr[n] = fmaf(b, s, __fmul_rn(a, c));
-        vi[n] = fmaf(-a, s, __fmul_rn(b, c));
+        v[n] = k2_ffma2(make_float2(b, -a), make_float2(s, s), k2_fmul2(make_float2(a, b), make_float2(c, c)));   // (a + i b)(c - i s)
     });
-    float tr[3][3], ti[3][3];   // [b][c]
+    float2 t[3][3];   // [b][c]
     static_for<0, 3>([&](auto bc) {
         constexpr int b = decltype(bc)::value;
-        k2_dft3(vr[b], vi[b], vr[3 + b], vi[3 + b], vr[6 + b], vi[6 + b], tr[b][0], ti[b][0], tr[b][1], ti[b][1], tr[b][2], ti[b][2]);
+        k2_dft3(v[b], v[3 + b], v[6 + b], t[b][0], t[b][1], t[b][2]);
     });
     static_for<0, 4>([&](auto ic) {
         constexpr int b = 1 + decltype(ic)::value / 2, c = 1 + decltype(ic)::value % 2;
         constexpr int e = b * c == 1 ? 0 : (b * c == 2 ? 1 : 2);   // W9^{bc}: exponents 1, 2, 4
         constexpr float wr = L3_D4_W9[0][e], wi = L3_D4_W9[1][e];
-        const float zr = tr[b][c], zi = ti[b][c];
-        tr[b][c] = fmaf(-zi, wi, __fmul_rn(zr, wr));
-        ti[b][c] = fmaf(zr, wi, __fmul_rn(zi, wr));
+        const float2 z = t[b][c];
+        t[b][c] = k2_ffma2(make_float2(-z.y, z.x), make_float2(wi, wi), k2_fmul2(z, make_float2(wr, wr)));
     });
     static_for<0, 3>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        float yr[3], yi[3];
-        k2_dft3(tr[0][c], ti[0][c], tr[1][c], ti[1][c], tr[2][c], ti[2][c], yr[0], yi[0], yr[1], yi[1], yr[2], yi[2]);
+        float2 y[3];
+        k2_dft3(t[0][c], t[1][c], t[2][c], y[0], y[1], y[2]);
         static_for<0, 3>([&](auto dc) {
             constexpr int d = decltype(dc)::value, k = c + 3 * d;
-            float re = yr[d], im = yi[d];
+            float2 r = y[d];
             if constexpr (k != 0) {
                 constexpr float pc = L3_D4_POST[0][k], ps = L3_D4_POST[1][k];
-                re = fmaf(yi[d], ps, __fmul_rn(yr[d], pc));
-                im = fmaf(-yr[d], ps, __fmul_rn(yi[d], pc));
+                r = k2_ffma2(make_float2(y[d].y, -y[d].x), make_float2(ps, ps), k2_fmul2(y[d], make_float2(pc, pc)));   // y (pc - i ps)
             }
-            u[2 * k] = re;
-            u[17 - 2 * k] = -im;
+            u[2 * k] = r.x;
+            u[17 - 2 * k] = -r.y;
         });
     });
 }
@@ -206,19 +228,23 @@ __device__ __forceinline__ void k2_polyphase(const K2Smem& S, const float* __res
     float mx = 0.0f;
 #pragma unroll
     for (int r = 0; r < 15; r++) { Av[r] = prv[r * ROW + ia]; Bv[r] = prv[r * ROW + ib]; }
+    // two output rows (t, t + 1) per chain, as the two halves of packed f32x2 operations: each half is the scalar fmaf chain of
+    // its row, p ascending (FFMA2 with the window weight as the broadcast operand: 144 instructions for the 288 multiply-adds)
 #pragma unroll
-    for (int t = 0; t < 18; t++) {
+    for (int t = 0; t < 18; t += 2) {
         Av[15 + t] = cur[t * ROW + ia];
         Bv[15 + t] = cur[t * ROW + ib];
-        float a = 0.0f;
+        Av[16 + t] = cur[(t + 1) * ROW + ia];
+        Bv[16 + t] = cur[(t + 1) * ROW + ib];
+        float2 a = make_float2(0.0f, 0.0f);
 #pragma unroll
         for (int p = 0; p < 8; p++) {
-            a = fmaf(Av[15 + t - 2 * p], wa[p], a);
-            a = fmaf(Bv[15 + t - 2 * p - 1], wb[p], a);
+            a = k2_ffma2(make_float2(Av[15 + t - 2 * p], Av[16 + t - 2 * p]), make_float2(wa[p], wa[p]), a);
+            a = k2_ffma2(make_float2(Bv[14 + t - 2 * p], Bv[15 + t - 2 * p]), make_float2(wb[p], wb[p]), a);
         }
-        if (CLAMP) a = fminf(1.0f, fmaxf(-1.0f, a));
-        if (PEAK) mx = fmaxf(mx, fabsf(a));
-        else dst[32 * t] = a;
+        if (CLAMP) { a.x = fminf(1.0f, fmaxf(-1.0f, a.x)); a.y = fminf(1.0f, fmaxf(-1.0f, a.y)); }
+        if (PEAK) mx = fmaxf(mx, fmaxf(fabsf(a.x), fabsf(a.y)));
+        else { dst[32 * t] = a.x; dst[32 * t + 32] = a.y; }
     }
     if (PEAK) {
         const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));   // non-negative floats order like their bit patterns
@@ -255,7 +281,6 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
     }
     if (tid < 32) { S.ia[tid] = T->synth_ia[tid]; S.ib[tid] = T->synth_ib[tid]; }
     if (tid < 14) S.isr[tid / 7][tid % 7] = T->is_ratio[tid / 7][tid % 7];
-    if (tid < 128) (&S.isl[0][0][0])[tid] = (&T->is_lsf[0][0][0])[tid];
     for (int i = tid; i < K2_SLOTS * SLOTF; i += K2_THREADS) { (&S.A[0][0])[i] = 0.0f; (&S.S2[0][0])[i] = 0.0f; }
     if (tid == 0) k2_mbar_init(&S.mbar, 1);
     // side info of every granule-channel of the run, one thread each
@@ -401,42 +426,37 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
                 for (int it = 0; it < NIT; it++) {
                     const int pr = lane + 32 * my_ch + 32 * NCH * it;
                     if (pr >= lim9) break;
-                    float v[2][2];
+                    // the two lines of a pair are the halves of packed f32x2 operations; the sign goes onto the table value
+                    // before the multiplication ((-p) * g == -(p * g) in IEEE arithmetic)
+                    float2 v[2];
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++) {
                         const uint32_t packed = pk[it][ch];
                         const float gn = gq[it][ch];
                         const int q0 = (int)(int16_t)(packed & 0xFFFFu), q1 = (int)packed >> 16;
-                        const float m0 = __fmul_rn(__ldg(&T->pow43[abs(q0)]), gn);
-                        const float m1 = __fmul_rn(__ldg(&T->pow43[abs(q1)]), gn);
-                        v[ch][0] = q0 < 0 ? -m0 : m0;
-                        v[ch][1] = q1 < 0 ? -m1 : m1;
+                        const float p0 = __uint_as_float(__float_as_uint(__ldg(&T->pow43[abs(q0)])) | ((packed << 16) & 0x80000000u));
+                        const float p1 = __uint_as_float(__float_as_uint(__ldg(&T->pow43[abs(q1)])) | (packed & 0x80000000u));
+                        v[ch] = k2_fmul2(make_float2(p0, p1), make_float2(gn, gn));
                     }
                     uint32_t ipos = 255;
                     if (!PLAIN && NCH == 2 && ist) ipos = S.istab[my_gi][S.code[tsel1][2 * pr]];
                     if (!PLAIN && NCH == 2 && ipos != 255) {
-                        const float kl = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][0][ipos & 31] : S.isr[0][ipos & 7];
-                        const float kr = tr.gpf == 1 ? S.isl[S.iscale[my_gi]][1][ipos & 31] : S.isr[1][ipos & 7];
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const float l = v[0][h];
-                            v[0][h] = __fmul_rn(l, kl);
-                            v[NCH - 1][h] = __fmul_rn(l, kr);
-                        }
+                        const float kl = tr.gpf == 1 ? __ldg(&T->is_lsf[S.iscale[my_gi]][0][ipos & 31]) : S.isr[0][ipos & 7];   // (MPEG-2 intensity stereo is rare: its table stays in global memory)
+                        const float kr = tr.gpf == 1 ? __ldg(&T->is_lsf[S.iscale[my_gi]][1][ipos & 31]) : S.isr[1][ipos & 7];
+                        const float2 l = v[0];
+                        v[0] = k2_fmul2(l, make_float2(kl, kl));
+                        v[NCH - 1] = k2_fmul2(l, make_float2(kr, kr));
                     } else if (NCH == 2 && ms) {
-#pragma unroll
-                        for (int h = 0; h < 2; h++) {
-                            const float a = v[0][h], c = v[NCH - 1][h];
-                            v[0][h] = __fmul_rn(__fadd_rn(a, c), L3_INV_SQRT2);
-                            v[NCH - 1][h] = __fmul_rn(__fsub_rn(a, c), L3_INV_SQRT2);
-                        }
+                        const float2 l = v[0], r = v[NCH - 1];
+                        v[0] = k2_fmul2(k2_fadd2(l, r), make_float2(L3_INV_SQRT2, L3_INV_SQRT2));
+                        v[NCH - 1] = k2_fmul2(k2_fsub2(l, r), make_float2(L3_INV_SQRT2, L3_INV_SQRT2));
                     }
 #pragma unroll
                     for (int ch = 0; ch < NCH; ch++) {
                         float* x = ch ? x1 : x0;
                         const int tsel = ch ? tsel1 : tsel0;
-                        if (PLAIN || tsel == 0) *reinterpret_cast<float2*>(x + 2 * pr) = make_float2(v[ch][0], v[ch][1]);
-                        else { x[S.scat[tsel - 1][2 * pr]] = v[ch][0]; x[S.scat[tsel - 1][2 * pr + 1]] = v[ch][1]; }
+                        if (PLAIN || tsel == 0) *reinterpret_cast<float2*>(x + 2 * pr) = v[ch];
+                        else { x[S.scat[tsel - 1][2 * pr]] = v[ch].x; x[S.scat[tsel - 1][2 * pr + 1]] = v[ch].y; }
                     }
                 }
             };
@@ -540,12 +560,14 @@ __device__ __forceinline__ void k2_body(K2Smem& S, const uint8_t* __restrict__ c
             if (g3 < gcount) {
                 float* a = S.A[(g3 % NS) * NCH + q % NCH] + t * ROW;
                 const float* s = S.S2[((g3 + NS - 1) % NS) * NCH + q % NCH] + t * ROW;
+                float2* a2 = reinterpret_cast<float2*>(a);
+                const float2* s2 = reinterpret_cast<const float2*>(s);
                 float x[32];
 #pragma unroll
-                for (int i = 0; i < 32; i++) x[i] = __fadd_rn(a[i], s[i]);
-                Dct2<32, 0>::run(x);
+                for (int i = 0; i < 16; i++) { const float2 v = k2_fadd2(a2[i], s2[i]); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+                k2_dct32(x);
 #pragma unroll
-                for (int i = 0; i < 32; i++) a[i] = x[i];
+                for (int i = 0; i < 16; i++) a2[i] = make_float2(x[2 * i], x[2 * i + 1]);
             }
         } else if (tid == 5 * 32 && b + 1 < n_batches) {
             issue_copy(b + 1);   // P1 of this batch has consumed the staging buffers (barrier above)

@@ -49,3 +49,39 @@ __device__ __forceinline__ void k2_cp_async16(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void k2_cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void k2_cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// Packed f32x2 arithmetic (sm_100+: FFMA2 / FADD2 / FMUL2 in the SASS): two IEEE round-to-nearest operations per instruction, each
+// half rounded exactly like the scalar __fmaf_rn / __fadd_rn / __fmul_rn (no flush-to-zero, no contraction across halves).  The
+// kernels that use them are bound by instruction issue, not by the FMA pipe: the pipe does the same work, in half the issue
+// slots.  A half built as make_float2(w, w) costs nothing: ptxas folds it into the instruction's scalar-broadcast operand.
+__device__ __forceinline__ float2 k2_ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 k2_fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 k2_fsub2(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// The packed product is written as fma(a, b, -0.0): x + (-0.0) == x for every x, signed zeros included.  A plain mul.rn.f32x2 is
+// not safe: ptxas 12.9 contracts it with a following add.rn.f32x2 / sub.rn.f32x2 into one FFMA2 (it honours .rn for the scalar
+// forms only; --fmad=false does not stop it, and a literal -0.0 addend is folded back into a multiplication first), which rounds
+// once instead of twice.  The -0.0 therefore comes from constant memory, where ptxas cannot see its value; it costs one register
+// per thread and no instruction (FFMA2 takes it as a scalar-broadcast operand).  tools/f32x2_check.cu checks the instructions
+// themselves against the scalar forms on the device.
+__constant__ float K2_NEGZERO = -0.0f;
+__device__ __forceinline__ float2 k2_fmul2(float2 a, float2 b) {
+    float2 d;
+    const float nz = K2_NEGZERO;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %6}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(nz));
+    return d;
+}

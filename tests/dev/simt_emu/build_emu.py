@@ -35,6 +35,11 @@ PTX_HELPERS = {
     "k2_cp_async_commit": "",
     "k2_cp_async_wait1": "",
     "k2_cp_async_wait0": "",
+    # packed f32x2: each half is the scalar IEEE operation (the build has -ffp-contract=off; fmaf is the fused form)
+    "k2_ffma2": "return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));",
+    "k2_fadd2": "return make_float2(a.x + b.x, a.y + b.y);",
+    "k2_fsub2": "return make_float2(a.x - b.x, a.y - b.y);",
+    "k2_fmul2": "return make_float2(a.x * b.x, a.y * b.y);",
 }
 
 
