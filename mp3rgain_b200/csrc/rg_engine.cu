@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -114,8 +115,11 @@ struct rg_engine {
     int n_sms = 148;
     int k4_staged = -1;                   // K4 through the shared-memory ring: 1 always, 0 never, -1 (default) while file images are still arriving
     bool timeline = false;                // development aid: print every batch's kernel intervals to stderr
+    std::chrono::steady_clock::time_point t0_host;   // (timeline) host clock at the call's first event
+    double host_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_host).count(); }
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
+    double group_first_div = 12.0, group_growth = 1.6;   // size schedule of the first groups (rg_engine_decode.inl, index_enqueue)
     RgCoefExact coef_exact[12];      // K4 coefficient rows (passed by value at launch)
     RgCoefFast coef_fast[12];
     double edge_tol = 1e-9;
@@ -307,6 +311,8 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
     if (!strcmp(key, "k4_staged")) { e->k4_staged = (int)value; return RG_OK; }
     if (!strcmp(key, "timeline")) { e->timeline = value != 0; return RG_OK; }
+    if (!strcmp(key, "group_first_div")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_first_div = value; return RG_OK; }
+    if (!strcmp(key, "group_growth")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_growth = value; return RG_OK; }
     if (!strcmp(key, "group_bytes_min")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_bytes_min = (uint64_t)value; return RG_OK; }
     if (!strcmp(key, "run_granules")) {
         if (value < 2 || value > K2_MAX_G - 2) return RG_ERR_INVALID_ARG;

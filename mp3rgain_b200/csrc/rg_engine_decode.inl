@@ -122,14 +122,20 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     // the number of tracks); about eight, never smaller than 32 MiB, when the bytes are still arriving from the host, so
     // that indexing starts as soon as the first group has landed
     const uint64_t gbytes = (e->pipeline && c->pending_in) ? std::max<uint64_t>(bytes / 8 + 1, e->group_bytes_min) : ~0ull;
-    // (the first two groups are a quarter and a half of that: the pipeline starts as soon as a few files have landed.  Shrinking
-    // the LAST groups as well -- so that a copy-bound call ends sooner after its last byte -- was tried and changed nothing
-    // measurable on one GPU, pinned or pageable: profiles/r2_e2e_group_sweep.log)
+    // The first groups are smaller -- gbytes / group_first_div, each next one group_growth times its predecessor until gbytes is
+    // reached -- so that decoding starts as soon as a few files have landed.  The bytes arrive about 1.7 times faster than the
+    // kernels consume them, so a group may be up to that much larger than the one being decoded without starving the decode
+    // stream; doubling (the first schedule: 1/4, 1/2, 1) left 1.7 and 3.0 ms of bubbles behind the first two batches
+    // (profiles/r2_timeline_e2e_groups.log).  Shrinking the LAST groups as well -- so that a copy-bound call ends sooner after
+    // its last byte -- was tried and changed nothing measurable on one GPU, pinned or pageable (profiles/r2_e2e_group_sweep.log).
     uint64_t acc = 0;
+    double lim = gbytes == ~0ull ? 0.0 : std::max<double>((double)gbytes / e->group_first_div, 1.0);
     for (size_t i = 0; i < n; i++) {
-        const size_t k = ip.group_begin.size();   // groups started so far
-        const uint64_t lim = gbytes == ~0ull ? gbytes : (k <= 1 ? gbytes / 4 : (k == 2 ? gbytes / 2 : gbytes));
-        if (i == 0 || acc >= lim) { ip.group_begin.push_back(i); acc = 0; }
+        if (i == 0 || (gbytes != ~0ull && (double)acc >= lim)) {
+            if (i) lim = std::min<double>((double)gbytes, lim * e->group_growth);
+            ip.group_begin.push_back(i);
+            acc = 0;
+        }
         acc += c->len[i];
     }
     ip.group_begin.push_back(n);
@@ -232,6 +238,13 @@ static int index_absorb(rg_engine* e, rg_corpus* c, IndexPlan& ip, size_t upto, 
         CK(cudaEventSynchronize(e->pool_event(4 * g + 3)));
         float ms = 0;
         if (cudaEventElapsedTime(&ms, e->pool_event(4 * g + 1), e->pool_event(4 * g + 2)) == cudaSuccess) e->stats.last_ms_index += ms;
+        if (e->timeline) {
+            float t[4] = {};
+            if (c->pending_in) cudaEventElapsedTime(&t[0], e->ev[7], e->pool_event(4 * g));
+            for (int q = 1; q < 4; q++) cudaEventElapsedTime(&t[q], e->ev[7], e->pool_event(4 * g + q));
+            fprintf(stderr, "[rg timeline] group %2zu (%4zu tracks): copied %6.2f  K0 %6.2f-%6.2f  meta on host %6.2f  absorbed at host time %6.2f\n",
+                    g, ip.group_begin[g + 1] - ip.group_begin[g], t[0], t[1], t[2], t[3], e->host_ms());
+        }
         for (size_t i = ip.group_begin[g]; i < ip.group_begin[g + 1]; i++) {
             const TrackMeta& m = ip.meta[i];
             int st = m.status;
@@ -393,6 +406,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
     if (first_bad) *first_bad = -1;
     if (!n) return RG_OK;
     CK(cudaEventRecord(e->ev[7], e->stream));
+    e->t0_host = std::chrono::steady_clock::now();
     const bool exact_all = (e->flags & RG_FLAG_EXACT_IIR) != 0;
     IndexPlan ip;
     int rc = index_enqueue(e, c, ip);
@@ -473,8 +487,11 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
         for (size_t i = next; i < t1; i++) x.ids[i - next] = (uint32_t)i;
         x.hist_host = hist_out ? hist_out + next * RG_HIST_BINS : nullptr;
         x.images_arriving = c->pending_in != nullptr;
+        const double h0 = e->timeline ? e->host_ms() : 0.0;
         rc = decode_enqueue(e, c, ip, x);
+        const double h1 = e->timeline ? e->host_ms() : 0.0;
         if (rc == RG_OK) rc = stage_b_enqueue(e, x, exact_all, hist_out != nullptr, d_album_hist, d_album_peak, !exact_all, true);
+        if (e->timeline) fprintf(stderr, "[rg timeline] host: batch %zu (%zu tracks) decode_enqueue %6.2f-%6.2f stage_b_enqueue -%6.2f\n", k, t1 - next, h0, h1, e->host_ms());
         if (rc != RG_OK) return fail(rc);
         x.busy = true;
         e->stats.last_batches++;

@@ -107,7 +107,7 @@ def build(force=False):
         with open(os.path.join(SCRATCH, "mp3rgain_b200", "csrc", dst), "w") as fh:
             fh.write(text)
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w"] + (
-           ["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + [
+           ["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + os.environ.get("RG_EMU_EXTRA", "").split() + [
            "-I", HERE, "-o", OUT, os.path.join(SCRATCH, "mp3rgain_b200", "csrc", "rg_engine.cpp")]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:

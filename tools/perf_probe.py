@@ -21,6 +21,7 @@ t = time.time()
 pool = synth_corpus.GroupPool(seed=1, n_groups=256, group_len=32, intensity_prob=0.02)
 imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
 print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
+_lib.LIB_PATH = os.environ.get("RG_LIB", _lib.LIB_PATH)   # a variant build of the engine (kernel experiments)
 lib = _lib.load()
 eng = m.Engine(device=0, exact=exact)
 for kv in os.environ.get("RG_OPTS", "").split(","):   # e.g. RG_OPTS=k2_smem_pad=30000,iir_block_windows=16
