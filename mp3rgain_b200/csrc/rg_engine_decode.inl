@@ -126,8 +126,10 @@ static int index_enqueue(rg_engine* e, rg_corpus* c, IndexPlan& ip) {
     // reached -- so that decoding starts as soon as a few files have landed.  The bytes arrive about 1.7 times faster than the
     // kernels consume them, so a group may be up to that much larger than the one being decoded without starving the decode
     // stream; doubling (the first schedule: 1/4, 1/2, 1) left 1.7 and 3.0 ms of bubbles behind the first two batches
-    // (profiles/r2_timeline_e2e_groups.log).  Shrinking the LAST groups as well -- so that a copy-bound call ends sooner after
-    // its last byte -- was tried and changed nothing measurable on one GPU, pinned or pageable (profiles/r2_e2e_group_sweep.log).
+    // (profiles/r2_timeline_e2e_groups.log).
+    // Shrinking the LAST groups as well -- so that a bus-bound call ends sooner after its last byte -- changed nothing, neither on
+    // one GPU (pinned or pageable: profiles/r2_e2e_group_sweep.log) nor with eight ranks pulling through one host at once
+    // (profiles/r2_e2e_8gpu_tail_groups.log), and was removed again.
     uint64_t acc = 0;
     double lim = gbytes == ~0ull ? 0.0 : std::max<double>((double)gbytes / e->group_first_div, 1.0);
     for (size_t i = 0; i < n; i++) {

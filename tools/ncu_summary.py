@@ -20,6 +20,7 @@ rep, out_csv, comment = sys.argv[1], sys.argv[2], sys.argv[3]
 rows = list(csv.reader(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}
+data = [r for r in data if not r[col["Kernel Name"]].startswith("k_fetch_desc")]   # descriptor fetches: microseconds, not part of the summary
 names = [r[col["Kernel Name"]] for r in data]
 short = [n.split("(")[0].replace("void ", "") for n in names]
 stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
@@ -46,6 +47,15 @@ if "--traffic" in sys.argv:
         old = json.load(open(out_json))
     except Exception:  # noqa: BLE001
         old = {}
+    # a kernel this capture did not reach (ncu -c N stops after N launches) keeps the figures of the previous capture
+    kept = []
+    for okey, oval in old.items():
+        if okey.startswith("per_kernel_gbytes_%d_tracks" % n_tracks):
+            for name, v in oval["read"].items():
+                if name not in rd:
+                    rd[name] = v; wr[name] = oval["write"].get(name, 0.0); kept.append(name)
+    if kept:
+        comment += " (" + ", ".join(kept) + ": unchanged kernels, figures of the previous capture)"
     tj = {"source": comment + ": dram__bytes_read.sum + dram__bytes_write.sum of the first launch of each kernel, divided by %d tracks (%s)" % (n_tracks, out_csv),
           "k_hybrid_synth_dram_bytes_per_track": (rd.get("k_hybrid_synth", 0) + wr.get("k_hybrid_synth", 0)) * 1e9 / n_tracks,
           "all_kernels_dram_bytes_per_track": (sum(rd.values()) + sum(wr.values())) * 1e9 / n_tracks,

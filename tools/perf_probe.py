@@ -23,7 +23,8 @@ imgs = [pool.track(1000 + i, n_frames) for i in range(n_tracks)]
 print("corpus built in %.1fs, %.1f MB" % (time.time() - t, sum(len(i) for i in imgs) / 1e6), flush=True)
 _lib.LIB_PATH = os.environ.get("RG_LIB", _lib.LIB_PATH)   # a variant build of the engine (kernel experiments)
 lib = _lib.load()
-eng = m.Engine(device=0, exact=exact)
+DEV = int(os.environ.get("LOCAL_RANK", "0"))   # under torchrun: one probe per GPU at the same time (shared-host contention)
+eng = m.Engine(device=DEV, exact=exact)
 for kv in os.environ.get("RG_OPTS", "").split(","):   # e.g. RG_OPTS=k2_smem_pad=30000,iir_block_windows=16
     if "=" in kv:
         eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
@@ -60,18 +61,31 @@ if len(sys.argv) > 4 and sys.argv[4] == "e2e":
         arr2[i].data = pnp.ctypes.data + int(offs[i])
         arr2[i].len = len(im)
         arr2[i].track_index = -1
+    torch.cuda.set_device(DEV)
     dev = torch.empty(int(offs[-1]), dtype=torch.uint8, device="cuda")
     for it in range(3):
         torch.cuda.synchronize(); t = time.time(); dev.copy_(pinned, non_blocking=True); torch.cuda.synchronize(); dt = time.time() - t
         print("raw H2D %.1f ms  %.1f GB/s" % (dt * 1e3, offs[-1] / dt / 1e9), flush=True)
-    for it in range(4):
-        t = time.time()
-        rc = lib.rg_analyze_tracks(eng._h, arr2, n_tracks, out, None)
-        dt = time.time() - t
-        st = eng.stats()
-        print("e2e rc", rc, "wall %.3fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f | batches %d bw %d" % (
-            dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt,
-            st.last_batches, st.last_block_windows), flush=True)
+    # RG_E2E_SWEEP="k=v,k=v;k=v": option sets applied one after the other, four calls each.  Under torchrun the ranks meet at a
+    # barrier before every call, so that all GPUs of the box pull their bytes through the host at the same time.
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    for opts in os.environ.get("RG_E2E_SWEEP", "").split(";"):
+        for kv in opts.split(","):
+            if "=" in kv:
+                eng.set_option(kv.split("=")[0], float(kv.split("=")[1]))
+        for it in range(4):
+            if world > 1:
+                dist.barrier()
+            t = time.time()
+            rc = lib.rg_analyze_tracks(eng._h, arr2, n_tracks, out, None)
+            dt = time.time() - t
+            st = eng.stats()
+            print("e2e", opts, "rc", rc, "wall %.4fs | index %.1f huff %.1f hybrid %.1f iir %.1f hist %.1f | audio-h/s %.1f | batches %d bw %d" % (
+                dt, st.last_ms_index, st.last_ms_huffman, st.last_ms_hybrid, st.last_ms_iir, st.last_ms_hist, audio_s / 3600.0 / dt,
+                st.last_batches, st.last_block_windows), flush=True)
 
 if len(sys.argv) > 4 and sys.argv[4] == "peak":
     pk = (_lib.RgPeakResult * n_tracks)()
