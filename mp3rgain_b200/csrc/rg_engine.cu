@@ -82,6 +82,7 @@ struct BatchCtx {
     HostBuf h_desc_a, h_desc, h_tout;      // pinned: descriptor staging (decode / analysis), results
     cudaEvent_t ev_a[4] = {};              // decode stream: gather start, K1 end = K2 start, K2 end, gather end = K1 start
     cudaEvent_t ev_b[4] = {};              // analysis stream: K4 start, K4 end = K5 start, K5 end, results on the host
+    cudaEvent_t ev_x[4] = {};              // K4 of a batch with several sample rates: fork, and one join per side stream
     // host bookkeeping of the batch in flight
     bool busy = false, decoded = false, exact = false;
     bool images_arriving = false;          // the batch belongs to a call whose file images are still crossing the bus (K4 then reads through its ring)
@@ -105,6 +106,7 @@ struct rg_engine {
     // streams: file images in (copy), frame index (index), Huffman + hybrid (decode), IIR + histogram (stream)
     cudaStream_t stream = nullptr, s_copy = nullptr, s_index = nullptr, s_dec = nullptr;
     cudaStream_t s_index_x[3] = {};       // more index streams: K0 is latency-bound, so groups overlap each other
+    cudaStream_t s_k4x[3] = {};           // side streams of the analysis stream: the K4 launches of a batch's sample rates run side by side
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-group events of the pipelined path (grown on demand)
     // options
@@ -237,10 +239,12 @@ static int engine_init(rg_engine* e, const rg_config* cfg, int dev) {
     CK(cudaStreamCreateWithFlags(&e->s_index, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&e->s_dec, cudaStreamNonBlocking));
     for (auto& st : e->s_index_x) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& st : e->s_k4x) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : e->ev) CK(cudaEventCreate(&ev));
     for (auto& c : e->ctx) {
         for (auto& ev : c.ev_a) CK(cudaEventCreate(&ev));
         for (auto& ev : c.ev_b) CK(cudaEventCreate(&ev));
+        for (auto& ev : c.ev_x) CK(cudaEventCreate(&ev));
     }
     // coefficient rows as K4 wants them, b's of the Yule stage pre-scaled by 2^15 (see k_analysis.cuh)
     for (int r = 0; r < 12; r++) {
@@ -297,8 +301,9 @@ extern "C" void rg_engine_destroy(rg_engine* e) {
         c.h_tout.release();
         for (auto& ev : c.ev_a) if (ev) cudaEventDestroy(ev);
         for (auto& ev : c.ev_b) if (ev) cudaEventDestroy(ev);
+        for (auto& ev : c.ev_x) if (ev) cudaEventDestroy(ev);
     }
-    for (cudaStream_t st : {e->stream, e->s_copy, e->s_index, e->s_dec, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2]}) if (st) cudaStreamDestroy(st);
+    for (cudaStream_t st : {e->stream, e->s_copy, e->s_index, e->s_dec, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2], e->s_k4x[0], e->s_k4x[1], e->s_k4x[2]}) if (st) cudaStreamDestroy(st);
     delete e;
 }
 
@@ -360,23 +365,27 @@ static inline size_t up16(size_t b) { return (b + 15) & ~(size_t)15; }
 // Windows per time block of the time-blocked IIR.
 static uint32_t choose_block_windows(const rg_engine* e, const std::vector<PcmTrack>& tracks) {
     if (e->block_windows) return e->block_windows;
-    std::vector<std::pair<uint32_t, uint32_t>> nw;   // (windows, channels) per track
+    struct Nw { uint32_t windows, channels; int rate; };
+    std::vector<Nw> nw;
     for (const PcmTrack& t : tracks) {
         const uint32_t win = (uint32_t)(((uint64_t)t.sample_rate * 50) / 1000);
-        if (t.status == RG_OK && t.frames > 0 && win > 0) nw.push_back({(uint32_t)((t.frames + win - 1) / win), t.nch >= 2 ? 2u : 1u});
+        if (t.status == RG_OK && t.frames > 0 && win > 0) nw.push_back({(uint32_t)((t.frames + win - 1) / win), t.nch >= 2 ? 2u : 1u, t.rate_idx});
     }
     // Cost model (measured, tools/iir_bench.cu with the block length as a parameter): one CTA of chains already saturates an
-    // SM's FP64 pipe, all chains are equally long, and CTAs are handed to SMs greedily -- so the kernel takes
+    // SM's FP64 pipe, all chains are (about) equally long, and CTAs are handed to SMs greedily -- so the kernel takes
     // ceil(CTAs / SMs) rounds of (block + warm-up) windows each.  Pick the block length that minimises rounds x length
-    // (ties: the longer block, less warm-up work).
+    // (ties: the longer block, less warm-up work).  Every sample rate of the batch is a launch of its own (the coefficients are
+    // launch constants) with its own partly filled last CTA; the launches run side by side (stage_b_enqueue), so what counts
+    // is the sum of their CTAs.
     const uint64_t unit = e->k4_round ? e->k4_round : 148 * K4_FAST_THREADS;
+    const uint64_t T = e->k4_slim ? K4_SLIM_THREADS : K4_FAST_THREADS;
     uint32_t best = 16;
     uint64_t best_cost = ~0ull;
     for (uint32_t bw = 8; bw <= 96; bw++) {
-        uint64_t chains = 0;
-        for (auto& p : nw) chains += (uint64_t)((p.first + bw - 1) / bw) * p.second;
-        const uint64_t T = e->k4_slim ? K4_SLIM_THREADS : K4_FAST_THREADS;
-        const uint64_t ctas = (chains + T - 1) / T;
+        uint64_t chains[12] = {};
+        for (const Nw& p : nw) chains[p.rate >= 0 && p.rate < 12 ? p.rate : 0] += (uint64_t)((p.windows + bw - 1) / bw) * p.channels;
+        uint64_t ctas = 0;
+        for (uint64_t ch : chains) ctas += (ch + T - 1) / T;
         const uint64_t rounds = (ctas * T + unit - 1) / unit;
         const uint64_t cost = rounds * (bw + e->warm_windows);
         if (cost <= best_cost) { best_cost = cost; best = bw; }
@@ -504,8 +513,19 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
     float* d_peaks_sorted = c.d_peaks.as<float>();                      // written by K4 in launch order
     float* d_peaks_orig = c.d_peaks.as<float>() + chains.size();        // original order (only when mixed)
     CK(cudaEventRecord(c.ev_b[0], st));
+    // One launch per sample rate (chains are in rate order).  The launches of a batch with several rates go to side streams so
+    // that their CTAs share ONE set of rounds: back to back on one stream, a 60 / 40 split of a wave took two full rounds (the
+    // mixed corpus of BASELINE.json configs[3]: 49 ms of K4 per 1000 tracks instead of 25, profiles/r2_mixed_config_k4_rates.log).
+    if (mixed) CK(cudaEventRecord(c.ev_x[0], st));
+    const cudaStream_t st_main = st;
+    uint32_t n_side = 0, grp = 0;
     size_t i0 = 0;
     while (i0 < chains.size()) {
+        if (mixed && grp > 0) {
+            st = e->s_k4x[(grp - 1) % 3];
+            if (grp <= 3) { CK(cudaStreamWaitEvent(st, c.ev_x[0], 0)); n_side = grp; }
+        }
+        grp++;
         size_t i1 = i0;
         const uint32_t r = h_ch[i0].rate_idx;
         while (i1 < chains.size() && h_ch[i1].rate_idx == r) i1++;
@@ -531,6 +551,11 @@ static int stage_b_enqueue(rg_engine* e, BatchCtx& c, bool exact, bool want_hist
         i0 = i1;
     }
     CK(cudaGetLastError());
+    st = st_main;
+    for (uint32_t q = 0; q < n_side; q++) {
+        CK(cudaEventRecord(c.ev_x[1 + q], e->s_k4x[q]));
+        CK(cudaStreamWaitEvent(st, c.ev_x[1 + q], 0));
+    }
     const float* d_peaks_for_k5 = d_peaks_sorted;
     if (mixed) {
         k_scatter_f32<<<(unsigned)((chains.size() + 255) / 256), 256, 0, st>>>(d_peaks_sorted, c.d_perm.as<uint32_t>(), d_peaks_orig,

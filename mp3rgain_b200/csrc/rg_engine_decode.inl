@@ -391,7 +391,7 @@ static uint64_t track_scratch_bytes(const TrackMeta& m) {
 }
 
 static void drain_streams(rg_engine* e) {
-    for (cudaStream_t st : {e->s_copy, e->s_index, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2], e->s_dec, e->stream}) cudaStreamSynchronize(st);
+    for (cudaStream_t st : {e->s_copy, e->s_index, e->s_index_x[0], e->s_index_x[1], e->s_index_x[2], e->s_dec, e->s_k4x[0], e->s_k4x[1], e->s_k4x[2], e->stream}) cudaStreamSynchronize(st);
     for (auto& x : e->ctx) { x.busy = false; x.decoded = false; x.hist_host = nullptr; }
 }
 
