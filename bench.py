@@ -492,8 +492,8 @@ def main():
                 "kernel_ms_alone": alone,
                 "achieved_alone": total_bytes / (alone["k_hybrid_synth"] / 1000.0) / 1e9,
                 "staged_dram_gbs_whole_step": (staged * n / (wall_ms / 1000.0) / 1e9) if staged else None,
-                "note": "no kernel of this path is HBM-bound: k_hybrid_synth is instruction-issue bound (70 % issue-active in "
-                        "profiles/), k_iir FP64-pipe bound (88 %); the compressed stream is ~1 % of HBM peak by construction "
+                "note": "no kernel of this path is HBM-bound: k_hybrid_synth is bound by instruction issue and dependency latency (61 % issue-active "
+                        "after the packed-f32x2 rewrite, profiles/r2_ncu_full_100tracks_summary.csv), k_iir FP64-pipe bound (88 %); the compressed stream is ~1 % of HBM peak by construction "
                         "(DESIGN.md 6). staged_dram_gbs_whole_step = ncu DRAM bytes of all kernels (spectra, PCM round trips) / step time"}
 
     # ---- the roofline that actually binds the second-largest kernel: k_iir is FP64-pipe bound.  28 FP64 instructions per
