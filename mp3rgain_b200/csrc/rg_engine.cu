@@ -119,6 +119,7 @@ struct rg_engine {
     bool timeline = false;                // development aid: print every batch's kernel intervals to stderr
     std::chrono::steady_clock::time_point t0_host;   // (timeline) host clock at the call's first event
     double host_ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_host).count(); }
+    bool arena = true;                    // host buffers that form an arena are copied group by group (corpus_describe); false: always file by file
     bool pipeline = true;                 // false: one batch at a time, every kernel alone on the device (profiling)
     uint64_t group_bytes_min = 32ull << 20; // smallest copy / index group of the end-to-end path (tests shrink it)
     double group_first_div = 12.0, group_growth = 1.6;   // size schedule of the first groups (rg_engine_decode.inl, index_enqueue)
@@ -167,6 +168,7 @@ struct rg_corpus {
     std::vector<int32_t> track_index;
     std::vector<uint8_t> is_mp4;
     uint64_t total = 0;
+    bool arena = false;                    // the caller's buffers lie in one ascending run of host memory: the device keeps their spacing (corpus_describe)
     // host sources still being copied in (the end-to-end path): group g of tracks is resident once ev_copied[g] fires
     const rg_input* pending_in = nullptr;
 };
@@ -314,6 +316,7 @@ extern "C" int rg_engine_set_option(rg_engine* e, const char* key, double value)
     if (!strcmp(key, "iir_warm_windows")) { if (value < 0) return RG_ERR_INVALID_ARG; e->warm_windows = (uint32_t)value; return RG_OK; }
     if (!strcmp(key, "edge_tol")) { e->edge_tol = value; return RG_OK; }
     if (!strcmp(key, "pipeline")) { e->pipeline = value != 0; return RG_OK; }
+    if (!strcmp(key, "arena")) { e->arena = value != 0; return RG_OK; }
     if (!strcmp(key, "k4_staged")) { e->k4_staged = (int)value; return RG_OK; }
     if (!strcmp(key, "timeline")) { e->timeline = value != 0; return RG_OK; }
     if (!strcmp(key, "group_first_div")) { if (value < 1) return RG_ERR_INVALID_ARG; e->group_first_div = value; return RG_OK; }

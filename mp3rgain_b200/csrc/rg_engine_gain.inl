@@ -50,11 +50,7 @@ static int gain_impl(rg_engine* e, rg_corpus* c, rg_gain_stats* out, bool patch,
         cudaEvent_t ev_copied = e->pool_event(6 * g), ev0 = e->pool_event(6 * g + 1), ev1 = e->pool_event(6 * g + 2),
                     ev2 = e->pool_event(6 * g + 3), ev3 = e->pool_event(6 * g + 4);
         if (c->pending_in) {
-            for (size_t i = t0; i < t1; i++) {
-                if (!c->len[i]) continue;
-                CK(cudaMemcpyAsync(c->d_bytes + c->off[i], c->pending_in[i].data, c->len[i], cudaMemcpyHostToDevice, e->s_copy));
-                e->stats.h2d_bytes += c->len[i];
-            }
+            if (int r = copy_images(e, c, c->pending_in, t0, t1, e->s_copy)) return r;
             CK(cudaEventRecord(ev_copied, e->s_copy));
             CK(cudaStreamWaitEvent(st, ev_copied, 0));
         }

@@ -333,6 +333,54 @@ def test_batch_of_many_tracks_and_small_scratch(oracle):
         assert (res[i].histogram == ohist).all() and res[i].loudness_db == ores.loudness_db and res[i].peak == ores.peak
 
 
+def _arena(imgs, gaps):
+    """The images as slices of ONE host buffer, image k starting `gaps[k % len(gaps)]` + alignment padding after its predecessor."""
+    pos, offs = 0, []
+    for k, im in enumerate(imgs):
+        pos = (pos + 15) & ~15
+        if k:
+            pos += gaps[k % len(gaps)]
+        offs.append(pos)
+        pos += len(im)
+    buf = np.full(pos + 64, 0xA5, np.uint8)
+    for o, im in zip(offs, imgs):
+        buf[o:o + len(im)] = im
+    return buf, [buf[o:o + len(im)] for o, im in zip(offs, imgs)]
+
+
+def test_host_buffers_that_form_an_arena_cross_the_bus_group_by_group(oracle):
+    """Callers that keep their files in one run of host memory (<= 64 bytes apart, 16-byte multiples from the first) get one
+    copy per group instead of one per file and the caller's spacing on the device (corpus_describe).  Results -- analysis,
+    Mp3Analysis fields, patched images -- are those of separately allocated buffers; an empty file and a file that is not an
+    MP3 sit in the middle; a layout that does not qualify (a 96-byte gap) takes the per-file path."""
+    import mp3rgain_b200 as m
+    pool = synth_corpus.GroupPool(seed=5, n_groups=24, group_len=16)
+    imgs = [pool.track(700 + i, 64 + 16 * (i % 4)) for i in range(14)]
+    imgs[4] = np.zeros(0, np.uint8)
+    imgs[9] = np.full(5000, 0x11, np.uint8)
+    imgs[11] = synth_corpus.make_track(seed=77, n_frames=80, version=2, channels=1, br_idx=6, sr_idx=0)
+    with m.Engine(device=0, exact=False, scratch_bytes=16 << 20) as eng:
+        eng.set_option("group_bytes_min", 60_000)
+        want, wst = eng.analyze_images(imgs, want_hist=True)
+        wgain = eng.gain_analyze_images(imgs)
+        wpatched, wn = eng.gain_apply_images(imgs, 3)
+        for gaps in ((0, 16, 32, 48), (0,), (48, 0, 96)):
+            buf, views = _arena(imgs, gaps)
+            got, gst = eng.analyze_images(views, want_hist=True)
+            assert gst == wst
+            for a, b, st in zip(got, want, wst):
+                if st == 0:
+                    assert (a.histogram == b.histogram).all() and a.loudness_db == b.loudness_db and a.peak == b.peak and a.n_frames == b.n_frames
+            ggain = eng.gain_analyze_images(views)
+            assert [(g.status, g.frame_count, g.gain_sum, g.min_gain, g.max_gain) for g in ggain] == [
+                (g.status, g.frame_count, g.gain_sum, g.min_gain, g.max_gain) for g in wgain]
+            gpatched, gn = eng.gain_apply_images(views, 3)
+            assert list(gn) == list(wn) and all((a == b).all() for a, b in zip(gpatched, wpatched))
+            assert (buf[-64:] == 0xA5).all()     # the caller's memory is only read
+    rc, ores, ohist, info = oracle.analyze_mp3(imgs[11])
+    assert rc == 0 and (want[11].histogram == ohist).all()
+
+
 def test_mixed_corpus_through_the_pipeline(oracle):
     """BASELINE configs[3] in miniature: VBR 32-320 kbps, 44.1 / 48 / 32 kHz, mono and stereo, different lengths, plus
     files that fail (garbage, MPEG-2, empty) in the middle of the list -- all in ONE rg_analyze_tracks call that is forced
