@@ -66,7 +66,11 @@ typedef struct {
 } rg_config;
 
 /* One file image.  Stands in for the `&Path` argument of analyze_track (src/replaygain.rs:929):
- * the caller has read (or mmapped / pinned) the file; the engine borrows the bytes until the call returns. */
+ * the caller has read (or mmapped / pinned) the file; the engine borrows the bytes until the call returns.
+ * Pinned memory is copied at the full bus rate, pageable memory through the driver's staging.  When the non-empty buffers of a
+ * call ascend through memory at most 64 bytes apart, at 16-byte multiples from the first (files read into one arena), the
+ * engine copies them in runs and also READS the bytes between them (never writes; rg_engine_set_option("arena", 0) turns
+ * that off). */
 typedef struct {
     const uint8_t* data;
     uint64_t       len;
