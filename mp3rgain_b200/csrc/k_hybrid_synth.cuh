@@ -55,7 +55,9 @@ struct K2Smem {
     uint8_t code[3][576];                     // line -> band code: [0] long, [1] pure short, [2] mixed
     uint8_t ia[32], ib[32];
     uint8_t istab[K2_GC / 2][64];             // intensity stereo: is_pos per band of the right channel's partition, 255 = not intensity coded
-    int istop[K2_GC / 2][4];                  // highest non-zero band of the right channel: [0] long sfb, [1..3] short sfb per window
+    alignas(16) int istop[K2_GC / 2][4];      // highest non-zero band of the right channel: [0] long sfb, [1..3] short sfb per window
+                                              // (16-byte aligned: ptxas reads a pair's four words with ONE LDS.128; unaligned, that load reached
+                                              // into the neighbouring table and racecheck reported it against another pair's store)
     float isr[2][8];                          // MPEG-1: is_pos -> left / right factor
     uint8_t iscale[K2_GC / 2];                // MPEG-2: intensity_scale of the granule's right channel
     alignas(8) unsigned long long mbar;       // completion barrier of the spectra copy
