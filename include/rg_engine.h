@@ -209,7 +209,7 @@ typedef struct {
     int32_t  status;            /* RG_OK, or RG_ERR_NO_FRAMES */
     uint8_t  min_gain, max_gain;
     uint8_t  reserved[2];
-    uint32_t walk_rewalks;      /* 64 KiB segments the merge had to walk again (diagnostic) */
+    uint32_t walk_rewalks;      /* 4 KiB sub-segments (GF_SUB) the merge had to walk again (diagnostic) */
 } rg_gain_stats;
 
 /* mp3rgain::analyze (src/lib.rs:470-514), batched over n file images: the reference's own frame walk (iterate_frames,
