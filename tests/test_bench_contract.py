@@ -33,8 +33,13 @@ def test_reference_arm_prints_one_json_line():
 
 
 def test_last_gpu_bench_line_has_the_contract_keys():
-    path = os.path.join(ROOT, "profiles", "r1_bench_s8_1gpu.json")
+    path = os.path.join(ROOT, "profiles", "r2_bench_final_1gpu.json")
     d = json.load(open(path))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_final_reference_arm.json")))
+    assert ref["impl"] == "reference" and ref["config"] == d["config"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+    for name in ("album", "mixed", "stream"):
+        assert "error" not in d["configs"][name] and d["configs"][name]["value"] > 0, name
+    assert d["configs"]["album"]["histogram_is_the_sum"] is True
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
