@@ -9,7 +9,8 @@
 //              granule-channels with shuffles -> first and last bit of the thread's stretch of the stream
 //   stage      the CTA's slice of the main-data stream (24 KB at 128 kbps) arrives in shared memory as ONE bulk copy
 //              (cp.async.bulk + mbarrier); a slice that exceeds the 28 KB window (high bitrates) is walked in several windows
-//   sort       the 256 granule-channels are ordered by big_values (counting sort), so that the lanes of a warp leave the
+//   sort       the 256 granule-channels are ordered by big_values (counting sort; by staging window first when the slice needs
+//              several), so that the lanes of a warp leave the
 //              big-values loop together
 //   part 2     scalefactors -> one BYTE per scalefactor band (what to subtract from the granule's gain exponent; K2 looks
 //              the power of two up), resolved against granule 0 for scfsi; the 64-byte rows leave through the warp's tile
@@ -171,6 +172,7 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
 
     // ---- pre-pass, thread = granule-channel in stream order: side-info bits, position in the stream, sort key
     uint32_t key = 0x1FF;   // inactive slots sort last
+    uint32_t pre_start = 0;  // my granule-channel's first bit in the track's stream
     {
         const uint32_t g = blk.gc0 + tid;
         uint32_t p23 = 0, md_start = 0, inf = 0, W0 = 0, W1 = 0, W2 = 0, md_end = 0;
@@ -200,7 +202,8 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
             if ((uint32_t)o <= rem) before += up;
         }
         S.pre.side[tid][0] = W0; S.pre.side[tid][1] = W1; S.pre.side[tid][2] = W2;
-        S.pre.start[tid] = md_start * 8 + before;
+        pre_start = md_start * 8 + before;
+        S.pre.start[tid] = pre_start;
         S.pre.mdend[tid] = md_end;
         S.pre.info[tid] = inf;
 #pragma unroll
@@ -211,6 +214,17 @@ k_huffman(const uint8_t* __restrict__ corpus, const uint8_t* __restrict__ md, co
     {
         S.pre.cnt[tid] = 0; S.pre.cnt[tid + 256] = 0;
         __syncthreads();
+        // A slice longer than the staging window (256-320 kbps) is walked in several windows, each serving the granule-channels
+        // whose bits lie inside it -- consecutive ones in stream order.  Sorted by big_values alone they would be spread over all
+        // eight warps, and every warp would run every window's pass at a third of its lanes; with the (estimated) window as the
+        // major key a warp belongs to one window and sits the other passes out.  (The estimate only orders the workers: which
+        // window actually serves a granule-channel is decided in the loop below.)
+        {
+            const uint32_t n_act = min((uint32_t)K1_THREADS, n_gc - blk.gc0);
+            const uint32_t first = S.pre.start[0] >> 3, span = (S.pre.start[n_act - 1] >> 3) + 512u - first;   // part2_3_length < 4096 bits
+            if (span + K1_SLACK > K1_STAGE && key != 0x1FFu)
+                key = (min(3u, ((pre_start >> 3) - first) / (K1_STAGE - 1024u)) << 7) | (key >> 2);
+        }
         const uint32_t slot = atomicAdd(&S.pre.cnt[key], 1u);
         __syncthreads();
         const uint32_t c0 = S.pre.cnt[2 * tid], c1 = S.pre.cnt[2 * tid + 1];
