@@ -532,7 +532,7 @@ static int analyze_corpus_impl(rg_engine* e, rg_corpus* c, rg_track_result* out,
         x.ids.resize(t1 - next);
         for (size_t i = next; i < t1; i++) x.ids[i - next] = (uint32_t)i;
         x.hist_host = hist_out ? hist_out + next * RG_HIST_BINS : nullptr;
-        x.images_arriving = c->pending_in != nullptr;
+        x.images_arriving = c->pending_in != nullptr && ip.groups_absorbed + 1 < ip.group_begin.size();   // (frame-index kernels may still run beside this batch)
         const double h0 = e->timeline ? e->host_ms() : 0.0;
         rc = decode_enqueue(e, c, ip, x);
         const double h1 = e->timeline ? e->host_ms() : 0.0;
