@@ -517,6 +517,27 @@ def main():
                             "note": "achieved: CUDA events inside the timed (pipelined) step, where K1/K2 of the next batch share the "
                                     "SMs; achieved_alone: the same kernel with the pipeline off"}
 
+    # ---- and the one that binds the largest: k_hybrid_synth is bound by instruction issue (one warp instruction per SM
+    # sub-partition and clock).  Executed warp-instructions per track from the ncu capture (profiles/traffic.json, counted on
+    # the same corpus generator), over the kernel's time with the pipeline off, against 4 x SMs x the SM clock of this run.
+    try:
+        wi = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["warp_instructions_per_track"]["k_hybrid_synth"]
+        wi *= config["frames_decoded_per_track"] / 6912.0   # (the capture decoded 6912 frames per track)
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        try:
+            n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        except Exception:  # noqa: BLE001  (the interpreted build of the CPU suite has no device)
+            n_sms = 148
+        issue_peak = 4.0 * n_sms * sm_hz
+        roofline["issue"] = {"kernel": "k_hybrid_synth", "bound": "instruction issue", "unit": "T warp-instr/s", "peak": issue_peak / 1e12,
+                             "achieved_alone": wi * n / (alone["k_hybrid_synth"] / 1000.0) / 1e12,
+                             "frac_alone": wi * n / (alone["k_hybrid_synth"] / 1000.0) / issue_peak,
+                             "warp_instructions_per_track": wi,
+                             "note": "instruction count from ncu (3-min CBR-128 stereo tracks: 1212 per granule-channel), time from CUDA events of "
+                                     "this run with the pipeline off"}
+    except Exception:  # noqa: BLE001
+        pass
+
     line = {"metric": METRIC, "value": value, "unit": "audio-h/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_ms, "device_ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,

@@ -60,6 +60,9 @@ if "--traffic" in sys.argv:
           "k_hybrid_synth_dram_bytes_per_track": (rd.get("k_hybrid_synth", 0) + wr.get("k_hybrid_synth", 0)) * 1e9 / n_tracks,
           "all_kernels_dram_bytes_per_track": (sum(rd.values()) + sum(wr.values())) * 1e9 / n_tracks,
           "per_kernel_gbytes_%d_tracks" % n_tracks: {"read": rd, "write": wr}}
+    # warp-instructions per track of every kernel (issue roofline of bench.py)
+    inst = {s_: float(r[col["smsp__inst_executed.sum"]]) / n_tracks for s_, r in zip(short, data) if "smsp__inst_executed.sum" in col}
+    tj["warp_instructions_per_track"] = inst
     for key in ("k_gf_scan_dram_bytes_per_track", "k_gf_scan_source"):
         if key in old:
             tj[key] = old[key]
