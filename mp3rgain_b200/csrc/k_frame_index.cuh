@@ -353,6 +353,8 @@ k_index_finalize(const uint8_t* __restrict__ corpus, const TrackIn* __restrict__
 __global__ void __launch_bounds__(K0B_THREADS)
 k_md_gather(const uint8_t* __restrict__ corpus, uint8_t* __restrict__ md, const FrameRec* __restrict__ frames,
             const DecTrack* __restrict__ tracks, const RunDesc* __restrict__ runs) {
+    __shared__ uint16_t s_flen[3][16];   // MPEG-1 frame lengths by table (k0_frame_len divides: a fifth of this kernel's instructions)
+    k0_fill_flen(s_flen);
     const RunDesc run = runs[blockIdx.x];
     const DecTrack tr = tracks[run.track];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -361,7 +363,7 @@ k_md_gather(const uint8_t* __restrict__ corpus, uint8_t* __restrict__ md, const 
         const FrameRec rec = frames[tr.frame_base + f];
         const uint32_t h = rec.hdr;
         const int off = 4 + ((h & 0x10000u) ? 0 : 2) + k0_side_len(h);
-        const int flen = k0_frame_len(h);
+        const int flen = (((h >> 19) & 3) == 3) ? (int)s_flen[(h >> 10) & 3][(h >> 12) & 15] + (int)((h >> 9) & 1) : k0_frame_len(h);
         const int cap = flen > off ? flen - off : 0;
         const uint8_t* src = corpus + tr.corpus_off + rec.file_off + off;
         uint8_t* dst = md + tr.md_off + rec.md_end - cap;
